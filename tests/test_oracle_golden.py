@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import mg_oracle as O
+from oracle.c_oracle import COracle
 from tests.golden_util import ROLLOUT_CASES, load_case, GOLDEN_DIR
 
 
@@ -26,23 +27,30 @@ def test_pcg64_known_answers():
             assert u == want
 
 
-def test_obs_random_injected_states():
+@pytest.mark.parametrize("impl", ["python", "c"])
+def test_obs_random_injected_states(impl):
     d = np.load(f"{GOLDEN_DIR}/obs_random.npz")
     for c in range(len(d["W"])):
         W, H, n, V = (int(d[k][c]) for k in ("W", "H", "n", "V"))
         cfg = O.OracleConfig(W=W, H=H, n=n, V=V, see_through_walls=bool(d["stw"][c]))
-        grid = d["grid"][c, :W, :H]
+        grid = np.ascontiguousarray(d["grid"][c, :W, :H])
         agents = O.pack_agents(d["agents"][c, :n])
-        got = O.gen_obs_env(cfg, grid, agents)
+        if impl == "python":
+            got = O.gen_obs_env(cfg, grid, agents)
+        else:
+            z = np.zeros((1, 2), np.uint64)
+            got = COracle(cfg, grid[None], agents[None], z, z).gen_obs()[0]
         np.testing.assert_array_equal(got, d["obs"][c, :n, :V, :V], err_msg=f"case {c}")
 
 
+@pytest.mark.parametrize("impl", ["python", "c"])
 @pytest.mark.parametrize("name", ROLLOUT_CASES)
-def test_rollout_matches_reference(name):
+def test_rollout_matches_reference(name, impl):
     d, meta = load_case(name)
     cfg = cfg_from_meta(meta)
     B, T, J = meta["B"], meta["T"], meta["pool_J"]
-    ob = O.OracleBatch(cfg, d["init_grid"], O.pack_agents(d["init_agents"]), d["pcg_state"],
+    cls = O.OracleBatch if impl == "python" else COracle
+    ob = cls(cfg, d["init_grid"], O.pack_agents(d["init_agents"]), d["pcg_state"],
                        d["pcg_inc"], pool_grid=d["pool_grid"],
                        pool_agents=O.pack_agents(d["pool_agents"]),
                        layout_idx=np.arange(B) * J)
