@@ -1,0 +1,145 @@
+/*
+ * multigrid_b200 -- C ABI of the B200 (sm_100a) batched MultiGrid step/observe engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of ini/multigrid that this library replaces:
+ *
+ *     MultiGridEnv.step()            multigrid/base.py:303-346
+ *       -> handle_actions()          multigrid/base.py:378-476  (+ on_success/on_failure :478-532)
+ *       -> gen_obs()                 multigrid/base.py:348-376
+ *            -> gen_obs_grid_encoding  multigrid/utils/obs.py:66-102 (numba)
+ *
+ * The reference has no FFI of its own (it is Python + 8 numba functions); the seam a maintainer
+ * would bind is the array-level call `gen_obs_grid_encoding(grid_state, agent_state, view_size,
+ * see_through_walls)` and the `step()` method around it. INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - Plain C: pointers + sizes only. All `d_`/unprefixed data pointers are DEVICE pointers
+ *     (16-byte aligned, e.g. torch CUDA tensors); `h_` pointers are (pinned) HOST pointers.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream); no internal synchronisation, no global state, re-entrant across streams/devices.
+ *   - Return value: 0 = ok, >0 = cudaError_t of the launch, <0 = MG_ERR_* argument error.
+ *   - Batch axis first: env e owns slice e of every array ("env-major", each env's record is
+ *     contiguous, so a thread block's group of envs is one contiguous HBM span per array).
+ *
+ * State layout per env (all int8 values are < 128):
+ *   grid        int8  [W][H][3]   x-major like Grid.state (core/grid.py:54): (type,color,state)
+ *   agents      int8  [n][8]      {dir,x,y,terminated,carry_type,carry_color,carry_state,color}
+ *                                 = AgentState (core/agent.py:222-232) without the constant TYPE
+ *   step_count  int32
+ *   pcg_state   uint64[2]         {lo,hi} of numpy PCG64's 128-bit state (env.np_random)
+ *   pcg_inc     uint64[2]         {lo,hi} of its increment (constant)
+ *   layout_idx  int32             cursor into the reset-layout pool (auto-reset only)
+ * Outputs per env:
+ *   obs         int8  [n][obs_agent_stride]  first 3*V*V bytes of each agent slot = image[V][V][3]
+ *   reward      float64 [n]       bit-exact `1 - 0.9*(step_count/max_steps)` (base.py:598-602)
+ *   terminated  uint8 [n]
+ *   truncated   uint8
+ */
+#ifndef MULTIGRID_B200_H
+#define MULTIGRID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_ABI_VERSION 1
+
+/* MgConfig.flags */
+#define MG_FLAG_SEE_THROUGH_WALLS 0x01u /* agents[0].see_through_walls, base.py:364-365 */
+#define MG_FLAG_ALLOW_OVERLAP     0x02u /* allow_agent_overlap, base.py:95            */
+#define MG_FLAG_JOINT_REWARD      0x04u /* joint_reward, base.py:96                   */
+#define MG_FLAG_SUCCESS_ANY       0x08u /* success_termination_mode == 'any'          */
+#define MG_FLAG_FAILURE_ANY       0x10u /* failure_termination_mode == 'any'          */
+#define MG_FLAG_AUTO_RESET        0x20u /* engine extension: "next-step" auto reset   */
+
+/* MgConfig.hook: env-specific step() post-hooks */
+#define MG_HOOK_NONE 0
+#define MG_HOOK_BLOCKED_UNLOCK_PICKUP 1 /* envs/blockedunlockpickup.py:166-175 */
+
+#define MG_ERR_BAD_ARG   (-1)
+#define MG_ERR_ALIGNMENT (-2)
+#define MG_ERR_TOO_LARGE (-3)
+
+#define MG_MAX_VIEW 15     /* odd view sizes 3..15 */
+#define MG_MAX_AGENTS 32
+
+typedef struct MgConfig {
+    int32_t width, height;     /* grid size W,H (grid is [W][H][3]) */
+    int32_t num_agents;        /* n */
+    int32_t view_size;         /* V, odd, 3..MG_MAX_VIEW (core/agent.py:78-79) */
+    int32_t max_steps;
+    uint32_t flags;            /* MG_FLAG_* */
+    int32_t hook;              /* MG_HOOK_* */
+    int32_t obs_agent_stride;  /* bytes between agents in `obs`; multiple of 4, >= 3*V*V */
+    int32_t num_layouts;       /* K: size of the reset-layout pool (auto-reset) */
+    int32_t layout_stride;     /* on reset: layout_idx = (layout_idx + layout_stride) % K */
+} MgConfig;
+
+typedef struct MgState {
+    int8_t *grid;              /* [E][W][H][3] */
+    int8_t *agents;            /* [E][n][8]    */
+    int32_t *step_count;       /* [E]          */
+    uint64_t *pcg_state;       /* [E][2]       */
+    const uint64_t *pcg_inc;   /* [E][2]       */
+    int32_t *layout_idx;       /* [E]      (may be NULL without MG_FLAG_AUTO_RESET) */
+    const int8_t *pool_grid;   /* [K][W][H][3] (may be NULL without MG_FLAG_AUTO_RESET) */
+    const int8_t *pool_agents; /* [K][n][8]    (may be NULL without MG_FLAG_AUTO_RESET) */
+} MgState;
+
+typedef struct MgStepOut {
+    int8_t *obs;               /* [E][n][obs_agent_stride] (NULL allowed for mg_step) */
+    double *reward;            /* [E][n] */
+    uint8_t *terminated;       /* [E][n] */
+    uint8_t *truncated;        /* [E]    */
+    int32_t *status;           /* [1] device word, OR-ed with 1 when an action outside 0..6
+                                  (and != -1) was seen: the reference raises ValueError there
+                                  (base.py:473-474). May be NULL. */
+} MgStepOut;
+
+int mg_abi_version(void);
+const char *mg_error_string(int code);
+
+/* Smallest legal obs_agent_stride for a view size: 3*V*V rounded up to a multiple of 4. */
+int32_t mg_obs_agent_stride(int32_t view_size);
+
+/* Number of engine kernels launched by this process so far (for launch accounting). */
+int64_t mg_launch_count(void);
+
+/*
+ * gen_obs for every agent of every env. Pure function of (grid, agents).
+ * Replaces: gen_obs_grid_encoding (utils/obs.py:66-102) as called by MultiGridEnv.gen_obs
+ * (base.py:348-376); used for reset() observations.
+ */
+int mg_gen_obs(const MgConfig *cfg, int64_t num_envs, const int8_t *grid, const int8_t *agents,
+               int8_t *obs, void *stream);
+
+/*
+ * One lockstep transition for every env WITHOUT observations.
+ * Replaces: step_count bookkeeping + handle_actions + terminations/truncations of
+ * MultiGridEnv.step (base.py:333-340, 378-532) and the env post-hook selected by cfg->hook.
+ * actions: int8 [E][n], values 0..6 (core/actions.py:5-15) or -1 = agent id absent from the dict.
+ */
+int mg_step(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *actions,
+            const MgStepOut *out, void *stream);
+
+/* The fused hot path: mg_step followed by mg_gen_obs in ONE kernel (state read once).
+ * Replaces: MultiGridEnv.step (base.py:303-346). This is what BASELINE.json's metric measures. */
+int mg_step_obs(const MgConfig *cfg, int64_t num_envs, const MgState *state,
+                const int8_t *actions, const MgStepOut *out, void *stream);
+
+/*
+ * Host-buffer variant of mg_step_obs (what a CPU-side caller of env.step() sees):
+ * copies h_actions -> d_actions, runs the fused kernel, copies the outputs in `d_out` to the
+ * matching pointers in `h_out` (obs, reward, terminated, truncated; status is not copied).
+ * Host buffers should be pinned; everything is enqueued on `stream`, the caller synchronises.
+ */
+int mg_step_obs_host(const MgConfig *cfg, int64_t num_envs, const MgState *state,
+                     const int8_t *h_actions, int8_t *d_actions, const MgStepOut *d_out,
+                     const MgStepOut *h_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MULTIGRID_B200_H */

@@ -1,0 +1,108 @@
+"""ctypes binding of the C ABI declared in include/multigrid_b200.h.
+
+The shared library is built in-tree by `multigrid_b200.build` (nvcc, sm_100a). There is NO
+fallback: if the library is missing or fails to load, importing the engine raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "_lib", "libmultigrid_b200.so")
+
+# MgConfig.flags (include/multigrid_b200.h)
+FLAG_SEE_THROUGH_WALLS = 0x01
+FLAG_ALLOW_OVERLAP = 0x02
+FLAG_JOINT_REWARD = 0x04
+FLAG_SUCCESS_ANY = 0x08
+FLAG_FAILURE_ANY = 0x10
+FLAG_AUTO_RESET = 0x20
+
+HOOK_NONE = 0
+HOOK_BLOCKED_UNLOCK_PICKUP = 1
+
+ABI_VERSION = 1
+MAX_VIEW = 15
+MAX_AGENTS = 32
+
+
+class MgConfig(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("num_agents", C.c_int32),
+        ("view_size", C.c_int32), ("max_steps", C.c_int32), ("flags", C.c_uint32),
+        ("hook", C.c_int32), ("obs_agent_stride", C.c_int32), ("num_layouts", C.c_int32),
+        ("layout_stride", C.c_int32),
+    ]
+
+
+class MgState(C.Structure):
+    _fields_ = [
+        ("grid", C.c_void_p), ("agents", C.c_void_p), ("step_count", C.c_void_p),
+        ("pcg_state", C.c_void_p), ("pcg_inc", C.c_void_p), ("layout_idx", C.c_void_p),
+        ("pool_grid", C.c_void_p), ("pool_agents", C.c_void_p),
+    ]
+
+
+class MgStepOut(C.Structure):
+    _fields_ = [
+        ("obs", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p),
+        ("truncated", C.c_void_p), ("status", C.c_void_p),
+    ]
+
+
+EXPORTS = {
+    "mg_abi_version": (C.c_int, []),
+    "mg_error_string": (C.c_char_p, [C.c_int]),
+    "mg_obs_agent_stride": (C.c_int32, [C.c_int32]),
+    "mg_launch_count": (C.c_int64, []),
+    "mg_gen_obs": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                             C.c_void_p]),
+    "mg_step": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p,
+                          C.POINTER(MgStepOut), C.c_void_p]),
+    "mg_step_obs": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p,
+                              C.POINTER(MgStepOut), C.c_void_p]),
+    "mg_step_obs_host": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p,
+                                   C.c_void_p, C.POINTER(MgStepOut), C.POINTER(MgStepOut),
+                                   C.c_void_p]),
+}
+
+
+class EngineLibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA engine library (once). Raises EngineLibraryError when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineLibraryError(
+            f"{LIB_PATH} not found: build it with `python -m multigrid_b200.build` "
+            "(nvcc, sm_100a). multigrid_b200 has no CPU or PyTorch fallback.")
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as exc:  # e.g. libcudart missing
+        raise EngineLibraryError(f"cannot load {LIB_PATH}: {exc}") from exc
+    for name, (restype, argtypes) in EXPORTS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype, fn.argtypes = restype, argtypes
+    if lib.mg_abi_version() != ABI_VERSION:
+        raise EngineLibraryError(
+            f"ABI mismatch: library {lib.mg_abi_version()} != binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().mg_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {rc})")
+
+
+def obs_agent_stride(view_size: int) -> int:
+    return (3 * view_size * view_size + 3) & ~3

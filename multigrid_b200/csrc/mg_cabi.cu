@@ -1,0 +1,186 @@
+// multigrid_b200 -- C ABI (include/multigrid_b200.h) over the sm_100a kernels in mg_kernels.cuh.
+// Argument validation, launch geometry and kernel dispatch only; no torch, no global state
+// besides a launch counter.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+
+#include "mg_kernels.cuh"
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+
+constexpr int kMaxThreads = 256;
+constexpr int kSmemBudget = 200 * 1024;  // per block; B200 allows 227 KB opt-in
+
+int env_int(const char *name, int dflt) {
+    const char *s = std::getenv(name);
+    return (s && *s) ? std::atoi(s) : dflt;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int validate(const MgConfig *c, int64_t num_envs) {
+    if (!c || num_envs < 0 || num_envs > (1ll << 30)) return MG_ERR_BAD_ARG;
+    if (c->width < 1 || c->height < 1 || c->width > 127 || c->height > 127) return MG_ERR_BAD_ARG;
+    if (c->num_agents < 1 || c->num_agents > MG_MAX_AGENTS) return MG_ERR_BAD_ARG;
+    if (c->view_size < 3 || c->view_size > MG_MAX_VIEW || !(c->view_size & 1)) return MG_ERR_BAD_ARG;
+    if (c->max_steps < 1) return MG_ERR_BAD_ARG;
+    if (c->obs_agent_stride < 3 * c->view_size * c->view_size || (c->obs_agent_stride & 3)) return MG_ERR_BAD_ARG;
+    if ((c->flags & MG_FLAG_AUTO_RESET) && c->num_layouts < 1) return MG_ERR_BAD_ARG;
+    return 0;
+}
+
+int plan(mg::Params &p) { return mg::plan_launch(p, env_int("MG_EPB", 0), kMaxThreads, kSmemBudget); }
+
+template <int VT, int MODE>
+int launch(const mg::Params &p, cudaStream_t stream) {
+    auto kernel = mg::step_obs_kernel<VT, MODE>;
+    static thread_local int configured_dev_smem[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && configured_dev_smem[dev] < p.smem_bytes) {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (err != cudaSuccess) return (int)err;
+        configured_dev_smem[dev] = kSmemBudget;
+    }
+    const int blocks = (p.num_envs + p.epb - 1) / p.epb;
+    kernel<<<blocks, p.epb * p.tpe, p.smem_bytes, stream>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+template <int MODE>
+int dispatch(const mg::Params &p, cudaStream_t stream) {
+    if constexpr (MODE == mg::MODE_STEP) {
+        return launch<0, MODE>(p, stream);  // no observation phase: view size is irrelevant
+    } else {
+        const bool generic = env_int("MG_GENERIC_VIEW", 0) != 0;
+        if (!generic) {
+            switch (p.V) {
+                case 3: return launch<3, MODE>(p, stream);
+                case 5: return launch<5, MODE>(p, stream);
+                case 7: return launch<7, MODE>(p, stream);
+                case 9: return launch<9, MODE>(p, stream);
+                default: break;
+            }
+        }
+        return launch<0, MODE>(p, stream);
+    }
+}
+
+void fill_config(mg::Params &p, const MgConfig *c, int64_t num_envs) {
+    std::memset(&p, 0, sizeof(p));
+    p.W = c->width; p.H = c->height; p.n = c->num_agents; p.V = c->view_size;
+    p.max_steps = c->max_steps; p.flags = c->flags; p.hook = c->hook;
+    p.ostride = c->obs_agent_stride; p.K = c->num_layouts; p.lstride = c->layout_stride;
+    p.num_envs = (int32_t)num_envs;
+}
+
+int fill_state(mg::Params &p, const MgState *s) {
+    if (!s || !s->grid || !s->agents || !s->step_count) return MG_ERR_BAD_ARG;
+    if (p.n > 1 && (!s->pcg_state || !s->pcg_inc)) return MG_ERR_BAD_ARG;
+    if ((p.flags & MG_FLAG_AUTO_RESET) && (!s->layout_idx || !s->pool_grid || !s->pool_agents)) return MG_ERR_BAD_ARG;
+    if (!aligned16(s->grid) || !aligned16(s->agents) || !aligned16(s->pool_agents)) return MG_ERR_ALIGNMENT;
+    p.grid = s->grid; p.agents = s->agents; p.step_count = s->step_count;
+    p.pcg_state = s->pcg_state; p.pcg_inc = s->pcg_inc; p.layout_idx = s->layout_idx;
+    p.pool_grid = s->pool_grid; p.pool_agents = s->pool_agents;
+    return 0;
+}
+
+int fill_out(mg::Params &p, const MgStepOut *o, bool need_obs) {
+    if (!o || !o->reward || !o->terminated || !o->truncated) return MG_ERR_BAD_ARG;
+    if (need_obs && !o->obs) return MG_ERR_BAD_ARG;
+    if (need_obs && !aligned16(o->obs)) return MG_ERR_ALIGNMENT;
+    p.obs = o->obs; p.reward = o->reward; p.terminated = o->terminated; p.truncated = o->truncated;
+    p.status = o->status;
+    return 0;
+}
+
+template <int MODE>
+int step_common(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *actions,
+                const MgStepOut *out, void *stream) {
+    int rc = validate(cfg, num_envs);
+    if (rc) return rc;
+    if (num_envs == 0) return 0;
+    if (!actions) return MG_ERR_BAD_ARG;
+    mg::Params p;
+    fill_config(p, cfg, num_envs);
+    if ((rc = fill_state(p, state))) return rc;
+    if ((rc = fill_out(p, out, MODE == mg::MODE_STEP_OBS))) return rc;
+    p.actions = actions;
+    if ((rc = plan(p))) return rc;
+    return dispatch<MODE>(p, (cudaStream_t)stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mg_abi_version(void) { return MG_ABI_VERSION; }
+
+const char *mg_error_string(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case MG_ERR_BAD_ARG: return "multigrid_b200: bad argument";
+        case MG_ERR_ALIGNMENT: return "multigrid_b200: device pointers must be 16-byte aligned";
+        case MG_ERR_TOO_LARGE: return "multigrid_b200: grid/view too large for one thread block's shared memory";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "multigrid_b200: unknown error";
+    }
+}
+
+int32_t mg_obs_agent_stride(int32_t view_size) { return (3 * view_size * view_size + 3) & ~3; }
+
+int64_t mg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int mg_gen_obs(const MgConfig *cfg, int64_t num_envs, const int8_t *grid, const int8_t *agents,
+               int8_t *obs, void *stream) {
+    int rc = validate(cfg, num_envs);
+    if (rc) return rc;
+    if (num_envs == 0) return 0;
+    if (!grid || !agents || !obs) return MG_ERR_BAD_ARG;
+    if (!aligned16(grid) || !aligned16(agents) || !aligned16(obs)) return MG_ERR_ALIGNMENT;
+    mg::Params p;
+    fill_config(p, cfg, num_envs);
+    p.flags &= ~MG_FLAG_AUTO_RESET;
+    p.grid = const_cast<int8_t *>(grid);      // MODE_OBS never writes state
+    p.agents = const_cast<int8_t *>(agents);
+    p.obs = obs;
+    if ((rc = plan(p))) return rc;
+    return dispatch<mg::MODE_OBS>(p, (cudaStream_t)stream);
+}
+
+int mg_step(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *actions,
+            const MgStepOut *out, void *stream) {
+    return step_common<mg::MODE_STEP>(cfg, num_envs, state, actions, out, stream);
+}
+
+int mg_step_obs(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *actions,
+                const MgStepOut *out, void *stream) {
+    return step_common<mg::MODE_STEP_OBS>(cfg, num_envs, state, actions, out, stream);
+}
+
+int mg_step_obs_host(const MgConfig *cfg, int64_t num_envs, const MgState *state,
+                     const int8_t *h_actions, int8_t *d_actions, const MgStepOut *d_out,
+                     const MgStepOut *h_out, void *stream) {
+    int rc = validate(cfg, num_envs);
+    if (rc) return rc;
+    if (!h_actions || !d_actions || !d_out || !h_out || !h_out->obs || !h_out->reward ||
+        !h_out->terminated || !h_out->truncated) return MG_ERR_BAD_ARG;
+    if (num_envs == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t E = (size_t)num_envs, n = (size_t)cfg->num_agents;
+    cudaError_t err = cudaMemcpyAsync(d_actions, h_actions, E * n, cudaMemcpyHostToDevice, s);
+    if (err != cudaSuccess) return (int)err;
+    rc = step_common<mg::MODE_STEP_OBS>(cfg, num_envs, state, d_actions, d_out, stream);
+    if (rc) return rc;
+    if ((err = cudaMemcpyAsync(h_out->obs, d_out->obs, E * n * cfg->obs_agent_stride, cudaMemcpyDeviceToHost, s))) return (int)err;
+    if ((err = cudaMemcpyAsync(h_out->reward, d_out->reward, E * n * sizeof(double), cudaMemcpyDeviceToHost, s))) return (int)err;
+    if ((err = cudaMemcpyAsync(h_out->terminated, d_out->terminated, E * n, cudaMemcpyDeviceToHost, s))) return (int)err;
+    if ((err = cudaMemcpyAsync(h_out->truncated, d_out->truncated, E, cudaMemcpyDeviceToHost, s))) return (int)err;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,131 @@
+"""TEST INFRASTRUCTURE: ctypes front-end of the CPU thread-by-thread run of the CUDA phase
+functions (tests/hostsim/hostsim.cpp). Lets the kernel logic be diffed against the oracle in a
+container without a GPU. Not importable from the product package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from multigrid_b200 import _cabi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB = os.path.join(HERE, "_build", "libhostsim.so")
+MODE_OBS, MODE_STEP, MODE_STEP_OBS = 0, 1, 2
+
+
+def build():
+    srcs = [os.path.join(HERE, "hostsim.cpp"),
+            os.path.join(ROOT, "multigrid_b200", "csrc", "mg_kernels.cuh"),
+            os.path.join(ROOT, "include", "multigrid_b200.h")]
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    subprocess.check_call([
+        "/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=undefined",
+        "-fno-sanitize-recover=all", "-I", os.path.join(ROOT, "include"), "-o", LIB, srcs[0]])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.sim_run.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def aligned(shape, dtype):
+    """numpy array whose data pointer is 16-byte aligned (the ABI requires it)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    buf = np.zeros(nbytes + 16, dtype=np.uint8)
+    off = (-buf.ctypes.data) % 16
+    return buf[off:off + nbytes].view(dtype).reshape(shape)
+
+
+def aligned_copy(a, dtype):
+    out = aligned(np.shape(a), dtype)
+    out[...] = a
+    return out
+
+
+class SimEngine:
+    """Mirror of oracle.OracleBatch's interface on top of the host-simulated kernels."""
+
+    def __init__(self, cfg, grid, agents, pcg_state, pcg_inc, pool_grid=None, pool_agents=None,
+                 layout_idx=None, step_count=None, forced_epb=0, generic=0, split=False):
+        self.cfg, self.forced_epb, self.generic, self.split = cfg, forced_epb, generic, split
+        self.grid = aligned_copy(grid, np.int8)
+        self.agents = aligned_copy(agents, np.int8)
+        self.B = self.grid.shape[0]
+        self.pcg_state = aligned_copy(pcg_state, np.uint64)
+        self.pcg_inc = aligned_copy(pcg_inc, np.uint64)
+        self.step_count = aligned((self.B,), np.int32)
+        if step_count is not None:
+            self.step_count[...] = step_count
+        self.layout_idx = aligned((self.B,), np.int32)
+        if layout_idx is not None:
+            self.layout_idx[...] = layout_idx
+        self.pool_grid = aligned_copy(self.grid[:1] if pool_grid is None else pool_grid, np.int8)
+        self.pool_agents = aligned_copy(self.agents[:1] if pool_agents is None else pool_agents, np.int8)
+        self.stride = _cabi.obs_agent_stride(cfg.V)
+        flags = ((_cabi.FLAG_SEE_THROUGH_WALLS if cfg.see_through_walls else 0)
+                 | (_cabi.FLAG_ALLOW_OVERLAP if cfg.allow_agent_overlap else 0)
+                 | (_cabi.FLAG_JOINT_REWARD if cfg.joint_reward else 0)
+                 | (_cabi.FLAG_SUCCESS_ANY if cfg.success_any else 0)
+                 | (_cabi.FLAG_FAILURE_ANY if cfg.failure_any else 0)
+                 | (_cabi.FLAG_AUTO_RESET if cfg.auto_reset else 0))
+        self.c = _cabi.MgConfig(cfg.W, cfg.H, cfg.n, cfg.V, cfg.max_steps, flags, cfg.hook,
+                                self.stride, self.pool_grid.shape[0], cfg.layout_stride)
+        self.obs = aligned((self.B, cfg.n, self.stride), np.int8)
+        self.obs[...] = 0x55
+        self.reward = aligned((self.B, cfg.n), np.float64)
+        self.terminated = aligned((self.B, cfg.n), np.uint8)
+        self.truncated = aligned((self.B,), np.uint8)
+        self.status = aligned((1,), np.int32)
+        self.state = _cabi.MgState(_p(self.grid).value, _p(self.agents).value,
+                                   _p(self.step_count).value, _p(self.pcg_state).value,
+                                   _p(self.pcg_inc).value, _p(self.layout_idx).value,
+                                   _p(self.pool_grid).value, _p(self.pool_agents).value)
+        self.out = _cabi.MgStepOut(_p(self.obs).value, _p(self.reward).value,
+                                   _p(self.terminated).value, _p(self.truncated).value,
+                                   _p(self.status).value)
+
+    def _run(self, mode, actions=None):
+        rc = lib().sim_run(C.c_int(mode), C.byref(self.c), C.c_int64(self.B), C.byref(self.state),
+                           _p(actions), C.byref(self.out), C.c_int(self.forced_epb),
+                           C.c_int(self.generic))
+        assert rc == 0, rc
+
+    def _obs_view(self):
+        V = self.cfg.V
+        assert (self.obs[:, :, 3 * V * V:] == 0).all(), "padding bytes must be zero"
+        return self.obs[:, :, :3 * V * V].reshape(self.B, self.cfg.n, V, V, 3)
+
+    def gen_obs(self):
+        self._run(MODE_OBS)
+        return self._obs_view()
+
+    def step(self, actions):
+        actions = aligned_copy(actions, np.int8)
+        if self.split and not self.cfg.auto_reset:
+            # mg_step then mg_gen_obs: with a post-hook the observation must see pre-hook
+            # termination, which only the fused kernel provides; split is used hook-free.
+            self._run(MODE_STEP, actions)
+            self._run(MODE_OBS)
+        else:
+            self._run(MODE_STEP_OBS, actions)
+        if self.status[0] & 1:
+            raise ValueError("Unknown action")
+        return self._obs_view(), self.reward, self.terminated, self.truncated
