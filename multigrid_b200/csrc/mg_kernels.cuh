@@ -387,26 +387,27 @@ MG_HD void phase_step(const Params &p, uint8_t *smem, int blk, int tid, int nt) 
         uint32_t *ag = b.ag + i * n * 2;
         if constexpr (MODE == MODE_OBS) {
             stamp_agents(p, cells, ag);
-            continue;
-        }
-        for (int j = 0; j < n; j++) p.reward[(size_t)e * n + j] = 0.0;  // base.py:394
-        bool truncated = false;
-        if (b.rk[i] < 0) {
-            const int32_t sc = b.sc[i] + 1;  // base.py:333
-            b.sc[i] = sc;
-            handle_actions(p, b, i, e, cells, ag, sc);
-            truncated = sc >= p.max_steps;  // base.py:339
-            if (MODE == MODE_STEP_OBS) stamp_agents(p, cells, ag);  // obs sees pre-hook termination
-            if (p.hook == MG_HOOK_BLOCKED_UNLOCK_PICKUP) {  // envs/blockedunlockpickup.py:166-175
-                for (int k = 0; k < n; k++)
-                    if ((ag[k * 2 + 1] & 0xff) == T_BOX) on_success(p, ag, k, e, sc);
+        } else {
+            for (int j = 0; j < n; j++) p.reward[(size_t)e * n + j] = 0.0;  // base.py:394
+            bool truncated = false;
+            if (b.rk[i] < 0) {
+                const int32_t sc = b.sc[i] + 1;  // base.py:333
+                b.sc[i] = sc;
+                handle_actions(p, b, i, e, cells, ag, sc);
+                truncated = sc >= p.max_steps;  // base.py:339
+                if (MODE == MODE_STEP_OBS) stamp_agents(p, cells, ag);  // obs sees pre-hook termination
+                if (p.hook == MG_HOOK_BLOCKED_UNLOCK_PICKUP) {  // envs/blockedunlockpickup.py:166-175
+                    for (int k = 0; k < n; k++)
+                        if ((ag[k * 2 + 1] & 0xff) == T_BOX) on_success(p, ag, k, e, sc);
+                }
+            } else if (MODE == MODE_STEP_OBS) {
+                stamp_agents(p, cells, ag);
             }
-        } else if (MODE == MODE_STEP_OBS) {
-            stamp_agents(p, cells, ag);
+            for (int j = 0; j < n; j++)
+                p.terminated[(size_t)e * n + j] = (uint8_t)(((ag[j * 2] >> 24) & 0xff) != 0);
+            p.truncated[e] = (uint8_t)truncated;
+            p.step_count[e] = b.sc[i];
         }
-        for (int j = 0; j < n; j++) p.terminated[(size_t)e * n + j] = (uint8_t)(((ag[j * 2] >> 24) & 0xff) != 0);
-        p.truncated[e] = (uint8_t)truncated;
-        p.step_count[e] = b.sc[i];
     }
 }
 

@@ -1,0 +1,245 @@
+"""Device-resident batched state + the calls into the CUDA engine (C ABI, include/multigrid_b200.h).
+
+`StepEngine` owns the HBM tensors of `num_envs` environments and advances them with the fused
+sm_100a kernel. It is the array-level layer under `multigrid_b200.env.BatchedMultiGridEnv`
+(the Gymnasium-style surface); both are host-side Python, as in the reference.
+
+torch is used for device memory, streams and (optionally) torch.distributed only. There is no
+CPU or PyTorch fallback for the computation: without the CUDA library and a CUDA device,
+constructing a StepEngine raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+@dataclass
+class EngineConfig:
+    """Static per-batch configuration (mirrors MultiGridEnv.__init__ kwargs, base.py:85-207)."""
+    width: int
+    height: int
+    num_agents: int
+    view_size: int = 7
+    max_steps: int = 100
+    see_through_walls: bool = False
+    allow_agent_overlap: bool = True
+    joint_reward: bool = False
+    success_termination_mode: str = "any"
+    failure_termination_mode: str = "all"
+    hook: int = _cabi.HOOK_NONE
+    auto_reset: bool = False
+    layout_stride: int = 1
+
+    def __post_init__(self):
+        if self.view_size % 2 != 1 or self.view_size < 3:  # core/agent.py:78-79
+            raise AssertionError("agent_view_size must be odd and >= 3")
+        if self.view_size > _cabi.MAX_VIEW:
+            raise ValueError(f"agent_view_size > {_cabi.MAX_VIEW} is not supported")
+        if not 1 <= self.num_agents <= _cabi.MAX_AGENTS:
+            raise ValueError(f"num_agents must be in 1..{_cabi.MAX_AGENTS}")
+        for mode in (self.success_termination_mode, self.failure_termination_mode):
+            if mode not in ("any", "all"):
+                raise ValueError(f"termination mode must be 'any' or 'all', got {mode!r}")
+
+    @property
+    def flags(self) -> int:
+        return ((_cabi.FLAG_SEE_THROUGH_WALLS if self.see_through_walls else 0)
+                | (_cabi.FLAG_ALLOW_OVERLAP if self.allow_agent_overlap else 0)
+                | (_cabi.FLAG_JOINT_REWARD if self.joint_reward else 0)
+                | (_cabi.FLAG_SUCCESS_ANY if self.success_termination_mode == "any" else 0)
+                | (_cabi.FLAG_FAILURE_ANY if self.failure_termination_mode == "any" else 0)
+                | (_cabi.FLAG_AUTO_RESET if self.auto_reset else 0))
+
+
+def _as_i64_bits(a) -> np.ndarray:
+    """uint64 words -> int64 with the same bits (torch has no general uint64 support)."""
+    return np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)
+
+
+class StepEngine:
+    """HBM-resident state of `num_envs` envs + fused step/observe launches.
+
+    Layout (env-major): grid int8 (E,W,H,3); agents int8 (E,n,8) =
+    [dir,x,y,terminated,carry_type,carry_color,carry_state,color]; step_count int32 (E);
+    pcg_state / pcg_inc int64-bits (E,2) [lo,hi]; layout_idx int32 (E).
+    Outputs: obs int8 (E,n,stride) exposed as a (E,n,V,V,3) view; reward f64 (E,n);
+    terminated uint8 (E,n); truncated uint8 (E).
+    """
+
+    def __init__(self, cfg: EngineConfig, num_envs: int, device: torch.device | str | int = "cuda",
+                 pool_grid=None, pool_agents=None):
+        self.lib = _cabi.load()  # raises if the CUDA library is not built
+        if not torch.cuda.is_available():
+            raise RuntimeError("multigrid_b200 needs a CUDA device (no CPU fallback)")
+        self.cfg = cfg
+        self.num_envs = int(num_envs)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("multigrid_b200 state lives in GPU memory; device must be CUDA")
+        E, n, V = self.num_envs, cfg.num_agents, cfg.view_size
+        W, H = cfg.width, cfg.height
+        self.obs_stride = _cabi.obs_agent_stride(V)
+        dev = self.device
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
+        self.grid = z((E, W, H, 3), torch.int8)
+        self.agents = z((E, n, 8), torch.int8)
+        self.step_count = z((E,), torch.int32)
+        self.pcg_state = z((E, 2), torch.int64)
+        self.pcg_inc = z((E, 2), torch.int64)
+        self.layout_idx = z((E,), torch.int32)
+        self.actions = z((E, n), torch.int8)
+        self.obs_buf = z((E, n, self.obs_stride), torch.int8)
+        self.reward = z((E, n), torch.float64)
+        self.terminated = z((E, n), torch.uint8)
+        self.truncated = z((E,), torch.uint8)
+        self.status = z((1,), torch.int32)
+        self.pool_grid = None
+        self.pool_agents = None
+        if pool_grid is not None:
+            self.set_layout_pool(pool_grid, pool_agents)
+        self._host = None
+        self._c = None
+
+    # -- configuration / state injection ------------------------------------------------------
+    def set_layout_pool(self, pool_grid, pool_agents) -> None:
+        """Reset layouts: grid (K,W,H,3) int8 and packed agents (K,n,8) int8."""
+        cfg = self.cfg
+        pg = torch.as_tensor(np.ascontiguousarray(pool_grid, dtype=np.int8))
+        pa = torch.as_tensor(np.ascontiguousarray(pool_agents, dtype=np.int8))
+        assert pg.shape[1:] == (cfg.width, cfg.height, 3), pg.shape
+        assert pa.shape == (pg.shape[0], cfg.num_agents, 8), pa.shape
+        self.pool_grid = pg.to(self.device)
+        self.pool_agents = pa.to(self.device)
+        self._c = None
+
+    def load_state(self, grid=None, agents=None, step_count=None, pcg_state=None, pcg_inc=None,
+                   layout_idx=None) -> None:
+        """Inject state (numpy or torch, host or device). uint64 PCG words are passed as numpy."""
+        def put(dst, src, bits64=False):
+            if src is None:
+                return
+            if isinstance(src, torch.Tensor):
+                dst.copy_(src.to(dst.dtype).reshape(dst.shape))
+            else:
+                arr = _as_i64_bits(src) if bits64 else np.ascontiguousarray(src)
+                dst.copy_(torch.as_tensor(arr).to(dst.dtype).reshape(dst.shape))
+        put(self.grid, grid)
+        put(self.agents, agents)
+        put(self.step_count, step_count)
+        put(self.pcg_state, pcg_state, bits64=True)
+        put(self.pcg_inc, pcg_inc, bits64=True)
+        put(self.layout_idx, layout_idx)
+
+    def reset_from_pool(self, layout_idx=None) -> None:
+        """Host-driven reset of every env from the layout pool (step_count := 0)."""
+        if layout_idx is not None:
+            self.load_state(layout_idx=layout_idx)
+        idx = self.layout_idx.long()
+        self.grid.copy_(self.pool_grid[idx])
+        self.agents.copy_(self.pool_agents[idx])
+        self.step_count.zero_()
+
+    # -- C structs ---------------------------------------------------------------------------
+    def _structs(self):
+        if self._c is None:
+            cfg = self.cfg
+            if cfg.auto_reset and self.pool_grid is None:
+                raise RuntimeError("auto_reset needs a layout pool (set_layout_pool)")
+            K = 0 if self.pool_grid is None else int(self.pool_grid.shape[0])
+            c = _cabi.MgConfig(cfg.width, cfg.height, cfg.num_agents, cfg.view_size,
+                               cfg.max_steps, cfg.flags, cfg.hook, self.obs_stride, K,
+                               cfg.layout_stride)
+            p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+            st = _cabi.MgState(p(self.grid), p(self.agents), p(self.step_count), p(self.pcg_state),
+                               p(self.pcg_inc), p(self.layout_idx), p(self.pool_grid),
+                               p(self.pool_agents))
+            out = _cabi.MgStepOut(p(self.obs_buf), p(self.reward), p(self.terminated),
+                                  p(self.truncated), p(self.status))
+            self._c = (c, st, out)
+        return self._c
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def obs(self) -> torch.Tensor:
+        """(E, n, V, V, 3) int8 view of the padded observation buffer (zero-copy)."""
+        V = self.cfg.view_size
+        return self.obs_buf[:, :, :3 * V * V].unflatten(2, (V, V, 3))
+
+    @property
+    def direction(self) -> torch.Tensor:
+        """(E, n) int8: the 'direction' observation aliases the agent-state tensor."""
+        return self.agents[:, :, 0]
+
+    # -- launches ------------------------------------------------------------------------------
+    def gen_obs(self) -> torch.Tensor:
+        """mg_gen_obs: observations of the current state (used after reset)."""
+        c, st, out = self._structs()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.mg_gen_obs(C.byref(c), self.num_envs, self.grid.data_ptr(),
+                                            self.agents.data_ptr(), self.obs_buf.data_ptr(),
+                                            self._stream()), "mg_gen_obs")
+        return self.obs
+
+    def step(self, actions: torch.Tensor | None = None, fused: bool = True):
+        """mg_step_obs on device-resident int8 actions (E,n); -1 = agent absent.
+
+        Returns device views (obs, reward, terminated, truncated); they are overwritten by the
+        next call. Asynchronous on the current CUDA stream.
+        """
+        if actions is None:
+            actions = self.actions
+        if actions.dtype != torch.int8 or not actions.is_contiguous() or actions.device != self.device:
+            raise TypeError("actions must be a contiguous int8 CUDA tensor of shape (num_envs, n)")
+        c, st, out = self._structs()
+        fn = self.lib.mg_step_obs if fused else self.lib.mg_step
+        with torch.cuda.device(self.device):
+            _cabi.check(fn(C.byref(c), self.num_envs, C.byref(st), actions.data_ptr(), C.byref(out),
+                           self._stream()), "mg_step_obs" if fused else "mg_step")
+        return self.obs, self.reward, self.terminated, self.truncated
+
+    def host_buffers(self):
+        """Pinned host mirrors used by `step_host` (allocated on first use)."""
+        if self._host is None:
+            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
+            self._host = dict(actions=pin(self.actions), obs=pin(self.obs_buf),
+                              reward=pin(self.reward), terminated=pin(self.terminated),
+                              truncated=pin(self.truncated))
+        return self._host
+
+    def step_host(self, synchronize: bool = True):
+        """mg_step_obs_host: actions come from, and results go to, pinned HOST buffers.
+
+        Fill `host_buffers()['actions']` first. This is the end-to-end path a CPU-side caller of
+        `env.step()` sees: H2D actions + kernel + D2H (obs, reward, terminated, truncated).
+        """
+        h = self.host_buffers()
+        c, st, out = self._structs()
+        hout = _cabi.MgStepOut(h["obs"].data_ptr(), h["reward"].data_ptr(),
+                               h["terminated"].data_ptr(), h["truncated"].data_ptr(), None)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.mg_step_obs_host(
+                C.byref(c), self.num_envs, C.byref(st), h["actions"].data_ptr(),
+                self.actions.data_ptr(), C.byref(out), C.byref(hout), self._stream()),
+                "mg_step_obs_host")
+            if synchronize:
+                torch.cuda.current_stream(self.device).synchronize()
+        return h
+
+    def check_status(self) -> None:
+        """Raise ValueError if any kernel saw an action outside 0..6 (base.py:473-474). Syncs."""
+        if int(self.status.item()) & 1:
+            self.status.zero_()
+            raise ValueError("Unknown action")
+
+    def bytes_per_step(self) -> dict:
+        """h2d / d2h bytes of one `step_host` call."""
+        E, n = self.num_envs, self.cfg.num_agents
+        return dict(h2d=E * n, d2h=E * n * self.obs_stride + E * n * 8 + E * n + E)

@@ -1,0 +1,213 @@
+"""GPU parity tests proper: the sm_100a kernels, called through the C ABI, against
+(1) fixtures recorded from the unmodified reference, (2) the C oracle on seeded random states,
+(3) the BASELINE.json configurations at full size (direct diff against the C oracle plus
+size-independent properties). Bit-exact everywhere, including the float64 rewards."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import mg_oracle as O
+from oracle.c_oracle import COracle
+from tests.golden_util import ROLLOUT_CASES, load_case, GOLDEN_DIR
+from tests.randstate import random_batch
+from tests.test_oracle_golden import cfg_from_meta
+
+pytestmark = pytest.mark.gpu
+
+NTHREADS = max(1, len(os.sched_getaffinity(0)))
+
+
+def GpuEngine(*a, **k):
+    from tests.gpu_adapter import GpuEngine as G
+    return G(*a, **k)
+
+
+def assert_same(a, b, msg):
+    np.testing.assert_array_equal(a.grid, b.grid, err_msg=msg)
+    np.testing.assert_array_equal(a.agents, b.agents, err_msg=msg)
+    np.testing.assert_array_equal(a.step_count, b.step_count, err_msg=msg)
+    np.testing.assert_array_equal(a.pcg_state, b.pcg_state, err_msg=msg)
+    np.testing.assert_array_equal(a.layout_idx, b.layout_idx, err_msg=msg)
+
+
+@pytest.mark.parametrize("variant", ["device", "host", "split"])
+@pytest.mark.parametrize("name", ROLLOUT_CASES)
+def test_rollout_matches_reference(name, variant):
+    d, meta = load_case(name)
+    cfg = cfg_from_meta(meta)
+    if variant == "split" and (cfg.hook or cfg.auto_reset):
+        pytest.skip("split step/gen_obs is only equivalent without post-hook / auto-reset")
+    B, T, J = meta["B"], meta["T"], meta["pool_J"]
+    kw = dict(device={}, host=dict(host_path=True), split=dict(fused=False))[variant]
+    g = GpuEngine(cfg, d["init_grid"], O.pack_agents(d["init_agents"]), d["pcg_state"],
+                  d["pcg_inc"], pool_grid=d["pool_grid"],
+                  pool_agents=O.pack_agents(d["pool_agents"]), layout_idx=np.arange(B) * J, **kw)
+    np.testing.assert_array_equal(g.gen_obs(), d["obs0"])
+    for t in range(T):
+        obs, rew, term, trunc = g.step(d["actions"][t])
+        msg = f"{name} step {t}"
+        np.testing.assert_array_equal(obs, d["obs"][t], err_msg=msg)
+        assert (rew == d["reward"][t]).all(), msg  # bit-exact float64
+        np.testing.assert_array_equal(term, d["terminated"][t], err_msg=msg)
+        np.testing.assert_array_equal(trunc, d["truncated"][t], err_msg=msg)
+        if t % 10 == 0 or t == T - 1:
+            np.testing.assert_array_equal(g.grid, d["grid"][t], err_msg=msg)
+            np.testing.assert_array_equal(O.unpack_agents(g.agents), d["agents"][t], err_msg=msg)
+            np.testing.assert_array_equal(g.agents[..., O.A_DIR], d["direction"][t], err_msg=msg)
+            np.testing.assert_array_equal(g.step_count, d["step_count"][t], err_msg=msg)
+
+
+def test_obs_random_injected_states():
+    d = np.load(f"{GOLDEN_DIR}/obs_random.npz")
+    for c in range(len(d["W"])):
+        W, H, n, V = (int(d[k][c]) for k in ("W", "H", "n", "V"))
+        cfg = O.OracleConfig(W=W, H=H, n=n, V=V, see_through_walls=bool(d["stw"][c]))
+        grid = np.ascontiguousarray(d["grid"][c, :W, :H])[None]
+        agents = O.pack_agents(d["agents"][c, :n])[None]
+        z = np.zeros((1, 2), np.uint64)
+        got = GpuEngine(cfg, grid, agents, z, z).gen_obs()[0]
+        np.testing.assert_array_equal(got, d["obs"][c, :n, :V, :V], err_msg=f"case {c}")
+
+
+SOUP = [
+    (0, 1000, dict(W=8, H=8, n=4, V=7)),
+    (1, 777, dict(W=11, H=6, n=2, V=7, hook=1, joint_reward=True)),
+    (2, 203, dict(W=9, H=13, n=5, V=9, allow_agent_overlap=False, failure_any=True)),
+    (3, 515, dict(W=5, H=5, n=1, V=3, success_any=False)),
+    (4, 301, dict(W=16, H=16, n=8, V=9, joint_reward=True, success_any=False)),
+    (5, 203, dict(W=7, H=7, n=3, V=5, see_through_walls=True, auto_reset=True, max_steps=12)),
+    (6, 99, dict(W=10, H=6, n=12, V=11, max_steps=30, auto_reset=True, layout_stride=3)),
+    (7, 64, dict(W=6, H=9, n=2, V=13, allow_agent_overlap=False)),
+    (8, 1, dict(W=19, H=19, n=3, V=7)),
+    (9, 17, dict(W=25, H=25, n=2, V=15, auto_reset=True, max_steps=9)),
+]
+
+
+@pytest.mark.parametrize("seed,B,kw", SOUP)
+def test_random_soup_vs_c_oracle(seed, B, kw):
+    kw = dict(kw)
+    cfg = O.OracleConfig(max_steps=kw.pop("max_steps", 40), **kw)
+    st = random_batch(cfg, B, seed)
+    ora, g = COracle(cfg, **st), GpuEngine(cfg, **st)
+    np.testing.assert_array_equal(g.gen_obs(), ora.gen_obs())
+    rng = np.random.default_rng(seed + 100)
+    for t in range(50):
+        actions = rng.integers(-1, 7, size=(B, cfg.n)).astype(np.int8)
+        o1, r1, t1, tr1 = ora.step(actions)
+        o2, r2, t2, tr2 = g.step(actions)
+        msg = f"step {t}"
+        np.testing.assert_array_equal(o2, o1, err_msg=msg)
+        assert (r1 == r2).all(), msg
+        np.testing.assert_array_equal(t2, t1, err_msg=msg)
+        np.testing.assert_array_equal(tr2, tr1, err_msg=msg)
+        assert_same(g, ora, msg)
+
+
+def empty_layout(size, n):
+    """EmptyEnv._gen_grid with the default fixed start (envs/empty.py:151-170)."""
+    grid = np.zeros((1, size, size, 3), np.int8)
+    grid[..., 0] = O.EMPTY
+    for sl in (np.s_[0, 0, :], np.s_[0, size - 1, :], np.s_[0, :, 0], np.s_[0, :, size - 1]):
+        grid[sl] = (O.WALL, 5, 0)
+    grid[0, size - 2, size - 2] = (O.GOAL, 1, 0)
+    agents = np.zeros((1, n, 8), np.int8)
+    agents[..., O.A_X] = 1
+    agents[..., O.A_Y] = 1
+    agents[..., O.A_CT] = O.EMPTY
+    agents[..., O.A_COLOR] = np.arange(n) % 6
+    return grid, agents
+
+
+def seeded_pcg(B, base_seed):
+    st = np.zeros((B, 2), np.uint64)
+    inc = np.zeros((B, 2), np.uint64)
+    m = (1 << 64) - 1
+    for e in range(B):
+        s = np.random.PCG64(np.random.SeedSequence(base_seed + e)).state["state"]
+        st[e] = (s["state"] & m, s["state"] >> 64)
+        inc[e] = (s["inc"] & m, s["inc"] >> 64)
+    return st, inc
+
+
+FULL = [
+    ("Empty-8x8 n=4 E=65536 (BASELINE configs[1])", 8, 4, 7, 65536, 0),
+    ("BUP-shaped 11x6 n=2 E=32768 (configs[2], random layouts)", None, 2, 7, 32768, 1),
+    ("Empty-16x16 n=8 V=9 E=16384 (configs[3])", 16, 8, 9, 16384, 0),
+]
+
+
+@pytest.mark.parametrize("label,size,n,V,E,hook", FULL)
+def test_full_size_configs_vs_c_oracle(label, size, n, V, E, hook):
+    """BASELINE.json sizes: auto-reset rollout diffed against the C oracle every step, plus
+    size-independent properties (obs self cell == carried object; checksum of obs)."""
+    rng = np.random.default_rng(5)
+    if size is not None:
+        cfg = O.OracleConfig(W=size, H=size, n=n, V=V, max_steps=4 * size * size, auto_reset=True)
+        pool_grid, pool_agents = empty_layout(size, n)
+        st = dict(grid=np.repeat(pool_grid, E, 0), agents=np.repeat(pool_agents, E, 0),
+                  pool_grid=pool_grid, pool_agents=pool_agents,
+                  layout_idx=np.zeros(E, np.int32), step_count=np.zeros(E, np.int32))
+    else:
+        cfg = O.OracleConfig(W=11, H=6, n=n, V=V, max_steps=576, auto_reset=True, hook=hook,
+                             joint_reward=True)
+        st = random_batch(cfg, E, 9, K=4096)
+    # a slice of envs starts near the step limit so truncation + auto-reset are exercised
+    st["step_count"] = np.where(np.arange(E) % 7 == 0, cfg.max_steps - 3, 0).astype(np.int32)
+    st["pcg_state"], st["pcg_inc"] = seeded_pcg(E, 1234) if E <= 16384 else (
+        rng.integers(0, 2**63, (E, 2)).astype(np.uint64),
+        rng.integers(0, 2**63, (E, 2)).astype(np.uint64) | np.uint64(1))
+    ora, g = COracle(cfg, nthreads=NTHREADS, **st), GpuEngine(cfg, **st)
+    np.testing.assert_array_equal(g.gen_obs(), ora.gen_obs())
+    for t in range(12):
+        actions = rng.integers(0, 7, size=(E, n)).astype(np.int8)
+        o1, r1, t1, tr1 = ora.step(actions)
+        o2, r2, t2, tr2 = g.step(actions)
+        msg = f"{label} step {t}"
+        assert np.array_equal(o2, o1), msg
+        assert (r1 == r2).all(), msg
+        assert np.array_equal(t2, t1) and np.array_equal(tr2, tr1), msg
+        # property: every agent sees its carried object on its own cell (utils/obs.py:207)
+        assert np.array_equal(o2[:, :, V // 2, V - 1, :], g.agents[:, :, O.A_CT:O.A_CS + 1]), msg
+        assert int(o2.astype(np.int64).sum()) == int(o1.astype(np.int64).sum()), msg
+    assert_same(g, ora, label)
+
+
+@pytest.mark.parametrize("B", [1, 15, 16, 17, 129])
+def test_ragged_batch_sizes(B):
+    cfg = O.OracleConfig(W=8, H=8, n=4, V=7, max_steps=20, auto_reset=True)
+    st = random_batch(cfg, B, 42)
+    ora, g = COracle(cfg, **st), GpuEngine(cfg, **st)
+    rng = np.random.default_rng(1)
+    for t in range(30):
+        actions = rng.integers(0, 7, size=(B, cfg.n)).astype(np.int8)
+        o1, r1, t1, tr1 = ora.step(actions)
+        o2, r2, t2, tr2 = g.step(actions)
+        assert np.array_equal(o2, o1) and (r1 == r2).all()
+        assert np.array_equal(t2, t1) and np.array_equal(tr2, tr1)
+    assert_same(g, ora, f"B={B}")
+
+
+def test_unknown_action_raises_value_error():
+    cfg = O.OracleConfig(W=8, H=8, n=2, V=7)
+    st = random_batch(cfg, 4, 0)
+    st["agents"][..., O.A_TERM] = 0
+    g = GpuEngine(cfg, **st)
+    actions = np.zeros((4, 2), np.int8)
+    actions[2, 1] = 9
+    with pytest.raises(ValueError):  # base.py:473-474
+        g.step(actions)
+
+
+def test_misaligned_pointer_is_rejected():
+    import ctypes as C
+    import torch
+    from multigrid_b200 import _cabi
+    lib = _cabi.load()
+    c = _cabi.MgConfig(8, 8, 2, 7, 100, 0, 0, 148, 0, 1)
+    buf = torch.zeros(4096, dtype=torch.int8, device="cuda:0")
+    rc = lib.mg_gen_obs(C.byref(c), 1, buf.data_ptr() + 1, buf.data_ptr() + 1024,
+                        buf.data_ptr() + 2048, None)
+    assert rc == -2
+    c.view_size = 4
+    assert lib.mg_gen_obs(C.byref(c), 1, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), None) == -1
