@@ -1,0 +1,56 @@
+"""Host-side layout generators vs post-reset states recorded from the reference
+(tests/golden/*.npz hold init_grid/init_agents produced with known generator seeds)."""
+import numpy as np
+import pytest
+
+from multigrid_b200 import layouts as L
+from multigrid_b200.core.constants import Direction
+from oracle import mg_oracle as O
+from tests.golden_util import load_case
+
+
+def rngs(seed, b):
+    """The deterministic-oracle recipe of tests/golden/make_golden.py::make_env."""
+    return (np.random.default_rng(seed * 1000 + b),
+            np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed * 7919 + b))))
+
+
+CASES = [
+    ("empty8_n4", 2, lambda n: L.EmptyLayout(n, size=8)),
+    ("empty16_n8_v9", 4, lambda n: L.EmptyLayout(n, size=16)),
+    ("empty6r_n3_nooverlap_all", 5,
+     lambda n: L.EmptyLayout(n, size=6, agent_start_pos=None, agent_start_dir=None)),
+    ("empty5_n1", 6, lambda n: L.EmptyLayout(n, size=5)),
+    ("bup_n2", 3, lambda n: L.BlockedUnlockPickupLayout(n)),
+    ("playground_n3", 8, lambda n: L.PlaygroundLayout(n)),
+]
+
+
+@pytest.mark.parametrize("name,seed,make", CASES)
+def test_layout_matches_reference_reset(name, seed, make):
+    d, meta = load_case(name)
+    layout = make(meta["n"])
+    assert (layout.width, layout.height, layout.max_steps) == (meta["W"], meta["H"], meta["max_steps"])
+    assert layout.hook == meta["hook"]
+    M = (1 << 64) - 1
+    for b in range(meta["B"]):
+        layout_rng, order_rng = rngs(seed, b)
+        grid, agents, _ = layout.generate(layout_rng, order_rng)
+        np.testing.assert_array_equal(grid, d["init_grid"][b], err_msg=f"{name} env {b}")
+        np.testing.assert_array_equal(O.unpack_agents(agents), d["init_agents"][b])
+        # the order stream must be left exactly where the reference's reset leaves it
+        st = order_rng.bit_generator.state["state"]["state"]
+        assert [st & M, st >> 64] == [int(v) for v in d["pcg_state"][b]]
+
+
+def test_generate_pool_shapes_and_determinism():
+    layout = L.BlockedUnlockPickupLayout(2)
+    g1, a1, info = L.generate_pool(layout, 5, seed=7)
+    g2, a2, _ = L.generate_pool(layout, 5, seed=7)
+    assert g1.shape == (5, 11, 6, 3) and a1.shape == (5, 2, 8)
+    np.testing.assert_array_equal(g1, g2)
+    np.testing.assert_array_equal(a1, a2)
+    assert info[0]["mission"].startswith("pick up the ")
+    assert len({g.tobytes() for g in g1}) > 1
+    g, a, _ = L.generate_pool(L.EmptyLayout(4), 100, seed=0)
+    assert g.shape[0] == 1 and (a[0, :, 1:3] == 1).all() and (a[0, :, 0] == int(Direction.right)).all()
