@@ -12,8 +12,8 @@ namespace {
 
 std::atomic<int64_t> g_launches{0};
 
-constexpr int kMaxThreads = 256;
-constexpr int kSmemBudget = 200 * 1024;  // per block; B200 allows 227 KB opt-in
+constexpr int kSmemPerBlock = 227 * 1024;  // B200 opt-in maximum per block
+constexpr int kSmemPerSM = 228 * 1024;
 
 int env_int(const char *name, int dflt) {
     const char *s = std::getenv(name);
@@ -33,21 +33,27 @@ int validate(const MgConfig *c, int64_t num_envs) {
     return 0;
 }
 
-int plan(mg::Params &p) { return mg::plan_launch(p, env_int("MG_EPB", 0), kMaxThreads, kSmemBudget); }
+// Tuning / test knobs (read per call): MG_GROUP = envs per warp (16|32), MG_WPB = warps per block,
+// MG_NO_BULK=1 = plain loads/stores instead of TMA bulk copies.
+int plan(mg::Params &p) {
+    p.use_bulk = env_int("MG_NO_BULK", 0) ? 0 : 1;
+    return mg::plan_launch(p, env_int("MG_GROUP", 0), env_int("MG_WPB", 0), kSmemPerBlock, kSmemPerSM);
+}
 
 template <int VT, int MODE>
 int launch(const mg::Params &p, cudaStream_t stream) {
     auto kernel = mg::step_obs_kernel<VT, MODE>;
-    static thread_local int configured_dev_smem[64] = {0};
+    static thread_local bool configured_dev[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && configured_dev_smem[dev] < p.smem_bytes) {
-        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (dev >= 0 && dev < 64 && !configured_dev[dev]) {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock);
         if (err != cudaSuccess) return (int)err;
-        configured_dev_smem[dev] = kSmemBudget;
+        configured_dev[dev] = true;
     }
-    const int blocks = (p.num_envs + p.epb - 1) / p.epb;
-    kernel<<<blocks, p.epb * p.tpe, p.smem_bytes, stream>>>(p);
+    const int groups = (p.num_envs + p.G - 1) / p.G;
+    const int blocks = (groups + p.wpb - 1) / p.wpb;
+    kernel<<<blocks, p.wpb * mg::LANES, p.wpb * p.warp_bytes, stream>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
@@ -112,6 +118,10 @@ int step_common(const MgConfig *cfg, int64_t num_envs, const MgState *state, con
     if ((rc = fill_out(p, out, MODE == mg::MODE_STEP_OBS))) return rc;
     p.actions = actions;
     if ((rc = plan(p))) return rc;
+    // TMA bulk copies need 16-byte aligned spans; the small arrays may fall back to plain copies
+    if (!aligned16(p.actions) || !aligned16(p.step_count) || !aligned16(p.pcg_state) || !aligned16(p.pcg_inc) ||
+        !aligned16(p.layout_idx) || !aligned16(p.reward) || !aligned16(p.terminated) || !aligned16(p.truncated))
+        p.use_bulk = 0;
     return dispatch<MODE>(p, (cudaStream_t)stream);
 }
 

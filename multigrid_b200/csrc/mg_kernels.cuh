@@ -1,32 +1,38 @@
-// multigrid_b200 -- device code of the batched MultiGrid step/observe engine (sm_100a).
+// multigrid_b200 -- device code of the batched MultiGrid step/observe engine (sm_100a), kernel v2.
 //
-// One thread block advances `epb` consecutive envs. All of a block's state is one contiguous HBM
-// span per array (env-major layout), staged through shared memory with 16-byte accesses; the
-// per-env work then runs out of shared memory in bulk-synchronous phases:
+// One WARP advances one group of G consecutive envs (G = 16 or 32) and never talks to another warp:
+// no block-wide barrier anywhere, warps of a block drift apart and hide each other's latencies.
+// A group's state is one contiguous HBM span per array (env-major layout); the spans are moved with
+// 1-D TMA bulk copies (cp.async.bulk + mbarrier in, cp.async.bulk.bulk_group out), so loads and
+// stores cost the warp a handful of instructions; the per-env work runs out of shared memory:
 //
-//   P0 load      block-wide copy: raw grid span + agent span -> smem            (all threads)
-//   P0b reset    auto-reset decision per env, pool layout fetch                 (1 thread / env)
-//   P1 convert   3-byte cells -> 32-bit cell words (+ "opaque" bit for the scan) (tpe threads / env)
-//   P2 step      handle_actions: PCG64 draw, argsort, serial agent loop, rewards,
-//                termination, dirty-cell write-through, agent stamping, env hook (1 thread / env)
-//   P3 observe   per-agent view gather (closed-form slice+rotate), row-bitmask
-//                visibility scan, masking, 24->32 bit packing into smem          (1 thread / agent)
-//   P4 store     block-wide copy: obs span + agent span -> HBM                   (all threads)
+//   P0 load      TMA: grid / agents / pcg state+inc / actions / step_count / layout_idx -> smem
+//   P1 prep      zero rewards, wall sentinels of the padded cell array              (32 lanes, coop)
+//   P2 reset     auto-reset decision per env, pool layout fetch                     (1 lane / env)
+//   P3 convert   3-byte cells -> 32-bit cell words (+ "opaque" bit 31 for the scan) (32 lanes, coop)
+//   P4 step      handle_actions: PCG64 draw, argsort, serial agent loop, rewards,
+//                termination, dirty-cell write-through, env hook, agent stamping    (1 lane / env)
+//   P5 observe   32 agents per pass: view gather (closed-form slice+rotate), row-bitmask
+//                visibility scan, masking, 24->32 bit packing into the smem stage   (1 lane / agent)
+//                -> TMA bulk store of the pass's contiguous obs span
+//   P6 store     TMA: agents / pcg state / step_count / layout_idx / reward / terminated / truncated
 //
 // Reference semantics restated here (cited inline): multigrid/base.py:303-532,598-602,
 // multigrid/utils/obs.py:46-316, multigrid/core/world_object.py:197-233,452-474,599-605.
 //
 // The file also compiles as plain C++ (no __CUDACC__): tests/hostsim runs the very same phase
-// functions thread-by-thread on the CPU to check the logic against the oracle without a GPU.
-// That build is test infrastructure; the product only ever launches the CUDA kernels.
+// functions lane-by-lane on the CPU (a phase boundary == __syncwarp) to check the logic against the
+// oracle without a GPU. That build is test infrastructure; the product only launches the CUDA kernels.
 #pragma once
 #include <stdint.h>
 #include "multigrid_b200.h"
 
 #ifdef __CUDACC__
 #define MG_HD __host__ __device__ __forceinline__
+#define MG_HD_COLD __host__ __device__ __noinline__  // rarely-run helpers: one copy, small I-cache footprint
 #else
 #define MG_HD inline
+#define MG_HD_COLD inline
 #endif
 
 namespace mg {
@@ -36,62 +42,87 @@ enum : int { S_OPEN = 0, S_CLOSED, S_LOCKED };
 enum : int { ACT_LEFT = 0, ACT_RIGHT, ACT_FORWARD, ACT_PICKUP, ACT_DROP, ACT_TOGGLE, ACT_DONE };
 enum : int { MODE_OBS = 0, MODE_STEP = 1, MODE_STEP_OBS = 2 };
 
-// 32-bit cell word: type | color<<8 | state<<16 | opaque<<24
+// 32-bit cell word: type | color<<8 | state<<16 | opaque<<31
+constexpr uint32_t OPAQUE_BIT = 1u << 31;
 constexpr uint32_t CELL_EMPTY = T_EMPTY;
-constexpr uint32_t CELL_WALL = T_WALL | (5u << 8) | (1u << 24);  // WALL_ENCODING, utils/obs.py:14
-constexpr uint32_t OPAQUE_BIT = 1u << 24;
-
-struct u4 { uint32_t x, y, z, w; };
+constexpr uint32_t CELL_WALL = T_WALL | (5u << 8) | OPAQUE_BIT;  // WALL_ENCODING, utils/obs.py:14
+constexpr int LANES = 32;
 
 struct Params {
     // config
     int32_t W, H, n, V, max_steps;
     uint32_t flags;
     int32_t hook, ostride, K, lstride;
-    int32_t num_envs, epb, tpe;
+    int32_t num_envs, G, wpb, use_bulk;
     // state (device)
     int8_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;
     int32_t *layout_idx; const int8_t *pool_grid; const int8_t *pool_agents;
     const int8_t *actions;
     // outputs (device)
     int8_t *obs; double *reward; uint8_t *terminated; uint8_t *truncated; int32_t *status;
-    // shared-memory carve-up (byte offsets, all multiples of 16)
-    int32_t cstride;  // words per env in the cell array (W*H rounded up to odd)
-    int32_t off_cells, off_stage, off_agents, off_keys, off_order, off_sc, off_rk, smem_bytes;
+    // derived geometry. The cell array of an env is (W+1) x (H+1) words, row stride Hp = H+1:
+    // row x = W and column y = H hold WALL sentinels, every out-of-range coordinate maps there.
+    int32_t Hp, cstride, grid_bytes, quads;
+    uint32_t rcp_n, rcp_h, rcp_q;  // ceil(2^32 / d) for d = n, H, quads (see fastdiv)
+    // per-warp shared-memory carve-up (byte offsets, all multiples of 16)
+    int32_t off_cells, off_stage, off_ag, off_pcg, off_inc, off_act, off_sc, off_lidx, off_rk,
+        off_rew, off_term, off_trunc, off_mbar, warp_bytes;
 };
 
 MG_HD int align16(int x) { return (x + 15) & ~15; }
+inline uint32_t rcp32(int d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / (uint32_t)d + 1ull); }
 
-// Fills the derived fields; returns the dynamic shared memory size for (epb, tpe).
+// Fills the derived fields for group size p.G; returns the shared memory bytes of one warp.
 inline int carve_smem(Params &p) {
-    const int WH = p.W * p.H;
-    p.cstride = WH | 1;
-    int raw = p.epb * WH * 3, stage = p.epb * p.n * p.ostride;
+    const int WH = p.W * p.H, G = p.G, n = p.n;
+    p.Hp = p.H + 1;
+    p.cstride = ((p.W + 1) * p.Hp) | 1;
+    p.grid_bytes = 3 * WH;
+    p.quads = (WH & 3) == 0 ? WH / 4 : 0;  // 0: byte-wise convert
+    p.rcp_n = rcp32(n); p.rcp_h = rcp32(p.H); p.rcp_q = rcp32(p.quads);
+    // "stage" is reused over time: raw grid bytes (P0-P3), sort keys + order (P4), obs pass (P5)
+    int stage = G * p.grid_bytes;
+    if (LANES * p.ostride > stage) stage = LANES * p.ostride;
+    if (G * n * 9 + 16 > stage) stage = G * n * 9 + 16;
     int off = 0;
-    p.off_cells = off;  off += align16(p.epb * p.cstride * 4);
-    p.off_stage = off;  off += align16(raw > stage ? raw : stage);
-    p.off_agents = off; off += align16(p.epb * p.n * 8);
-    p.off_keys = off;   off += align16(p.epb * p.n * 8);
-    p.off_order = off;  off += align16(p.epb * p.n);
-    p.off_sc = off;     off += align16(p.epb * 4);
-    p.off_rk = off;     off += align16(p.epb * 4);
-    p.smem_bytes = off;
+    p.off_cells = off; off += align16(G * p.cstride * 4);
+    p.off_stage = off; off += align16(stage);
+    p.off_ag = off;    off += align16(G * n * 8);
+    p.off_pcg = off;   off += align16(G * 16);
+    p.off_inc = off;   off += align16(G * 16);
+    p.off_act = off;   off += align16(G * n);
+    p.off_sc = off;    off += align16(G * 4);
+    p.off_lidx = off;  off += align16(G * 4);
+    p.off_rk = off;    off += align16(G * 4);
+    p.off_rew = off;   off += align16(G * n * 8);
+    p.off_term = off;  off += align16(G * n);
+    p.off_trunc = off; off += align16(G);
+    p.off_mbar = off;  off += 16;
+    p.warp_bytes = off;
     return off;
 }
 
-// Launch geometry: tpe threads per env (one per agent, at most 8), epb envs per block (a multiple
-// of 16 so every block's spans start 16-byte aligned), epb*tpe <= max_threads.
-// Returns 0, or MG_ERR_TOO_LARGE when even 16 envs do not fit `smem_budget`.
-inline int plan_launch(Params &p, int forced_epb, int max_threads, int smem_budget) {
-    p.tpe = p.n < 8 ? p.n : 8;
-    int epb = 16 * (max_threads / (16 * p.tpe));
-    if (epb > 128) epb = 128;
-    if (forced_epb > 0 && forced_epb % 16 == 0 && forced_epb * p.tpe <= max_threads) epb = forced_epb;
-    for (; epb >= 16; epb -= 16) {
-        p.epb = epb;
-        if (carve_smem(p) <= smem_budget) return 0;
+// Launch geometry: G envs per warp (16, or 32 when forced and it fits), wpb warps per block chosen
+// to maximise resident warps per SM. Returns 0, or MG_ERR_TOO_LARGE when 16 envs do not fit.
+inline int plan_launch(Params &p, int forced_G, int forced_wpb, int smem_per_block, int smem_per_sm) {
+    p.G = (forced_G == 32) ? 32 : 16;
+    if (carve_smem(p) > smem_per_block) {
+        p.G = 16;
+        if (carve_smem(p) > smem_per_block) return MG_ERR_TOO_LARGE;
     }
-    return MG_ERR_TOO_LARGE;
+    int best = 0, best_wpb = 1;
+    for (int wpb = 8; wpb >= 1; wpb >>= 1) {
+        const int bytes = wpb * p.warp_bytes;
+        if (bytes > smem_per_block) continue;
+        int blocks = smem_per_sm / (bytes + 1024);  // 1 KB per block is reserved by the driver
+        if (blocks > 32) blocks = 32;
+        int warps = blocks * wpb;
+        if (warps > 64) warps = 64;
+        if (warps > best) { best = warps; best_wpb = wpb; }
+    }
+    p.wpb = best_wpb;
+    if (forced_wpb > 0 && forced_wpb <= 8 && forced_wpb * p.warp_bytes <= smem_per_block) p.wpb = forced_wpb;
+    return 0;
 }
 
 // ---- small portable intrinsics ----------------------------------------------------------------
@@ -106,13 +137,29 @@ MG_HD uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
 #endif
 }
 
-MG_HD uint32_t bitrev(uint32_t v, int nbits) {  // reverse the low `nbits` bits
+MG_HD uint32_t brev32(uint32_t v) {
 #ifdef __CUDA_ARCH__
-    return __brev(v) >> (32 - nbits);
+    return __brev(v);
 #else
     uint32_t r = 0;
-    for (int i = 0; i < nbits; i++) r |= ((v >> i) & 1u) << (nbits - 1 - i);
+    for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
     return r;
+#endif
+}
+
+MG_HD uint32_t shl1_in(uint32_t acc, uint32_t w) {  // (acc << 1) | (w >> 31): one funnel shift
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(w, acc, 1);
+#else
+    return (acc << 1) | (w >> 31);
+#endif
+}
+
+MG_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
 
@@ -123,6 +170,9 @@ MG_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
     return (uint64_t)(((unsigned __int128)a * b) >> 64);
 #endif
 }
+
+// x / d for small x (x * d < 2^32) with rcp = rcp32(d); rcp == 0 encodes d == 1.
+MG_HD uint32_t fastdiv(uint32_t x, uint32_t rcp) { return rcp ? mulhi32(x, rcp) : x; }
 
 // numpy Generator(PCG64).random() (call site base.py:399): 128-bit LCG step + XSL-RR output;
 // returns the top 53 bits (the double is key * 2^-53, so integer order == double order).
@@ -160,104 +210,182 @@ MG_HD void status_or(int32_t *status, int32_t v) {
 #endif
 }
 
-// Block-wide copy of a contiguous span. 16-byte vectors when both ends allow it.
-MG_HD void coop_copy(void *dst, const void *src, int nbytes, int tid, int nt) {
-    if ((((uintptr_t)dst | (uintptr_t)src) & 15u) == 0) {
+// Warp-cooperative plain copy of a contiguous span (the non-TMA path: ragged tail groups, and
+// everything under tests/hostsim). 16-byte vectors when both ends allow it, else 4-byte, else bytes.
+MG_HD_COLD void warp_copy(void *dst, const void *src, int nbytes, int lane) {
+    const uintptr_t both = (uintptr_t)dst | (uintptr_t)src;
+    if ((both & 15u) == 0) {
         const int nv = nbytes >> 4;
-        u4 *d = (u4 *)dst; const u4 *s = (const u4 *)src;
-        for (int v = tid; v < nv; v += nt) d[v] = s[v];
-        for (int b = (nv << 4) + tid; b < nbytes; b += nt) ((uint8_t *)dst)[b] = ((const uint8_t *)src)[b];
+#ifdef __CUDACC__
+        uint4 *d = (uint4 *)dst; const uint4 *s = (const uint4 *)src;
+#else
+        struct alignas(16) V16 { uint32_t v[4]; };
+        V16 *d = (V16 *)dst; const V16 *s = (const V16 *)src;
+#endif
+#pragma unroll 1
+        for (int v = lane; v < nv; v += LANES) d[v] = s[v];
+#pragma unroll 1
+        for (int b = (nv << 4) + lane; b < nbytes; b += LANES) ((uint8_t *)dst)[b] = ((const uint8_t *)src)[b];
+    } else if ((both & 3u) == 0) {
+        const int nw = nbytes >> 2;
+#pragma unroll 1
+        for (int v = lane; v < nw; v += LANES) ((uint32_t *)dst)[v] = ((const uint32_t *)src)[v];
+#pragma unroll 1
+        for (int b = (nw << 2) + lane; b < nbytes; b += LANES) ((uint8_t *)dst)[b] = ((const uint8_t *)src)[b];
     } else {
-        for (int b = tid; b < nbytes; b += nt) ((uint8_t *)dst)[b] = ((const uint8_t *)src)[b];
+#pragma unroll 1
+        for (int b = lane; b < nbytes; b += LANES) ((uint8_t *)dst)[b] = ((const uint8_t *)src)[b];
     }
 }
 
 MG_HD uint32_t cell_word(uint32_t t, uint32_t c, uint32_t s) {
     // see_behind (utils/obs.py:47-63): walls and non-open doors block the view
-    uint32_t opaque = (t == T_WALL) | ((t == T_DOOR) & (s != S_OPEN));
-    return t | (c << 8) | (s << 16) | (opaque << 24);
+    const uint32_t opaque = (uint32_t)(t == T_WALL) | (uint32_t)((t == T_DOOR) & (s != S_OPEN));
+    return t | (c << 8) | (s << 16) | (opaque << 31);
 }
 
-struct Block {
-    int e0, ne;  // first global env of this block, number of valid envs
-    uint32_t *cells; uint8_t *stage; uint32_t *ag; uint64_t *keys; uint8_t *order; int32_t *sc; int32_t *rk;
+MG_HD uint32_t cell_word24(uint32_t c) {  // c = type | color<<8 | state<<16
+    const uint32_t t = c & 0xffu;
+    const uint32_t opaque = (uint32_t)(t == T_WALL) | (uint32_t)((t == T_DOOR) & ((c >> 16) != S_OPEN));
+    return c | (opaque << 31);
+}
+
+// One warp's view of its group: e0 = first global env, ne = number of valid envs.
+struct Group {
+    int e0, ne;
+    uint32_t *cells; uint8_t *stage; uint32_t *ag; uint64_t *pcg; uint64_t *inc; int8_t *act;
+    int32_t *sc; int32_t *lidx; int32_t *rk; double *rew; uint8_t *term; uint8_t *trunc;
+    uint64_t *keys; uint8_t *order;  // alias the stage during P4
 };
 
-MG_HD Block block_view(const Params &p, uint8_t *smem, int blk) {
-    Block b;
-    b.e0 = blk * p.epb;
-    b.ne = p.num_envs - b.e0 < p.epb ? p.num_envs - b.e0 : p.epb;
-    b.cells = (uint32_t *)(smem + p.off_cells);
-    b.stage = smem + p.off_stage;
-    b.ag = (uint32_t *)(smem + p.off_agents);
-    b.keys = (uint64_t *)(smem + p.off_keys);
-    b.order = smem + p.off_order;
-    b.sc = (int32_t *)(smem + p.off_sc);
-    b.rk = (int32_t *)(smem + p.off_rk);
-    return b;
+MG_HD Group group_view(const Params &p, uint8_t *ws, int group) {
+    Group g;
+    g.e0 = group * p.G;
+    g.ne = p.num_envs - g.e0 < p.G ? p.num_envs - g.e0 : p.G;
+    g.cells = (uint32_t *)(ws + p.off_cells);
+    g.stage = ws + p.off_stage;
+    g.ag = (uint32_t *)(ws + p.off_ag);
+    g.pcg = (uint64_t *)(ws + p.off_pcg);
+    g.inc = (uint64_t *)(ws + p.off_inc);
+    g.act = (int8_t *)(ws + p.off_act);
+    g.sc = (int32_t *)(ws + p.off_sc);
+    g.lidx = (int32_t *)(ws + p.off_lidx);
+    g.rk = (int32_t *)(ws + p.off_rk);
+    g.rew = (double *)(ws + p.off_rew);
+    g.term = ws + p.off_term;
+    g.trunc = ws + p.off_trunc;
+    g.keys = (uint64_t *)g.stage;
+    g.order = g.stage + align16(p.G * p.n * 8);
+    return g;
 }
 
-// ---- P0: load ------------------------------------------------------------------------------------
+// ---- P0 (plain path): load ------------------------------------------------------------------------
 template <int MODE>
-MG_HD void phase_load(const Params &p, uint8_t *smem, int blk, int tid, int nt) {
-    Block b = block_view(p, smem, blk);
-    const int WH3 = p.W * p.H * 3;
-    coop_copy(b.stage, p.grid + (size_t)b.e0 * WH3, b.ne * WH3, tid, nt);
-    coop_copy(b.ag, p.agents + (size_t)b.e0 * p.n * 8, b.ne * p.n * 8, tid, nt);
-    for (int i = tid; i < b.ne; i += nt) {
-        b.rk[i] = -1;
-        if (MODE != MODE_OBS) b.sc[i] = p.step_count[b.e0 + i];
+MG_HD void phase_load_plain(const Params &p, const Group &g, int lane) {
+    const size_t e0 = (size_t)g.e0;
+    const int ne = g.ne, n = p.n;
+    warp_copy(g.stage, p.grid + e0 * p.grid_bytes, ne * p.grid_bytes, lane);
+    warp_copy(g.ag, p.agents + e0 * n * 8, ne * n * 8, lane);
+    if (MODE != MODE_OBS) {
+        warp_copy(g.act, p.actions + e0 * n, ne * n, lane);
+        warp_copy(g.sc, p.step_count + e0, ne * 4, lane);
+        if (n > 1) {
+            warp_copy(g.pcg, p.pcg_state + 2 * e0, ne * 16, lane);
+            warp_copy(g.inc, p.pcg_inc + 2 * e0, ne * 16, lane);
+        }
+        if (p.flags & MG_FLAG_AUTO_RESET) warp_copy(g.lidx, p.layout_idx + e0, ne * 4, lane);
     }
 }
 
-// ---- P0b: auto-reset decision ("next-step" mode; is_done = base.py:534-539) -------------------------
-MG_HD void phase_reset(const Params &p, uint8_t *smem, int blk, int tid, int nt) {
-    Block b = block_view(p, smem, blk);
-    for (int i = tid; i < b.ne; i += nt) {
+// ---- P1: prep (rewards := 0, base.py:394; reset marks; wall sentinels) -------------------------------
+template <int MODE>
+MG_HD void phase_prep(const Params &p, const Group &g, int lane) {
+    const int ne = g.ne;
+    if (MODE != MODE_OBS) {
+        for (int i = lane; i < ne * p.n; i += LANES) g.rew[i] = 0.0;
+        for (int i = lane; i < ne; i += LANES) g.rk[i] = -1;
+    }
+    // sentinel row x = W (Hp words) and sentinel column y = H (W words) of every env
+    const int W = p.W, H = p.H, Hp = p.Hp;
+    for (int i = 0; i < ne; i++) {
+        uint32_t *c = g.cells + i * p.cstride;
+        for (int j = lane; j < Hp + W; j += LANES) {
+            const int idx = j < Hp ? W * Hp + j : (j - Hp) * Hp + H;
+            c[idx] = CELL_WALL;
+        }
+    }
+}
+
+// ---- P2: auto-reset decision ("next-step" mode; is_done = base.py:534-539) --------------------------
+MG_HD void phase_reset(const Params &p, const Group &g, int lane) {
+    for (int i = lane; i < g.ne; i += LANES) {
         uint32_t all_term = 1;
-        for (int j = 0; j < p.n; j++) all_term &= ((b.ag[(i * p.n + j) * 2] >> 24) & 0xff) != 0;
-        if (all_term || b.sc[i] >= p.max_steps) {
-            const int e = b.e0 + i;
-            int k = (int)(((int64_t)p.layout_idx[e] + p.lstride) % p.K);
-            p.layout_idx[e] = k;
-            b.rk[i] = k;
-            b.sc[i] = 0;
+        for (int j = 0; j < p.n; j++) all_term &= ((g.ag[(i * p.n + j) * 2] >> 24) & 0xff) != 0;
+        if (all_term || g.sc[i] >= p.max_steps) {
+            int k = (int)(((int64_t)g.lidx[i] + p.lstride) % p.K);
+            g.lidx[i] = k;
+            g.rk[i] = k;
+            g.sc[i] = 0;
             const uint32_t *src = (const uint32_t *)(p.pool_agents + (size_t)k * p.n * 8);
-            for (int j = 0; j < p.n * 2; j++) b.ag[i * p.n * 2 + j] = src[j];
+            for (int j = 0; j < p.n * 2; j++) g.ag[i * p.n * 2 + j] = src[j];
         }
     }
 }
 
-// ---- P1: 3-byte cells -> cell words ----------------------------------------------------------------
-MG_HD void phase_convert(const Params &p, uint8_t *smem, int blk, int tid, int nt) {
-    Block b = block_view(p, smem, blk);
-    const int WH = p.W * p.H;
-    const int i = tid / p.tpe, lane = tid - i * p.tpe;
-    if (i >= b.ne) return;
-    const int k = b.rk[i];
-    uint32_t *dst = b.cells + i * p.cstride;
-    if (k < 0) {
-        const uint8_t *src = b.stage + i * WH * 3;
-        for (int c = lane; c < WH; c += p.tpe)
-            dst[c] = cell_word(src[3 * c], src[3 * c + 1], src[3 * c + 2]);
-    } else {  // env was reset: take the layout from the pool and write it through to the state
-        const uint8_t *src = (const uint8_t *)p.pool_grid + (size_t)k * WH * 3;
-        uint8_t *g = (uint8_t *)p.grid + (size_t)(b.e0 + i) * WH * 3;
-        for (int c = lane; c < WH; c += p.tpe) {
-            uint8_t t = src[3 * c], col = src[3 * c + 1], s = src[3 * c + 2];
-            g[3 * c] = t; g[3 * c + 1] = col; g[3 * c + 2] = s;
-            dst[c] = cell_word(t, col, s);
+// Envs that were reset take their grid from the layout pool: into the raw stage (for P3) and
+// written through to the state in HBM.
+MG_HD void phase_reset_grid(const Params &p, const Group &g, int lane) {
+    for (int i = 0; i < g.ne; i++) {
+        const int k = g.rk[i];
+        if (k < 0) continue;
+        const int8_t *src = p.pool_grid + (size_t)k * p.grid_bytes;
+        warp_copy(g.stage + i * p.grid_bytes, src, p.grid_bytes, lane);
+        warp_copy(p.grid + (size_t)(g.e0 + i) * p.grid_bytes, src, p.grid_bytes, lane);
+    }
+}
+
+// ---- P3: 3-byte cells -> cell words -----------------------------------------------------------------
+MG_HD void phase_convert(const Params &p, const Group &g, int lane) {
+    const int H = p.H;
+    if (p.quads) {  // 4 cells = 3 aligned words per item
+        const int Q = p.quads, items = g.ne * Q;
+        for (int it = lane; it < items; it += LANES) {
+            const int i = (int)fastdiv((uint32_t)it, p.rcp_q), q = it - i * Q;
+            const uint32_t *rw = (const uint32_t *)(g.stage + i * p.grid_bytes) + 3 * q;
+            const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
+            uint32_t c[4];
+            c[0] = w0 & 0x00ffffffu;
+            c[1] = byte_perm(w0, w1, 0x0543u) & 0x00ffffffu;
+            c[2] = byte_perm(w1, w2, 0x0432u) & 0x00ffffffu;
+            c[3] = w2 >> 8;
+            uint32_t *dst = g.cells + i * p.cstride;
+            const int ci = 4 * q;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int x = (int)fastdiv((uint32_t)(ci + j), p.rcp_h);  // idx = x*Hp + y = ci + x
+                dst[ci + j + x] = cell_word24(c[j]);
+            }
+        }
+    } else {
+        const int WH = p.W * p.H;
+        for (int i = 0; i < g.ne; i++) {
+            const uint8_t *src = g.stage + i * p.grid_bytes;
+            uint32_t *dst = g.cells + i * p.cstride;
+            for (int ci = lane; ci < WH; ci += LANES) {
+                const int x = ci / H;
+                dst[ci + x] = cell_word(src[3 * ci], src[3 * ci + 1], src[3 * ci + 2]);
+            }
         }
     }
 }
 
-// ---- P2: transition --------------------------------------------------------------------------------
-MG_HD void store_cell(const Params &p, int e, int idx, uint32_t w) {  // dirty-cell write-through
-    uint8_t *g = (uint8_t *)p.grid + ((size_t)e * p.W * p.H + idx) * 3;
+// ---- P4: transition --------------------------------------------------------------------------------
+MG_HD void store_cell(const Params &p, int e, int x, int y, uint32_t w) {  // dirty-cell write-through
+    uint8_t *g = (uint8_t *)p.grid + ((size_t)e * p.W * p.H + x * p.H + y) * 3;
     g[0] = (uint8_t)w; g[1] = (uint8_t)(w >> 8); g[2] = (uint8_t)(w >> 16);
 }
 
-MG_HD void on_success(const Params &p, uint32_t *ag, int k, int e, int32_t sc) {  // base.py:478-507
+MG_HD void on_success(const Params &p, uint32_t *ag, double *rew, int k, int32_t sc) {  // base.py:478-507
     if (p.flags & MG_FLAG_SUCCESS_ANY) {
         for (int j = 0; j < p.n; j++) ag[j * 2] |= 1u << 24;
     } else {
@@ -265,9 +393,9 @@ MG_HD void on_success(const Params &p, uint32_t *ag, int k, int e, int32_t sc) {
     }
     const double r = reward_value(sc, p.max_steps);
     if (p.flags & MG_FLAG_JOINT_REWARD) {
-        for (int j = 0; j < p.n; j++) p.reward[(size_t)e * p.n + j] = r;
+        for (int j = 0; j < p.n; j++) rew[j] = r;
     } else {
-        p.reward[(size_t)e * p.n + k] = r;
+        rew[k] = r;
     }
 }
 
@@ -286,29 +414,30 @@ MG_HD bool agent_at(const Params &p, const uint32_t *ag, uint32_t xy) {  // xy =
 }
 
 // MultiGridEnv.handle_actions (base.py:378-476) for local env i; `ag` = this env's agent words.
-MG_HD void handle_actions(const Params &p, const Block &b, int i, int e, uint32_t *cells,
-                          uint32_t *ag, int32_t sc) {
-    const int n = p.n, H = p.H, epb = p.epb;
+MG_HD void handle_actions(const Params &p, const Group &g, int i, uint32_t *cells, uint32_t *ag,
+                          double *rew, int32_t sc) {
+    const int n = p.n, G = p.G, e = g.e0 + i;
     if (n > 1) {  // base.py:399: order = np_random.random(size=n).argsort()
-        uint64_t lo = p.pcg_state[2 * (size_t)e], hi = p.pcg_state[2 * (size_t)e + 1];
-        const uint64_t ilo = p.pcg_inc[2 * (size_t)e], ihi = p.pcg_inc[2 * (size_t)e + 1];
-        for (int j = 0; j < n; j++) b.keys[j * epb + i] = pcg64_next53(lo, hi, ilo, ihi);
-        p.pcg_state[2 * (size_t)e] = lo; p.pcg_state[2 * (size_t)e + 1] = hi;
+        uint64_t lo = g.pcg[2 * i], hi = g.pcg[2 * i + 1];
+        const uint64_t ilo = g.inc[2 * i], ihi = g.inc[2 * i + 1];
+        for (int j = 0; j < n; j++) g.keys[j * G + i] = pcg64_next53(lo, hi, ilo, ihi);
+        g.pcg[2 * i] = lo; g.pcg[2 * i + 1] = hi;
         for (int j = 0; j < n; j++) {  // rank = position in the ascending (stable) order
-            const uint64_t kj = b.keys[j * epb + i];
+            const uint64_t kj = g.keys[j * G + i];
             int r = 0;
             for (int q = 0; q < n; q++) {
-                const uint64_t kq = b.keys[q * epb + i];
+                const uint64_t kq = g.keys[q * G + i];
                 r += (kq < kj) | ((kq == kj) & (q < j));
             }
-            b.order[r * epb + i] = (uint8_t)j;
+            g.order[r * G + i] = (uint8_t)j;
         }
     } else {
-        b.order[i] = 0;  // base.py:396-397
+        g.order[i] = 0;  // base.py:396-397
     }
+    const int8_t *act_e = g.act + i * n;
     for (int r = 0; r < n; r++) {
-        const int k = b.order[r * epb + i];
-        const int act = p.actions[(size_t)e * n + k];
+        const int k = g.order[r * G + i];
+        const int act = act_e[k];
         uint32_t a0 = ag[k * 2], a1 = ag[k * 2 + 1];
         if (act < 0) continue;            // id not in the action dict (base.py:403-404)
         if ((a0 >> 24) & 0xff) continue;  // terminated (base.py:408-409)
@@ -319,8 +448,8 @@ MG_HD void handle_actions(const Params &p, const Block &b, int i, int e, uint32_
         if (act > ACT_DONE) { status_or(p.status, 1); continue; }  // reference: ValueError
         const int dx = (dir == 0) - (dir == 2), dy = (dir == 1) - (dir == 3);  // constants.py:21-30
         const int fx = (int)((a0 >> 8) & 0xff) + dx, fy = (int)((a0 >> 16) & 0xff) + dy;
-        if ((unsigned)fx >= (unsigned)p.W || (unsigned)fy >= (unsigned)H) continue;
-        const int idx = fx * H + fy;
+        if ((unsigned)fx >= (unsigned)p.W || (unsigned)fy >= (unsigned)p.H) continue;
+        const int idx = fx * p.Hp + fy;
         const uint32_t cw = cells[idx];
         const uint32_t t = cw & 0xff, col = (cw >> 8) & 0xff, st = (cw >> 16) & 0xff;
         const uint32_t fxy = (uint32_t)fx | ((uint32_t)fy << 8);
@@ -330,19 +459,19 @@ MG_HD void handle_actions(const Params &p, const Block &b, int i, int e, uint32_
             if (!can_overlap) continue;
             if (!(p.flags & MG_FLAG_ALLOW_OVERLAP) && agent_at(p, ag, fxy)) continue;
             ag[k * 2] = (a0 & 0xff0000ffu) | (fxy << 8);
-            if (t == T_GOAL) on_success(p, ag, k, e, sc);
+            if (t == T_GOAL) on_success(p, ag, rew, k, sc);
             if (t == T_LAVA) on_failure(p, ag, k);
         } else if (act == ACT_PICKUP) {  // base.py:439-446
             if (((t == T_KEY) | (t == T_BALL) | (t == T_BOX)) && (a1 & 0xff) == T_EMPTY) {
                 ag[k * 2 + 1] = (a1 & 0xff000000u) | (cw & 0x00ffffffu);
                 cells[idx] = CELL_EMPTY;
-                store_cell(p, e, idx, CELL_EMPTY);
+                store_cell(p, e, fx, fy, CELL_EMPTY);
             }
         } else if (act == ACT_DROP) {  // base.py:449-459
             if ((a1 & 0xff) != T_EMPTY && t == T_EMPTY && !agent_at(p, ag, fxy)) {
                 const uint32_t w = cell_word(a1 & 0xff, (a1 >> 8) & 0xff, (a1 >> 16) & 0xff);
                 cells[idx] = w;
-                store_cell(p, e, idx, w);
+                store_cell(p, e, fx, fy, w);
                 ag[k * 2 + 1] = (a1 & 0xff000000u) | CELL_EMPTY;
             }
         } else {  // toggle, base.py:462-467
@@ -356,11 +485,11 @@ MG_HD void handle_actions(const Params &p, const Block &b, int i, int e, uint32_
                 if (ns != st) {
                     const uint32_t w = cell_word(t, col, ns);
                     cells[idx] = w;
-                    store_cell(p, e, idx, w);
+                    store_cell(p, e, fx, fy, w);
                 }
             } else if (t == T_BOX) {  // Box.toggle, core/world_object.py:599-605 (contains is None)
                 cells[idx] = CELL_EMPTY;
-                store_cell(p, e, idx, CELL_EMPTY);
+                store_cell(p, e, fx, fy, CELL_EMPTY);
             }
         }
     }
@@ -374,174 +503,336 @@ MG_HD void stamp_agents(const Params &p, uint32_t *cells, const uint32_t *ag) {
         if ((a0 >> 24) & 0xff) continue;
         const int x = (a0 >> 8) & 0xff, y = (a0 >> 16) & 0xff;
         if ((unsigned)x >= (unsigned)p.W || (unsigned)y >= (unsigned)p.H) continue;
-        cells[x * p.H + y] = T_AGENT | ((a1 >> 24) << 8) | ((a0 & 0xff) << 16);
+        cells[x * p.Hp + y] = T_AGENT | ((a1 >> 24) << 8) | ((a0 & 0xff) << 16);
     }
 }
 
 template <int MODE>
-MG_HD void phase_step(const Params &p, uint8_t *smem, int blk, int tid, int nt) {
-    Block b = block_view(p, smem, blk);
-    for (int i = tid; i < b.ne; i += nt) {
-        const int e = b.e0 + i, n = p.n;
-        uint32_t *cells = b.cells + i * p.cstride;
-        uint32_t *ag = b.ag + i * n * 2;
+MG_HD void phase_step(const Params &p, const Group &g, int lane) {
+    for (int i = lane; i < g.ne; i += LANES) {
+        const int n = p.n;
+        uint32_t *cells = g.cells + i * p.cstride;
+        uint32_t *ag = g.ag + i * n * 2;
         if constexpr (MODE == MODE_OBS) {
             stamp_agents(p, cells, ag);
         } else {
-            for (int j = 0; j < n; j++) p.reward[(size_t)e * n + j] = 0.0;  // base.py:394
+            double *rew = g.rew + i * n;
             bool truncated = false;
-            if (b.rk[i] < 0) {
-                const int32_t sc = b.sc[i] + 1;  // base.py:333
-                b.sc[i] = sc;
-                handle_actions(p, b, i, e, cells, ag, sc);
+            if (g.rk[i] < 0) {
+                const int32_t sc = g.sc[i] + 1;  // base.py:333
+                g.sc[i] = sc;
+                handle_actions(p, g, i, cells, ag, rew, sc);
                 truncated = sc >= p.max_steps;  // base.py:339
                 if (MODE == MODE_STEP_OBS) stamp_agents(p, cells, ag);  // obs sees pre-hook termination
                 if (p.hook == MG_HOOK_BLOCKED_UNLOCK_PICKUP) {  // envs/blockedunlockpickup.py:166-175
                     for (int k = 0; k < n; k++)
-                        if ((ag[k * 2 + 1] & 0xff) == T_BOX) on_success(p, ag, k, e, sc);
+                        if ((ag[k * 2 + 1] & 0xff) == T_BOX) on_success(p, ag, rew, k, sc);
                 }
             } else if (MODE == MODE_STEP_OBS) {
                 stamp_agents(p, cells, ag);
             }
-            for (int j = 0; j < n; j++)
-                p.terminated[(size_t)e * n + j] = (uint8_t)(((ag[j * 2] >> 24) & 0xff) != 0);
-            p.truncated[e] = (uint8_t)truncated;
-            p.step_count[e] = b.sc[i];
+            for (int j = 0; j < n; j++) g.term[i * n + j] = (uint8_t)(((ag[j * 2] >> 24) & 0xff) != 0);
+            g.trunc[i] = (uint8_t)truncated;
         }
     }
 }
 
-// ---- P3: observation of one agent -------------------------------------------------------------------
+// ---- P5: observation of one agent -------------------------------------------------------------------
 // Closed form of get_view_exts + the rotation loop (utils/obs.py:175-202, 276-316):
 //   obs[a][b] = G'[pos + f*(V-1-b) + r*(a - V/2)],  f = DIR_TO_VEC[dir], r = (-f.y, f.x),
-// out of bounds -> wall. Visibility (utils/obs.py:236-273) as one bitmask per view row b.
-template <int VT>
-MG_HD void obs_agent(const Params &p, const uint32_t *cells, uint32_t a0, uint32_t a1, uint8_t *out) {
-    const int V = VT ? VT : p.V, half = V >> 1, W = p.W, H = p.H;
+// out of bounds -> wall (the sentinel row/column of the padded cell array).
+// Visibility (utils/obs.py:236-273) as one bitmask per view row b. With s = see-through mask of the
+// row and v = cells already visible, the two serial sweeps are a rightward then a leftward flood of v
+// through s (carry chains of an addition), and the spill into row b-1 is A | A<<1 | A>>1 with
+// A = visible & see-through.
+struct ViewGeom {
+    int pf, sf, Lf, stf;  // forward axis: agent coordinate, sign, length, word stride
+    int pl, sl, Ll, stl;  // lateral axis
+    uint32_t carry;       // carried object as a cell word (utils/obs.py:207)
+};
+
+MG_HD ViewGeom view_geom(const Params &p, uint32_t a0, uint32_t a1) {
+    ViewGeom v;
     const uint32_t dir = a0 & 3u;
     const int px = (a0 >> 8) & 0xff, py = (a0 >> 16) & 0xff;
-    const bool horiz = !(dir & 1u);               // forward axis is x for right/left
-    const int sf = (dir & 2u) ? -1 : 1;           // forward sign
-    const int sl = (dir == 0u || dir == 3u) ? 1 : -1;  // lateral sign (r = (-f.y, f.x))
-    const int pf = horiz ? px : py, Lf = horiz ? W : H;
-    const int pl = horiz ? py : px, Ll = horiz ? H : W;
-    const int df = sf * (horiz ? H : 1), dl = sl * (horiz ? 1 : H);
-    const int idx0 = px * H + py - dl * half;
-    const uint32_t full = (1u << V) - 1u;
-    const bool stw = (p.flags & MG_FLAG_SEE_THROUGH_WALLS) != 0;
-    const uint32_t carry = a1 & 0x00ffffffu;      // utils/obs.py:207
+    const bool horiz = !(dir & 1u);                    // forward axis is x for right/left
+    v.sf = (dir & 2u) ? -1 : 1;                        // forward sign
+    v.sl = (dir == 0u || dir == 3u) ? 1 : -1;          // lateral sign (r = (-f.y, f.x))
+    v.pf = horiz ? px : py; v.Lf = horiz ? p.W : p.H; v.stf = horiz ? p.Hp : 1;
+    v.pl = horiz ? py : px; v.Ll = horiz ? p.H : p.W; v.stl = horiz ? 1 : p.Hp;
+    v.carry = cell_word24(a1 & 0x00ffffffu);
+    return v;
+}
 
-    uint32_t colok = 0;                           // lateral coordinate in range, per view column a
-#pragma unroll
-    for (int a = 0; a < V; a++) colok |= (uint32_t)((unsigned)(pl + sl * (a - half)) < (unsigned)Ll) << a;
-
-    uint32_t cr[VT ? VT * VT : 1];
-    uint32_t vis = 1u << half;                    // vis_mask[V//2][V-1] = True (utils/obs.py:252)
-#pragma unroll
-    for (int b = V - 1; b >= 0; b--) {
-        const int d = V - 1 - b;
-        const bool rowok = (unsigned)(pf + sf * d) < (unsigned)Lf;
-        const int ridx = idx0 + df * d;
-        uint32_t see = 0;
-#pragma unroll
-        for (int a = 0; a < V; a++) {
-            uint32_t c = CELL_WALL;
-            if (rowok && ((colok >> a) & 1u)) c = cells[ridx + dl * a];
-            if (b == V - 1 && a == half) c = carry;
-            see |= (((c >> 24) & 1u) ^ 1u) << a;
-            if (VT) {
-                cr[VT ? a * VT + b : 0] = c;
-            } else {
-                uint8_t *o = out + (a * V + b) * 3;
-                o[0] = (uint8_t)c; o[1] = (uint8_t)(c >> 8); o[2] = (uint8_t)(c >> 16);
-            }
-        }
-        uint32_t m = full;
-        if (!stw) {  // get_vis_mask row b: forward sweep, backward sweep, spill into row b-1
-            m = vis;
-            m |= ((see + (m & see)) ^ see) & full;            // i = 0..V-2 ascending
-            const uint32_t af = m & see & (full >> 1);
-            uint32_t nxt = af | (af << 1);
-            uint32_t mr = bitrev(m, V);
-            const uint32_t sr = bitrev(see, V);
-            mr |= ((sr + (mr & sr)) ^ sr) & full;             // i = V-1..1 descending
-            m = bitrev(mr, V);
-            const uint32_t ab = m & see & (full & ~1u);
-            nxt |= ab | (ab >> 1);
-            vis = nxt & full;
-        }
-        if (VT) {
-#pragma unroll
-            for (int a = 0; a < V; a++)
-                if (!((m >> a) & 1u)) cr[VT ? a * VT + b : 0] = 0;  // UNSEEN, utils/obs.py:95-100
-        } else {
-            for (int a = 0; a < V; a++)
-                if (!((m >> a) & 1u)) {
-                    uint8_t *o = out + (a * V + b) * 3;
-                    o[0] = 0; o[1] = 0; o[2] = 0;
-                }
-        }
-    }
-    if (VT) {  // 24-bit cells -> dense byte stream, written as 32-bit words
-        constexpr int NC = VT ? VT * VT : 1;
-        constexpr int NW = (3 * NC + 3) / 4;
-        uint32_t *o32 = (uint32_t *)out;
-#pragma unroll
-        for (int w = 0; w < NW; w++) {
-            const int i0 = (4 * w) / 3, sh = 4 * w - 3 * i0;  // first cell, byte offset inside it
-            const uint32_t c0 = cr[i0 < NC ? i0 : 0];
-            const uint32_t c1 = (i0 + 1 < NC) ? cr[i0 + 1 < NC ? i0 + 1 : 0] : 0u;
-            const uint32_t sel = sh == 0 ? 0x4210u : (sh == 1 ? 0x5421u : 0x6542u);
-            o32[w] = byte_perm(c0 & 0x00ffffffu, c1 & 0x00ffffffu, sel);
-        }
-        for (int w = NW; w * 4 < p.ostride; w++) o32[w] = 0;
-    } else {
-        for (int q = 3 * V * V; q < p.ostride; q++) out[q] = 0;
-    }
+MG_HD void vis_row(uint32_t &vis, uint32_t see, uint32_t full, uint32_t &m_out) {
+    uint32_t m = vis;
+    m |= ((see + (m & see)) ^ see) & full;              // i = 0..V-2 ascending  (utils/obs.py:256-262)
+    // bit-reversed (cell 0 at bit 31): a carry now runs towards lower cells; it falls off bit 31
+    const uint32_t sr = brev32(see);
+    uint32_t mr = brev32(m);
+    mr |= (sr + (mr & sr)) ^ sr;                        // i = V-1..1 descending (utils/obs.py:264-270)
+    m = brev32(mr);
+    const uint32_t a = m & see;
+    vis = (a | (a << 1) | (a >> 1)) & full;
+    m_out = m;
 }
 
 template <int VT>
-MG_HD void phase_obs(const Params &p, uint8_t *smem, int blk, int tid, int nt) {
-    Block b = block_view(p, smem, blk);
-    const int i = tid / p.tpe, lane = tid - i * p.tpe;
-    if (i >= b.ne) return;
-    const uint32_t *cells = b.cells + i * p.cstride;
-    for (int k = lane; k < p.n; k += p.tpe) {
-        const uint32_t a0 = b.ag[(i * p.n + k) * 2], a1 = b.ag[(i * p.n + k) * 2 + 1];
-        obs_agent<VT>(p, cells, a0, a1, b.stage + (size_t)(i * p.n + k) * p.ostride);
+MG_HD void obs_agent(const Params &p, const uint32_t *cells, uint32_t a0, uint32_t a1, uint8_t *out) {
+    constexpr int V = VT, half = VT / 2;
+    const ViewGeom g = view_geom(p, a0, a1);
+    const uint32_t full = (1u << V) - 1u;
+    const bool stw = (p.flags & MG_FLAG_SEE_THROUGH_WALLS) != 0;
+
+    int coloff[V];
+#pragma unroll
+    for (int a = 0; a < V; a++) {
+        int c = g.pl + g.sl * (a - half);
+        c = (unsigned)c < (unsigned)g.Ll ? c : g.Ll;
+        coloff[a] = c * g.stl;
     }
+    uint32_t cr[V * V];
+    uint32_t vis = 1u << half;                          // vis_mask[V//2][V-1] = True (utils/obs.py:252)
+#pragma unroll
+    for (int b = V - 1; b >= 0; b--) {
+        int r = g.pf + g.sf * (V - 1 - b);
+        r = (unsigned)r < (unsigned)g.Lf ? r : g.Lf;
+        const uint32_t *row = cells + r * g.stf;
+        uint32_t opq = 0;
+#pragma unroll
+        for (int a = V - 1; a >= 0; a--) {
+            uint32_t c = row[coloff[a]];
+            if (b == V - 1 && a == half) c = g.carry;
+            cr[a * V + b] = c;
+            opq = shl1_in(opq, c);
+        }
+        uint32_t m = full;
+        if (!stw) vis_row(vis, ~opq & full, full, m);
+#pragma unroll
+        for (int a = 0; a < V; a++)
+            if (!((m >> a) & 1u)) cr[a * V + b] = 0;    // UNSEEN, utils/obs.py:95-100
+    }
+    // 24-bit cells -> dense byte stream, written as 32-bit words (bit 31 is never selected)
+    constexpr int NC = V * V, NW = (3 * NC + 3) / 4;
+    uint32_t *o32 = (uint32_t *)out;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        const int i0 = (4 * w) / 3, sh = 4 * w - 3 * i0;  // first cell, byte offset inside it
+        const uint32_t c0 = cr[i0 < NC ? i0 : 0];
+        const uint32_t c1 = (i0 + 1 < NC) ? cr[i0 + 1 < NC ? i0 + 1 : 0] : 0u;
+        const uint32_t sel = sh == 0 ? 0x4210u : (sh == 1 ? 0x5421u : 0x6542u);
+        o32[w] = byte_perm(c0, c1, sel);  // c1 == 0 past the last cell: padding bytes are zero
+    }
+    for (int w = NW; w * 4 < p.ostride; w++) o32[w] = 0;
 }
 
-// ---- P4: store -------------------------------------------------------------------------------------
-template <int MODE>
-MG_HD void phase_store(const Params &p, uint8_t *smem, int blk, int tid, int nt) {
-    Block b = block_view(p, smem, blk);
-    if (MODE != MODE_STEP)
-        coop_copy(p.obs + (size_t)b.e0 * p.n * p.ostride, b.stage, b.ne * p.n * p.ostride, tid, nt);
-    if (MODE != MODE_OBS)
-        coop_copy(p.agents + (size_t)b.e0 * p.n * 8, b.ag, b.ne * p.n * 8, tid, nt);
+// Any odd V up to MG_MAX_VIEW: same algorithm, rolled loops, bytes written straight to the stage.
+MG_HD void obs_agent_generic(const Params &p, const uint32_t *cells, uint32_t a0, uint32_t a1, uint8_t *out) {
+    const int V = p.V, half = V >> 1;
+    const ViewGeom g = view_geom(p, a0, a1);
+    const uint32_t full = (1u << V) - 1u;
+    const bool stw = (p.flags & MG_FLAG_SEE_THROUGH_WALLS) != 0;
+    uint32_t vis = 1u << half;
+    for (int b = V - 1; b >= 0; b--) {
+        int r = g.pf + g.sf * (V - 1 - b);
+        r = (unsigned)r < (unsigned)g.Lf ? r : g.Lf;
+        const uint32_t *row = cells + r * g.stf;
+        uint32_t opq = 0;
+        for (int a = V - 1; a >= 0; a--) {
+            int c = g.pl + g.sl * (a - half);
+            c = (unsigned)c < (unsigned)g.Ll ? c : g.Ll;
+            uint32_t w = row[c * g.stl];
+            if (b == V - 1 && a == half) w = g.carry;
+            opq = shl1_in(opq, w);
+            uint8_t *o = out + (a * V + b) * 3;
+            o[0] = (uint8_t)w; o[1] = (uint8_t)(w >> 8); o[2] = (uint8_t)(w >> 16);
+        }
+        uint32_t m = full;
+        if (!stw) vis_row(vis, ~opq & full, full, m);
+        for (int a = 0; a < V; a++)
+            if (!((m >> a) & 1u)) {
+                uint8_t *o = out + (a * V + b) * 3;
+                o[0] = 0; o[1] = 0; o[2] = 0;
+            }
+    }
+    for (int q = 3 * V * V; q < p.ostride; q++) out[q] = 0;
+}
+
+// One pass: lane handles agent task `pass*32 + lane` of the group (tasks are env-major, so a pass
+// is a contiguous span of the obs array). Returns nothing; the caller stores the stage.
+template <int VT>
+MG_HD void phase_obs(const Params &p, const Group &g, int pass, int lane) {
+    const int t = pass * LANES + lane;
+    if (t >= g.ne * p.n) return;
+    const int i = (int)fastdiv((uint32_t)t, p.rcp_n);
+    const uint32_t *cells = g.cells + i * p.cstride;
+    const uint32_t a0 = g.ag[t * 2], a1 = g.ag[t * 2 + 1];
+    uint8_t *out = g.stage + lane * p.ostride;
+    if constexpr (VT != 0) obs_agent<VT>(p, cells, a0, a1, out);
+    else obs_agent_generic(p, cells, a0, a1, out);
+}
+
+MG_HD int obs_passes(const Params &p, const Group &g) { return (g.ne * p.n + LANES - 1) / LANES; }
+
+MG_HD void phase_obs_store_plain(const Params &p, const Group &g, int pass, int lane) {
+    const int cnt = g.ne * p.n - pass * LANES < LANES ? g.ne * p.n - pass * LANES : LANES;
+    warp_copy(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, g.stage, cnt * p.ostride, lane);
+}
+
+// ---- P6 (plain path): store --------------------------------------------------------------------------
+MG_HD void phase_store_plain(const Params &p, const Group &g, int lane) {
+    const size_t e0 = (size_t)g.e0;
+    const int ne = g.ne, n = p.n;
+    warp_copy(p.agents + e0 * n * 8, g.ag, ne * n * 8, lane);
+    warp_copy(p.step_count + e0, g.sc, ne * 4, lane);
+    if (n > 1) warp_copy(p.pcg_state + 2 * e0, g.pcg, ne * 16, lane);
+    if (p.flags & MG_FLAG_AUTO_RESET) warp_copy(p.layout_idx + e0, g.lidx, ne * 4, lane);
+    warp_copy(p.reward + e0 * n, g.rew, ne * n * 8, lane);
+    warp_copy(p.terminated + e0 * n, g.term, ne * n, lane);
+    warp_copy(p.truncated + e0, g.trunc, ne, lane);
 }
 
 #ifdef __CUDACC__
+// ---- TMA bulk copies + mbarrier (sm_90+/sm_100a PTX) -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (TMA) reads that follow
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int MODE>
+__device__ __forceinline__ void load_bulk(const Params &p, const Group &g, uint64_t *bar) {
+    const size_t e0 = (size_t)g.e0;
+    const uint32_t G = (uint32_t)p.G, n = (uint32_t)p.n;
+    uint32_t total = G * p.grid_bytes + G * n * 8;
+    if (MODE != MODE_OBS) {
+        total += G * n + G * 4;
+        if (n > 1) total += 2 * G * 16;
+        if (p.flags & MG_FLAG_AUTO_RESET) total += G * 4;
+    }
+    mbar_expect_tx(bar, total);
+    bulk_g2s(g.stage, p.grid + e0 * p.grid_bytes, G * p.grid_bytes, bar);
+    bulk_g2s(g.ag, p.agents + e0 * n * 8, G * n * 8, bar);
+    if (MODE != MODE_OBS) {
+        bulk_g2s(g.act, p.actions + e0 * n, G * n, bar);
+        bulk_g2s(g.sc, p.step_count + e0, G * 4, bar);
+        if (n > 1) {
+            bulk_g2s(g.pcg, p.pcg_state + 2 * e0, G * 16, bar);
+            bulk_g2s(g.inc, p.pcg_inc + 2 * e0, G * 16, bar);
+        }
+        if (p.flags & MG_FLAG_AUTO_RESET) bulk_g2s(g.lidx, p.layout_idx + e0, G * 4, bar);
+    }
+}
+
+__device__ __forceinline__ void store_bulk(const Params &p, const Group &g) {
+    const size_t e0 = (size_t)g.e0;
+    const uint32_t G = (uint32_t)p.G, n = (uint32_t)p.n;
+    bulk_s2g(p.agents + e0 * n * 8, g.ag, G * n * 8);
+    bulk_s2g(p.step_count + e0, g.sc, G * 4);
+    if (n > 1) bulk_s2g(p.pcg_state + 2 * e0, g.pcg, G * 16);
+    if (p.flags & MG_FLAG_AUTO_RESET) bulk_s2g(p.layout_idx + e0, g.lidx, G * 4);
+    bulk_s2g(p.reward + e0 * n, g.rew, G * n * 8);
+    bulk_s2g(p.terminated + e0 * n, g.term, G * n);
+    bulk_s2g(p.truncated + e0, g.trunc, G);
+    bulk_commit();
+}
+
 template <int VT, int MODE>
 __global__ void __launch_bounds__(256) step_obs_kernel(const __grid_constant__ Params p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int blk = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    phase_load<MODE>(p, smem, blk, tid, nt);
-    __syncthreads();
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int group = blockIdx.x * p.wpb + warp;
+    if (group * p.G >= p.num_envs) return;  // whole warp
+    uint8_t *ws = smem + warp * p.warp_bytes;
+    const Group g = group_view(p, ws, group);
+    uint64_t *bar = (uint64_t *)(ws + p.off_mbar);
+    // TMA needs 16-byte multiples: full groups only (G % 16 == 0 makes every span aligned)
+    const bool bulk = p.use_bulk && g.ne == p.G;
+
+    if (bulk) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            load_bulk<MODE>(p, g, bar);
+        }
+    } else {
+        phase_load_plain<MODE>(p, g, lane);
+    }
+    phase_prep<MODE>(p, g, lane);  // touches only rewards / marks / sentinels: overlaps the load
+    __syncwarp();
+    if (bulk) mbar_wait(bar, 0);
     if (MODE != MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
-        phase_reset(p, smem, blk, tid, nt);
-        __syncthreads();
+        phase_reset(p, g, lane);
+        __syncwarp();
+        phase_reset_grid(p, g, lane);
+        __syncwarp();
     }
-    phase_convert(p, smem, blk, tid, nt);
-    __syncthreads();
-    phase_step<MODE>(p, smem, blk, tid, nt);
-    __syncthreads();
+    phase_convert(p, g, lane);
+    __syncwarp();
+    phase_step<MODE>(p, g, lane);
+    __syncwarp();
     if (MODE != MODE_STEP) {
-        phase_obs<VT>(p, smem, blk, tid, nt);
-        __syncthreads();
+        const int passes = obs_passes(p, g);
+        for (int pass = 0; pass < passes; pass++) {
+            if (bulk && pass > 0) {  // the previous pass's TMA store must be done reading the stage
+                if (lane == 0) bulk_wait_read();
+                __syncwarp();
+            }
+            phase_obs<VT>(p, g, pass, lane);
+            if (bulk) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    const int left = g.ne * p.n - pass * LANES;
+                    const uint32_t cnt = left < LANES ? left : LANES;
+                    bulk_s2g(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, g.stage,
+                             cnt * p.ostride);
+                    bulk_commit();
+                }
+            } else {
+                __syncwarp();
+                phase_obs_store_plain(p, g, pass, lane);
+                __syncwarp();
+            }
+        }
     }
-    phase_store<MODE>(p, smem, blk, tid, nt);
+    if (MODE != MODE_OBS) {
+        if (bulk) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) store_bulk(p, g);
+        } else {
+            phase_store_plain(p, g, lane);
+        }
+    }
+    if (bulk && lane == 0) bulk_wait_all();  // smem must stay valid until the TMA stores have read it
 }
 #endif
 

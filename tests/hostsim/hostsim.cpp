@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE: runs the phase functions of multigrid_b200/csrc/mg_kernels.cuh on the CPU,
-// "thread" by "thread" and phase by phase (a phase boundary == __syncthreads), so the kernel logic
-// can be checked against the oracle in a container without a GPU. Never loaded by the product.
+// lane by lane and phase by phase (a phase boundary == __syncwarp), so the kernel logic can be
+// checked against the oracle in a container without a GPU. The TMA bulk copies of the CUDA build
+// are replaced by the kernel's own plain-copy path. Never loaded by the product.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -10,43 +11,54 @@
 namespace {
 
 template <int VT, int MODE>
-void run_blocks(const mg::Params &p) {
-    std::vector<uint8_t> smem_store(p.smem_bytes + 16);
-    uint8_t *smem = smem_store.data();
-    smem += (16 - (reinterpret_cast<uintptr_t>(smem) & 15)) & 15;
-    const int nt = p.epb * p.tpe;
-    const int blocks = (p.num_envs + p.epb - 1) / p.epb;
-    for (int blk = 0; blk < blocks; blk++) {
-        std::memset(smem, 0xCD, p.smem_bytes);  // poison: catches reads of unwritten smem
-        for (int t = 0; t < nt; t++) mg::phase_load<MODE>(p, smem, blk, t, nt);
-        if (MODE != mg::MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET))
-            for (int t = 0; t < nt; t++) mg::phase_reset(p, smem, blk, t, nt);
-        for (int t = 0; t < nt; t++) mg::phase_convert(p, smem, blk, t, nt);
-        for (int t = 0; t < nt; t++) mg::phase_step<MODE>(p, smem, blk, t, nt);
-        if (MODE != mg::MODE_STEP)
-            for (int t = 0; t < nt; t++) mg::phase_obs<VT>(p, smem, blk, t, nt);
-        for (int t = 0; t < nt; t++) mg::phase_store<MODE>(p, smem, blk, t, nt);
+void run_groups(const mg::Params &p) {
+    std::vector<uint8_t> smem_store(p.warp_bytes + 128);
+    uint8_t *ws = smem_store.data();
+    ws += (128 - (reinterpret_cast<uintptr_t>(ws) & 127)) & 127;
+    const int groups = (p.num_envs + p.G - 1) / p.G;
+    const int L = mg::LANES;
+    for (int grp = 0; grp < groups; grp++) {
+        std::memset(ws, 0xCD, p.warp_bytes);  // poison: catches reads of unwritten smem
+        const mg::Group g = mg::group_view(p, ws, grp);
+        for (int l = 0; l < L; l++) mg::phase_load_plain<MODE>(p, g, l);
+        for (int l = 0; l < L; l++) mg::phase_prep<MODE>(p, g, l);
+        if (MODE != mg::MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
+            for (int l = 0; l < L; l++) mg::phase_reset(p, g, l);
+            for (int l = 0; l < L; l++) mg::phase_reset_grid(p, g, l);
+        }
+        for (int l = 0; l < L; l++) mg::phase_convert(p, g, l);
+        for (int l = 0; l < L; l++) mg::phase_step<MODE>(p, g, l);
+        if (MODE != mg::MODE_STEP) {
+            const int passes = mg::obs_passes(p, g);
+            for (int pass = 0; pass < passes; pass++) {
+                for (int l = 0; l < L; l++) mg::phase_obs<VT>(p, g, pass, l);
+                for (int l = 0; l < L; l++) mg::phase_obs_store_plain(p, g, pass, l);
+            }
+        }
+        if (MODE != mg::MODE_OBS)
+            for (int l = 0; l < L; l++) mg::phase_store_plain(p, g, l);
     }
 }
 
 template <int MODE>
 void dispatch(const mg::Params &p, int generic) {
+    if (MODE == mg::MODE_STEP) return run_groups<0, MODE>(p);
     if (!generic) {
         switch (p.V) {
-            case 3: return run_blocks<3, MODE>(p);
-            case 5: return run_blocks<5, MODE>(p);
-            case 7: return run_blocks<7, MODE>(p);
-            case 9: return run_blocks<9, MODE>(p);
+            case 3: return run_groups<3, MODE>(p);
+            case 5: return run_groups<5, MODE>(p);
+            case 7: return run_groups<7, MODE>(p);
+            case 9: return run_groups<9, MODE>(p);
             default: break;
         }
     }
-    run_blocks<0, MODE>(p);
+    run_groups<0, MODE>(p);
 }
 
 }  // namespace
 
 extern "C" int sim_run(int mode, const MgConfig *c, int64_t num_envs, const MgState *s,
-                       const int8_t *actions, const MgStepOut *o, int forced_epb, int generic) {
+                       const int8_t *actions, const MgStepOut *o, int forced_group, int generic) {
     mg::Params p;
     std::memset(&p, 0, sizeof(p));
     p.W = c->width; p.H = c->height; p.n = c->num_agents; p.V = c->view_size;
@@ -60,7 +72,7 @@ extern "C" int sim_run(int mode, const MgConfig *c, int64_t num_envs, const MgSt
     p.actions = actions;
     p.obs = o->obs; p.reward = o->reward; p.terminated = o->terminated; p.truncated = o->truncated;
     p.status = o->status;
-    int rc = mg::plan_launch(p, forced_epb, 256, 200 * 1024);
+    int rc = mg::plan_launch(p, forced_group, 0, 227 * 1024, 228 * 1024);
     if (rc) return rc;
     if (mode == mg::MODE_OBS) dispatch<mg::MODE_OBS>(p, generic);
     else if (mode == mg::MODE_STEP) dispatch<mg::MODE_STEP>(p, generic);

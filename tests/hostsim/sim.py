@@ -64,8 +64,8 @@ class SimEngine:
     """Mirror of oracle.OracleBatch's interface on top of the host-simulated kernels."""
 
     def __init__(self, cfg, grid, agents, pcg_state, pcg_inc, pool_grid=None, pool_agents=None,
-                 layout_idx=None, step_count=None, forced_epb=0, generic=0, split=False):
-        self.cfg, self.forced_epb, self.generic, self.split = cfg, forced_epb, generic, split
+                 layout_idx=None, step_count=None, forced_group=0, generic=0, split=False):
+        self.cfg, self.forced_group, self.generic, self.split = cfg, forced_group, generic, split
         self.grid = aligned_copy(grid, np.int8)
         self.agents = aligned_copy(agents, np.int8)
         self.B = self.grid.shape[0]
@@ -104,7 +104,7 @@ class SimEngine:
 
     def _run(self, mode, actions=None):
         rc = lib().sim_run(C.c_int(mode), C.byref(self.c), C.c_int64(self.B), C.byref(self.state),
-                           _p(actions), C.byref(self.out), C.c_int(self.forced_epb),
+                           _p(actions), C.byref(self.out), C.c_int(self.forced_group),
                            C.c_int(self.generic))
         assert rc == 0, rc
 

@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Kernel-only timing sweep of the fused step+observe kernel over the launch knobs
+(MG_GROUP, MG_WPB, MG_NO_BULK) and over the BASELINE.json configurations.
+
+    python tools/kbench.py [--configs empty8,bup,empty16] [--steps 200]
+
+Not the bench contract (that is bench.py): a development tool to pick launch geometry.
+"""
+from __future__ import annotations
+
+import argparse
+import itertools
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from multigrid_b200.engine import EngineConfig, StepEngine  # noqa: E402
+
+CONFIGS = {
+    # name: (W, H, n, V, E, max_steps, mutable_grid)
+    "empty8": (8, 8, 4, 7, 65536, 256, False),
+    "bup": (11, 6, 2, 7, 32768, 576, True),
+    "empty16": (16, 16, 8, 9, 16384, 1024, False),
+}
+
+
+def layout(W, H, n):
+    grid = np.zeros((1, W, H, 3), np.int8)
+    grid[..., 0] = 1
+    grid[0, 0, :] = grid[0, W - 1, :] = (2, 5, 0)
+    grid[0, :, 0] = grid[0, :, H - 1] = (2, 5, 0)
+    grid[0, W - 2, H - 2] = (8, 1, 0)
+    agents = np.zeros((1, n, 8), np.int8)
+    agents[..., 1] = 1
+    agents[..., 2] = 1
+    agents[..., 4] = 1
+    agents[..., 7] = np.arange(n) % 6
+    return grid, agents
+
+
+def time_config(name, steps, knobs, replicas=8):
+    W, H, n, V, E, max_steps, mutable = CONFIGS[name]
+    dev = torch.device("cuda", 0)
+    cfg = EngineConfig(width=W, height=H, num_agents=n, view_size=V, max_steps=max_steps, auto_reset=True)
+    pg, pa = layout(W, H, n)
+    engines = []
+    for r in range(replicas):
+        eng = StepEngine(cfg, E, dev, pg, pa)
+        st, inc = bench.pcg_words(r * E, E)
+        eng.load_state(np.repeat(pg, E, 0), np.repeat(pa, E, 0), None, st, inc, None)
+        engines.append(eng)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    tape = torch.randint(0, 7, (32, E, n), generator=gen, device=dev, dtype=torch.int32).to(torch.int8)
+    for k in range(64):
+        engines[k % replicas].step(tape[k % 32])
+    torch.cuda.synchronize()
+    bpe = bench.algorithmic_bytes_per_env_step(W, H, n, V, mutable)
+    out = []
+    for knob in knobs:
+        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK"):
+            os.environ.pop(key, None)
+        os.environ.update({k: str(v) for k, v in knob.items()})
+        stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(stream):
+            for k in range(4):
+                engines[k % replicas].step(tape[k % 32])
+            stream.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream):
+                for k in range(steps):
+                    engines[k % replicas].step(tape[k % 32])
+        torch.cuda.synchronize()
+        best = 1e9
+        for rep in range(3):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                ev0.record(stream)
+                graph.replay()
+                ev1.record(stream)
+            torch.cuda.synchronize()
+            best = min(best, ev0.elapsed_time(ev1))
+        us = 1e3 * best / steps
+        rec = dict(config=name, **knob, us_per_launch=round(us, 2),
+                   gagent_steps_s=round(E * n / us / 1e3, 2), gbs=round(bpe * E / us / 1e3, 1))
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="empty8")
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--groups", default="16,32")
+    ap.add_argument("--wpbs", default="0,1,2,4,8")
+    ap.add_argument("--nobulk", default="0,1")
+    args = ap.parse_args()
+    knobs = []
+    for g, w, nb in itertools.product(args.groups.split(","), args.wpbs.split(","), args.nobulk.split(",")):
+        k = {"MG_GROUP": int(g)}
+        if int(w):
+            k["MG_WPB"] = int(w)
+        if int(nb):
+            k["MG_NO_BULK"] = 1
+        knobs.append(k)
+    for name in args.configs.split(","):
+        time_config(name, args.steps, knobs)
+
+
+if __name__ == "__main__":
+    main()
