@@ -29,7 +29,7 @@ int validate(const MgConfig *c, int64_t num_envs) {
     if (c->view_size < 3 || c->view_size > MG_MAX_VIEW || !(c->view_size & 1)) return MG_ERR_BAD_ARG;
     if (c->max_steps < 1) return MG_ERR_BAD_ARG;
     if (c->obs_agent_stride < 3 * c->view_size * c->view_size || (c->obs_agent_stride & 3)) return MG_ERR_BAD_ARG;
-    if ((c->flags & MG_FLAG_AUTO_RESET) && c->num_layouts < 1) return MG_ERR_BAD_ARG;
+    if ((c->flags & MG_FLAG_AUTO_RESET) && (c->num_layouts < 1 || c->layout_stride < 0)) return MG_ERR_BAD_ARG;
     return 0;
 }
 

@@ -62,11 +62,10 @@ struct Params {
     int8_t *obs; double *reward; uint8_t *terminated; uint8_t *truncated; int32_t *status;
     // derived geometry. The cell array of an env is (W+1) x (H+1) words, row stride Hp = H+1:
     // row x = W and column y = H hold WALL sentinels, every out-of-range coordinate maps there.
-    int32_t Hp, cstride, grid_bytes, quads;
-    uint32_t rcp_n, rcp_h, rcp_q;  // ceil(2^32 / d) for d = n, H, quads (see fastdiv)
+    int32_t Hp, cstride, WH, grid_bytes;
+    uint32_t rcp_n, rcp_h, rcp_wh, rcp_q;  // ceil(2^32 / d) for d = n, H, W*H, W*H/4 (see fastdiv)
     // per-warp shared-memory carve-up (byte offsets, all multiples of 16)
-    int32_t off_cells, off_stage, off_ag, off_pcg, off_inc, off_act, off_sc, off_lidx, off_rk,
-        off_rew, off_term, off_trunc, off_mbar, warp_bytes;
+    int32_t off_cells, off_stage, off_ag, off_act, off_rk, off_mbar, warp_bytes;
 };
 
 MG_HD int align16(int x) { return (x + 15) & ~15; }
@@ -74,29 +73,22 @@ inline uint32_t rcp32(int d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / (u
 
 // Fills the derived fields for group size p.G; returns the shared memory bytes of one warp.
 inline int carve_smem(Params &p) {
-    const int WH = p.W * p.H, G = p.G, n = p.n;
+    const int G = p.G, n = p.n;
+    p.WH = p.W * p.H;
     p.Hp = p.H + 1;
     p.cstride = ((p.W + 1) * p.Hp) | 1;
-    p.grid_bytes = 3 * WH;
-    p.quads = (WH & 3) == 0 ? WH / 4 : 0;  // 0: byte-wise convert
-    p.rcp_n = rcp32(n); p.rcp_h = rcp32(p.H); p.rcp_q = rcp32(p.quads);
-    // "stage" is reused over time: raw grid bytes (P0-P3), sort keys + order (P4), obs pass (P5)
+    p.grid_bytes = 3 * p.WH;
+    p.rcp_n = rcp32(n); p.rcp_h = rcp32(p.H); p.rcp_wh = rcp32(p.WH); p.rcp_q = rcp32(p.WH / 4);
+    // "stage" is reused over time: raw grid bytes (P0-P3), sort keys + order (P4, n > 4), obs pass (P5)
     int stage = G * p.grid_bytes;
     if (LANES * p.ostride > stage) stage = LANES * p.ostride;
-    if (G * n * 9 + 16 > stage) stage = G * n * 9 + 16;
+    if (n > 4 && G * n * 9 + 16 > stage) stage = G * n * 9 + 16;
     int off = 0;
     p.off_cells = off; off += align16(G * p.cstride * 4);
     p.off_stage = off; off += align16(stage);
     p.off_ag = off;    off += align16(G * n * 8);
-    p.off_pcg = off;   off += align16(G * 16);
-    p.off_inc = off;   off += align16(G * 16);
     p.off_act = off;   off += align16(G * n);
-    p.off_sc = off;    off += align16(G * 4);
-    p.off_lidx = off;  off += align16(G * 4);
     p.off_rk = off;    off += align16(G * 4);
-    p.off_rew = off;   off += align16(G * n * 8);
-    p.off_term = off;  off += align16(G * n);
-    p.off_trunc = off; off += align16(G);
     p.off_mbar = off;  off += 16;
     p.warp_bytes = off;
     return off;
@@ -250,12 +242,26 @@ MG_HD uint32_t cell_word24(uint32_t c) {  // c = type | color<<8 | state<<16
     return c | (opaque << 31);
 }
 
+// 4 consecutive 3-byte cells (12 bytes = words w0,w1,w2) -> 4 cell words. The opaque test runs on
+// all four cells at once, one byte lane per cell (all encoded values are < 0x80).
+MG_HD void cell_words_x4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t out[4]) {
+    const uint32_t T = byte_perm(byte_perm(w0, w1, 0x0630u), w2, 0x5210u);  // type bytes: 0,3,6,9
+    const uint32_t S = byte_perm(byte_perm(w0, w1, 0x0052u), w2, 0x7410u);  // state bytes: 2,5,8,11
+    // x + 0x7f sets bit 7 of a byte lane iff x != 0 (x < 0x80: no carry between lanes)
+    const uint32_t K = 0x7f7f7f7fu;
+    const uint32_t not_wall = (T ^ 0x02020202u) + K, not_door = (T ^ 0x04040404u) + K, not_open = S + K;
+    const uint32_t O = (~not_wall | (~not_door & not_open)) & 0x80808080u;  // 0x80 per opaque cell
+    out[0] = byte_perm(w0, O, 0x4210u);
+    out[1] = byte_perm(byte_perm(w0, w1, 0x0543u), O, 0x5210u);
+    out[2] = byte_perm(byte_perm(w1, w2, 0x0432u), O, 0x6210u);
+    out[3] = byte_perm(w2, O, 0x7321u);
+}
+
 // One warp's view of its group: e0 = first global env, ne = number of valid envs.
 struct Group {
     int e0, ne;
-    uint32_t *cells; uint8_t *stage; uint32_t *ag; uint64_t *pcg; uint64_t *inc; int8_t *act;
-    int32_t *sc; int32_t *lidx; int32_t *rk; double *rew; uint8_t *term; uint8_t *trunc;
-    uint64_t *keys; uint8_t *order;  // alias the stage during P4
+    uint32_t *cells; uint8_t *stage; uint32_t *ag; int8_t *act; int32_t *rk;
+    uint64_t *keys; uint8_t *order;  // alias the stage during P4 (n > 4 only)
 };
 
 MG_HD Group group_view(const Params &p, uint8_t *ws, int group) {
@@ -265,138 +271,162 @@ MG_HD Group group_view(const Params &p, uint8_t *ws, int group) {
     g.cells = (uint32_t *)(ws + p.off_cells);
     g.stage = ws + p.off_stage;
     g.ag = (uint32_t *)(ws + p.off_ag);
-    g.pcg = (uint64_t *)(ws + p.off_pcg);
-    g.inc = (uint64_t *)(ws + p.off_inc);
     g.act = (int8_t *)(ws + p.off_act);
-    g.sc = (int32_t *)(ws + p.off_sc);
-    g.lidx = (int32_t *)(ws + p.off_lidx);
     g.rk = (int32_t *)(ws + p.off_rk);
-    g.rew = (double *)(ws + p.off_rew);
-    g.term = ws + p.off_term;
-    g.trunc = ws + p.off_trunc;
     g.keys = (uint64_t *)g.stage;
     g.order = g.stage + align16(p.G * p.n * 8);
     return g;
 }
 
-// ---- P0 (plain path): load ------------------------------------------------------------------------
+// The per-env phases (reset decision, transition) run one lane per env. With G = 16 the upper half
+// warp SHADOWS the lower half on the GPU: lane l and lane l+16 do identical work on identical data
+// (duplicate stores of identical values), so the warp never splits into two half-warps that would
+// then run the observation phase twice at half width. The host simulator runs lanes one after the
+// other, so there only lanes < G act.
+MG_HD int lane_env(const Params &p, const Group &g, int lane) {
+#ifdef __CUDA_ARCH__
+    const int i = lane & (p.G - 1);
+#else
+    const int i = lane < p.G ? lane : p.G;
+#endif
+    return i < g.ne ? i : -1;
+}
+
+// Per-env scalars the env's lane keeps in registers from load to store.
+struct alignas(16) U128 { uint64_t lo, hi; };
+struct EnvRegs {
+    uint64_t lo, hi, ilo, ihi;  // numpy PCG64 state / increment
+    int32_t sc, lidx;           // step_count, layout cursor
+};
+
+// ---- P0: load ------------------------------------------------------------------------------------
+template <int MODE>
+MG_HD void env_load(const Params &p, const Group &g, int i, EnvRegs &r) {
+    r.lo = r.hi = r.ilo = r.ihi = 0; r.sc = 0; r.lidx = 0;
+    if (MODE == MODE_OBS || i < 0) return;
+    const size_t e = (size_t)(g.e0 + i);
+    r.sc = p.step_count[e];
+    if (p.n > 1) {
+        const U128 s = *(const U128 *)(p.pcg_state + 2 * e), c = *(const U128 *)(p.pcg_inc + 2 * e);
+        r.lo = s.lo; r.hi = s.hi; r.ilo = c.lo; r.ihi = c.hi;
+    }
+    if (p.flags & MG_FLAG_AUTO_RESET) r.lidx = p.layout_idx[e];
+}
+
 template <int MODE>
 MG_HD void phase_load_plain(const Params &p, const Group &g, int lane) {
     const size_t e0 = (size_t)g.e0;
-    const int ne = g.ne, n = p.n;
-    warp_copy(g.stage, p.grid + e0 * p.grid_bytes, ne * p.grid_bytes, lane);
-    warp_copy(g.ag, p.agents + e0 * n * 8, ne * n * 8, lane);
-    if (MODE != MODE_OBS) {
-        warp_copy(g.act, p.actions + e0 * n, ne * n, lane);
-        warp_copy(g.sc, p.step_count + e0, ne * 4, lane);
-        if (n > 1) {
-            warp_copy(g.pcg, p.pcg_state + 2 * e0, ne * 16, lane);
-            warp_copy(g.inc, p.pcg_inc + 2 * e0, ne * 16, lane);
-        }
-        if (p.flags & MG_FLAG_AUTO_RESET) warp_copy(g.lidx, p.layout_idx + e0, ne * 4, lane);
-    }
-}
-
-// ---- P1: prep (rewards := 0, base.py:394; reset marks; wall sentinels) -------------------------------
-template <int MODE>
-MG_HD void phase_prep(const Params &p, const Group &g, int lane) {
-    const int ne = g.ne;
-    if (MODE != MODE_OBS) {
-        for (int i = lane; i < ne * p.n; i += LANES) g.rew[i] = 0.0;
-        for (int i = lane; i < ne; i += LANES) g.rk[i] = -1;
-    }
-    // sentinel row x = W (Hp words) and sentinel column y = H (W words) of every env
-    const int W = p.W, H = p.H, Hp = p.Hp;
-    for (int i = 0; i < ne; i++) {
-        uint32_t *c = g.cells + i * p.cstride;
-        for (int j = lane; j < Hp + W; j += LANES) {
-            const int idx = j < Hp ? W * Hp + j : (j - Hp) * Hp + H;
-            c[idx] = CELL_WALL;
-        }
-    }
+    warp_copy(g.stage, p.grid + e0 * p.grid_bytes, g.ne * p.grid_bytes, lane);
+    warp_copy(g.ag, p.agents + e0 * p.n * 8, g.ne * p.n * 8, lane);
+    if (MODE != MODE_OBS) warp_copy(g.act, p.actions + e0 * p.n, g.ne * p.n, lane);
 }
 
 // ---- P2: auto-reset decision ("next-step" mode; is_done = base.py:534-539) --------------------------
-MG_HD void phase_reset(const Params &p, const Group &g, int lane) {
-    for (int i = lane; i < g.ne; i += LANES) {
-        uint32_t all_term = 1;
-        for (int j = 0; j < p.n; j++) all_term &= ((g.ag[(i * p.n + j) * 2] >> 24) & 0xff) != 0;
-        if (all_term || g.sc[i] >= p.max_steps) {
-            int k = (int)(((int64_t)g.lidx[i] + p.lstride) % p.K);
-            g.lidx[i] = k;
-            g.rk[i] = k;
-            g.sc[i] = 0;
-            const uint32_t *src = (const uint32_t *)(p.pool_agents + (size_t)k * p.n * 8);
-            for (int j = 0; j < p.n * 2; j++) g.ag[i * p.n * 2 + j] = src[j];
-        }
+MG_HD void phase_reset(const Params &p, const Group &g, int i, EnvRegs &r) {
+    if (i < 0) return;
+    uint32_t all_term = 1;
+    for (int j = 0; j < p.n; j++) all_term &= ((g.ag[(i * p.n + j) * 2] >> 24) & 0xff) != 0;
+    int k = -1;
+    if (all_term || r.sc >= p.max_steps) {
+        k = (int)(((uint32_t)r.lidx + (uint32_t)p.lstride) % (uint32_t)p.K);
+        r.lidx = k;
+        r.sc = 0;
+        const uint32_t *src = (const uint32_t *)(p.pool_agents + (size_t)k * p.n * 8);
+        for (int j = 0; j < p.n * 2; j++) g.ag[i * p.n * 2 + j] = src[j];
     }
+    g.rk[i] = k;
 }
 
 // Envs that were reset take their grid from the layout pool: into the raw stage (for P3) and
-// written through to the state in HBM.
-MG_HD void phase_reset_grid(const Params &p, const Group &g, int lane) {
+// written through to the state in HBM. `pending` = bit per env of the group that was reset.
+MG_HD void phase_reset_grid(const Params &p, const Group &g, uint32_t pending, int lane) {
     for (int i = 0; i < g.ne; i++) {
-        const int k = g.rk[i];
-        if (k < 0) continue;
-        const int8_t *src = p.pool_grid + (size_t)k * p.grid_bytes;
+        if (!((pending >> i) & 1u)) continue;
+        const int8_t *src = p.pool_grid + (size_t)g.rk[i] * p.grid_bytes;
         warp_copy(g.stage + i * p.grid_bytes, src, p.grid_bytes, lane);
         warp_copy(p.grid + (size_t)(g.e0 + i) * p.grid_bytes, src, p.grid_bytes, lane);
     }
 }
 
-// ---- P3: 3-byte cells -> cell words -----------------------------------------------------------------
+MG_HD uint32_t reset_mask_host(const Group &g) {  // hostsim only; the kernel uses a ballot
+    uint32_t m = 0;
+    for (int i = 0; i < g.ne; i++) m |= (uint32_t)(g.rk[i] >= 0) << i;
+    return m;
+}
+
+// ---- P3: 3-byte cells -> cell words, plus the wall sentinels ------------------------------------------
+// Writes cell ci of an env and the sentinels next to it: (x, H) after the last cell of row x,
+// (W, y) below the last row, (W, H) in the corner.
+MG_HD void put_cell(const Params &p, uint32_t *dst, int ci, uint32_t w) {
+    const int x = (int)fastdiv((uint32_t)ci, p.rcp_h), y = ci - x * p.H;
+    const int idx = ci + x;  // x*Hp + y
+    dst[idx] = w;
+    const bool last_y = y == p.H - 1, last_x = x == p.W - 1;
+    if (last_y) dst[idx + 1] = CELL_WALL;
+    if (last_x) dst[idx + p.Hp] = CELL_WALL;
+    if (last_x && last_y) dst[idx + p.Hp + 1] = CELL_WALL;
+}
+
 MG_HD void phase_convert(const Params &p, const Group &g, int lane) {
-    const int H = p.H;
-    if (p.quads) {  // 4 cells = 3 aligned words per item
-        const int Q = p.quads, items = g.ne * Q;
+    const int WH = p.WH, H = p.H;
+    if ((WH & 3) == 0 && (H & 3) == 0) {
+        // 4 cells = 3 aligned words, all in one grid row
+        const int Q = WH >> 2, items = g.ne * Q;
         for (int it = lane; it < items; it += LANES) {
             const int i = (int)fastdiv((uint32_t)it, p.rcp_q), q = it - i * Q;
             const uint32_t *rw = (const uint32_t *)(g.stage + i * p.grid_bytes) + 3 * q;
-            const uint32_t w0 = rw[0], w1 = rw[1], w2 = rw[2];
             uint32_t c[4];
-            c[0] = w0 & 0x00ffffffu;
-            c[1] = byte_perm(w0, w1, 0x0543u) & 0x00ffffffu;
-            c[2] = byte_perm(w1, w2, 0x0432u) & 0x00ffffffu;
-            c[3] = w2 >> 8;
+            cell_words_x4(rw[0], rw[1], rw[2], c);
             uint32_t *dst = g.cells + i * p.cstride;
-            const int ci = 4 * q;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int x = (int)fastdiv((uint32_t)(ci + j), p.rcp_h);  // idx = x*Hp + y = ci + x
-                dst[ci + j + x] = cell_word24(c[j]);
+            const int ci = 4 * q, x = (int)fastdiv((uint32_t)ci, p.rcp_h), y = ci - x * H;
+            uint32_t *d = dst + ci + x;
+            d[0] = c[0]; d[1] = c[1]; d[2] = c[2]; d[3] = c[3];
+            const bool last_y = y + 4 == H, last_x = x == p.W - 1;
+            if (last_y) d[4] = CELL_WALL;
+            if (last_x) {
+                uint32_t *s = d + p.Hp;
+                s[0] = CELL_WALL; s[1] = CELL_WALL; s[2] = CELL_WALL; s[3] = CELL_WALL;
+                if (last_y) s[4] = CELL_WALL;
             }
         }
     } else {
-        const int WH = p.W * p.H;
-        for (int i = 0; i < g.ne; i++) {
-            const uint8_t *src = g.stage + i * p.grid_bytes;
-            uint32_t *dst = g.cells + i * p.cstride;
-            for (int ci = lane; ci < WH; ci += LANES) {
-                const int x = ci / H;
-                dst[ci + x] = cell_word(src[3 * ci], src[3 * ci + 1], src[3 * ci + 2]);
+        // the group's raw bytes as one flat stream of cells: quads may straddle rows and envs
+        const int cells = g.ne * WH, nq = cells >> 2;
+        const uint32_t *rw0 = (const uint32_t *)g.stage;
+        for (int q = lane; q < nq; q += LANES) {
+            uint32_t c[4];
+            cell_words_x4(rw0[3 * q], rw0[3 * q + 1], rw0[3 * q + 2], c);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int fc = 4 * q + j, i = (int)fastdiv((uint32_t)fc, p.rcp_wh);
+                put_cell(p, g.cells + i * p.cstride, fc - i * WH, c[j]);
             }
+        }
+        for (int fc = (nq << 2) + lane; fc < cells; fc += LANES) {  // ragged tail group only
+            const int i = (int)fastdiv((uint32_t)fc, p.rcp_wh);
+            const uint8_t *src = g.stage + 3 * fc;
+            put_cell(p, g.cells + i * p.cstride, fc - i * WH, cell_word(src[0], src[1], src[2]));
         }
     }
 }
 
 // ---- P4: transition --------------------------------------------------------------------------------
 MG_HD void store_cell(const Params &p, int e, int x, int y, uint32_t w) {  // dirty-cell write-through
-    uint8_t *g = (uint8_t *)p.grid + ((size_t)e * p.W * p.H + x * p.H + y) * 3;
+    uint8_t *g = (uint8_t *)p.grid + ((size_t)e * p.WH + x * p.H + y) * 3;
     g[0] = (uint8_t)w; g[1] = (uint8_t)(w >> 8); g[2] = (uint8_t)(w >> 16);
 }
 
-MG_HD void on_success(const Params &p, uint32_t *ag, double *rew, int k, int32_t sc) {  // base.py:478-507
+MG_HD uint32_t all_agents(const Params &p) { return p.n >= 32 ? 0xffffffffu : (1u << p.n) - 1u; }
+
+// base.py:478-507. Every reward handed out in one step has the same value (same step_count), so
+// the step only records WHO is rewarded; `rewarded` = bit per agent.
+MG_HD void on_success(const Params &p, uint32_t *ag, uint32_t &rewarded, int k) {
     if (p.flags & MG_FLAG_SUCCESS_ANY) {
         for (int j = 0; j < p.n; j++) ag[j * 2] |= 1u << 24;
     } else {
         ag[k * 2] |= 1u << 24;
     }
-    const double r = reward_value(sc, p.max_steps);
-    if (p.flags & MG_FLAG_JOINT_REWARD) {
-        for (int j = 0; j < p.n; j++) rew[j] = r;
-    } else {
-        rew[k] = r;
-    }
+    rewarded |= (p.flags & MG_FLAG_JOINT_REWARD) ? all_agents(p) : (1u << k);
 }
 
 MG_HD void on_failure(const Params &p, uint32_t *ag, int k) {  // base.py:509-532
@@ -413,30 +443,49 @@ MG_HD bool agent_at(const Params &p, const uint32_t *ag, uint32_t xy) {  // xy =
     return hit;
 }
 
+// base.py:399: order = np_random.random(size=n).argsort(). Returns the order packed 4 bits per rank
+// (n <= 4, keys in registers) or writes g.order (n > 4, keys in the stage).
+MG_HD uint32_t draw_order(const Params &p, const Group &g, int i, EnvRegs &r) {
+    const int n = p.n, G = p.G;
+    if (n == 1) return 0;  // base.py:396-397
+    if (n <= 4) {
+        uint64_t k[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) k[j] = j < n ? pcg64_next53(r.lo, r.hi, r.ilo, r.ihi) : ~0ull;
+        uint32_t rank[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int j = q + 1; j < 4; j++) {  // stable ascending: q < j goes first on ties
+                const uint32_t q_first = k[q] <= k[j];
+                rank[j] += q_first; rank[q] += q_first ^ 1u;
+            }
+        uint32_t ord = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) ord |= (uint32_t)j << (4 * rank[j]);
+        return ord;
+    }
+    for (int j = 0; j < n; j++) g.keys[j * G + i] = pcg64_next53(r.lo, r.hi, r.ilo, r.ihi);
+    for (int j = 0; j < n; j++) {  // rank = position in the ascending (stable) order
+        const uint64_t kj = g.keys[j * G + i];
+        int rk = 0;
+        for (int q = 0; q < n; q++) {
+            const uint64_t kq = g.keys[q * G + i];
+            rk += (kq < kj) | ((kq == kj) & (q < j));
+        }
+        g.order[rk * G + i] = (uint8_t)j;
+    }
+    return 0;
+}
+
 // MultiGridEnv.handle_actions (base.py:378-476) for local env i; `ag` = this env's agent words.
 MG_HD void handle_actions(const Params &p, const Group &g, int i, uint32_t *cells, uint32_t *ag,
-                          double *rew, int32_t sc) {
+                          EnvRegs &er, uint32_t &rewarded) {
     const int n = p.n, G = p.G, e = g.e0 + i;
-    if (n > 1) {  // base.py:399: order = np_random.random(size=n).argsort()
-        uint64_t lo = g.pcg[2 * i], hi = g.pcg[2 * i + 1];
-        const uint64_t ilo = g.inc[2 * i], ihi = g.inc[2 * i + 1];
-        for (int j = 0; j < n; j++) g.keys[j * G + i] = pcg64_next53(lo, hi, ilo, ihi);
-        g.pcg[2 * i] = lo; g.pcg[2 * i + 1] = hi;
-        for (int j = 0; j < n; j++) {  // rank = position in the ascending (stable) order
-            const uint64_t kj = g.keys[j * G + i];
-            int r = 0;
-            for (int q = 0; q < n; q++) {
-                const uint64_t kq = g.keys[q * G + i];
-                r += (kq < kj) | ((kq == kj) & (q < j));
-            }
-            g.order[r * G + i] = (uint8_t)j;
-        }
-    } else {
-        g.order[i] = 0;  // base.py:396-397
-    }
+    const uint32_t ord = draw_order(p, g, i, er);
     const int8_t *act_e = g.act + i * n;
     for (int r = 0; r < n; r++) {
-        const int k = g.order[r * G + i];
+        const int k = n <= 4 ? (int)((ord >> (4 * r)) & 15u) : (int)g.order[r * G + i];
         const int act = act_e[k];
         uint32_t a0 = ag[k * 2], a1 = ag[k * 2 + 1];
         if (act < 0) continue;            // id not in the action dict (base.py:403-404)
@@ -459,7 +508,7 @@ MG_HD void handle_actions(const Params &p, const Group &g, int i, uint32_t *cell
             if (!can_overlap) continue;
             if (!(p.flags & MG_FLAG_ALLOW_OVERLAP) && agent_at(p, ag, fxy)) continue;
             ag[k * 2] = (a0 & 0xff0000ffu) | (fxy << 8);
-            if (t == T_GOAL) on_success(p, ag, rew, k, sc);
+            if (t == T_GOAL) on_success(p, ag, rewarded, k);
             if (t == T_LAVA) on_failure(p, ag, k);
         } else if (act == ACT_PICKUP) {  // base.py:439-446
             if (((t == T_KEY) | (t == T_BALL) | (t == T_BOX)) && (a1 & 0xff) == T_EMPTY) {
@@ -507,33 +556,45 @@ MG_HD void stamp_agents(const Params &p, uint32_t *cells, const uint32_t *ag) {
     }
 }
 
+// The env's lane: transition, then every per-env output straight from registers to HBM
+// (lane <-> env, env-major arrays: the warp's accesses are contiguous).
 template <int MODE>
-MG_HD void phase_step(const Params &p, const Group &g, int lane) {
-    for (int i = lane; i < g.ne; i += LANES) {
-        const int n = p.n;
-        uint32_t *cells = g.cells + i * p.cstride;
-        uint32_t *ag = g.ag + i * n * 2;
-        if constexpr (MODE == MODE_OBS) {
-            stamp_agents(p, cells, ag);
-        } else {
-            double *rew = g.rew + i * n;
-            bool truncated = false;
-            if (g.rk[i] < 0) {
-                const int32_t sc = g.sc[i] + 1;  // base.py:333
-                g.sc[i] = sc;
-                handle_actions(p, g, i, cells, ag, rew, sc);
-                truncated = sc >= p.max_steps;  // base.py:339
-                if (MODE == MODE_STEP_OBS) stamp_agents(p, cells, ag);  // obs sees pre-hook termination
-                if (p.hook == MG_HOOK_BLOCKED_UNLOCK_PICKUP) {  // envs/blockedunlockpickup.py:166-175
-                    for (int k = 0; k < n; k++)
-                        if ((ag[k * 2 + 1] & 0xff) == T_BOX) on_success(p, ag, rew, k, sc);
-                }
-            } else if (MODE == MODE_STEP_OBS) {
-                stamp_agents(p, cells, ag);
-            }
-            for (int j = 0; j < n; j++) g.term[i * n + j] = (uint8_t)(((ag[j * 2] >> 24) & 0xff) != 0);
-            g.trunc[i] = (uint8_t)truncated;
+MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r) {
+    if (i < 0) return;
+    const int n = p.n;
+    uint32_t *cells = g.cells + i * p.cstride;
+    uint32_t *ag = g.ag + i * n * 2;
+    if constexpr (MODE == MODE_OBS) {
+        stamp_agents(p, cells, ag);
+    } else {
+        const size_t e = (size_t)(g.e0 + i);
+        const bool was_reset = (p.flags & MG_FLAG_AUTO_RESET) && g.rk[i] >= 0;
+        uint32_t rewarded = 0;
+        bool truncated = false;
+        if (!was_reset) {
+            r.sc += 1;  // base.py:333
+            handle_actions(p, g, i, cells, ag, r, rewarded);
+            truncated = r.sc >= p.max_steps;  // base.py:339
         }
+        if (MODE == MODE_STEP_OBS) stamp_agents(p, cells, ag);  // obs sees pre-hook termination
+        if (!was_reset && p.hook == MG_HOOK_BLOCKED_UNLOCK_PICKUP) {  // envs/blockedunlockpickup.py:166-175
+            for (int k = 0; k < n; k++)
+                if ((ag[k * 2 + 1] & 0xff) == T_BOX) on_success(p, ag, rewarded, k);
+        }
+        p.step_count[e] = r.sc;
+        if (n > 1) { U128 s; s.lo = r.lo; s.hi = r.hi; *(U128 *)(p.pcg_state + 2 * e) = s; }
+        if (p.flags & MG_FLAG_AUTO_RESET) p.layout_idx[e] = r.lidx;
+        p.truncated[e] = (uint8_t)truncated;
+        const double rv = rewarded ? reward_value(r.sc, p.max_steps) : 0.0;  // base.py:394, 598-602
+        if (n == 4) {
+            uint32_t tw = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) tw |= (uint32_t)(((ag[j * 2] >> 24) & 0xff) != 0) << (8 * j);
+            *(uint32_t *)(p.terminated + e * 4) = tw;
+        } else {
+            for (int j = 0; j < n; j++) p.terminated[e * n + j] = (uint8_t)(((ag[j * 2] >> 24) & 0xff) != 0);
+        }
+        for (int j = 0; j < n; j++) p.reward[e * n + j] = ((rewarded >> j) & 1u) ? rv : 0.0;
     }
 }
 
@@ -546,7 +607,7 @@ MG_HD void phase_step(const Params &p, const Group &g, int lane) {
 // through s (carry chains of an addition), and the spill into row b-1 is A | A<<1 | A>>1 with
 // A = visible & see-through.
 struct ViewGeom {
-    int pf, sf, Lf, stf;  // forward axis: agent coordinate, sign, length, word stride
+    int pf, sf, Lf, stf;  // forward axis: agent coordinate, sign, length, BYTE stride
     int pl, sl, Ll, stl;  // lateral axis
     uint32_t carry;       // carried object as a cell word (utils/obs.py:207)
 };
@@ -558,8 +619,8 @@ MG_HD ViewGeom view_geom(const Params &p, uint32_t a0, uint32_t a1) {
     const bool horiz = !(dir & 1u);                    // forward axis is x for right/left
     v.sf = (dir & 2u) ? -1 : 1;                        // forward sign
     v.sl = (dir == 0u || dir == 3u) ? 1 : -1;          // lateral sign (r = (-f.y, f.x))
-    v.pf = horiz ? px : py; v.Lf = horiz ? p.W : p.H; v.stf = horiz ? p.Hp : 1;
-    v.pl = horiz ? py : px; v.Ll = horiz ? p.H : p.W; v.stl = horiz ? 1 : p.Hp;
+    v.pf = horiz ? px : py; v.Lf = horiz ? p.W : p.H; v.stf = horiz ? 4 * p.Hp : 4;
+    v.pl = horiz ? py : px; v.Ll = horiz ? p.H : p.W; v.stl = horiz ? 4 : 4 * p.Hp;
     v.carry = cell_word24(a1 & 0x00ffffffu);
     return v;
 }
@@ -577,14 +638,26 @@ MG_HD void vis_row(uint32_t &vis, uint32_t see, uint32_t full, uint32_t &m_out) 
     m_out = m;
 }
 
+MG_HD uint32_t keep_if(uint32_t c, uint32_t m, uint32_t bit) {  // c if (m & bit) else UNSEEN (0,0,0)
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("{\n.reg .pred p;\n.reg .b32 t;\nand.b32 t, %1, %2;\nsetp.ne.u32 p, t, 0;\nselp.b32 %0, %3, 0, p;\n}"
+        : "=r"(r) : "r"(m), "r"(bit), "r"(c));
+    return r;
+#else
+    return (m & bit) ? c : 0u;
+#endif
+}
+
 template <int VT>
 MG_HD void obs_agent(const Params &p, const uint32_t *cells, uint32_t a0, uint32_t a1, uint8_t *out) {
     constexpr int V = VT, half = VT / 2;
     const ViewGeom g = view_geom(p, a0, a1);
     const uint32_t full = (1u << V) - 1u;
     const bool stw = (p.flags & MG_FLAG_SEE_THROUGH_WALLS) != 0;
+    const uint8_t *base = (const uint8_t *)cells;
 
-    int coloff[V];
+    int coloff[V];  // byte offsets of the view columns
 #pragma unroll
     for (int a = 0; a < V; a++) {
         int c = g.pl + g.sl * (a - half);
@@ -597,20 +670,21 @@ MG_HD void obs_agent(const Params &p, const uint32_t *cells, uint32_t a0, uint32
     for (int b = V - 1; b >= 0; b--) {
         int r = g.pf + g.sf * (V - 1 - b);
         r = (unsigned)r < (unsigned)g.Lf ? r : g.Lf;
-        const uint32_t *row = cells + r * g.stf;
+        const uint8_t *row = base + r * g.stf;
         uint32_t opq = 0;
 #pragma unroll
         for (int a = V - 1; a >= 0; a--) {
-            uint32_t c = row[coloff[a]];
+            uint32_t c = *(const uint32_t *)(row + coloff[a]);
             if (b == V - 1 && a == half) c = g.carry;
             cr[a * V + b] = c;
             opq = shl1_in(opq, c);
         }
-        uint32_t m = full;
-        if (!stw) vis_row(vis, ~opq & full, full, m);
+        if (!stw) {
+            uint32_t m;
+            vis_row(vis, ~opq & full, full, m);
 #pragma unroll
-        for (int a = 0; a < V; a++)
-            if (!((m >> a) & 1u)) cr[a * V + b] = 0;    // UNSEEN, utils/obs.py:95-100
+            for (int a = 0; a < V; a++) cr[a * V + b] = keep_if(cr[a * V + b], m, 1u << a);  // utils/obs.py:95-100
+        }
     }
     // 24-bit cells -> dense byte stream, written as 32-bit words (bit 31 is never selected)
     constexpr int NC = V * V, NW = (3 * NC + 3) / 4;
@@ -632,16 +706,17 @@ MG_HD void obs_agent_generic(const Params &p, const uint32_t *cells, uint32_t a0
     const ViewGeom g = view_geom(p, a0, a1);
     const uint32_t full = (1u << V) - 1u;
     const bool stw = (p.flags & MG_FLAG_SEE_THROUGH_WALLS) != 0;
+    const uint8_t *base = (const uint8_t *)cells;
     uint32_t vis = 1u << half;
     for (int b = V - 1; b >= 0; b--) {
         int r = g.pf + g.sf * (V - 1 - b);
         r = (unsigned)r < (unsigned)g.Lf ? r : g.Lf;
-        const uint32_t *row = cells + r * g.stf;
+        const uint8_t *row = base + r * g.stf;
         uint32_t opq = 0;
         for (int a = V - 1; a >= 0; a--) {
             int c = g.pl + g.sl * (a - half);
             c = (unsigned)c < (unsigned)g.Ll ? c : g.Ll;
-            uint32_t w = row[c * g.stl];
+            uint32_t w = *(const uint32_t *)(row + c * g.stl);
             if (b == V - 1 && a == half) w = g.carry;
             opq = shl1_in(opq, w);
             uint8_t *o = out + (a * V + b) * 3;
@@ -659,7 +734,7 @@ MG_HD void obs_agent_generic(const Params &p, const uint32_t *cells, uint32_t a0
 }
 
 // One pass: lane handles agent task `pass*32 + lane` of the group (tasks are env-major, so a pass
-// is a contiguous span of the obs array). Returns nothing; the caller stores the stage.
+// is a contiguous span of the obs array).
 template <int VT>
 MG_HD void phase_obs(const Params &p, const Group &g, int pass, int lane) {
     const int t = pass * LANES + lane;
@@ -679,17 +754,9 @@ MG_HD void phase_obs_store_plain(const Params &p, const Group &g, int pass, int 
     warp_copy(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, g.stage, cnt * p.ostride, lane);
 }
 
-// ---- P6 (plain path): store --------------------------------------------------------------------------
+// ---- P6 (plain path): agents back to HBM --------------------------------------------------------------
 MG_HD void phase_store_plain(const Params &p, const Group &g, int lane) {
-    const size_t e0 = (size_t)g.e0;
-    const int ne = g.ne, n = p.n;
-    warp_copy(p.agents + e0 * n * 8, g.ag, ne * n * 8, lane);
-    warp_copy(p.step_count + e0, g.sc, ne * 4, lane);
-    if (n > 1) warp_copy(p.pcg_state + 2 * e0, g.pcg, ne * 16, lane);
-    if (p.flags & MG_FLAG_AUTO_RESET) warp_copy(p.layout_idx + e0, g.lidx, ne * 4, lane);
-    warp_copy(p.reward + e0 * n, g.rew, ne * n * 8, lane);
-    warp_copy(p.terminated + e0 * n, g.term, ne * n, lane);
-    warp_copy(p.truncated + e0, g.trunc, ne, lane);
+    warp_copy(p.agents + (size_t)g.e0 * p.n * 8, g.ag, g.ne * p.n * 8, lane);
 }
 
 #ifdef __CUDACC__
@@ -733,36 +800,11 @@ __device__ __forceinline__ void load_bulk(const Params &p, const Group &g, uint6
     const size_t e0 = (size_t)g.e0;
     const uint32_t G = (uint32_t)p.G, n = (uint32_t)p.n;
     uint32_t total = G * p.grid_bytes + G * n * 8;
-    if (MODE != MODE_OBS) {
-        total += G * n + G * 4;
-        if (n > 1) total += 2 * G * 16;
-        if (p.flags & MG_FLAG_AUTO_RESET) total += G * 4;
-    }
+    if (MODE != MODE_OBS) total += G * n;
     mbar_expect_tx(bar, total);
     bulk_g2s(g.stage, p.grid + e0 * p.grid_bytes, G * p.grid_bytes, bar);
     bulk_g2s(g.ag, p.agents + e0 * n * 8, G * n * 8, bar);
-    if (MODE != MODE_OBS) {
-        bulk_g2s(g.act, p.actions + e0 * n, G * n, bar);
-        bulk_g2s(g.sc, p.step_count + e0, G * 4, bar);
-        if (n > 1) {
-            bulk_g2s(g.pcg, p.pcg_state + 2 * e0, G * 16, bar);
-            bulk_g2s(g.inc, p.pcg_inc + 2 * e0, G * 16, bar);
-        }
-        if (p.flags & MG_FLAG_AUTO_RESET) bulk_g2s(g.lidx, p.layout_idx + e0, G * 4, bar);
-    }
-}
-
-__device__ __forceinline__ void store_bulk(const Params &p, const Group &g) {
-    const size_t e0 = (size_t)g.e0;
-    const uint32_t G = (uint32_t)p.G, n = (uint32_t)p.n;
-    bulk_s2g(p.agents + e0 * n * 8, g.ag, G * n * 8);
-    bulk_s2g(p.step_count + e0, g.sc, G * 4);
-    if (n > 1) bulk_s2g(p.pcg_state + 2 * e0, g.pcg, G * 16);
-    if (p.flags & MG_FLAG_AUTO_RESET) bulk_s2g(p.layout_idx + e0, g.lidx, G * 4);
-    bulk_s2g(p.reward + e0 * n, g.rew, G * n * 8);
-    bulk_s2g(p.terminated + e0 * n, g.term, G * n);
-    bulk_s2g(p.truncated + e0, g.trunc, G);
-    bulk_commit();
+    if (MODE != MODE_OBS) bulk_g2s(g.act, p.actions + e0 * n, G * n, bar);
 }
 
 template <int VT, int MODE>
@@ -776,6 +818,7 @@ __global__ void __launch_bounds__(256) step_obs_kernel(const __grid_constant__ P
     uint64_t *bar = (uint64_t *)(ws + p.off_mbar);
     // TMA needs 16-byte multiples: full groups only (G % 16 == 0 makes every span aligned)
     const bool bulk = p.use_bulk && g.ne == p.G;
+    const int env = lane_env(p, g, lane);
 
     if (bulk) {
         if (lane == 0) {
@@ -785,26 +828,26 @@ __global__ void __launch_bounds__(256) step_obs_kernel(const __grid_constant__ P
     } else {
         phase_load_plain<MODE>(p, g, lane);
     }
-    phase_prep<MODE>(p, g, lane);  // touches only rewards / marks / sentinels: overlaps the load
+    EnvRegs er;
+    env_load<MODE>(p, g, env, er);  // the env's scalars, straight into its lane's registers
     __syncwarp();
     if (bulk) mbar_wait(bar, 0);
     if (MODE != MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
-        phase_reset(p, g, lane);
-        __syncwarp();
-        phase_reset_grid(p, g, lane);
+        phase_reset(p, g, env, er);
+        const uint32_t pending = __ballot_sync(0xffffffffu, env >= 0 && g.rk[env] >= 0) & (p.G == 32 ? 0xffffffffu : 0xffffu);
+        if (pending) {
+            __syncwarp();
+            phase_reset_grid(p, g, pending, lane);
+        }
         __syncwarp();
     }
     phase_convert(p, g, lane);
     __syncwarp();
-    phase_step<MODE>(p, g, lane);
+    phase_step<MODE>(p, g, env, er);
     __syncwarp();
     if (MODE != MODE_STEP) {
         const int passes = obs_passes(p, g);
         for (int pass = 0; pass < passes; pass++) {
-            if (bulk && pass > 0) {  // the previous pass's TMA store must be done reading the stage
-                if (lane == 0) bulk_wait_read();
-                __syncwarp();
-            }
             phase_obs<VT>(p, g, pass, lane);
             if (bulk) {
                 fence_async_smem();
@@ -815,7 +858,9 @@ __global__ void __launch_bounds__(256) step_obs_kernel(const __grid_constant__ P
                     bulk_s2g(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, g.stage,
                              cnt * p.ostride);
                     bulk_commit();
+                    if (pass + 1 < passes) bulk_wait_read();  // the stage is rewritten by the next pass
                 }
+                __syncwarp();
             } else {
                 __syncwarp();
                 phase_obs_store_plain(p, g, pass, lane);
@@ -825,9 +870,12 @@ __global__ void __launch_bounds__(256) step_obs_kernel(const __grid_constant__ P
     }
     if (MODE != MODE_OBS) {
         if (bulk) {
-            fence_async_smem();
+            if (MODE == MODE_STEP) fence_async_smem();  // (the obs passes already fenced)
             __syncwarp();
-            if (lane == 0) store_bulk(p, g);
+            if (lane == 0) {
+                bulk_s2g(p.agents + (size_t)g.e0 * p.n * 8, g.ag, (uint32_t)(p.G * p.n * 8));
+                bulk_commit();
+            }
         } else {
             phase_store_plain(p, g, lane);
         }

@@ -20,14 +20,18 @@ void run_groups(const mg::Params &p) {
     for (int grp = 0; grp < groups; grp++) {
         std::memset(ws, 0xCD, p.warp_bytes);  // poison: catches reads of unwritten smem
         const mg::Group g = mg::group_view(p, ws, grp);
+        mg::EnvRegs er[mg::LANES];
+        int env[mg::LANES];
+        for (int l = 0; l < L; l++) env[l] = mg::lane_env(p, g, l);
         for (int l = 0; l < L; l++) mg::phase_load_plain<MODE>(p, g, l);
-        for (int l = 0; l < L; l++) mg::phase_prep<MODE>(p, g, l);
+        for (int l = 0; l < L; l++) mg::env_load<MODE>(p, g, env[l], er[l]);
         if (MODE != mg::MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
-            for (int l = 0; l < L; l++) mg::phase_reset(p, g, l);
-            for (int l = 0; l < L; l++) mg::phase_reset_grid(p, g, l);
+            for (int l = 0; l < L; l++) mg::phase_reset(p, g, env[l], er[l]);
+            const uint32_t pending = mg::reset_mask_host(g);
+            for (int l = 0; l < L; l++) mg::phase_reset_grid(p, g, pending, l);
         }
         for (int l = 0; l < L; l++) mg::phase_convert(p, g, l);
-        for (int l = 0; l < L; l++) mg::phase_step<MODE>(p, g, l);
+        for (int l = 0; l < L; l++) mg::phase_step<MODE>(p, g, env[l], er[l]);
         if (MODE != mg::MODE_STEP) {
             const int passes = mg::obs_passes(p, g);
             for (int pass = 0; pass < passes; pass++) {
