@@ -97,7 +97,7 @@ inline int carve_smem(Params &p) {
 // Launch geometry: G envs per warp (16, or 32 when forced and it fits), wpb warps per block chosen
 // to maximise resident warps per SM. Returns 0, or MG_ERR_TOO_LARGE when 16 envs do not fit.
 inline int plan_launch(Params &p, int forced_G, int forced_wpb, int smem_per_block, int smem_per_sm) {
-    p.G = (forced_G == 32) ? 32 : 16;
+    p.G = (forced_G == 32 || forced_G == 8) ? forced_G : 16;
     if (carve_smem(p) > smem_per_block) {
         p.G = 16;
         if (carve_smem(p) > smem_per_block) return MG_ERR_TOO_LARGE;
@@ -355,21 +355,25 @@ MG_HD uint32_t reset_mask_host(const Group &g) {  // hostsim only; the kernel us
 }
 
 // ---- P3: 3-byte cells -> cell words, plus the wall sentinels ------------------------------------------
-// Writes cell ci of an env and the sentinels next to it: (x, H) after the last cell of row x,
-// (W, y) below the last row, (W, H) in the corner.
+// The env's lane writes its wall sentinels: row x = W (Hp words) and column y = H (W words).
+// Independent of the loaded data, so it runs while the TMA load is in flight.
+MG_HD void phase_sentinels(const Params &p, const Group &g, int i) {
+    if (i < 0) return;
+    uint32_t *c = g.cells + i * p.cstride;
+    uint32_t *row = c + p.W * p.Hp;
+    for (int j = 0; j < p.Hp; j++) row[j] = CELL_WALL;
+    uint32_t *col = c + p.H;
+    for (int x = 0; x < p.W; x++) col[x * p.Hp] = CELL_WALL;
+}
+
 MG_HD void put_cell(const Params &p, uint32_t *dst, int ci, uint32_t w) {
-    const int x = (int)fastdiv((uint32_t)ci, p.rcp_h), y = ci - x * p.H;
-    const int idx = ci + x;  // x*Hp + y
-    dst[idx] = w;
-    const bool last_y = y == p.H - 1, last_x = x == p.W - 1;
-    if (last_y) dst[idx + 1] = CELL_WALL;
-    if (last_x) dst[idx + p.Hp] = CELL_WALL;
-    if (last_x && last_y) dst[idx + p.Hp + 1] = CELL_WALL;
+    const int x = (int)fastdiv((uint32_t)ci, p.rcp_h);
+    dst[ci + x] = w;  // x*Hp + y
 }
 
 MG_HD void phase_convert(const Params &p, const Group &g, int lane) {
-    const int WH = p.WH, H = p.H;
-    if ((WH & 3) == 0 && (H & 3) == 0) {
+    const int WH = p.WH;
+    if ((WH & 3) == 0 && (p.H & 3) == 0) {
         // 4 cells = 3 aligned words, all in one grid row
         const int Q = WH >> 2, items = g.ne * Q;
         for (int it = lane; it < items; it += LANES) {
@@ -378,16 +382,9 @@ MG_HD void phase_convert(const Params &p, const Group &g, int lane) {
             uint32_t c[4];
             cell_words_x4(rw[0], rw[1], rw[2], c);
             uint32_t *dst = g.cells + i * p.cstride;
-            const int ci = 4 * q, x = (int)fastdiv((uint32_t)ci, p.rcp_h), y = ci - x * H;
+            const int ci = 4 * q, x = (int)fastdiv((uint32_t)ci, p.rcp_h);
             uint32_t *d = dst + ci + x;
             d[0] = c[0]; d[1] = c[1]; d[2] = c[2]; d[3] = c[3];
-            const bool last_y = y + 4 == H, last_x = x == p.W - 1;
-            if (last_y) d[4] = CELL_WALL;
-            if (last_x) {
-                uint32_t *s = d + p.Hp;
-                s[0] = CELL_WALL; s[1] = CELL_WALL; s[2] = CELL_WALL; s[3] = CELL_WALL;
-                if (last_y) s[4] = CELL_WALL;
-            }
         }
     } else {
         // the group's raw bytes as one flat stream of cells: quads may straddle rows and envs
@@ -650,7 +647,7 @@ MG_HD uint32_t keep_if(uint32_t c, uint32_t m, uint32_t bit) {  // c if (m & bit
 }
 
 template <int VT>
-MG_HD void obs_agent(const Params &p, const uint32_t *cells, uint32_t a0, uint32_t a1, uint8_t *out) {
+MG_HD void obs_compute(const Params &p, const uint32_t *cells, uint32_t a0, uint32_t a1, uint32_t (&cr)[VT * VT]) {
     constexpr int V = VT, half = VT / 2;
     const ViewGeom g = view_geom(p, a0, a1);
     const uint32_t full = (1u << V) - 1u;
@@ -664,7 +661,6 @@ MG_HD void obs_agent(const Params &p, const uint32_t *cells, uint32_t a0, uint32
         c = (unsigned)c < (unsigned)g.Ll ? c : g.Ll;
         coloff[a] = c * g.stl;
     }
-    uint32_t cr[V * V];
     uint32_t vis = 1u << half;                          // vis_mask[V//2][V-1] = True (utils/obs.py:252)
 #pragma unroll
     for (int b = V - 1; b >= 0; b--) {
@@ -686,8 +682,12 @@ MG_HD void obs_agent(const Params &p, const uint32_t *cells, uint32_t a0, uint32
             for (int a = 0; a < V; a++) cr[a * V + b] = keep_if(cr[a * V + b], m, 1u << a);  // utils/obs.py:95-100
         }
     }
-    // 24-bit cells -> dense byte stream, written as 32-bit words (bit 31 is never selected)
-    constexpr int NC = V * V, NW = (3 * NC + 3) / 4;
+}
+
+// 24-bit cells -> dense byte stream, written as 32-bit words (bit 31 is never selected)
+template <int VT>
+MG_HD void obs_pack_store(const Params &p, const uint32_t (&cr)[VT * VT], uint8_t *out) {
+    constexpr int NC = VT * VT, NW = (3 * NC + 3) / 4;
     uint32_t *o32 = (uint32_t *)out;
 #pragma unroll
     for (int w = 0; w < NW; w++) {
@@ -734,17 +734,18 @@ MG_HD void obs_agent_generic(const Params &p, const uint32_t *cells, uint32_t a0
 }
 
 // One pass: lane handles agent task `pass*32 + lane` of the group (tasks are env-major, so a pass
-// is a contiguous span of the obs array).
-template <int VT>
-MG_HD void phase_obs(const Params &p, const Group &g, int pass, int lane) {
-    const int t = pass * LANES + lane;
-    if (t >= g.ne * p.n) return;
-    const int i = (int)fastdiv((uint32_t)t, p.rcp_n);
-    const uint32_t *cells = g.cells + i * p.cstride;
-    const uint32_t a0 = g.ag[t * 2], a1 = g.ag[t * 2 + 1];
-    uint8_t *out = g.stage + lane * p.ostride;
-    if constexpr (VT != 0) obs_agent<VT>(p, cells, a0, a1, out);
-    else obs_agent_generic(p, cells, a0, a1, out);
+// is a contiguous span of the obs array). Split in two so that the wait for the previous pass's
+// TMA store (which reads the stage) sits between the register work and the stage writes.
+struct ObsTask { const uint32_t *cells; uint32_t a0, a1; bool valid; };
+
+MG_HD ObsTask obs_task(const Params &p, const Group &g, int pass, int lane) {
+    ObsTask t;
+    const int id = pass * LANES + lane;
+    t.valid = id < g.ne * p.n;
+    const int idc = t.valid ? id : 0;
+    t.cells = g.cells + (int)fastdiv((uint32_t)idc, p.rcp_n) * p.cstride;
+    t.a0 = g.ag[idc * 2]; t.a1 = g.ag[idc * 2 + 1];
+    return t;
 }
 
 MG_HD int obs_passes(const Params &p, const Group &g) { return (g.ne * p.n + LANES - 1) / LANES; }
@@ -808,7 +809,7 @@ __device__ __forceinline__ void load_bulk(const Params &p, const Group &g, uint6
 }
 
 template <int VT, int MODE>
-__global__ void __launch_bounds__(256) step_obs_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(256, VT >= 9 ? 2 : 3) step_obs_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = blockIdx.x * p.wpb + warp;
@@ -830,11 +831,12 @@ __global__ void __launch_bounds__(256) step_obs_kernel(const __grid_constant__ P
     }
     EnvRegs er;
     env_load<MODE>(p, g, env, er);  // the env's scalars, straight into its lane's registers
+    phase_sentinels(p, g, env);
     __syncwarp();
     if (bulk) mbar_wait(bar, 0);
     if (MODE != MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
         phase_reset(p, g, env, er);
-        const uint32_t pending = __ballot_sync(0xffffffffu, env >= 0 && g.rk[env] >= 0) & (p.G == 32 ? 0xffffffffu : 0xffffu);
+        const uint32_t pending = __ballot_sync(0xffffffffu, env >= 0 && g.rk[env] >= 0) & (p.G == 32 ? 0xffffffffu : (1u << p.G) - 1u);
         if (pending) {
             __syncwarp();
             phase_reset_grid(p, g, pending, lane);
@@ -848,7 +850,23 @@ __global__ void __launch_bounds__(256) step_obs_kernel(const __grid_constant__ P
     if (MODE != MODE_STEP) {
         const int passes = obs_passes(p, g);
         for (int pass = 0; pass < passes; pass++) {
-            phase_obs<VT>(p, g, pass, lane);
+            const ObsTask t = obs_task(p, g, pass, lane);
+            uint8_t *out = g.stage + lane * p.ostride;
+            if constexpr (VT != 0) {
+                uint32_t cr[VT ? VT * VT : 1];
+                if (t.valid) obs_compute<VT>(p, t.cells, t.a0, t.a1, cr);
+                if (bulk && pass > 0) {  // the previous pass's TMA store must be done reading the stage
+                    if (lane == 0) bulk_wait_read();
+                    __syncwarp();
+                }
+                if (t.valid) obs_pack_store<VT>(p, cr, out);
+            } else {
+                if (bulk && pass > 0) {
+                    if (lane == 0) bulk_wait_read();
+                    __syncwarp();
+                }
+                if (t.valid) obs_agent_generic(p, t.cells, t.a0, t.a1, out);
+            }
             if (bulk) {
                 fence_async_smem();
                 __syncwarp();
@@ -858,9 +876,7 @@ __global__ void __launch_bounds__(256) step_obs_kernel(const __grid_constant__ P
                     bulk_s2g(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, g.stage,
                              cnt * p.ostride);
                     bulk_commit();
-                    if (pass + 1 < passes) bulk_wait_read();  // the stage is rewritten by the next pass
                 }
-                __syncwarp();
             } else {
                 __syncwarp();
                 phase_obs_store_plain(p, g, pass, lane);
@@ -880,7 +896,7 @@ __global__ void __launch_bounds__(256) step_obs_kernel(const __grid_constant__ P
             phase_store_plain(p, g, lane);
         }
     }
-    if (bulk && lane == 0) bulk_wait_all();  // smem must stay valid until the TMA stores have read it
+    if (bulk && lane == 0) bulk_wait_read();  // smem must stay valid until the TMA stores have read it
 }
 #endif
 

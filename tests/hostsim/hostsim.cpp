@@ -10,6 +10,20 @@
 
 namespace {
 
+template <int VT>
+void obs_lane(const mg::Params &p, const mg::Group &g, int pass, int lane) {
+    const mg::ObsTask t = mg::obs_task(p, g, pass, lane);
+    if (!t.valid) return;
+    uint8_t *out = g.stage + lane * p.ostride;
+    if constexpr (VT != 0) {
+        uint32_t cr[VT ? VT * VT : 1];
+        mg::obs_compute<VT>(p, t.cells, t.a0, t.a1, cr);
+        mg::obs_pack_store<VT>(p, cr, out);
+    } else {
+        mg::obs_agent_generic(p, t.cells, t.a0, t.a1, out);
+    }
+}
+
 template <int VT, int MODE>
 void run_groups(const mg::Params &p) {
     std::vector<uint8_t> smem_store(p.warp_bytes + 128);
@@ -25,6 +39,7 @@ void run_groups(const mg::Params &p) {
         for (int l = 0; l < L; l++) env[l] = mg::lane_env(p, g, l);
         for (int l = 0; l < L; l++) mg::phase_load_plain<MODE>(p, g, l);
         for (int l = 0; l < L; l++) mg::env_load<MODE>(p, g, env[l], er[l]);
+        for (int l = 0; l < L; l++) mg::phase_sentinels(p, g, env[l]);
         if (MODE != mg::MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
             for (int l = 0; l < L; l++) mg::phase_reset(p, g, env[l], er[l]);
             const uint32_t pending = mg::reset_mask_host(g);
@@ -35,7 +50,7 @@ void run_groups(const mg::Params &p) {
         if (MODE != mg::MODE_STEP) {
             const int passes = mg::obs_passes(p, g);
             for (int pass = 0; pass < passes; pass++) {
-                for (int l = 0; l < L; l++) mg::phase_obs<VT>(p, g, pass, l);
+                for (int l = 0; l < L; l++) obs_lane<VT>(p, g, pass, l);
                 for (int l = 0; l < L; l++) mg::phase_obs_store_plain(p, g, pass, l);
             }
         }

@@ -173,7 +173,7 @@ def test_full_size_configs_vs_c_oracle(label, size, n, V, E, hook):
     assert_same(g, ora, label)
 
 
-KNOBS = [dict(MG_NO_BULK="1"), dict(MG_GROUP="32"), dict(MG_GROUP="32", MG_WPB="1"),
+KNOBS = [dict(MG_NO_BULK="1"), dict(MG_GROUP="8"), dict(MG_GROUP="32"), dict(MG_GROUP="32", MG_WPB="1"),
          dict(MG_WPB="8"), dict(MG_WPB="1", MG_NO_BULK="1")]
 
 
