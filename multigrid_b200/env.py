@@ -1,0 +1,301 @@
+"""`BatchedMultiGridEnv`: the reference's `MultiGridEnv` surface over `num_envs` lock-stepped envs.
+
+Mirrors multigrid/base.py:36-841 for the hot path -- `reset(seed)`, `step(actions)` returning
+per-agent dicts keyed `0..n-1`, `agents[i]`, `grid.state`, `agent_states`, `step_count`,
+`max_steps`, `is_done()`, `observation_space` / `action_space` -- with one difference: every
+value gains a leading `num_envs` axis and lives on the GPU (`image: (E,V,V,3) int8`,
+`direction / reward / terminated / truncated: (E,)`). Host code is Python, like the reference;
+the state lives in HBM and is advanced by the sm_100a kernels behind the C ABI
+(multigrid_b200.engine.StepEngine). No CPU fallback: constructing an env without the CUDA
+library or a CUDA device raises.
+
+Seeding: env e of the batch behaves like a reference env whose
+`env.np_random` was seeded with `seed + e` (gymnasium `reset(seed=...)`): the per-step agent
+order (base.py:399) is drawn in-kernel from that PCG64 stream, bit-exactly. Layout randomness
+comes from separate host generators, as in the reference (RandomMixin, utils/random.py:14-21).
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Iterable, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi, spaces
+from .core.constants import Action, Color, Direction, Type
+from .engine import EngineConfig, StepEngine
+from .layouts import A_COLOR, A_CC, A_CS, A_CT, A_DIR, A_TERM, A_X, A_Y, Layout
+
+_M64 = (1 << 64) - 1
+
+
+def pcg64_words(seeds: Sequence[int]) -> tuple[np.ndarray, np.ndarray]:
+    """(state, inc) as uint64 [E,2] {lo,hi} of `Generator(PCG64(SeedSequence(seed)))` per seed --
+    what gymnasium's `reset(seed=...)` installs as `env.np_random`."""
+    st = np.empty((len(seeds), 2), np.uint64)
+    inc = np.empty((len(seeds), 2), np.uint64)
+    for e, s in enumerate(seeds):
+        d = np.random.PCG64(np.random.SeedSequence(int(s))).state["state"]
+        st[e] = (d["state"] & _M64, d["state"] >> 64)
+        inc[e] = (d["inc"] & _M64, d["inc"] >> 64)
+    return st, inc
+
+
+def generator_words(gen: np.random.Generator) -> tuple[tuple[int, int], tuple[int, int]]:
+    d = gen.bit_generator.state["state"]
+    return (d["state"] & _M64, d["state"] >> 64), (d["inc"] & _M64, d["inc"] >> 64)
+
+
+def entropy_words(count: int) -> tuple[np.ndarray, np.ndarray]:
+    """Unseeded reset: any (state, odd inc) pair is a valid PCG64 stream."""
+    rng = np.random.default_rng()
+    st = rng.integers(0, 1 << 64, size=(count, 2), dtype=np.uint64)
+    inc = rng.integers(0, 1 << 64, size=(count, 2), dtype=np.uint64)
+    inc[:, 0] |= np.uint64(1)
+    return st, inc
+
+
+class Missions:
+    """Per-env mission strings without materialising `num_envs` Python strings per step."""
+
+    def __init__(self, table: list[str], index: torch.Tensor | None):
+        self.table, self.index = table, index
+
+    def __getitem__(self, e: int) -> str:
+        return self.table[0] if self.index is None else self.table[int(self.index[e]) % len(self.table)]
+
+    def __len__(self):
+        return 0 if self.index is None else int(self.index.shape[0])
+
+    def __repr__(self):
+        return f"Missions({self.table[0]!r})" if len(self.table) == 1 else f"Missions(<{len(self.table)} strings>)"
+
+
+class BatchedGrid:
+    """`env.grid`: `state` is the (num_envs, width, height, 3) int8 tensor of Grid.state
+    (core/grid.py:54, x-major)."""
+
+    def __init__(self, engine: StepEngine):
+        self._engine = engine
+        self.width, self.height = engine.cfg.width, engine.cfg.height
+
+    @property
+    def state(self) -> torch.Tensor:
+        return self._engine.grid
+
+
+class BatchedAgent:
+    """`env.agents[i]`: what adapters read from `Agent` (core/agent.py:73-109), batched."""
+
+    def __init__(self, env: "BatchedMultiGridEnv", index: int):
+        self._env, self.index = env, index
+        self.view_size = env.agent_view_size
+        self.see_through_walls = env.see_through_walls
+        self.color = Color.cycle(index + 1)[index]
+        V = self.view_size
+        self.observation_space = spaces.Dict({
+            "image": spaces.Box(low=0, high=255, shape=(V, V, 3), dtype=np.int64),
+            "direction": spaces.Discrete(len(Direction)),
+            "mission": spaces.Text(max_length=256),
+        })
+        self.action_space = spaces.Discrete(len(Action))
+
+    @property
+    def state(self) -> torch.Tensor:
+        """(E, 8) int8 packed record [dir,x,y,terminated,carry_type,carry_color,carry_state,color]."""
+        return self._env.engine.agents[:, self.index]
+
+    @property
+    def pos(self) -> torch.Tensor:
+        return self.state[:, A_X:A_Y + 1]
+
+    @property
+    def dir(self) -> torch.Tensor:
+        return self.state[:, A_DIR]
+
+    @property
+    def terminated(self) -> torch.Tensor:
+        return self.state[:, A_TERM] != 0
+
+    @property
+    def carrying(self) -> torch.Tensor:
+        """(E, 3) encoding of the carried object; (1,0,0) = nothing (core/agent.py:342)."""
+        return self.state[:, A_CT:A_CS + 1]
+
+    @property
+    def mission(self):
+        return self._env.missions
+
+
+class BatchedMultiGridEnv:
+    """`num_envs` lock-stepped MultiGrid envs of one layout family on one GPU."""
+
+    metadata = {"render_modes": []}
+
+    def __init__(self, layout: Layout, num_envs: int = 1, device: str | torch.device = "cuda",
+                 max_steps: int | None = None, see_through_walls: bool = False,
+                 agent_view_size: int = 7, allow_agent_overlap: bool = True,
+                 joint_reward: bool = False, success_termination_mode: str = "any",
+                 failure_termination_mode: str = "all", auto_reset: bool = False,
+                 pool_size: int | None = None, layout_seed: int | None = None,
+                 first_env: int = 0, render_mode: str | None = None):
+        if render_mode is not None:
+            raise NotImplementedError("rendering is out of scope of the batched engine")
+        self.layout = layout
+        self.num_envs = int(num_envs)
+        self.num_agents = layout.num_agents
+        self.width, self.height = layout.width, layout.height
+        self.max_steps = int(max_steps or layout.max_steps)
+        self.agent_view_size, self.see_through_walls = agent_view_size, see_through_walls
+        self.allow_agent_overlap, self.joint_reward = allow_agent_overlap, joint_reward
+        self.success_termination_mode = success_termination_mode
+        self.failure_termination_mode = failure_termination_mode
+        self.auto_reset = auto_reset
+        self.first_env = int(first_env)  # global id of local env 0 (multi-GPU sharding)
+        self.layout_seed = layout_seed
+        self.pool_size = 1 if layout.deterministic else min(self.num_envs, pool_size or 4096)
+        cfg = EngineConfig(
+            width=self.width, height=self.height, num_agents=self.num_agents,
+            view_size=agent_view_size, max_steps=self.max_steps,
+            see_through_walls=see_through_walls, allow_agent_overlap=allow_agent_overlap,
+            joint_reward=joint_reward, success_termination_mode=success_termination_mode,
+            failure_termination_mode=failure_termination_mode, hook=layout.hook,
+            auto_reset=auto_reset)
+        self.engine = StepEngine(cfg, self.num_envs, device)
+        self.device = self.engine.device
+        self.grid = BatchedGrid(self.engine)
+        self.agents = [BatchedAgent(self, i) for i in range(self.num_agents)]
+        self.observation_space = spaces.Dict({i: a.observation_space for i, a in enumerate(self.agents)})
+        self.action_space = spaces.Dict({i: a.action_space for i, a in enumerate(self.agents)})
+        self.missions = Missions([layout.mission], None)
+        self._actions = torch.full((self.num_envs, self.num_agents), -1, dtype=torch.int8,
+                                   device=self.device)
+        self._needs_reset = True
+
+    # -- reference attributes -------------------------------------------------------------------
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def agent_states(self) -> torch.Tensor:
+        """(E, n, 8) int8 packed AgentState (core/agent.py:222-232 without the constant TYPE)."""
+        return self.engine.agents
+
+    @property
+    def step_count(self) -> torch.Tensor:
+        return self.engine.step_count
+
+    def is_done(self) -> torch.Tensor:
+        """(E,) bool: base.py:534-539."""
+        term = self.engine.agents[:, :, A_TERM] != 0
+        return (self.engine.step_count >= self.max_steps) | term.all(dim=1)
+
+    # -- reset ----------------------------------------------------------------------------------
+    def _seeds(self, seed) -> np.ndarray | None:
+        if seed is None:
+            return None
+        if np.ndim(seed) == 0:
+            return int(seed) + self.first_env + np.arange(self.num_envs, dtype=np.int64)
+        seeds = np.asarray(seed, dtype=np.int64)
+        if seeds.shape != (self.num_envs,):
+            raise ValueError(f"seed must be an int or {self.num_envs} ints")
+        return seeds
+
+    def reset(self, seed=None, options: dict | None = None):
+        """-> (obs, infos). `seed`: int (env e gets seed + first_env + e) or one int per env.
+        `options['layout_rngs']`: one numpy Generator per pool entry (parity tests)."""
+        self.engine.check_status()
+        options = options or {}
+        E, K = self.num_envs, self.pool_size
+        seeds = self._seeds(seed)
+        st, inc = entropy_words(E) if seeds is None else pcg64_words(seeds)
+        layout_rngs = options.get("layout_rngs")
+        grids, agents, infos = [], [], []
+        for k in range(K):
+            if layout_rngs is not None:
+                lrng = layout_rngs[k]
+            elif self.layout_seed is not None:
+                lrng = np.random.default_rng([int(self.layout_seed), self.first_env + k])
+            else:
+                lrng = np.random.default_rng()
+            if self.layout.deterministic:
+                orng = None
+            else:  # env k's own order stream: reset-time draws (door positions) advance it
+                orng = np.random.Generator(np.random.PCG64())
+                s = orng.bit_generator.state
+                s["state"] = {"state": int(st[k, 0]) | (int(st[k, 1]) << 64),
+                              "inc": int(inc[k, 0]) | (int(inc[k, 1]) << 64)}
+                orng.bit_generator.state = s
+            g, a, info = self.layout.generate(lrng, orng)
+            if orng is not None:
+                st[k], _ = generator_words(orng)
+            grids.append(g)
+            agents.append(a)
+            infos.append(info)
+        pool_grid, pool_agents = np.stack(grids), np.stack(agents)
+        self.engine.set_layout_pool(pool_grid, pool_agents)
+        table = [info.get("mission", self.layout.mission) for info in infos]
+        idx = np.arange(E, dtype=np.int32) % K
+        self.engine.load_state(layout_idx=idx, pcg_state=st, pcg_inc=inc)
+        self.engine.reset_from_pool()
+        self.missions = Missions(table, None if len(set(table)) == 1 else self.engine.layout_idx)
+        self._needs_reset = False
+        return self._obs(self.engine.gen_obs()), defaultdict(dict)
+
+    # -- step -----------------------------------------------------------------------------------
+    def _obs(self, image: torch.Tensor) -> dict:
+        direction = self.engine.direction
+        return {i: {"image": image[:, i], "direction": direction[:, i], "mission": self.missions}
+                for i in range(self.num_agents)}
+
+    def _action_tensor(self, actions) -> torch.Tensor:
+        E, n = self.num_envs, self.num_agents
+        if isinstance(actions, torch.Tensor):
+            if actions.shape != (E, n):
+                raise ValueError(f"actions tensor must have shape ({E}, {n})")
+            if actions.dtype == torch.int8 and actions.device == self.device and actions.is_contiguous():
+                return actions
+            self._actions.copy_(actions)
+            return self._actions
+        if isinstance(actions, np.ndarray):
+            self._actions.copy_(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.int8)).reshape(E, n))
+            return self._actions
+        # dict {agent_id: action}; ids missing from the dict do not act (base.py:403-404)
+        self._actions.fill_(-1)
+        for i, a in actions.items():
+            if not 0 <= int(i) < n:
+                continue
+            if isinstance(a, torch.Tensor):
+                self._actions[:, i] = a.to(self.device, torch.int8)
+            elif np.ndim(a) == 0:
+                if not 0 <= int(a) < len(Action):
+                    raise ValueError(f"Unknown action: {a}")  # base.py:473-474
+                self._actions[:, i] = int(a)
+            else:
+                self._actions[:, i] = torch.as_tensor(np.asarray(a, dtype=np.int8), device=self.device)
+        return self._actions
+
+    def step(self, actions):
+        """-> (obs, rewards, terminations, truncations, infos), dicts keyed by agent index whose
+        values are batched device tensors (views of engine buffers, overwritten by the next call).
+        Asynchronous: nothing here synchronises with the GPU. Out-of-range actions inside tensors
+        are flagged on the device and raise ValueError at the next `reset()` / `check()`."""
+        if self._needs_reset:
+            raise RuntimeError("call reset() before step()")
+        image, reward, terminated, truncated = self.engine.step(self._action_tensor(actions))
+        term_b, trunc_b = terminated.view(torch.bool), truncated.view(torch.bool)
+        n = self.num_agents
+        return (self._obs(image),
+                {i: reward[:, i] for i in range(n)},
+                {i: term_b[:, i] for i in range(n)},
+                {i: trunc_b for i in range(n)},
+                defaultdict(dict))
+
+    def check(self) -> None:
+        """Synchronise and raise ValueError if a kernel saw an unknown action (base.py:473-474)."""
+        self.engine.check_status()
+
+    def close(self) -> None:
+        pass

@@ -1,0 +1,144 @@
+"""The reference-facing env layer (multigrid_b200.env / .envs): registry, seeding, dict API.
+
+Rollouts through `make(id, ...)` + `reset(seed)` + `step({agent: action})` are compared with the
+fixtures recorded from the unmodified reference (tests/golden/make_golden.py): same env ids, same
+kwargs, same generator seeds, same action tapes. CPU runs use the host-simulated kernels
+(tests/hostsim) behind the env layer; `-m gpu` runs use the real CUDA engine."""
+import numpy as np
+import pytest
+import torch
+
+import multigrid_b200.env as env_mod
+from multigrid_b200.envs import CONFIGURATIONS, NOT_YET, make
+from oracle import mg_oracle as O
+from tests.golden_util import load_case
+
+REFERENCE_IDS = [  # multigrid/envs/__init__.py:38-52
+    'MultiGrid-BlockedUnlockPickup-v0', 'MultiGrid-Empty-5x5-v0', 'MultiGrid-Empty-Random-5x5-v0',
+    'MultiGrid-Empty-6x6-v0', 'MultiGrid-Empty-Random-6x6-v0', 'MultiGrid-Empty-8x8-v0',
+    'MultiGrid-Empty-16x16-v0', 'MultiGrid-LockedHallway-2Rooms-v0',
+    'MultiGrid-LockedHallway-4Rooms-v0', 'MultiGrid-LockedHallway-6Rooms-v0',
+    'MultiGrid-Playground-v0', 'MultiGrid-RedBlueDoors-6x6-v0', 'MultiGrid-RedBlueDoors-8x8-v0']
+
+# (fixture, env id, kwargs, generator seed of make_golden.run_case)
+CASES = [
+    ("empty8_n2", "MultiGrid-Empty-8x8-v0", dict(agents=2), 1),
+    ("empty8_n4", "MultiGrid-Empty-8x8-v0", dict(agents=4), 2),
+    ("bup_n2", "MultiGrid-BlockedUnlockPickup-v0", dict(agents=2), 3),
+    ("empty16_n8_v9", "MultiGrid-Empty-16x16-v0", dict(agents=8, agent_view_size=9), 4),
+    ("empty6r_n3_nooverlap_all", "MultiGrid-Empty-Random-6x6-v0",
+     dict(agents=3, allow_agent_overlap=False, success_termination_mode="all", agent_start_dir=None), 5),
+    ("empty5_n1", "MultiGrid-Empty-5x5-v0", dict(agents=1, agent_view_size=3), 6),
+    ("empty8_n4_joint_stw", "MultiGrid-Empty-8x8-v0",
+     dict(agents=4, joint_reward=True, see_through_walls=True, agent_view_size=5), 7),
+    ("playground_n3", "MultiGrid-Playground-v0", dict(agents=3), 8),
+]
+
+
+def test_registry_covers_the_reference_ids():
+    assert sorted(list(CONFIGURATIONS) + list(NOT_YET)) == sorted(REFERENCE_IDS)
+    with pytest.raises(KeyError):
+        make("MultiGrid-Nope-v0")
+    with pytest.raises(NotImplementedError):
+        make("MultiGrid-RedBlueDoors-6x6-v0")
+
+
+def test_pcg64_words_match_numpy_generators():
+    st, inc = env_mod.pcg64_words([0, 7, 123456789])
+    for row, seed in enumerate([0, 7, 123456789]):
+        ref = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        assert env_mod.generator_words(ref) == (tuple(int(v) for v in st[row]), tuple(int(v) for v in inc[row]))
+    st, inc = env_mod.entropy_words(5)
+    assert (inc[:, 0] & np.uint64(1)).all()
+
+
+def test_no_cuda_means_no_env():
+    if torch.cuda.is_available():
+        pytest.skip("needs a box without CUDA")
+    with pytest.raises(RuntimeError):  # no CPU fallback in the product path
+        make("MultiGrid-Empty-8x8-v0", agents=2, num_envs=4)
+
+
+def rollout_case(name, env_id, kwargs, seed, device, T_max):
+    d, meta = load_case(name)
+    B, T, n = meta["B"], min(meta["T"], T_max), meta["n"]
+    env = make(env_id, num_envs=B, device=device, pool_size=B, **kwargs)
+    assert (env.width, env.height, env.max_steps, env.num_agents) == (meta["W"], meta["H"], meta["max_steps"], n)
+    obs, infos = env.reset(seed=[seed * 7919 + b for b in range(B)],
+                           options=dict(layout_rngs=[np.random.default_rng(seed * 1000 + b) for b in range(B)]))
+    np.testing.assert_array_equal(env.grid.state.cpu().numpy(), d["init_grid"])
+    np.testing.assert_array_equal(O.unpack_agents(env.agent_states.cpu().numpy()), d["init_agents"])
+    for i in range(n):
+        np.testing.assert_array_equal(obs[i]["image"].cpu().numpy(), d["obs0"][:, i])
+        np.testing.assert_array_equal(obs[i]["direction"].cpu().numpy(), d["dir0"][:, i])
+    for t in range(T):
+        acts = d["actions"][t]  # (B, n), -1 = id absent from the dict
+        if (acts < 0).any():
+            actions = torch.from_numpy(acts)
+        elif t % 2:
+            actions = {i: acts[:, i] for i in range(n)}
+        else:
+            actions = {i: torch.from_numpy(acts[:, i]) for i in range(n)}
+        obs, rew, term, trunc, infos = env.step(actions)
+        msg = f"{name} step {t}"
+        assert sorted(obs) == sorted(rew) == sorted(term) == sorted(trunc) == list(range(n))
+        for i in range(n):
+            np.testing.assert_array_equal(obs[i]["image"].cpu().numpy(), d["obs"][t][:, i], err_msg=msg)
+            np.testing.assert_array_equal(obs[i]["direction"].cpu().numpy(), d["direction"][t][:, i], err_msg=msg)
+            assert (rew[i].cpu().numpy() == d["reward"][t][:, i]).all(), msg
+            np.testing.assert_array_equal(term[i].cpu().numpy(), d["terminated"][t][:, i].astype(bool), err_msg=msg)
+            np.testing.assert_array_equal(trunc[i].cpu().numpy(), d["truncated"][t].astype(bool), err_msg=msg)
+            assert term[i].dtype == torch.bool and rew[i].dtype == torch.float64
+    done = env.is_done().cpu().numpy()
+    exp = (d["step_count"][T - 1] >= meta["max_steps"]) | d["agents"][T - 1][:, :, 5].astype(bool).all(1)
+    np.testing.assert_array_equal(done, exp)
+    env.check()
+    return env
+
+
+@pytest.mark.parametrize("name,env_id,kwargs,seed", CASES)
+def test_env_api_rollout_hostsim(name, env_id, kwargs, seed, monkeypatch):
+    from tests.hostsim.fake_engine import HostSimStepEngine
+    monkeypatch.setattr(env_mod, "StepEngine", HostSimStepEngine)
+    env = rollout_case(name, env_id, kwargs, seed, "cpu", T_max=60)
+    a = env.agents[0]
+    assert a.observation_space["image"].shape == (a.view_size, a.view_size, 3)
+    assert a.action_space.n == 7 and env.unwrapped is env
+    assert a.pos.shape == (env.num_envs, 2) and a.carrying.shape == (env.num_envs, 3)
+    assert isinstance(env.missions[0], str)
+
+
+def test_scalar_actions_and_unknown_action(monkeypatch):
+    from tests.hostsim.fake_engine import HostSimStepEngine
+    monkeypatch.setattr(env_mod, "StepEngine", HostSimStepEngine)
+    env = make("MultiGrid-Empty-5x5-v0", agents=2, num_envs=3, device="cpu")
+    with pytest.raises(RuntimeError):
+        env.step({0: 0})
+    env.reset(seed=5)
+    obs, rew, term, trunc, _ = env.step({0: 2})  # agent 1 absent from the dict: does not act
+    assert (env.agents[0].pos.numpy() == (2, 1)).all() and (env.agents[1].pos.numpy() == (1, 1)).all()
+    with pytest.raises(ValueError):
+        env.step({0: 7})
+    assert env.missions[1] == "get to the green goal square"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,env_id,kwargs,seed", CASES)
+def test_env_api_rollout_gpu(name, env_id, kwargs, seed):
+    rollout_case(name, env_id, kwargs, seed, "cuda:0", T_max=10**9)
+
+
+@pytest.mark.gpu
+def test_env_seed_int_matches_per_env_seeds():
+    a = make("MultiGrid-Empty-8x8-v0", agents=4, num_envs=64, device="cuda:0")
+    b = make("MultiGrid-Empty-8x8-v0", agents=4, num_envs=32, device="cuda:0", first_env=32)
+    a.reset(seed=100)
+    b.reset(seed=100)  # the second shard of the same global batch
+    rng = np.random.default_rng(0)
+    for t in range(40):
+        acts = torch.from_numpy(rng.integers(0, 7, (64, 4)).astype(np.int8)).cuda()
+        oa = a.step(acts)
+        ob = b.step(acts[32:].contiguous())
+        for i in range(4):
+            assert torch.equal(oa[0][i]["image"][32:], ob[0][i]["image"])
+            assert torch.equal(oa[1][i][32:], ob[1][i])
