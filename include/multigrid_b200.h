@@ -22,7 +22,13 @@
  *     contiguous, so a thread block's group of envs is one contiguous HBM span per array).
  *
  * State layout per env (all int8 values are < 128):
- *   grid        int8  [W][H][3]   x-major like Grid.state (core/grid.py:54): (type,color,state)
+ *   grid        uint32 [W+1][H+1] CELL WORDS, x-major like Grid.state (core/grid.py:54):
+ *                                 type | color<<8 | state<<16 | opaque<<31, where opaque = wall or
+ *                                 non-open door (see_behind, utils/obs.py:47-63). Row x = W and
+ *                                 column y = H are WALL sentinels (out-of-bounds view cells read
+ *                                 them). Bytes 0..2 of word (x,y) ARE Grid.state[x,y,:]; build it
+ *                                 from / turn it into the reference's (W,H,3) bytes with
+ *                                 mg_pack_grid / mg_unpack_grid.
  *   agents      int8  [n][8]      {dir,x,y,terminated,carry_type,carry_color,carry_state,color}
  *                                 = AgentState (core/agent.py:222-232) without the constant TYPE
  *   step_count  int32
@@ -44,7 +50,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 1
+#define MG_ABI_VERSION 2
 
 /* MgConfig.flags */
 #define MG_FLAG_SEE_THROUGH_WALLS 0x01u /* agents[0].see_through_walls, base.py:364-365 */
@@ -78,13 +84,13 @@ typedef struct MgConfig {
 } MgConfig;
 
 typedef struct MgState {
-    int8_t *grid;              /* [E][W][H][3] */
+    uint32_t *grid;            /* [E][W+1][H+1] cell words */
     int8_t *agents;            /* [E][n][8]    */
     int32_t *step_count;       /* [E]          */
     uint64_t *pcg_state;       /* [E][2]       */
     const uint64_t *pcg_inc;   /* [E][2]       */
     int32_t *layout_idx;       /* [E]      (may be NULL without MG_FLAG_AUTO_RESET) */
-    const int8_t *pool_grid;   /* [K][W][H][3] (may be NULL without MG_FLAG_AUTO_RESET) */
+    const uint32_t *pool_grid; /* [K][W+1][H+1] cell words (may be NULL without MG_FLAG_AUTO_RESET) */
     const int8_t *pool_agents; /* [K][n][8]    (may be NULL without MG_FLAG_AUTO_RESET) */
 } MgState;
 
@@ -104,6 +110,20 @@ const char *mg_error_string(int code);
 /* Smallest legal obs_agent_stride for a view size: 3*V*V rounded up to a multiple of 4. */
 int32_t mg_obs_agent_stride(int32_t view_size);
 
+/* Cell words per env: (W+1)*(H+1). */
+int64_t mg_cells_per_env(int32_t width, int32_t height);
+
+/*
+ * Layout conversion between the reference's Grid.state bytes, int8 [E][W][H][3]
+ * (core/grid.py:54, Grid.encode :310-327), and the engine's cell words (adds the opaque bit and the
+ * wall sentinels / drops them). Replaces nothing on the hot path: it is how state enters and
+ * leaves the engine (reset, state injection, inspection).
+ */
+int mg_pack_grid(int32_t width, int32_t height, int64_t num_envs, const int8_t *grid3, uint32_t *cells,
+                 void *stream);
+int mg_unpack_grid(int32_t width, int32_t height, int64_t num_envs, const uint32_t *cells, int8_t *grid3,
+                   void *stream);
+
 /* Number of engine kernels launched by this process so far (for launch accounting). */
 int64_t mg_launch_count(void);
 
@@ -112,7 +132,7 @@ int64_t mg_launch_count(void);
  * Replaces: gen_obs_grid_encoding (utils/obs.py:66-102) as called by MultiGridEnv.gen_obs
  * (base.py:348-376); used for reset() observations.
  */
-int mg_gen_obs(const MgConfig *cfg, int64_t num_envs, const int8_t *grid, const int8_t *agents,
+int mg_gen_obs(const MgConfig *cfg, int64_t num_envs, const uint32_t *grid, const int8_t *agents,
                int8_t *obs, void *stream);
 
 /*

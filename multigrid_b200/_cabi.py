@@ -22,7 +22,7 @@ FLAG_AUTO_RESET = 0x20
 HOOK_NONE = 0
 HOOK_BLOCKED_UNLOCK_PICKUP = 1
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_VIEW = 15
 MAX_AGENTS = 32
 
@@ -56,6 +56,9 @@ EXPORTS = {
     "mg_error_string": (C.c_char_p, [C.c_int]),
     "mg_obs_agent_stride": (C.c_int32, [C.c_int32]),
     "mg_launch_count": (C.c_int64, []),
+    "mg_cells_per_env": (C.c_int64, [C.c_int32, C.c_int32]),
+    "mg_pack_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mg_unpack_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_gen_obs": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_void_p]),
     "mg_step": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p,

@@ -143,9 +143,33 @@ const char *mg_error_string(int code) {
 
 int32_t mg_obs_agent_stride(int32_t view_size) { return (3 * view_size * view_size + 3) & ~3; }
 
+int64_t mg_cells_per_env(int32_t width, int32_t height) { return mg::cells_per_env(width, height); }
+
+int mg_pack_grid(int32_t width, int32_t height, int64_t num_envs, const int8_t *grid3, uint32_t *cells,
+                 void *stream) {
+    if (width < 1 || height < 1 || width > 127 || height > 127 || num_envs < 0) return MG_ERR_BAD_ARG;
+    if (num_envs == 0) return 0;
+    if (!grid3 || !cells) return MG_ERR_BAD_ARG;
+    const int64_t total = num_envs * mg::cells_per_env(width, height);
+    mg::pack_grid_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(width, height, total, grid3, cells);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int mg_unpack_grid(int32_t width, int32_t height, int64_t num_envs, const uint32_t *cells, int8_t *grid3,
+                   void *stream) {
+    if (width < 1 || height < 1 || width > 127 || height > 127 || num_envs < 0) return MG_ERR_BAD_ARG;
+    if (num_envs == 0) return 0;
+    if (!grid3 || !cells) return MG_ERR_BAD_ARG;
+    const int64_t total = num_envs * width * height;
+    mg::unpack_grid_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(width, height, total, cells, grid3);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 int64_t mg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int mg_gen_obs(const MgConfig *cfg, int64_t num_envs, const int8_t *grid, const int8_t *agents,
+int mg_gen_obs(const MgConfig *cfg, int64_t num_envs, const uint32_t *grid, const int8_t *agents,
                int8_t *obs, void *stream) {
     int rc = validate(cfg, num_envs);
     if (rc) return rc;
@@ -155,7 +179,7 @@ int mg_gen_obs(const MgConfig *cfg, int64_t num_envs, const int8_t *grid, const 
     mg::Params p;
     fill_config(p, cfg, num_envs);
     p.flags &= ~MG_FLAG_AUTO_RESET;
-    p.grid = const_cast<int8_t *>(grid);      // MODE_OBS never writes state
+    p.grid = const_cast<uint32_t *>(grid);    // MODE_OBS never writes state
     p.agents = const_cast<int8_t *>(agents);
     p.obs = obs;
     if ((rc = plan(p))) return rc;

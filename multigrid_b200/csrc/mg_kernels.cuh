@@ -6,16 +6,21 @@
 // 1-D TMA bulk copies (cp.async.bulk + mbarrier in, cp.async.bulk.bulk_group out), so loads and
 // stores cost the warp a handful of instructions; the per-env work runs out of shared memory:
 //
-//   P0 load      TMA: grid / agents / pcg state+inc / actions / step_count / layout_idx -> smem
-//   P1 prep      zero rewards, wall sentinels of the padded cell array              (32 lanes, coop)
-//   P2 reset     auto-reset decision per env, pool layout fetch                     (1 lane / env)
-//   P3 convert   3-byte cells -> 32-bit cell words (+ "opaque" bit 31 for the scan) (32 lanes, coop)
-//   P4 step      handle_actions: PCG64 draw, argsort, serial agent loop, rewards,
-//                termination, dirty-cell write-through, env hook, agent stamping    (1 lane / env)
-//   P5 observe   32 agents per pass: view gather (closed-form slice+rotate), row-bitmask
+//   P0 load      TMA: cell words / agents / actions -> smem; pcg state+inc / step_count /
+//                layout_idx -> registers of the env's lane (coalesced: lane <-> env)
+//   P1 reset     auto-reset decision per env, pool layout fetch                     (1 lane / env)
+//   P2 step      handle_actions: PCG64 draw, argsort, serial agent loop, rewards,
+//                termination, dirty-cell write-through, env hook, agent stamping;
+//                per-env outputs straight from registers to HBM                     (1 lane / env)
+//   P3 observe   32 agents per pass: view gather (closed-form slice+rotate), row-bitmask
 //                visibility scan, masking, 24->32 bit packing into the smem stage   (1 lane / agent)
 //                -> TMA bulk store of the pass's contiguous obs span
-//   P6 store     TMA: agents / pcg state / step_count / layout_idx / reward / terminated / truncated
+//   P4 store     TMA: agents
+//
+// The grid lives in HBM as 32-bit CELL WORDS (type | color<<8 | state<<16 | opaque<<31) in a
+// padded (W+1) x (H+1) array per env whose last row and column are WALL sentinels, i.e. exactly the
+// layout the observation gather wants in shared memory: the TMA load is the whole "load" phase.
+// mg_pack_grid / mg_unpack_grid convert from / to the reference's (W,H,3) byte layout.
 //
 // Reference semantics restated here (cited inline): multigrid/base.py:303-532,598-602,
 // multigrid/utils/obs.py:46-316, multigrid/core/world_object.py:197-233,452-474,599-605.
@@ -55,15 +60,15 @@ struct Params {
     int32_t hook, ostride, K, lstride;
     int32_t num_envs, G, wpb, use_bulk;
     // state (device)
-    int8_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;
-    int32_t *layout_idx; const int8_t *pool_grid; const int8_t *pool_agents;
+    uint32_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;
+    int32_t *layout_idx; const uint32_t *pool_grid; const int8_t *pool_agents;
     const int8_t *actions;
     // outputs (device)
     int8_t *obs; double *reward; uint8_t *terminated; uint8_t *truncated; int32_t *status;
     // derived geometry. The cell array of an env is (W+1) x (H+1) words, row stride Hp = H+1:
     // row x = W and column y = H hold WALL sentinels, every out-of-range coordinate maps there.
-    int32_t Hp, cstride, WH, grid_bytes;
-    uint32_t rcp_n, rcp_h, rcp_wh, rcp_q;  // ceil(2^32 / d) for d = n, H, W*H, W*H/4 (see fastdiv)
+    int32_t Hp, cstride;
+    uint32_t rcp_n;  // ceil(2^32 / n) (see fastdiv)
     // per-warp shared-memory carve-up (byte offsets, all multiples of 16)
     int32_t off_cells, off_stage, off_ag, off_act, off_rk, off_mbar, warp_bytes;
 };
@@ -71,17 +76,17 @@ struct Params {
 MG_HD int align16(int x) { return (x + 15) & ~15; }
 inline uint32_t rcp32(int d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / (uint32_t)d + 1ull); }
 
+// Number of cell words per env in HBM and in shared memory.
+inline int64_t cells_per_env(int W, int H) { return (int64_t)(W + 1) * (H + 1); }
+
 // Fills the derived fields for group size p.G; returns the shared memory bytes of one warp.
 inline int carve_smem(Params &p) {
     const int G = p.G, n = p.n;
-    p.WH = p.W * p.H;
     p.Hp = p.H + 1;
-    p.cstride = ((p.W + 1) * p.Hp) | 1;
-    p.grid_bytes = 3 * p.WH;
-    p.rcp_n = rcp32(n); p.rcp_h = rcp32(p.H); p.rcp_wh = rcp32(p.WH); p.rcp_q = rcp32(p.WH / 4);
-    // "stage" is reused over time: raw grid bytes (P0-P3), sort keys + order (P4, n > 4), obs pass (P5)
-    int stage = G * p.grid_bytes;
-    if (LANES * p.ostride > stage) stage = LANES * p.ostride;
+    p.cstride = (p.W + 1) * p.Hp;
+    p.rcp_n = rcp32(n);
+    // "stage": sort keys + order during the transition (n > 4), then the obs pass
+    int stage = LANES * p.ostride;
     if (n > 4 && G * n * 9 + 16 > stage) stage = G * n * 9 + 16;
     int off = 0;
     p.off_cells = off; off += align16(G * p.cstride * 4);
@@ -316,7 +321,7 @@ MG_HD void env_load(const Params &p, const Group &g, int i, EnvRegs &r) {
 template <int MODE>
 MG_HD void phase_load_plain(const Params &p, const Group &g, int lane) {
     const size_t e0 = (size_t)g.e0;
-    warp_copy(g.stage, p.grid + e0 * p.grid_bytes, g.ne * p.grid_bytes, lane);
+    warp_copy(g.cells, p.grid + e0 * p.cstride, g.ne * p.cstride * 4, lane);
     warp_copy(g.ag, p.agents + e0 * p.n * 8, g.ne * p.n * 8, lane);
     if (MODE != MODE_OBS) warp_copy(g.act, p.actions + e0 * p.n, g.ne * p.n, lane);
 }
@@ -337,14 +342,14 @@ MG_HD void phase_reset(const Params &p, const Group &g, int i, EnvRegs &r) {
     g.rk[i] = k;
 }
 
-// Envs that were reset take their grid from the layout pool: into the raw stage (for P3) and
-// written through to the state in HBM. `pending` = bit per env of the group that was reset.
+// Envs that were reset take their cells from the layout pool: into shared memory and written
+// through to the state in HBM. `pending` = bit per env of the group that was reset.
 MG_HD void phase_reset_grid(const Params &p, const Group &g, uint32_t pending, int lane) {
     for (int i = 0; i < g.ne; i++) {
         if (!((pending >> i) & 1u)) continue;
-        const int8_t *src = p.pool_grid + (size_t)g.rk[i] * p.grid_bytes;
-        warp_copy(g.stage + i * p.grid_bytes, src, p.grid_bytes, lane);
-        warp_copy(p.grid + (size_t)(g.e0 + i) * p.grid_bytes, src, p.grid_bytes, lane);
+        const uint32_t *src = p.pool_grid + (size_t)g.rk[i] * p.cstride;
+        warp_copy(g.cells + i * p.cstride, src, p.cstride * 4, lane);
+        warp_copy(p.grid + (size_t)(g.e0 + i) * p.cstride, src, p.cstride * 4, lane);
     }
 }
 
@@ -354,63 +359,9 @@ MG_HD uint32_t reset_mask_host(const Group &g) {  // hostsim only; the kernel us
     return m;
 }
 
-// ---- P3: 3-byte cells -> cell words, plus the wall sentinels ------------------------------------------
-// The env's lane writes its wall sentinels: row x = W (Hp words) and column y = H (W words).
-// Independent of the loaded data, so it runs while the TMA load is in flight.
-MG_HD void phase_sentinels(const Params &p, const Group &g, int i) {
-    if (i < 0) return;
-    uint32_t *c = g.cells + i * p.cstride;
-    uint32_t *row = c + p.W * p.Hp;
-    for (int j = 0; j < p.Hp; j++) row[j] = CELL_WALL;
-    uint32_t *col = c + p.H;
-    for (int x = 0; x < p.W; x++) col[x * p.Hp] = CELL_WALL;
-}
-
-MG_HD void put_cell(const Params &p, uint32_t *dst, int ci, uint32_t w) {
-    const int x = (int)fastdiv((uint32_t)ci, p.rcp_h);
-    dst[ci + x] = w;  // x*Hp + y
-}
-
-MG_HD void phase_convert(const Params &p, const Group &g, int lane) {
-    const int WH = p.WH;
-    if ((WH & 3) == 0 && (p.H & 3) == 0) {
-        // 4 cells = 3 aligned words, all in one grid row
-        const int Q = WH >> 2, items = g.ne * Q;
-        for (int it = lane; it < items; it += LANES) {
-            const int i = (int)fastdiv((uint32_t)it, p.rcp_q), q = it - i * Q;
-            const uint32_t *rw = (const uint32_t *)(g.stage + i * p.grid_bytes) + 3 * q;
-            uint32_t c[4];
-            cell_words_x4(rw[0], rw[1], rw[2], c);
-            uint32_t *dst = g.cells + i * p.cstride;
-            const int ci = 4 * q, x = (int)fastdiv((uint32_t)ci, p.rcp_h);
-            uint32_t *d = dst + ci + x;
-            d[0] = c[0]; d[1] = c[1]; d[2] = c[2]; d[3] = c[3];
-        }
-    } else {
-        // the group's raw bytes as one flat stream of cells: quads may straddle rows and envs
-        const int cells = g.ne * WH, nq = cells >> 2;
-        const uint32_t *rw0 = (const uint32_t *)g.stage;
-        for (int q = lane; q < nq; q += LANES) {
-            uint32_t c[4];
-            cell_words_x4(rw0[3 * q], rw0[3 * q + 1], rw0[3 * q + 2], c);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int fc = 4 * q + j, i = (int)fastdiv((uint32_t)fc, p.rcp_wh);
-                put_cell(p, g.cells + i * p.cstride, fc - i * WH, c[j]);
-            }
-        }
-        for (int fc = (nq << 2) + lane; fc < cells; fc += LANES) {  // ragged tail group only
-            const int i = (int)fastdiv((uint32_t)fc, p.rcp_wh);
-            const uint8_t *src = g.stage + 3 * fc;
-            put_cell(p, g.cells + i * p.cstride, fc - i * WH, cell_word(src[0], src[1], src[2]));
-        }
-    }
-}
-
 // ---- P4: transition --------------------------------------------------------------------------------
-MG_HD void store_cell(const Params &p, int e, int x, int y, uint32_t w) {  // dirty-cell write-through
-    uint8_t *g = (uint8_t *)p.grid + ((size_t)e * p.WH + x * p.H + y) * 3;
-    g[0] = (uint8_t)w; g[1] = (uint8_t)(w >> 8); g[2] = (uint8_t)(w >> 16);
+MG_HD void store_cell(const Params &p, int e, int idx, uint32_t w) {  // dirty-cell write-through
+    p.grid[(size_t)e * p.cstride + idx] = w;
 }
 
 MG_HD uint32_t all_agents(const Params &p) { return p.n >= 32 ? 0xffffffffu : (1u << p.n) - 1u; }
@@ -511,13 +462,13 @@ MG_HD void handle_actions(const Params &p, const Group &g, int i, uint32_t *cell
             if (((t == T_KEY) | (t == T_BALL) | (t == T_BOX)) && (a1 & 0xff) == T_EMPTY) {
                 ag[k * 2 + 1] = (a1 & 0xff000000u) | (cw & 0x00ffffffu);
                 cells[idx] = CELL_EMPTY;
-                store_cell(p, e, fx, fy, CELL_EMPTY);
+                store_cell(p, e, idx, CELL_EMPTY);
             }
         } else if (act == ACT_DROP) {  // base.py:449-459
             if ((a1 & 0xff) != T_EMPTY && t == T_EMPTY && !agent_at(p, ag, fxy)) {
                 const uint32_t w = cell_word(a1 & 0xff, (a1 >> 8) & 0xff, (a1 >> 16) & 0xff);
                 cells[idx] = w;
-                store_cell(p, e, fx, fy, w);
+                store_cell(p, e, idx, w);
                 ag[k * 2 + 1] = (a1 & 0xff000000u) | CELL_EMPTY;
             }
         } else {  // toggle, base.py:462-467
@@ -531,11 +482,11 @@ MG_HD void handle_actions(const Params &p, const Group &g, int i, uint32_t *cell
                 if (ns != st) {
                     const uint32_t w = cell_word(t, col, ns);
                     cells[idx] = w;
-                    store_cell(p, e, fx, fy, w);
+                    store_cell(p, e, idx, w);
                 }
             } else if (t == T_BOX) {  // Box.toggle, core/world_object.py:599-605 (contains is None)
                 cells[idx] = CELL_EMPTY;
-                store_cell(p, e, fx, fy, CELL_EMPTY);
+                store_cell(p, e, idx, CELL_EMPTY);
             }
         }
     }
@@ -800,12 +751,40 @@ template <int MODE>
 __device__ __forceinline__ void load_bulk(const Params &p, const Group &g, uint64_t *bar) {
     const size_t e0 = (size_t)g.e0;
     const uint32_t G = (uint32_t)p.G, n = (uint32_t)p.n;
-    uint32_t total = G * p.grid_bytes + G * n * 8;
+    uint32_t total = G * p.cstride * 4 + G * n * 8;
     if (MODE != MODE_OBS) total += G * n;
     mbar_expect_tx(bar, total);
-    bulk_g2s(g.stage, p.grid + e0 * p.grid_bytes, G * p.grid_bytes, bar);
+    bulk_g2s(g.cells, p.grid + e0 * p.cstride, G * p.cstride * 4, bar);
     bulk_g2s(g.ag, p.agents + e0 * n * 8, G * n * 8, bar);
     if (MODE != MODE_OBS) bulk_g2s(g.act, p.actions + e0 * n, G * n, bar);
+}
+
+// ---- layout conversion kernels (API utilities, not on the hot path) -----------------------------------
+// (E,W,H,3) bytes as in Grid.state (core/grid.py:54)  <->  padded cell words. One thread per word.
+__global__ void pack_grid_kernel(int W, int H, int64_t total, const int8_t *__restrict__ grid3,
+                                 uint32_t *__restrict__ cells) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int Hp = H + 1, cs = (W + 1) * Hp;
+    const int64_t e = idx / cs;
+    const int c = (int)(idx - e * cs), x = c / Hp, y = c - x * Hp;
+    uint32_t w = CELL_WALL;
+    if (x < W && y < H) {
+        const uint8_t *src = (const uint8_t *)grid3 + ((e * W + x) * H + y) * 3;
+        w = cell_word(src[0], src[1], src[2]);
+    }
+    cells[idx] = w;
+}
+
+__global__ void unpack_grid_kernel(int W, int H, int64_t total, const uint32_t *__restrict__ cells,
+                                   int8_t *__restrict__ grid3) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over E*W*H
+    if (idx >= total) return;
+    const int64_t e = idx / (W * H);
+    const int c = (int)(idx - e * (W * H)), x = c / H, y = c - x * H;
+    const uint32_t w = cells[e * (int64_t)(W + 1) * (H + 1) + x * (H + 1) + y];
+    uint8_t *dst = (uint8_t *)grid3 + idx * 3;
+    dst[0] = (uint8_t)w; dst[1] = (uint8_t)(w >> 8); dst[2] = (uint8_t)(w >> 16);
 }
 
 template <int VT, int MODE>
@@ -831,7 +810,6 @@ __global__ void __launch_bounds__(256, VT >= 9 ? 2 : 3) step_obs_kernel(const __
     }
     EnvRegs er;
     env_load<MODE>(p, g, env, er);  // the env's scalars, straight into its lane's registers
-    phase_sentinels(p, g, env);
     __syncwarp();
     if (bulk) mbar_wait(bar, 0);
     if (MODE != MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
@@ -843,8 +821,6 @@ __global__ void __launch_bounds__(256, VT >= 9 ? 2 : 3) step_obs_kernel(const __
         }
         __syncwarp();
     }
-    phase_convert(p, g, lane);
-    __syncwarp();
     phase_step<MODE>(p, g, env, er);
     __syncwarp();
     if (MODE != MODE_STEP) {

@@ -65,7 +65,9 @@ def _as_i64_bits(a) -> np.ndarray:
 class StepEngine:
     """HBM-resident state of `num_envs` envs + fused step/observe launches.
 
-    Layout (env-major): grid int8 (E,W,H,3); agents int8 (E,n,8) =
+    Layout (env-major): cells int32 (E,W+1,H+1) = cell words
+    type|color<<8|state<<16|opaque<<31 with wall sentinels in the last row/column (`grid` is the
+    zero-copy (E,W,H,3) int8 view of their low three bytes = Grid.state); agents int8 (E,n,8) =
     [dir,x,y,terminated,carry_type,carry_color,carry_state,color]; step_count int32 (E);
     pcg_state / pcg_inc int64-bits (E,2) [lo,hi]; layout_idx int32 (E).
     Outputs: obs int8 (E,n,stride) exposed as a (E,n,V,V,3) view; reward f64 (E,n);
@@ -87,7 +89,7 @@ class StepEngine:
         self.obs_stride = _cabi.obs_agent_stride(V)
         dev = self.device
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
-        self.grid = z((E, W, H, 3), torch.int8)
+        self.cells = z((E, W + 1, H + 1), torch.int32)
         self.agents = z((E, n, 8), torch.int8)
         self.step_count = z((E,), torch.int32)
         self.pcg_state = z((E, 2), torch.int64)
@@ -106,15 +108,39 @@ class StepEngine:
         self._host = None
         self._c = None
 
+    # -- grid layout ---------------------------------------------------------------------------
+    @property
+    def grid(self) -> torch.Tensor:
+        """(E, W, H, 3) int8 = Grid.state (core/grid.py:54): zero-copy view of bytes 0..2 of the
+        cell words. Read freely; WRITE through `load_state(grid=...)`, which also maintains the
+        opaque bit the observation kernel reads."""
+        W, H = self.cfg.width, self.cfg.height
+        return self.cells.view(torch.int8).view(self.num_envs, W + 1, H + 1, 4)[:, :W, :H, :3]
+
+    def _pack(self, grid3, out_cells: torch.Tensor) -> None:
+        """mg_pack_grid: (K,W,H,3) bytes (numpy / torch, host / device) -> cell words in `out_cells`."""
+        W, H = self.cfg.width, self.cfg.height
+        if isinstance(grid3, torch.Tensor):
+            g = grid3.to(self.device, torch.int8).contiguous()
+        else:
+            g = torch.as_tensor(np.ascontiguousarray(grid3, dtype=np.int8)).to(self.device)
+        K = out_cells.shape[0]
+        assert g.numel() == K * W * H * 3, (tuple(g.shape), K, W, H)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.mg_pack_grid(W, H, K, g.data_ptr(), out_cells.data_ptr(), self._stream()),
+                        "mg_pack_grid")
+
     # -- configuration / state injection ------------------------------------------------------
     def set_layout_pool(self, pool_grid, pool_agents) -> None:
         """Reset layouts: grid (K,W,H,3) int8 and packed agents (K,n,8) int8."""
         cfg = self.cfg
-        pg = torch.as_tensor(np.ascontiguousarray(pool_grid, dtype=np.int8))
+        pg = np.ascontiguousarray(pool_grid, dtype=np.int8)
         pa = torch.as_tensor(np.ascontiguousarray(pool_agents, dtype=np.int8))
         assert pg.shape[1:] == (cfg.width, cfg.height, 3), pg.shape
         assert pa.shape == (pg.shape[0], cfg.num_agents, 8), pa.shape
-        self.pool_grid = pg.to(self.device)
+        self.pool_grid = torch.zeros((pg.shape[0], cfg.width + 1, cfg.height + 1), dtype=torch.int32,
+                                     device=self.device)
+        self._pack(pg, self.pool_grid)
         self.pool_agents = pa.to(self.device)
         self._c = None
 
@@ -129,7 +155,8 @@ class StepEngine:
             else:
                 arr = _as_i64_bits(src) if bits64 else np.ascontiguousarray(src)
                 dst.copy_(torch.as_tensor(arr).to(dst.dtype).reshape(dst.shape))
-        put(self.grid, grid)
+        if grid is not None:
+            self._pack(grid, self.cells)
         put(self.agents, agents)
         put(self.step_count, step_count)
         put(self.pcg_state, pcg_state, bits64=True)
@@ -141,7 +168,7 @@ class StepEngine:
         if layout_idx is not None:
             self.load_state(layout_idx=layout_idx)
         idx = self.layout_idx.long()
-        self.grid.copy_(self.pool_grid[idx])
+        self.cells.copy_(self.pool_grid[idx])
         self.agents.copy_(self.pool_agents[idx])
         self.step_count.zero_()
 
@@ -156,7 +183,7 @@ class StepEngine:
                                cfg.max_steps, cfg.flags, cfg.hook, self.obs_stride, K,
                                cfg.layout_stride)
             p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
-            st = _cabi.MgState(p(self.grid), p(self.agents), p(self.step_count), p(self.pcg_state),
+            st = _cabi.MgState(p(self.cells), p(self.agents), p(self.step_count), p(self.pcg_state),
                                p(self.pcg_inc), p(self.layout_idx), p(self.pool_grid),
                                p(self.pool_agents))
             out = _cabi.MgStepOut(p(self.obs_buf), p(self.reward), p(self.terminated),
@@ -183,7 +210,7 @@ class StepEngine:
         """mg_gen_obs: observations of the current state (used after reset)."""
         c, st, out = self._structs()
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.mg_gen_obs(C.byref(c), self.num_envs, self.grid.data_ptr(),
+            _cabi.check(self.lib.mg_gen_obs(C.byref(c), self.num_envs, self.cells.data_ptr(),
                                             self.agents.data_ptr(), self.obs_buf.data_ptr(),
                                             self._stream()), "mg_gen_obs")
         return self.obs

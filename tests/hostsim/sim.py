@@ -60,15 +60,32 @@ def aligned_copy(a, dtype):
     return out
 
 
+def pack_cells(grid3):
+    """(K,W,H,3) int8 -> (K,W+1,H+1) uint32 cell words with wall sentinels (numpy restatement of
+    mg_pack_grid; bit 31 = opaque = wall or non-open door)."""
+    g = np.asarray(grid3).astype(np.uint32)
+    K, W, H, _ = g.shape
+    t, c, s = g[..., 0], g[..., 1], g[..., 2]
+    opaque = ((t == 2) | ((t == 4) & (s != 0))).astype(np.uint32)
+    cells = np.full((K, W + 1, H + 1), 2 | (5 << 8) | (1 << 31), np.uint32)
+    cells[:, :W, :H] = t | (c << 8) | (s << 16) | (opaque << 31)
+    return cells
+
+
+def unpack_cells(cells, W, H):
+    w = np.asarray(cells)[:, :W, :H]
+    return np.stack([w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff], -1).astype(np.int8)
+
+
 class SimEngine:
     """Mirror of oracle.OracleBatch's interface on top of the host-simulated kernels."""
 
     def __init__(self, cfg, grid, agents, pcg_state, pcg_inc, pool_grid=None, pool_agents=None,
                  layout_idx=None, step_count=None, forced_group=0, generic=0, split=False):
         self.cfg, self.forced_group, self.generic, self.split = cfg, forced_group, generic, split
-        self.grid = aligned_copy(grid, np.int8)
+        self.cells = aligned_copy(pack_cells(grid), np.uint32)
         self.agents = aligned_copy(agents, np.int8)
-        self.B = self.grid.shape[0]
+        self.B = self.cells.shape[0]
         self.pcg_state = aligned_copy(pcg_state, np.uint64)
         self.pcg_inc = aligned_copy(pcg_inc, np.uint64)
         self.step_count = aligned((self.B,), np.int32)
@@ -77,7 +94,7 @@ class SimEngine:
         self.layout_idx = aligned((self.B,), np.int32)
         if layout_idx is not None:
             self.layout_idx[...] = layout_idx
-        self.pool_grid = aligned_copy(self.grid[:1] if pool_grid is None else pool_grid, np.int8)
+        self.pool_grid = aligned_copy(self.cells[:1] if pool_grid is None else pack_cells(pool_grid), np.uint32)
         self.pool_agents = aligned_copy(self.agents[:1] if pool_agents is None else pool_agents, np.int8)
         self.stride = _cabi.obs_agent_stride(cfg.V)
         flags = ((_cabi.FLAG_SEE_THROUGH_WALLS if cfg.see_through_walls else 0)
@@ -94,13 +111,17 @@ class SimEngine:
         self.terminated = aligned((self.B, cfg.n), np.uint8)
         self.truncated = aligned((self.B,), np.uint8)
         self.status = aligned((1,), np.int32)
-        self.state = _cabi.MgState(_p(self.grid).value, _p(self.agents).value,
+        self.state = _cabi.MgState(_p(self.cells).value, _p(self.agents).value,
                                    _p(self.step_count).value, _p(self.pcg_state).value,
                                    _p(self.pcg_inc).value, _p(self.layout_idx).value,
                                    _p(self.pool_grid).value, _p(self.pool_agents).value)
         self.out = _cabi.MgStepOut(_p(self.obs).value, _p(self.reward).value,
                                    _p(self.terminated).value, _p(self.truncated).value,
                                    _p(self.status).value)
+
+    @property
+    def grid(self):
+        return unpack_cells(self.cells, self.cfg.W, self.cfg.H)
 
     def _run(self, mode, actions=None):
         rc = lib().sim_run(C.c_int(mode), C.byref(self.c), C.c_int64(self.B), C.byref(self.state),
