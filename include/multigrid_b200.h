@@ -124,6 +124,11 @@ int mg_pack_grid(int32_t width, int32_t height, int64_t num_envs, const int8_t *
 int mg_unpack_grid(int32_t width, int32_t height, int64_t num_envs, const uint32_t *cells, int8_t *grid3,
                    void *stream);
 
+/* Diagnostics: when set to a device buffer of 8 uint64 per warp (= per group of envs), every
+ * following launch records %globaltimer at its phase boundaries (slots 0..4) and the SM id (slot 7).
+ * NULL (the default) disables it. Used by tools/trace_timeline.py; not part of the hot path. */
+void mg_debug_set_trace(void *device_buffer);
+
 /* Number of engine kernels launched by this process so far (for launch accounting). */
 int64_t mg_launch_count(void);
 

@@ -56,6 +56,7 @@ EXPORTS = {
     "mg_error_string": (C.c_char_p, [C.c_int]),
     "mg_obs_agent_stride": (C.c_int32, [C.c_int32]),
     "mg_launch_count": (C.c_int64, []),
+    "mg_debug_set_trace": (None, [C.c_void_p]),
     "mg_cells_per_env": (C.c_int64, [C.c_int32, C.c_int32]),
     "mg_pack_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_unpack_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -11,6 +11,7 @@
 namespace {
 
 std::atomic<int64_t> g_launches{0};
+std::atomic<unsigned long long *> g_trace{nullptr};  // diagnostics only (mg_debug_set_trace)
 
 constexpr int kSmemPerBlock = 227 * 1024;  // B200 opt-in maximum per block
 constexpr int kSmemPerSM = 228 * 1024;
@@ -37,6 +38,7 @@ int validate(const MgConfig *c, int64_t num_envs) {
 // MG_NO_BULK=1 = plain loads/stores instead of TMA bulk copies.
 int plan(mg::Params &p) {
     p.use_bulk = env_int("MG_NO_BULK", 0) ? 0 : 1;
+    p.generic_view = env_int("MG_GENERIC_VIEW", 0) ? 1 : 0;
     return mg::plan_launch(p, env_int("MG_GROUP", 0), env_int("MG_WPB", 0), kSmemPerBlock, kSmemPerSM);
 }
 
@@ -63,8 +65,7 @@ int dispatch(const mg::Params &p, cudaStream_t stream) {
     if constexpr (MODE == mg::MODE_STEP) {
         return launch<0, MODE>(p, stream);  // no observation phase: view size is irrelevant
     } else {
-        const bool generic = env_int("MG_GENERIC_VIEW", 0) != 0;
-        if (!generic) {
+        if (!p.generic_view) {
             switch (p.V) {
                 case 3: return launch<3, MODE>(p, stream);
                 case 5: return launch<5, MODE>(p, stream);
@@ -83,6 +84,7 @@ void fill_config(mg::Params &p, const MgConfig *c, int64_t num_envs) {
     p.max_steps = c->max_steps; p.flags = c->flags; p.hook = c->hook;
     p.ostride = c->obs_agent_stride; p.K = c->num_layouts; p.lstride = c->layout_stride;
     p.num_envs = (int32_t)num_envs;
+    p.trace = g_trace.load(std::memory_order_relaxed);
 }
 
 int fill_state(mg::Params &p, const MgState *s) {
@@ -168,6 +170,8 @@ int mg_unpack_grid(int32_t width, int32_t height, int64_t num_envs, const uint32
 }
 
 int64_t mg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+void mg_debug_set_trace(void *device_buffer) { g_trace.store((unsigned long long *)device_buffer, std::memory_order_relaxed); }
 
 int mg_gen_obs(const MgConfig *cfg, int64_t num_envs, const uint32_t *grid, const int8_t *agents,
                int8_t *obs, void *stream) {

@@ -58,19 +58,22 @@ struct Params {
     int32_t W, H, n, V, max_steps;
     uint32_t flags;
     int32_t hook, ostride, K, lstride;
-    int32_t num_envs, G, wpb, use_bulk;
+    int32_t num_envs, G, wpb, use_bulk, generic_view;
     // state (device)
     uint32_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;
     int32_t *layout_idx; const uint32_t *pool_grid; const int8_t *pool_agents;
     const int8_t *actions;
     // outputs (device)
     int8_t *obs; double *reward; uint8_t *terminated; uint8_t *truncated; int32_t *status;
+    unsigned long long *trace;  // diagnostics: 8 timestamps per warp (mg_debug_set_trace), normally NULL
     // derived geometry. The cell array of an env is (W+1) x (H+1) words, row stride Hp = H+1:
     // row x = W and column y = H hold WALL sentinels, every out-of-range coordinate maps there.
     int32_t Hp, cstride;
     uint32_t rcp_n;  // ceil(2^32 / n) (see fastdiv)
     // per-warp shared-memory carve-up (byte offsets, all multiples of 16)
-    int32_t off_cells, off_stage, off_ag, off_act, off_rk, off_mbar, warp_bytes;
+    int32_t off_cells, off_stage, off_keys, off_ag, off_act, off_rk, off_mbar, warp_bytes;
+    // obs stage aliased onto the cells of the passes already gathered (see carve_smem)
+    int32_t alias, pass_cell_bytes, stage_bytes, stage_extra;
 };
 
 MG_HD int align16(int x) { return (x + 15) & ~15; }
@@ -85,12 +88,26 @@ inline int carve_smem(Params &p) {
     p.Hp = p.H + 1;
     p.cstride = (p.W + 1) * p.Hp;
     p.rcp_n = rcp32(n);
-    // "stage": sort keys + order during the transition (n > 4), then the obs pass
-    int stage = LANES * p.ostride;
-    if (n > 4 && G * n * 9 + 16 > stage) stage = G * n * 9 + 16;
+    const bool unrolled_view = !p.generic_view && (p.V == 3 || p.V == 5 || p.V == 7 || p.V == 9);
+    // An obs pass (32 agent tasks = 32/n envs when n divides 32) only reads the cells of ITS envs,
+    // and it has them in registers before it writes its packed result. So the stage of pass q can
+    // live on top of the cells of passes <= q: the region is [extra][cells pass 0][cells pass 1]...
+    // and stage q = the stage_bytes that END where the cells of pass q end.
+    p.stage_bytes = LANES * p.ostride;
+    p.pass_cell_bytes = (LANES / n) * p.cstride * 4;
+    p.alias = unrolled_view && n <= LANES && LANES % n == 0 && (G * n) % LANES == 0 &&
+              p.pass_cell_bytes % 16 == 0;
+    p.stage_extra = 0;
     int off = 0;
-    p.off_cells = off; off += align16(G * p.cstride * 4);
-    p.off_stage = off; off += align16(stage);
+    if (p.alias) {
+        p.stage_extra = p.stage_bytes > p.pass_cell_bytes ? align16(p.stage_bytes - p.pass_cell_bytes) : 0;
+        p.off_stage = off; off += p.stage_extra;
+        p.off_cells = off; off += align16(G * p.cstride * 4);
+    } else {
+        p.off_cells = off; off += align16(G * p.cstride * 4);
+        p.off_stage = off; off += align16(p.stage_bytes);
+    }
+    p.off_keys = off;  off += n > 4 ? align16(G * n * 8) + align16(G * n) : 0;  // sort keys + order
     p.off_ag = off;    off += align16(G * n * 8);
     p.off_act = off;   off += align16(G * n);
     p.off_rk = off;    off += align16(G * 4);
@@ -108,7 +125,7 @@ inline int plan_launch(Params &p, int forced_G, int forced_wpb, int smem_per_blo
         if (carve_smem(p) > smem_per_block) return MG_ERR_TOO_LARGE;
     }
     int best = 0, best_wpb = 1;
-    for (int wpb = 8; wpb >= 1; wpb >>= 1) {
+    for (int wpb = 4; wpb >= 1; wpb >>= 1) {
         const int bytes = wpb * p.warp_bytes;
         if (bytes > smem_per_block) continue;
         int blocks = smem_per_sm / (bytes + 1024);  // 1 KB per block is reserved by the driver
@@ -118,7 +135,7 @@ inline int plan_launch(Params &p, int forced_G, int forced_wpb, int smem_per_blo
         if (warps > best) { best = warps; best_wpb = wpb; }
     }
     p.wpb = best_wpb;
-    if (forced_wpb > 0 && forced_wpb <= 8 && forced_wpb * p.warp_bytes <= smem_per_block) p.wpb = forced_wpb;
+    if (forced_wpb > 0 && forced_wpb <= 4 && forced_wpb * p.warp_bytes <= smem_per_block) p.wpb = forced_wpb;
     return 0;
 }
 
@@ -266,7 +283,7 @@ MG_HD void cell_words_x4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t out[4])
 struct Group {
     int e0, ne;
     uint32_t *cells; uint8_t *stage; uint32_t *ag; int8_t *act; int32_t *rk;
-    uint64_t *keys; uint8_t *order;  // alias the stage during P4 (n > 4 only)
+    uint64_t *keys; uint8_t *order;  // n > 4 only
 };
 
 MG_HD Group group_view(const Params &p, uint8_t *ws, int group) {
@@ -274,12 +291,12 @@ MG_HD Group group_view(const Params &p, uint8_t *ws, int group) {
     g.e0 = group * p.G;
     g.ne = p.num_envs - g.e0 < p.G ? p.num_envs - g.e0 : p.G;
     g.cells = (uint32_t *)(ws + p.off_cells);
-    g.stage = ws + p.off_stage;
+    g.stage = ws + p.off_stage;  // pass 0's (see stage_of)
     g.ag = (uint32_t *)(ws + p.off_ag);
     g.act = (int8_t *)(ws + p.off_act);
     g.rk = (int32_t *)(ws + p.off_rk);
-    g.keys = (uint64_t *)g.stage;
-    g.order = g.stage + align16(p.G * p.n * 8);
+    g.keys = (uint64_t *)(ws + p.off_keys);
+    g.order = ws + p.off_keys + align16(p.G * p.n * 8);
     return g;
 }
 
@@ -603,25 +620,23 @@ MG_HD void obs_compute(const Params &p, const uint32_t *cells, uint32_t a0, uint
     const ViewGeom g = view_geom(p, a0, a1);
     const uint32_t full = (1u << V) - 1u;
     const bool stw = (p.flags & MG_FLAG_SEE_THROUGH_WALLS) != 0;
-    const uint8_t *base = (const uint8_t *)cells;
-
-    int coloff[V];  // byte offsets of the view columns
+    const uint8_t *colp[V];  // view column a -> its cell in grid row / column 0 (one add per cell below)
 #pragma unroll
     for (int a = 0; a < V; a++) {
         int c = g.pl + g.sl * (a - half);
         c = (unsigned)c < (unsigned)g.Ll ? c : g.Ll;
-        coloff[a] = c * g.stl;
+        colp[a] = (const uint8_t *)cells + c * g.stl;
     }
     uint32_t vis = 1u << half;                          // vis_mask[V//2][V-1] = True (utils/obs.py:252)
 #pragma unroll
     for (int b = V - 1; b >= 0; b--) {
         int r = g.pf + g.sf * (V - 1 - b);
         r = (unsigned)r < (unsigned)g.Lf ? r : g.Lf;
-        const uint8_t *row = base + r * g.stf;
+        const int rowoff = r * g.stf;
         uint32_t opq = 0;
 #pragma unroll
         for (int a = V - 1; a >= 0; a--) {
-            uint32_t c = *(const uint32_t *)(row + coloff[a]);
+            uint32_t c = *(const uint32_t *)(colp[a] + rowoff);
             if (b == V - 1 && a == half) c = g.carry;
             cr[a * V + b] = c;
             opq = shl1_in(opq, c);
@@ -701,9 +716,14 @@ MG_HD ObsTask obs_task(const Params &p, const Group &g, int pass, int lane) {
 
 MG_HD int obs_passes(const Params &p, const Group &g) { return (g.ne * p.n + LANES - 1) / LANES; }
 
+// Where pass `pass` packs its 32 observations (see carve_smem).
+MG_HD uint8_t *stage_of(const Params &p, const Group &g, int pass) {
+    return p.alias ? g.stage + (pass + 1) * p.pass_cell_bytes + p.stage_extra - p.stage_bytes : g.stage;
+}
+
 MG_HD void phase_obs_store_plain(const Params &p, const Group &g, int pass, int lane) {
     const int cnt = g.ne * p.n - pass * LANES < LANES ? g.ne * p.n - pass * LANES : LANES;
-    warp_copy(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, g.stage, cnt * p.ostride, lane);
+    warp_copy(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, stage_of(p, g, pass), cnt * p.ostride, lane);
 }
 
 // ---- P6 (plain path): agents back to HBM --------------------------------------------------------------
@@ -747,6 +767,15 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // generic-proxy smem writes -> visible to the async proxy (TMA) reads that follow
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ void trace_mark(const Params &p, int group, int lane, int slot) {
+    if (p.trace && lane == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (slot == 7) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); t = smid; }
+        p.trace[(size_t)group * 8 + slot] = t;
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void load_bulk(const Params &p, const Group &g, uint64_t *bar) {
     const size_t e0 = (size_t)g.e0;
@@ -787,8 +816,9 @@ __global__ void unpack_grid_kernel(int W, int H, int64_t total, const uint32_t *
     dst[0] = (uint8_t)w; dst[1] = (uint8_t)(w >> 8); dst[2] = (uint8_t)(w >> 16);
 }
 
+// <= 4 warps per block; register cap: 72 (7 blocks x 128 threads per SM) up to V = 7, 128 for V = 9
 template <int VT, int MODE>
-__global__ void __launch_bounds__(256, VT >= 9 ? 2 : 3) step_obs_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = blockIdx.x * p.wpb + warp;
@@ -799,6 +829,8 @@ __global__ void __launch_bounds__(256, VT >= 9 ? 2 : 3) step_obs_kernel(const __
     // TMA needs 16-byte multiples: full groups only (G % 16 == 0 makes every span aligned)
     const bool bulk = p.use_bulk && g.ne == p.G;
     const int env = lane_env(p, g, lane);
+    trace_mark(p, group, lane, 0);
+    trace_mark(p, group, lane, 7);
 
     if (bulk) {
         if (lane == 0) {
@@ -812,6 +844,7 @@ __global__ void __launch_bounds__(256, VT >= 9 ? 2 : 3) step_obs_kernel(const __
     env_load<MODE>(p, g, env, er);  // the env's scalars, straight into its lane's registers
     __syncwarp();
     if (bulk) mbar_wait(bar, 0);
+    trace_mark(p, group, lane, 1);
     if (MODE != MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
         phase_reset(p, g, env, er);
         const uint32_t pending = __ballot_sync(0xffffffffu, env >= 0 && g.rk[env] >= 0) & (p.G == 32 ? 0xffffffffu : (1u << p.G) - 1u);
@@ -823,18 +856,19 @@ __global__ void __launch_bounds__(256, VT >= 9 ? 2 : 3) step_obs_kernel(const __
     }
     phase_step<MODE>(p, g, env, er);
     __syncwarp();
+    trace_mark(p, group, lane, 2);
     if (MODE != MODE_STEP) {
         const int passes = obs_passes(p, g);
         for (int pass = 0; pass < passes; pass++) {
             const ObsTask t = obs_task(p, g, pass, lane);
-            uint8_t *out = g.stage + lane * p.ostride;
+            uint8_t *stage = stage_of(p, g, pass), *out = stage + lane * p.ostride;
             if constexpr (VT != 0) {
                 uint32_t cr[VT ? VT * VT : 1];
                 if (t.valid) obs_compute<VT>(p, t.cells, t.a0, t.a1, cr);
-                if (bulk && pass > 0) {  // the previous pass's TMA store must be done reading the stage
-                    if (lane == 0) bulk_wait_read();
-                    __syncwarp();
-                }
+                // the previous pass's TMA store must be done reading its stage, and (aliased stage)
+                // every lane must be done gathering before the cells under the stage are overwritten
+                if (bulk && pass > 0 && lane == 0) bulk_wait_read();
+                __syncwarp();
                 if (t.valid) obs_pack_store<VT>(p, cr, out);
             } else {
                 if (bulk && pass > 0) {
@@ -849,7 +883,7 @@ __global__ void __launch_bounds__(256, VT >= 9 ? 2 : 3) step_obs_kernel(const __
                 if (lane == 0) {
                     const int left = g.ne * p.n - pass * LANES;
                     const uint32_t cnt = left < LANES ? left : LANES;
-                    bulk_s2g(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, g.stage,
+                    bulk_s2g(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, stage,
                              cnt * p.ostride);
                     bulk_commit();
                 }
@@ -860,6 +894,7 @@ __global__ void __launch_bounds__(256, VT >= 9 ? 2 : 3) step_obs_kernel(const __
             }
         }
     }
+    trace_mark(p, group, lane, 3);
     if (MODE != MODE_OBS) {
         if (bulk) {
             if (MODE == MODE_STEP) fence_async_smem();  // (the obs passes already fenced)
@@ -873,6 +908,7 @@ __global__ void __launch_bounds__(256, VT >= 9 ? 2 : 3) step_obs_kernel(const __
         }
     }
     if (bulk && lane == 0) bulk_wait_read();  // smem must stay valid until the TMA stores have read it
+    trace_mark(p, group, lane, 4);
 }
 #endif
 

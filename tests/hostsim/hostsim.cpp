@@ -10,17 +10,22 @@
 
 namespace {
 
+// One obs pass: every lane gathers into its registers first, then every lane packs (the stage may
+// alias cells the pass has just read: see carve_smem).
 template <int VT>
-void obs_lane(const mg::Params &p, const mg::Group &g, int pass, int lane) {
-    const mg::ObsTask t = mg::obs_task(p, g, pass, lane);
-    if (!t.valid) return;
-    uint8_t *out = g.stage + lane * p.ostride;
+void obs_pass(const mg::Params &p, const mg::Group &g, int pass) {
+    static uint32_t cr[mg::LANES][VT ? VT * VT : 1];
+    uint8_t *stage = mg::stage_of(p, g, pass);
+    mg::ObsTask t[mg::LANES];
+    for (int l = 0; l < mg::LANES; l++) t[l] = mg::obs_task(p, g, pass, l);
     if constexpr (VT != 0) {
-        uint32_t cr[VT ? VT * VT : 1];
-        mg::obs_compute<VT>(p, t.cells, t.a0, t.a1, cr);
-        mg::obs_pack_store<VT>(p, cr, out);
+        for (int l = 0; l < mg::LANES; l++)
+            if (t[l].valid) mg::obs_compute<VT>(p, t[l].cells, t[l].a0, t[l].a1, cr[l]);
+        for (int l = 0; l < mg::LANES; l++)
+            if (t[l].valid) mg::obs_pack_store<VT>(p, cr[l], stage + l * p.ostride);
     } else {
-        mg::obs_agent_generic(p, t.cells, t.a0, t.a1, out);
+        for (int l = 0; l < mg::LANES; l++)
+            if (t[l].valid) mg::obs_agent_generic(p, t[l].cells, t[l].a0, t[l].a1, stage + l * p.ostride);
     }
 }
 
@@ -48,7 +53,7 @@ void run_groups(const mg::Params &p) {
         if (MODE != mg::MODE_STEP) {
             const int passes = mg::obs_passes(p, g);
             for (int pass = 0; pass < passes; pass++) {
-                for (int l = 0; l < L; l++) obs_lane<VT>(p, g, pass, l);
+                obs_pass<VT>(p, g, pass);
                 for (int l = 0; l < L; l++) mg::phase_obs_store_plain(p, g, pass, l);
             }
         }
@@ -82,6 +87,7 @@ extern "C" int sim_run(int mode, const MgConfig *c, int64_t num_envs, const MgSt
     p.max_steps = c->max_steps; p.flags = c->flags; p.hook = c->hook;
     p.ostride = c->obs_agent_stride; p.K = c->num_layouts; p.lstride = c->layout_stride;
     p.num_envs = (int32_t)num_envs;
+    p.generic_view = generic & 1;
     if (mode == mg::MODE_OBS) p.flags &= ~MG_FLAG_AUTO_RESET;
     p.grid = s->grid; p.agents = s->agents; p.step_count = s->step_count;
     p.pcg_state = s->pcg_state; p.pcg_inc = s->pcg_inc; p.layout_idx = s->layout_idx;

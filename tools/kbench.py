@@ -63,7 +63,7 @@ def time_config(name, steps, knobs, replicas=8):
     bpe = bench.algorithmic_bytes_per_env_step(W, H, n, V, mutable)
     out = []
     for knob in knobs:
-        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK"):
+        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_STEP", "MG_GENERIC_VIEW"):
             os.environ.pop(key, None)
         os.environ.update({k: str(v) for k, v in knob.items()})
         stream = torch.cuda.Stream(device=dev)
@@ -100,6 +100,7 @@ def main():
     ap.add_argument("--groups", default="16,32")
     ap.add_argument("--wpbs", default="0,1,2,4,8")
     ap.add_argument("--nobulk", default="0,1")
+    ap.add_argument("--extra", default="", help="comma list of extra KEY=VAL knob sets to also try, e.g. MG_GENERIC_STEP=1")
     args = ap.parse_args()
     knobs = []
     for g, w, nb in itertools.product(args.groups.split(","), args.wpbs.split(","), args.nobulk.split(",")):
@@ -109,6 +110,9 @@ def main():
         if int(nb):
             k["MG_NO_BULK"] = 1
         knobs.append(k)
+        for kv in [x for x in args.extra.split(",") if x]:
+            key, val = kv.split("=")
+            knobs.append({**k, key: val})
     for name in args.configs.split(","):
         time_config(name, args.steps, knobs)
 

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Per-warp phase timeline of ONE steady-state launch of the fused kernel (diagnostics).
+
+    python tools/trace_timeline.py [--config empty8]
+
+Uses mg_debug_set_trace: each warp records %globaltimer at start / after load / after step /
+after obs / end. Prints the distribution of phase durations and of start/end times relative to
+the first warp, i.e. how much of the launch is exposed load latency, tail, etc.
+"""
+import argparse, json, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
+import bench, kbench  # noqa: E402
+from multigrid_b200 import _cabi  # noqa: E402
+from multigrid_b200.engine import EngineConfig, StepEngine  # noqa: E402
+
+ap = argparse.ArgumentParser(); ap.add_argument("--config", default="empty8"); ap.add_argument("--group", type=int, default=16)
+args = ap.parse_args()
+W, H, n, V, E, max_steps, _ = kbench.CONFIGS[args.config]
+dev = torch.device("cuda", 0); lib = _cabi.load()
+cfg = EngineConfig(width=W, height=H, num_agents=n, view_size=V, max_steps=max_steps, auto_reset=True)
+pg, pa = kbench.layout(W, H, n)
+engines = []
+for r in range(8):
+    eng = StepEngine(cfg, E, dev, pg, pa)
+    st, inc = bench.pcg_words(r * E, E)
+    eng.load_state(np.repeat(pg, E, 0), np.repeat(pa, E, 0), None, st, inc, None)
+    engines.append(eng)
+tape = torch.randint(0, 7, (32, E, n), device=dev, dtype=torch.int32).to(torch.int8)
+for k in range(96):
+    engines[k % 8].step(tape[k % 32])
+torch.cuda.synchronize()
+groups = (E + args.group - 1) // args.group
+buf = torch.zeros((groups, 8), dtype=torch.int64, device=dev)
+lib.mg_debug_set_trace(buf.data_ptr())
+engines[0].step(tape[0])
+torch.cuda.synchronize()
+lib.mg_debug_set_trace(None)
+t = buf.cpu().numpy().astype(np.float64)
+t0 = t[:, 0].min()
+rel = (t[:, :5] - t0) / 1e3  # us
+names = ["start", "loaded", "stepped", "observed", "end"]
+print(f"launch span: {rel[:, 4].max():.2f} us, groups {groups}")
+for i, nm in enumerate(names):
+    q = np.percentile(rel[:, i], [0, 10, 50, 90, 100])
+    print(f"{nm:9s} t(us) min/p10/p50/p90/max = " + " ".join(f"{v:7.2f}" for v in q))
+for a, b, nm in [(0, 1, "load wait"), (1, 2, "reset+step"), (2, 3, "obs"), (3, 4, "store+drain"), (0, 4, "warp life")]:
+    d = rel[:, b] - rel[:, a]
+    q = np.percentile(d, [0, 10, 50, 90, 100])
+    print(f"{nm:11s} dur(us) min/p10/p50/p90/max = " + " ".join(f"{v:7.2f}" for v in q) + f"  mean {d.mean():.2f}")
+# concurrency over time
+edges = np.linspace(0, rel[:, 4].max(), 25)
+act = [(np.sum((rel[:, 0] <= x) & (rel[:, 4] > x)), np.sum((rel[:, 0] <= x) & (rel[:, 1] > x))) for x in edges]
+print("t(us): resident warps / of which waiting for load")
+print(" ".join(f"{x:.1f}:{a}/{b}" for x, (a, b) in zip(edges, act)))
+sm = t[:, 7].astype(int)
+print("warps per SM min/max:", np.bincount(sm, minlength=148).min(), np.bincount(sm, minlength=148).max())
