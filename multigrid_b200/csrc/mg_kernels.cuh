@@ -445,9 +445,8 @@ MG_HD uint32_t draw_order(const Params &p, const Group &g, int i, EnvRegs &r) {
 
 // MultiGridEnv.handle_actions (base.py:378-476) for local env i; `ag` = this env's agent words.
 MG_HD void handle_actions(const Params &p, const Group &g, int i, uint32_t *cells, uint32_t *ag,
-                          EnvRegs &er, uint32_t &rewarded) {
+                          uint32_t ord, uint32_t &rewarded) {
     const int n = p.n, G = p.G, e = g.e0 + i;
-    const uint32_t ord = draw_order(p, g, i, er);
     const int8_t *act_e = g.act + i * n;
     for (int r = 0; r < n; r++) {
         const int k = n <= 4 ? (int)((ord >> (4 * r)) & 15u) : (int)g.order[r * G + i];
@@ -523,8 +522,21 @@ MG_HD void stamp_agents(const Params &p, uint32_t *cells, const uint32_t *ag) {
 
 // The env's lane: transition, then every per-env output straight from registers to HBM
 // (lane <-> env, env-major arrays: the warp's accesses are contiguous).
+// The agent order of this step only needs the env's PCG64 registers, not the TMA-loaded state, so
+// it is drawn while the load is still in flight. `r` is advanced speculatively: phase_step keeps
+// the advanced state only if the env really steps (an env that auto-resets consumes no draw).
+struct OrderDraw { uint32_t ord; uint64_t lo0, hi0; };
+
 template <int MODE>
-MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r) {
+MG_HD OrderDraw phase_draw(const Params &p, const Group &g, int i, EnvRegs &r) {
+    OrderDraw d;
+    d.ord = 0; d.lo0 = r.lo; d.hi0 = r.hi;
+    if (MODE != MODE_OBS && i >= 0) d.ord = draw_order(p, g, i, r);
+    return d;
+}
+
+template <int MODE>
+MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const OrderDraw &d) {
     if (i < 0) return;
     const int n = p.n;
     uint32_t *cells = g.cells + i * p.cstride;
@@ -538,8 +550,10 @@ MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r) {
         bool truncated = false;
         if (!was_reset) {
             r.sc += 1;  // base.py:333
-            handle_actions(p, g, i, cells, ag, r, rewarded);
+            handle_actions(p, g, i, cells, ag, d.ord, rewarded);
             truncated = r.sc >= p.max_steps;  // base.py:339
+        } else {
+            r.lo = d.lo0; r.hi = d.hi0;  // no step, no draw
         }
         if (MODE == MODE_STEP_OBS) stamp_agents(p, cells, ag);  // obs sees pre-hook termination
         if (!was_reset && p.hook == MG_HOOK_BLOCKED_UNLOCK_PICKUP) {  // envs/blockedunlockpickup.py:166-175
@@ -614,34 +628,61 @@ MG_HD uint32_t keep_if(uint32_t c, uint32_t m, uint32_t bit) {  // c if (m & bit
 #endif
 }
 
+// Shared-memory cell addressing for the gather: 32-bit shared-window addresses on the GPU so that
+// one integer add per cell forms the address (the compiler otherwise re-derives base + offset per
+// cell), plain pointers in the host simulator.
+#ifdef __CUDA_ARCH__
+typedef uint32_t cell_addr_t;
+__device__ __forceinline__ cell_addr_t cell_base(const uint32_t *cells) { return (uint32_t)__cvta_generic_to_shared(cells); }
+template <bool FENCE>
+__device__ __forceinline__ uint32_t cell_load(cell_addr_t a) {
+    uint32_t v;
+    if (FENCE) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+#else
+typedef const uint8_t *cell_addr_t;
+inline cell_addr_t cell_base(const uint32_t *cells) { return (const uint8_t *)cells; }
+template <bool FENCE>
+inline uint32_t cell_load(cell_addr_t a) { return *(const uint32_t *)a; }
+#endif
+
 template <int VT>
 MG_HD void obs_compute(const Params &p, const uint32_t *cells, uint32_t a0, uint32_t a1, uint32_t (&cr)[VT * VT]) {
     constexpr int V = VT, half = VT / 2;
     const ViewGeom g = view_geom(p, a0, a1);
     const uint32_t full = (1u << V) - 1u;
     const bool stw = (p.flags & MG_FLAG_SEE_THROUGH_WALLS) != 0;
-    const uint8_t *colp[V];  // view column a -> its cell in grid row / column 0 (one add per cell below)
+
+    cell_addr_t colp[V];  // view column a -> its cell in grid row / column 0 (one add per cell below)
 #pragma unroll
     for (int a = 0; a < V; a++) {
         int c = g.pl + g.sl * (a - half);
         c = (unsigned)c < (unsigned)g.Ll ? c : g.Ll;
-        colp[a] = (const uint8_t *)cells + c * g.stl;
+        colp[a] = cell_base(cells) + c * g.stl;
     }
-    uint32_t vis = 1u << half;                          // vis_mask[V//2][V-1] = True (utils/obs.py:252)
+    // all V*V gathers first (independent loads in flight together) ...
 #pragma unroll
     for (int b = V - 1; b >= 0; b--) {
         int r = g.pf + g.sf * (V - 1 - b);
         r = (unsigned)r < (unsigned)g.Lf ? r : g.Lf;
         const int rowoff = r * g.stf;
-        uint32_t opq = 0;
 #pragma unroll
         for (int a = V - 1; a >= 0; a--) {
-            uint32_t c = *(const uint32_t *)(colp[a] + rowoff);
-            if (b == V - 1 && a == half) c = g.carry;
-            cr[a * V + b] = c;
-            opq = shl1_in(opq, c);
+            if (b == V - 1 && a == half) cr[a * V + b] = g.carry;
+            else if (b == V - 1 && a == V - 1) cr[a * V + b] = cell_load<true>(colp[a] + rowoff);
+            else cr[a * V + b] = cell_load<false>(colp[a] + rowoff);
         }
-        if (!stw) {
+    }
+    // ... then the row-by-row visibility scan and masking, on registers only
+    if (!stw) {
+        uint32_t vis = 1u << half;                      // vis_mask[V//2][V-1] = True (utils/obs.py:252)
+#pragma unroll
+        for (int b = V - 1; b >= 0; b--) {
+            uint32_t opq = 0;
+#pragma unroll
+            for (int a = V - 1; a >= 0; a--) opq = shl1_in(opq, cr[a * V + b]);
             uint32_t m;
             vis_row(vis, ~opq & full, full, m);
 #pragma unroll
@@ -842,6 +883,7 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
     }
     EnvRegs er;
     env_load<MODE>(p, g, env, er);  // the env's scalars, straight into its lane's registers
+    const OrderDraw draw = phase_draw<MODE>(p, g, env, er);
     __syncwarp();
     if (bulk) mbar_wait(bar, 0);
     trace_mark(p, group, lane, 1);
@@ -854,7 +896,7 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
         }
         __syncwarp();
     }
-    phase_step<MODE>(p, g, env, er);
+    phase_step<MODE>(p, g, env, er, draw);
     __syncwarp();
     trace_mark(p, group, lane, 2);
     if (MODE != MODE_STEP) {

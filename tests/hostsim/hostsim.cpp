@@ -44,12 +44,14 @@ void run_groups(const mg::Params &p) {
         for (int l = 0; l < L; l++) env[l] = mg::lane_env(p, g, l);
         for (int l = 0; l < L; l++) mg::phase_load_plain<MODE>(p, g, l);
         for (int l = 0; l < L; l++) mg::env_load<MODE>(p, g, env[l], er[l]);
+        mg::OrderDraw draw[mg::LANES];
+        for (int l = 0; l < L; l++) draw[l] = mg::phase_draw<MODE>(p, g, env[l], er[l]);
         if (MODE != mg::MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
             for (int l = 0; l < L; l++) mg::phase_reset(p, g, env[l], er[l]);
             const uint32_t pending = mg::reset_mask_host(g);
             for (int l = 0; l < L; l++) mg::phase_reset_grid(p, g, pending, l);
         }
-        for (int l = 0; l < L; l++) mg::phase_step<MODE>(p, g, env[l], er[l]);
+        for (int l = 0; l < L; l++) mg::phase_step<MODE>(p, g, env[l], er[l], draw[l]);
         if (MODE != mg::MODE_STEP) {
             const int passes = mg::obs_passes(p, g);
             for (int pass = 0; pass < passes; pass++) {
