@@ -41,6 +41,15 @@ def algorithmic_bytes_per_env_step(W, H, n, V, mutable_grid=False):
     return reads + writes
 
 
+def layout_bytes_per_env_step(W, H, n, V, auto_reset=True):
+    """Bytes the engine's HBM layout actually moves per env-step: padded 4-byte
+    cell words, 8-byte agent records, int32 counters, 148-byte obs slots."""
+    ostride = (3 * V * V + 3) & ~3
+    reads = 4 * (W + 1) * (H + 1) + 8 * n + 4 + 16 + 16 + n + (4 if auto_reset else 0)
+    writes = 8 * n + 4 + 16 + n * ostride + 8 * n + n + 1 + (4 if auto_reset else 0)
+    return reads + writes
+
+
 def empty_layout(size, n):
     """EmptyEnv._gen_grid, fixed start (envs/empty.py:151-170), packed engine layout."""
     grid = np.zeros((1, size, size, 3), np.int8)
@@ -318,7 +327,8 @@ def run_engine(args):
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "algorithmic_bytes_per_env_step": bpe,
-                         "kernel": "mg::step_obs_kernel<7, MODE_STEP_OBS>",
+                         "actual_bytes_per_env_step": layout_bytes_per_env_step(SIZE, SIZE, n, VIEW),
+                         "kernel": "mg::step_obs_kernel<7, MODE_STEP_OBS> (one launch = 65536 env-steps)",
                          "avg_launch_us": 1e3 * ms / K},
         }
         if world == 1 and not args.no_cpu_baseline:
