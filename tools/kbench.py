@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel-only timing sweep of the fused step+observe kernel over the launch knobs
-(MG_GROUP, MG_WPB, MG_NO_BULK) and over the BASELINE.json configurations.
+(MG_PPB, MG_NO_BULK, ...) and over the BASELINE.json configurations.
 
     python tools/kbench.py [--configs empty8,bup,empty16] [--steps 200]
 
@@ -63,7 +63,7 @@ def time_config(name, steps, knobs, replicas=8):
     bpe = bench.algorithmic_bytes_per_env_step(W, H, n, V, mutable)
     out = []
     for knob in knobs:
-        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_STEP", "MG_GENERIC_VIEW"):
+        for key in ("MG_PPB", "MG_NO_BULK", "MG_GENERIC_VIEW"):
             os.environ.pop(key, None)
         os.environ.update({k: str(v) for k, v in knob.items()})
         stream = torch.cuda.Stream(device=dev)
@@ -97,16 +97,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="empty8")
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--groups", default="16,32")
-    ap.add_argument("--wpbs", default="0,1,2,4,8")
-    ap.add_argument("--nobulk", default="0,1")
+    ap.add_argument("--ppbs", default="0,1,2")
+    ap.add_argument("--nobulk", default="0")
     ap.add_argument("--extra", default="", help="comma list of extra KEY=VAL knob sets to also try, e.g. MG_GENERIC_STEP=1")
     args = ap.parse_args()
     knobs = []
-    for g, w, nb in itertools.product(args.groups.split(","), args.wpbs.split(","), args.nobulk.split(",")):
-        k = {"MG_GROUP": int(g)}
+    for w, nb in itertools.product(args.ppbs.split(","), args.nobulk.split(",")):
+        k = {}
         if int(w):
-            k["MG_WPB"] = int(w)
+            k["MG_PPB"] = int(w)
         if int(nb):
             k["MG_NO_BULK"] = 1
         knobs.append(k)
