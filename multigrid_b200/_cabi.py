@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "_lib", "libmultigrid_b200.so")
+LIB_PATH = os.environ.get("MG_LIB") or os.path.join(PKG_DIR, "_lib", "libmultigrid_b200.so")  # MG_LIB: diagnostics builds
 
 # MgConfig.flags (include/multigrid_b200.h)
 FLAG_SEE_THROUGH_WALLS = 0x01

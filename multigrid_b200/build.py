@@ -31,15 +31,26 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(SRC_DIR, d)) > built for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+TRACE_OUT = os.path.join(PKG_DIR, "_lib", "libmultigrid_b200_trace.so")
+
+
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True builds the diagnostics variant (-DMG_TRACE, per-warp phase timestamps) next to the
+    product library; tools/trace_timeline.py loads it through MG_LIB."""
+    if trace:
+        return _compile(TRACE_OUT, verbose, ["-DMG_TRACE"])
     if not force and not is_stale():
         return OUT
+    return _compile(OUT, verbose, [])
+
+
+def _compile(OUT: str, verbose: bool, extra: list) -> str:
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = [
         _nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
         "-shared", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
         "-I", os.path.join(ROOT, "include"), "-o", OUT,
-    ] + [os.path.join(SRC_DIR, s) for s in SOURCES]
+    ] + extra + [os.path.join(SRC_DIR, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))
@@ -48,4 +59,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

@@ -814,13 +814,17 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // generic-proxy smem writes -> visible to the async proxy (TMA) reads that follow
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Compiled in only with -DMG_TRACE (python -m multigrid_b200.build --trace): the product build has
+// no trace instructions.
 __device__ __forceinline__ void trace_mark(const Params &p, int group, int lane, int slot) {
+#ifdef MG_TRACE
     if (p.trace && lane == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         if (slot == 7) { unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); t = smid; }
         p.trace[(size_t)group * 8 + slot] = t;
     }
+#endif
 }
 
 template <int MODE>

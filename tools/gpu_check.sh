@@ -12,6 +12,6 @@ tail -c 3000 $OUT/${TAG}_bench.json
 timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 80 -c 200 --csv \
     --log-file $OUT/${TAG}_launches.csv python bench.py --steps 64 --warmup 4 --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_obs_kernel -s 80 -c 2 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_obs_kernel -s 80 -c 1 \
     -f -o $OUT/${TAG}_prof python bench.py --steps 16 --warmup 4 --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 ls -la $OUT

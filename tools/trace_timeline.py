@@ -7,10 +7,14 @@ Uses mg_debug_set_trace: each warp records %globaltimer at start / after load / 
 after obs / end. Prints the distribution of phase durations and of start/end times relative to
 the first warp, i.e. how much of the launch is exposed load latency, tail, etc.
 """
-import argparse, json, os, sys
+import argparse, json, os, subprocess, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
+TRACE_LIB = os.path.join(ROOT, "multigrid_b200", "_lib", "libmultigrid_b200_trace.so")
+if not os.path.exists(TRACE_LIB):
+    subprocess.check_call([sys.executable, "-m", "multigrid_b200.build", "--trace"], cwd=ROOT)
+os.environ["MG_LIB"] = TRACE_LIB
 import bench, kbench  # noqa: E402
 from multigrid_b200 import _cabi  # noqa: E402
 from multigrid_b200.engine import EngineConfig, StepEngine  # noqa: E402
