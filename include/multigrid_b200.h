@@ -63,6 +63,7 @@ extern "C" {
 /* MgConfig.hook: env-specific step() post-hooks */
 #define MG_HOOK_NONE 0
 #define MG_HOOK_BLOCKED_UNLOCK_PICKUP 1 /* envs/blockedunlockpickup.py:166-175 */
+#define MG_HOOK_RED_BLUE_DOORS 2        /* envs/redbluedoors.py:170-187 */
 
 #define MG_ERR_BAD_ARG   (-1)
 #define MG_ERR_ALIGNMENT (-2)

@@ -21,6 +21,7 @@ FLAG_AUTO_RESET = 0x20
 
 HOOK_NONE = 0
 HOOK_BLOCKED_UNLOCK_PICKUP = 1
+HOOK_RED_BLUE_DOORS = 2
 
 ABI_VERSION = 2
 MAX_VIEW = 15

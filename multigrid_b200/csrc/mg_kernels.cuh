@@ -55,6 +55,10 @@ enum : int { MODE_OBS = 0, MODE_STEP = 1, MODE_STEP_OBS = 2 };
 
 // 32-bit cell word: type | color<<8 | state<<16 | opaque<<31
 constexpr uint32_t OPAQUE_BIT = 1u << 31;
+// bit 24: the Door OBJECT of this cell is closed although the state byte (what grid.state shows and
+// observations read) says open. Only RedBlueDoorsEnv.step creates this: it closes the blue door's
+// object without grid.update() (envs/redbluedoors.py:185). Rules read the object, obs the array.
+constexpr uint32_t DOOR_OBJ_CLOSED = 1u << 24;
 constexpr uint32_t CELL_EMPTY = T_EMPTY;
 constexpr uint32_t CELL_WALL = T_WALL | (5u << 8) | OPAQUE_BIT;  // WALL_ENCODING, utils/obs.py:14
 constexpr int LANES = 32;
@@ -463,7 +467,8 @@ MG_HD void handle_actions(const Params &p, const Group &g, int i, uint32_t *cell
         if ((unsigned)fx >= (unsigned)p.W || (unsigned)fy >= (unsigned)p.H) continue;
         const int idx = fx * p.Hp + fy;
         const uint32_t cw = cells[idx];
-        const uint32_t t = cw & 0xff, col = (cw >> 8) & 0xff, st = (cw >> 16) & 0xff;
+        const uint32_t t = cw & 0xff, col = (cw >> 8) & 0xff;
+        const uint32_t st = (cw & DOOR_OBJ_CLOSED) ? (uint32_t)S_CLOSED : ((cw >> 16) & 0xff);
         const uint32_t fxy = (uint32_t)fx | ((uint32_t)fy << 8);
         if (act == ACT_FORWARD) {  // base.py:420-436
             const bool can_overlap = (t == T_EMPTY) | (t == T_FLOOR) | (t == T_GOAL) | (t == T_LAVA) |
@@ -508,11 +513,13 @@ MG_HD void handle_actions(const Params &p, const Group &g, int i, uint32_t *cell
 }
 
 // gen_obs_grid, utils/obs.py:163-171: stamp non-terminated agents, ascending index (highest wins)
-MG_HD void stamp_agents(const Params &p, uint32_t *cells, const uint32_t *ag) {
+// `terminated` = bit per agent, taken BEFORE the env post-hook ran (the reference builds the
+// observation before the hook, base.py:337 vs envs/*.py step()).
+MG_HD void stamp_agents(const Params &p, uint32_t *cells, const uint32_t *ag, uint32_t terminated) {
     if (p.n <= 1) return;  // utils/obs.py:172-173
     for (int j = 0; j < p.n; j++) {
         const uint32_t a0 = ag[j * 2], a1 = ag[j * 2 + 1];
-        if ((a0 >> 24) & 0xff) continue;
+        if ((terminated >> j) & 1u) continue;
         const int x = (a0 >> 8) & 0xff, y = (a0 >> 16) & 0xff;
         if ((unsigned)x >= (unsigned)p.W || (unsigned)y >= (unsigned)p.H) continue;
         cells[x * p.Hp + y] = T_AGENT | ((a1 >> 24) << 8) | ((a0 & 0xff) << 16);
@@ -534,6 +541,46 @@ MG_HD OrderDraw phase_draw(const Params &p, const Group &g, int i, EnvRegs &r) {
     return d;
 }
 
+MG_HD uint32_t terminated_mask(const Params &p, const uint32_t *ag) {
+    uint32_t m = 0;
+    for (int j = 0; j < p.n; j++) m |= (uint32_t)(((ag[j * 2] >> 24) & 0xff) != 0) << j;
+    return m;
+}
+
+// RedBlueDoorsEnv.step post-hook (envs/redbluedoors.py:170-187): for every agent whose action was
+// `toggle` (terminated or not), in agent order: if the cell in front of it is the (open) blue
+// door, then success if the red door is open, else failure and the blue door is closed again.
+// Runs on the un-stamped cells (before stamping).
+MG_HD void hook_red_blue_doors(const Params &p, const Group &g, int i, const uint32_t *cells, uint32_t *ag,
+                               uint32_t &rewarded) {
+    const int n = p.n, e = g.e0 + i;
+    const uint32_t DOOR_BLUE = T_DOOR | (2u << 8), DOOR_RED = T_DOOR | (0u << 8);
+    bool blue_closed = false;
+    for (int k = 0; k < n; k++) {
+        if (g.act[i * n + k] != ACT_TOGGLE) continue;
+        const uint32_t a0 = ag[k * 2], dir = a0 & 3u;
+        const int fx = (int)((a0 >> 8) & 0xff) + (dir == 0) - (dir == 2);
+        const int fy = (int)((a0 >> 16) & 0xff) + (dir == 1) - (dir == 3);
+        if ((unsigned)fx >= (unsigned)p.W || (unsigned)fy >= (unsigned)p.H) continue;
+        const int idx = fx * p.Hp + fy;
+        const uint32_t cw = cells[idx];
+        if ((cw & 0xffffu) != DOOR_BLUE || ((cw >> 16) & 0xff) != S_OPEN || (cw & DOOR_OBJ_CLOSED) || blue_closed) continue;
+        bool red_open = false;  // the env's only red door (x-major scan)
+        for (int x = 0; x < p.W; x++)
+            for (int y = 0; y < p.H; y++) {
+                const uint32_t c = cells[x * p.Hp + y];
+                if ((c & 0xffffu) == DOOR_RED) { red_open = ((c >> 16) & 0xff) == S_OPEN; x = p.W; break; }
+            }
+        if (red_open) {
+            on_success(p, ag, rewarded, k);
+        } else {
+            on_failure(p, ag, k);
+            blue_closed = true;  // self.blue_door.is_open = False, WITHOUT grid.update(): state byte stays open
+            store_cell(p, e, idx, cw | DOOR_OBJ_CLOSED);
+        }
+    }
+}
+
 template <int MODE>
 MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const OrderDraw &d) {
     if (i < 0) return;
@@ -541,7 +588,7 @@ MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const 
     uint32_t *cells = g.cells + i * p.cstride;
     uint32_t *ag = g.ag + i * n * 2;
     if constexpr (MODE == MODE_OBS) {
-        stamp_agents(p, cells, ag);
+        stamp_agents(p, cells, ag, terminated_mask(p, ag));
     } else {
         const size_t e = (size_t)(g.e0 + i);
         const bool was_reset = (p.flags & MG_FLAG_AUTO_RESET) && g.rk[i] >= 0;
@@ -554,11 +601,13 @@ MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const 
         } else {
             r.lo = d.lo0; r.hi = d.hi0;  // no step, no draw
         }
-        if (MODE == MODE_STEP_OBS) stamp_agents(p, cells, ag);  // obs sees pre-hook termination
+        const uint32_t pre_hook_terminated = terminated_mask(p, ag);
         if (!was_reset && p.hook == MG_HOOK_BLOCKED_UNLOCK_PICKUP) {  // envs/blockedunlockpickup.py:166-175
             for (int k = 0; k < n; k++)
                 if ((ag[k * 2 + 1] & 0xff) == T_BOX) on_success(p, ag, rewarded, k);
         }
+        if (!was_reset && p.hook == MG_HOOK_RED_BLUE_DOORS) hook_red_blue_doors(p, g, i, cells, ag, rewarded);
+        if (MODE == MODE_STEP_OBS) stamp_agents(p, cells, ag, pre_hook_terminated);  // obs sees pre-hook state
         p.step_count[e] = r.sc;
         if (n > 1) { U128 s; s.lo = r.lo; s.hi = r.hi; *(U128 *)(p.pcg_state + 2 * e) = s; }
         if (p.flags & MG_FLAG_AUTO_RESET) p.layout_idx[e] = r.lidx;

@@ -14,7 +14,10 @@ When gymnasium is importable the ids are also registered there (entry point = `m
 from __future__ import annotations
 
 from ..env import BatchedMultiGridEnv
-from ..layouts import BlockedUnlockPickupLayout, EmptyLayout, PlaygroundLayout
+from ..layouts import BlockedUnlockPickupLayout, EmptyLayout, PlaygroundLayout, RedBlueDoorsLayout
+
+# envs/redbluedoors.py:102-109
+_RBD_DEFAULTS = dict(joint_reward=True, success_termination_mode='any', failure_termination_mode='any')
 
 # id -> (layout class, layout kwargs, env defaults of the reference env class)
 CONFIGURATIONS = {
@@ -27,17 +30,19 @@ CONFIGURATIONS = {
     'MultiGrid-Empty-8x8-v0': (EmptyLayout, {}, {}),
     'MultiGrid-Empty-16x16-v0': (EmptyLayout, {'size': 16}, {}),
     'MultiGrid-Playground-v0': (PlaygroundLayout, {}, {}),
+    'MultiGrid-RedBlueDoors-6x6-v0': (RedBlueDoorsLayout, {'size': 6}, _RBD_DEFAULTS),
+    'MultiGrid-RedBlueDoors-8x8-v0': (RedBlueDoorsLayout, {'size': 8}, _RBD_DEFAULTS),
 }
 
 # Reference ids whose step() post-hooks are not built yet.
 NOT_YET = ('MultiGrid-LockedHallway-2Rooms-v0', 'MultiGrid-LockedHallway-4Rooms-v0',
-           'MultiGrid-LockedHallway-6Rooms-v0', 'MultiGrid-RedBlueDoors-6x6-v0',
-           'MultiGrid-RedBlueDoors-8x8-v0')
+           'MultiGrid-LockedHallway-6Rooms-v0')
 
 _LAYOUT_KEYS = {
     EmptyLayout: ('size', 'agent_start_pos', 'agent_start_dir'),
     BlockedUnlockPickupLayout: ('room_size',),
     PlaygroundLayout: ('room_size', 'num_rows', 'num_cols'),
+    RedBlueDoorsLayout: ('size',),
 }
 
 

@@ -354,6 +354,31 @@ class PlaygroundLayout(Layout):
         return c.grid, c.agents, {}
 
 
+class RedBlueDoorsLayout(Layout):
+    """RedBlueDoorsEnv._gen_grid (envs/redbluedoors.py:142-168)."""
+    hook = 2  # MG_HOOK_RED_BLUE_DOORS
+    mission = "open the red door then the blue door"
+
+    def __init__(self, num_agents, size=8, max_steps=None):
+        self.size = size
+        super().__init__(2 * size, size, num_agents, max_steps or 20 * size ** 2)
+
+    def generate(self, layout_rng, order_rng):
+        W, H = self.width, self.height
+        c = Canvas(W, H, self.num_agents, layout_rng, order_rng)
+        room_top, room_size = (W // 4, 0), (W // 2, H)
+        c.wall_rect(0, 0, W, H)
+        c.wall_rect(*room_top, *room_size)
+        for k in range(self.num_agents):
+            c.place_agent(k, top=room_top, size=room_size)
+        y = c.rand_int(1, H - 1)
+        c.set(room_top[0], y, encode(Type.door, Color.red, State.closed))
+        y = c.rand_int(1, H - 1)
+        c.set(room_top[0] + room_size[0] - 1, y, encode(Type.door, Color.blue, State.closed))
+        c.check()
+        return c.grid, c.agents, {}
+
+
 def generate_pool(layout: Layout, count: int, seed: int | None = None):
     """`count` episode layouts -> (grid (K,W,H,3), agents (K,n,8), infos). Deterministic layouts
     collapse to K=1."""

@@ -37,8 +37,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            build()
+        build()  # no-op when the library is newer than mg_oracle.c
         _lib = C.CDLL(LIB_PATH)
         _lib.mgo_max_threads.restype = C.c_int
     return _lib
@@ -76,6 +75,7 @@ class COracle:
         self.reward = np.zeros((self.B, cfg.n), np.float64)
         self.terminated = np.zeros((self.B, cfg.n), np.uint8)
         self.truncated = np.zeros((self.B,), np.uint8)
+        self.cell_flags = np.zeros((self.B, cfg.W * cfg.H), np.uint8)  # see mg_oracle.c handle_actions
 
     def _obs_view(self):
         V = self.cfg.V
@@ -93,7 +93,7 @@ class COracle:
             C.byref(self.c), C.c_int64(self.B), _p(self.grid), _p(self.agents),
             _p(self.step_count), _p(self.pcg_state), _p(self.pcg_inc), _p(self.layout_idx),
             _p(self.pool_grid), _p(self.pool_agents), _p(actions), _p(self.obs), _p(self.reward),
-            _p(self.terminated), _p(self.truncated), C.c_int(self.nthreads))
+            _p(self.terminated), _p(self.truncated), _p(self.cell_flags), C.c_int(self.nthreads))
         if rc == 1:
             raise ValueError("Unknown action")
         assert rc == 0

@@ -26,7 +26,7 @@ enum { T_UNSEEN, T_EMPTY, T_WALL, T_FLOOR, T_DOOR, T_KEY, T_BALL, T_BOX, T_GOAL,
 enum { S_OPEN, S_CLOSED, S_LOCKED };
 enum { ACT_LEFT, ACT_RIGHT, ACT_FORWARD, ACT_PICKUP, ACT_DROP, ACT_TOGGLE, ACT_DONE };
 enum { A_DIR, A_X, A_Y, A_TERM, A_CT, A_CC, A_CS, A_COLOR, A_DIM };
-enum { HOOK_NONE, HOOK_BUP };
+enum { HOOK_NONE, HOOK_BUP, HOOK_RBD };
 
 #define MGO_MAX_AGENTS 64
 #define MGO_MAX_VIEW 31
@@ -87,9 +87,13 @@ static int agent_present(const mgo_config *c, const int8_t *agents, int x, int y
 }
 
 /* MultiGridEnv.handle_actions (base.py:378-476) */
+/* cell_flags[x*H+y] & 1: the Door OBJECT there is closed although grid.state shows it open. The
+ * reference keeps both in sync with grid.update(), except RedBlueDoorsEnv.step, which closes the
+ * blue door's object without updating the array (envs/redbluedoors.py:185): the rules read the
+ * object, the observation reads the array. */
 static int handle_actions(const mgo_config *c, int8_t *grid, int8_t *agents, int32_t step_count,
                           uint64_t *pcg_state, const uint64_t *pcg_inc, const int8_t *actions,
-                          double *rew) {
+                          double *rew, uint8_t *cell_flags) {
     int n = c->n, H = c->H, bad = 0;
     int order[MGO_MAX_AGENTS];
     uint8_t scratch[MGO_MAX_AGENTS];
@@ -121,6 +125,7 @@ static int handle_actions(const mgo_config *c, int8_t *grid, int8_t *agents, int
         if (fx < 0 || fx >= c->W || fy < 0 || fy >= H) continue;
         int8_t *cell = grid + (fx * H + fy) * 3;
         int t = cell[0], col = cell[1], st = cell[2];
+        if (t == T_DOOR && (cell_flags[fx * H + fy] & 1)) st = S_CLOSED; /* what the object says */
         if (a == ACT_FORWARD) { /* base.py:420-436 */
             int can_overlap = t == T_EMPTY || t == T_FLOOR || t == T_GOAL || t == T_LAVA ||
                               (t == T_DOOR && st == S_OPEN);
@@ -146,6 +151,7 @@ static int handle_actions(const mgo_config *c, int8_t *grid, int8_t *agents, int
                 } else {
                     cell[2] = (st == S_OPEN) ? S_CLOSED : S_OPEN;
                 }
+                cell_flags[fx * H + fy] &= 0xFE; /* Door.toggle ends with grid.update() */
             } else if (t == T_BOX) { /* core/world_object.py:599-605, contains == None */
                 cell[0] = T_EMPTY; cell[1] = 0; cell[2] = 0;
             }
@@ -245,12 +251,39 @@ int mgo_gen_obs(const mgo_config *c, int64_t num_envs, const int8_t *grid, const
     return 0;
 }
 
+/* RedBlueDoorsEnv.step post-hook (envs/redbluedoors.py:170-187): every agent whose action was toggle,
+ * in agent order, terminated or not: front cell is the open blue door -> success if the red door is
+ * open, else failure and the blue door is closed again. Colors: red 0, blue 2 (constants.py:51-60). */
+static void hook_red_blue_doors(const mgo_config *c, int8_t *grid, int8_t *agents, const int8_t *actions,
+                                double *rew, uint8_t *term, int32_t step_count, uint8_t *cell_flags) {
+    for (int k = 0; k < c->n; k++) {
+        if (actions[k] != ACT_TOGGLE) continue;
+        const int8_t *ag = agents + k * A_DIM;
+        int fx = ag[A_X] + DIR_DX[ag[A_DIR] & 3], fy = ag[A_Y] + DIR_DY[ag[A_DIR] & 3];
+        if (fx < 0 || fx >= c->W || fy < 0 || fy >= c->H) continue;
+        int8_t *cell = grid + ((size_t)fx * c->H + fy) * 3;
+        if (cell[0] != T_DOOR || cell[1] != 2 || cell[2] != S_OPEN || (cell_flags[fx * c->H + fy] & 1)) continue;
+        int red_open = 0, found = 0;
+        for (int x = 0; x < c->W && !found; x++)
+            for (int y = 0; y < c->H; y++) {
+                const int8_t *r = grid + ((size_t)x * c->H + y) * 3;
+                if (r[0] == T_DOOR && r[1] == 0) { red_open = r[2] == S_OPEN; found = 1; break; }
+            }
+        if (red_open) {
+            on_success(c, agents, k, rew, term, step_count);
+        } else {
+            on_failure(c, agents, k, term);
+            cell_flags[fx * c->H + fy] |= 1; /* blue_door.is_open = False, WITHOUT grid.update() */
+        }
+    }
+}
+
 /* MultiGridEnv.step (base.py:303-346) + env post-hook, with the engine's "next-step" auto-reset */
 int mgo_step_obs(const mgo_config *c, int64_t num_envs, int8_t *grid, int8_t *agents,
                  int32_t *step_count, uint64_t *pcg_state, const uint64_t *pcg_inc,
                  int32_t *layout_idx, const int8_t *pool_grid, const int8_t *pool_agents,
                  const int8_t *actions, int8_t *obs, double *reward, uint8_t *terminated,
-                 uint8_t *truncated, int nthreads) {
+                 uint8_t *truncated, uint8_t *cell_flags /* [E][W*H] */, int nthreads) {
     if (c->n > MGO_MAX_AGENTS || c->V > MGO_MAX_VIEW) return -1;
     size_t gsz = (size_t)c->W * c->H * 3, asz = (size_t)c->n * A_DIM;
     size_t osz = (size_t)c->n * c->obs_agent_stride;
@@ -273,6 +306,7 @@ int mgo_step_obs(const mgo_config *c, int64_t num_envs, int8_t *grid, int8_t *ag
                     layout_idx[e] = k;
                     memcpy(g, pool_grid + (size_t)k * gsz, gsz);
                     memcpy(ag, pool_agents + (size_t)k * asz, asz);
+                    memset(cell_flags + e * (size_t)c->W * c->H, 0, (size_t)c->W * c->H);
                     step_count[e] = 0;
                     gen_obs_env(c, g, ag, obs + e * osz, scratch);
                     for (int j = 0; j < n; j++) term[j] = 0;
@@ -281,14 +315,17 @@ int mgo_step_obs(const mgo_config *c, int64_t num_envs, int8_t *grid, int8_t *ag
                 }
             }
             step_count[e] += 1; /* base.py:333 */
+            uint8_t *cf = cell_flags + e * (size_t)c->W * c->H;
             bad_any |= handle_actions(c, g, ag, step_count[e], pcg_state + 2 * e, pcg_inc + 2 * e,
-                                      actions + e * n, rew);
+                                      actions + e * n, rew, cf);
             gen_obs_env(c, g, ag, obs + e * osz, scratch);          /* base.py:337 */
             for (int j = 0; j < n; j++) term[j] = ag[j * A_DIM + A_TERM] != 0; /* base.py:338 */
             truncated[e] = step_count[e] >= c->max_steps;              /* base.py:339 */
             if (c->hook == HOOK_BUP) /* envs/blockedunlockpickup.py:166-175 */
                 for (int j = 0; j < n; j++)
                     if (ag[j * A_DIM + A_CT] == T_BOX) on_success(c, ag, j, rew, term, step_count[e]);
+            if (c->hook == HOOK_RBD) /* envs/redbluedoors.py:170-187 */
+                hook_red_blue_doors(c, g, ag, actions + e * n, rew, term, step_count[e], cf);
         }
         free(scratch);
     }

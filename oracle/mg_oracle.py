@@ -34,7 +34,8 @@ DIR_TO_VEC = ((1, 0), (0, 1), (-1, 0), (0, -1))  # core/constants.py:21-30
 WALL_ENCODING = (WALL, 5, 0)  # utils/obs.py:14  (grey wall)
 A_DIR, A_X, A_Y, A_TERM, A_CT, A_CC, A_CS, A_COLOR = range(8)
 
-HOOK_NONE, HOOK_BUP = 0, 1
+HOOK_NONE, HOOK_BUP, HOOK_RBD = 0, 1, 2
+RED, BLUE = 0, 2  # core/constants.py:51-60
 
 M64 = (1 << 64) - 1
 M128 = (1 << 128) - 1
@@ -174,8 +175,14 @@ def _on_failure(cfg, agents, k, terminated_out):  # base.py:509-532
         terminated_out[k] = 1
 
 
-def handle_actions_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions, rewards):
-    """`MultiGridEnv.handle_actions` (base.py:378-476) for one env. Mutates grid/agents/pcg."""
+def handle_actions_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions, rewards,
+                       cell_flags=None):
+    """`MultiGridEnv.handle_actions` (base.py:378-476) for one env. Mutates grid/agents/pcg.
+
+    `cell_flags[x, y] & 1`: the Door OBJECT at (x, y) is closed although `grid.state` shows it
+    open. The reference keeps objects and the int array in sync with `grid.update()`, except in
+    RedBlueDoorsEnv.step, which closes the blue door's object without updating the array
+    (envs/redbluedoors.py:185): rules read the object, observations read the array."""
     n = cfg.n
     scratch_term = np.zeros(n, dtype=np.uint8)
     if n == 1:
@@ -209,6 +216,8 @@ def handle_actions_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, action
         if not (0 <= fx < cfg.W and 0 <= fy < cfg.H):
             continue  # never reached in registered envs (outer wall ring); engine treats as no-op
         t, c, s_ = (int(v) for v in grid[fx, fy])
+        if cell_flags is not None and t == DOOR and cell_flags[fx, fy] & 1:
+            s_ = CLOSED  # what the Door object says
         agent_at_f = bool(((agents[:, A_X] == fx) & (agents[:, A_Y] == fy)).any())
         if a == FORWARD:  # base.py:420-436
             can_overlap = t in (EMPTY, FLOOR, GOAL, LAVA) or (t == DOOR and s_ == OPEN)
@@ -237,11 +246,13 @@ def handle_actions_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, action
                     grid[fx, fy, 2] = CLOSED
                 else:
                     grid[fx, fy, 2] = OPEN
+                if cell_flags is not None:
+                    cell_flags[fx, fy] &= 0xFE  # Door.toggle ends with grid.update(): in sync again
             elif t == BOX:  # Box.toggle (core/world_object.py:599-605); contains is None
                 grid[fx, fy] = (EMPTY, 0, 0)
 
 
-def step_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions):
+def step_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions, cell_flags=None):
     """`MultiGridEnv.step` (base.py:303-346) + env post-hook for one env.
 
     Returns (obs, reward f64 (n,), terminated u8 (n,), truncated bool, new_step_count).
@@ -249,7 +260,7 @@ def step_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions):
     n = cfg.n
     step_count = int(step_count) + 1  # base.py:333
     rewards = np.zeros(n, dtype=np.float64)
-    handle_actions_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions, rewards)
+    handle_actions_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions, rewards, cell_flags)
     obs = gen_obs_env(cfg, grid, agents)  # base.py:337
     terminated = agents[:, A_TERM].astype(np.uint8).copy()  # base.py:338
     truncated = step_count >= cfg.max_steps  # base.py:339
@@ -257,6 +268,26 @@ def step_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions):
         for k in range(n):
             if agents[k, A_CT] == BOX:
                 _on_success(cfg, agents, k, rewards, terminated, step_count)
+    if cfg.hook == HOOK_RBD:  # envs/redbluedoors.py:170-187
+        for k in range(n):
+            if actions[k] != TOGGLE:  # ids absent from the dict are -1
+                continue
+            dx, dy = DIR_TO_VEC[int(agents[k, A_DIR]) & 3]
+            fx, fy = int(agents[k, A_X]) + dx, int(agents[k, A_Y]) + dy
+            if not (0 <= fx < cfg.W and 0 <= fy < cfg.H):
+                continue
+            t, c, s = (int(v) for v in grid[fx, fy])
+            if cell_flags is not None and cell_flags[fx, fy] & 1:
+                s = CLOSED  # the object's state
+            if (t, c, s) != (DOOR, BLUE, OPEN):  # fwd_obj == self.blue_door and it is open
+                continue
+            red = [(x, y) for x in range(cfg.W) for y in range(cfg.H)
+                   if grid[x, y, 0] == DOOR and grid[x, y, 1] == RED]
+            if red and grid[red[0][0], red[0][1], 2] == OPEN:
+                _on_success(cfg, agents, k, rewards, terminated, step_count)
+            else:
+                _on_failure(cfg, agents, k, terminated)
+                cell_flags[fx, fy] |= 1  # self.blue_door.is_open = False, WITHOUT grid.update()
     return obs, rewards, terminated, truncated, step_count
 
 
@@ -306,6 +337,7 @@ class OracleBatch:
         self.layout_idx = (np.zeros(self.B, np.int32) if layout_idx is None
                            else np.array(layout_idx, dtype=np.int32))
         self.done = np.zeros(self.B, dtype=bool)
+        self.cell_flags = np.zeros(self.grid.shape[:3], dtype=np.uint8)  # see handle_actions_env
 
     def gen_obs(self):
         return np.stack([gen_obs_env(self.cfg, self.grid[b], self.agents[b])
@@ -325,10 +357,12 @@ class OracleBatch:
                 self.grid[b] = self.pool_grid[self.layout_idx[b]]
                 self.agents[b] = self.pool_agents[self.layout_idx[b]]
                 self.step_count[b] = 0
+                self.cell_flags[b] = 0
                 obs[b] = gen_obs_env(cfg, self.grid[b], self.agents[b])
                 continue
             o, r, t, tr, sc = step_env(cfg, self.grid[b], self.agents[b], self.step_count[b],
-                                       self.pcg_state[b], self.pcg_inc[b], actions[b])
+                                       self.pcg_state[b], self.pcg_inc[b], actions[b],
+                                       self.cell_flags[b])
             obs[b], rew[b], term[b], trunc[b] = o, r, t, tr
             self.step_count[b] = sc
         return obs, rew, term, trunc

@@ -216,7 +216,7 @@ def run_case(name, env_id, kwargs, B, T, seed, p_absent=0.0, action_p=None, auto
         joint_reward=int(env0.joint_reward),
         success_any=int(env0.success_termination_mode == "any"),
         failure_any=int(env0.failure_termination_mode == "any"),
-        hook={"BlockedUnlockPickupEnv": 1}.get(type(env0).__name__, 0),
+        hook={"BlockedUnlockPickupEnv": 1, "RedBlueDoorsEnv": 2}.get(type(env0).__name__, 0),
         auto_reset=int(auto_reset), pool_J=J,
     )
     rec = dict(
@@ -307,7 +307,40 @@ def pcg_kat(name):
 FWD_HEAVY = [0.15, 0.15, 0.30, 0.12, 0.10, 0.15, 0.03]
 PICKUP_HEAVY = [0.10, 0.10, 0.15, 0.40, 0.10, 0.10, 0.05]
 
+def rbd_open_doors(env):
+    """Open the red door (and for odd envs leave it closed) and put agent 0 in front of the blue
+    door, so that success, failure and the re-closing of the blue door (envs/redbluedoors.py:170-187)
+    all occur under random actions. State injection only."""
+    rx, ry = [(x, y) for x in range(env.width) for y in range(env.height) if env.grid.get(x, y) is env.red_door][0]
+    if env.np_random.random() < 0.5:
+        env.red_door.is_open = True
+        env.grid.update(rx, ry)  # keep grid.state in sync with the object, as Door.toggle does
+    bx, by = [(x, y) for x in range(env.width) for y in range(env.height) if env.grid.get(x, y) is env.blue_door][0]
+    env.agents[0].state.pos = (bx - 1, by)
+    env.agents[0].state.dir = 0
+    if env.num_agents > 1:
+        env.agents[1].state.pos = (rx + 1, ry)
+        env.agents[1].state.dir = 2
+
+
+TOGGLE_HEAVY = [0.10, 0.10, 0.15, 0.05, 0.05, 0.50, 0.05]
+
 if __name__ == "__main__":
+    only = set(sys.argv[1:])
+    _run_case, _pcg_kat, _random_obs_cases = run_case, pcg_kat, random_obs_cases
+
+    def run_case(name, *a, **k):  # noqa: F811  (`python make_golden.py NAME...` regenerates only those)
+        if not only or name in only:
+            _run_case(name, *a, **k)
+
+    def pcg_kat(name, *a, **k):  # noqa: F811
+        if not only or name in only:
+            _pcg_kat(name, *a, **k)
+
+    def random_obs_cases(name, *a, **k):  # noqa: F811
+        if not only or name in only:
+            _random_obs_cases(name, *a, **k)
+
     pcg_kat("pcg64_kat")
     random_obs_cases("obs_random", seed=11)
     # BASELINE.json configs[0..3]
@@ -350,3 +383,11 @@ if __name__ == "__main__":
              B=6, T=150, seed=31, action_p=FWD_HEAVY, auto_reset=True)
     run_case("bup_n2_autoreset", "MultiGrid-BlockedUnlockPickup-v0", dict(agents=2, max_steps=30),
              B=4, T=120, seed=32, action_p=FWD_HEAVY, auto_reset=True)
+    # RedBlueDoors post-hook (success / failure / blue door closed again), SURVEY.md section 8f N3
+    run_case("rbd_n2", "MultiGrid-RedBlueDoors-8x8-v0", dict(agents=2), B=8, T=150, seed=40,
+             action_p=TOGGLE_HEAVY, tweak=rbd_open_doors)
+    run_case("rbd6_n3_all", "MultiGrid-RedBlueDoors-6x6-v0",
+             dict(agents=3, success_termination_mode="all", failure_termination_mode="all",
+                  joint_reward=False), B=8, T=150, seed=41, action_p=TOGGLE_HEAVY, tweak=rbd_open_doors)
+    run_case("rbd_n2_autoreset", "MultiGrid-RedBlueDoors-6x6-v0", dict(agents=2, max_steps=40),
+             B=4, T=160, seed=42, action_p=TOGGLE_HEAVY, auto_reset=True)

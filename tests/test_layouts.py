@@ -23,6 +23,7 @@ CASES = [
     ("empty5_n1", 6, lambda n: L.EmptyLayout(n, size=5)),
     ("bup_n2", 3, lambda n: L.BlockedUnlockPickupLayout(n)),
     ("playground_n3", 8, lambda n: L.PlaygroundLayout(n)),
+    ("rbd_n2_autoreset", 42, lambda n: L.RedBlueDoorsLayout(n, size=6, max_steps=40)),
 ]
 
 
