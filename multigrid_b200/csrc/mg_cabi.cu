@@ -34,12 +34,12 @@ int validate(const MgConfig *c, int64_t num_envs) {
     return 0;
 }
 
-// Tuning / test knobs (read per call): MG_PPB = pairs of warps per block (1|2), MG_NO_BULK=1 = plain
-// loads/stores instead of TMA bulk copies, MG_GENERIC_VIEW=1 = rolled-loop observation for every V.
+// Tuning / test knobs (read per call): MG_GROUP = envs per warp (16|32), MG_WPB = warps per block,
+// MG_NO_BULK=1 = plain loads/stores instead of TMA bulk copies.
 int plan(mg::Params &p) {
     p.use_bulk = env_int("MG_NO_BULK", 0) ? 0 : 1;
     p.generic_view = env_int("MG_GENERIC_VIEW", 0) ? 1 : 0;
-    return mg::plan_launch(p, env_int("MG_PPB", 0), kSmemPerBlock, kSmemPerSM);
+    return mg::plan_launch(p, env_int("MG_GROUP", 0), env_int("MG_WPB", 0), kSmemPerBlock, kSmemPerSM);
 }
 
 template <int VT, int MODE>
@@ -53,9 +53,9 @@ int launch(const mg::Params &p, cudaStream_t stream) {
         if (err != cudaSuccess) return (int)err;
         configured_dev[dev] = true;
     }
-    const int groups = (p.num_envs + mg::GROUP - 1) / mg::GROUP;
-    const int blocks = (groups + p.ppb - 1) / p.ppb;
-    kernel<<<blocks, p.ppb * 2 * mg::LANES, p.ppb * p.pair_bytes, stream>>>(p);
+    const int groups = (p.num_envs + p.G - 1) / p.G;
+    const int blocks = (groups + p.wpb - 1) / p.wpb;
+    kernel<<<blocks, p.wpb * mg::LANES, p.wpb * p.warp_bytes, stream>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }

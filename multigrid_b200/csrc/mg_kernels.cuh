@@ -1,27 +1,21 @@
 // multigrid_b200 -- device code of the batched MultiGrid step/observe engine (sm_100a), kernel v2.
 //
-// A PAIR of warps advances one group of 32 consecutive envs and never talks to another pair: no
-// block-wide barrier anywhere (the pair meets twice on a 64-thread named barrier). A group's state
-// is one contiguous HBM span per array (env-major layout); the spans are moved with 1-D TMA bulk
-// copies (cp.async.bulk + mbarrier in, cp.async.bulk.bulk_group out), so loads and stores cost a
-// handful of instructions; the per-env work runs out of shared memory:
+// One WARP advances one group of G consecutive envs (G = 16 or 32) and never talks to another warp:
+// no block-wide barrier anywhere, warps of a block drift apart and hide each other's latencies.
+// A group's state is one contiguous HBM span per array (env-major layout); the spans are moved with
+// 1-D TMA bulk copies (cp.async.bulk + mbarrier in, cp.async.bulk.bulk_group out), so loads and
+// stores cost the warp a handful of instructions; the per-env work runs out of shared memory:
 //
-//   warp A  P0 load     TMA: cell words / agents / actions -> smem; pcg state+inc / step_count /
-//                       layout_idx -> registers of the env's lane (coalesced: lane <-> env)
-//           P1 draw     agent order of the step (PCG64 draws + rank sort) while the TMA is in flight
-//           P2 reset    auto-reset decision per env, pool layout fetch                (1 lane / env)
-//           P3 step     handle_actions: serial agent loop, rewards, termination, dirty-cell
-//                       write-through, env hook, agent stamping; per-env outputs straight from
-//                       registers to HBM                                              (1 lane / env)
-//   warp B  waits for P3 on the pair barrier (an idle warp costs no issue slots)
-//   A + B   P4 observe  32 agents per pass: view gather (closed-form slice+rotate), row-bitmask
-//                       visibility scan, masking, 24->32 bit packing into a smem stage (1 lane /
-//                       agent) -> TMA bulk store of the pass's contiguous obs span. The n passes of
-//                       a group are split evenly: B takes the first half in ascending order, A the
-//                       second half in descending order.
-//
-// The serial transition runs once per 32 envs with all 32 lanes busy, and the observation passes
-// (the bulk of the instructions) spread over twice as many warps.
+//   P0 load      TMA: cell words / agents / actions -> smem; pcg state+inc / step_count /
+//                layout_idx -> registers of the env's lane (coalesced: lane <-> env)
+//   P1 reset     auto-reset decision per env, pool layout fetch                     (1 lane / env)
+//   P2 step      handle_actions: PCG64 draw, argsort, serial agent loop, rewards,
+//                termination, dirty-cell write-through, env hook, agent stamping;
+//                per-env outputs straight from registers to HBM                     (1 lane / env)
+//   P3 observe   32 agents per pass: view gather (closed-form slice+rotate), row-bitmask
+//                visibility scan, masking, 24->32 bit packing into the smem stage   (1 lane / agent)
+//                -> TMA bulk store of the pass's contiguous obs span
+//   P4 store     TMA: agents
 //
 // The grid lives in HBM as 32-bit CELL WORDS (type | color<<8 | state<<16 | opaque<<31) in a
 // padded (W+1) x (H+1) array per env whose last row and column are WALL sentinels, i.e. exactly the
@@ -68,7 +62,7 @@ struct Params {
     int32_t W, H, n, V, max_steps;
     uint32_t flags;
     int32_t hook, ostride, K, lstride;
-    int32_t num_envs, ppb, use_bulk, generic_view;  // ppb = pairs of warps per block
+    int32_t num_envs, G, wpb, use_bulk, generic_view;
     // state (device)
     uint32_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;
     int32_t *layout_idx; const uint32_t *pool_grid; const int8_t *pool_agents;
@@ -80,11 +74,10 @@ struct Params {
     // row x = W and column y = H hold WALL sentinels, every out-of-range coordinate maps there.
     int32_t Hp, cstride;
     uint32_t rcp_n;  // ceil(2^32 / n) (see fastdiv)
-    // per-pair shared-memory carve-up (byte offsets, all multiples of 16)
-    int32_t off_cells, off_stage, off_keys, off_ag, off_act, off_rk, off_mbar, pair_bytes;
-    // obs passes: n per group; warp B runs passes [0, passes_b) ascending, warp A [passes_b, n) descending;
-    // alias = stages live on top of cells that are already gathered (see carve_smem)
-    int32_t passes_b, alias, pass_cell_bytes, stage_bytes;
+    // per-warp shared-memory carve-up (byte offsets, all multiples of 16)
+    int32_t off_cells, off_stage, off_keys, off_ag, off_act, off_rk, off_mbar, warp_bytes;
+    // obs stage aliased onto the cells of the passes already gathered (see carve_smem)
+    int32_t alias, pass_cell_bytes, stage_bytes, stage_extra;
 };
 
 MG_HD int align16(int x) { return (x + 15) & ~15; }
@@ -93,63 +86,60 @@ inline uint32_t rcp32(int d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / (u
 // Number of cell words per env in HBM and in shared memory.
 inline int64_t cells_per_env(int W, int H) { return (int64_t)(W + 1) * (H + 1); }
 
-constexpr int GROUP = 32;  // envs per pair of warps
-
-// Fills the derived fields; returns the shared memory bytes of one pair.
+// Fills the derived fields for group size p.G; returns the shared memory bytes of one warp.
 inline int carve_smem(Params &p) {
-    const int G = GROUP, n = p.n;
+    const int G = p.G, n = p.n;
     p.Hp = p.H + 1;
     p.cstride = (p.W + 1) * p.Hp;
     p.rcp_n = rcp32(n);
-    // A group has GROUP*n = 32n agent tasks = n passes. Warp B cannot start before warp A's
-    // transition is done, so from there on both have the same time left: split the passes evenly.
-    const int passes_a = n / 2;
-    p.passes_b = n - passes_a;
     const bool unrolled_view = !p.generic_view && (p.V == 3 || p.V == 5 || p.V == 7 || p.V == 9);
-    // An obs pass (32 tasks = 32/n envs when n divides 32) only reads the cells of ITS envs, and it
-    // has them in registers before it writes its packed result. So stages can live on top of cells
-    // that are already gathered: region = [front][cells pass 0][cells pass 1]...[back];
-    // B (ascending) packs pass q into the stage_bytes that END where the cells of pass q end,
-    // A (descending) packs pass q into the stage_bytes that START where the cells of pass q start.
+    // An obs pass (32 agent tasks = 32/n envs when n divides 32) only reads the cells of ITS envs,
+    // and it has them in registers before it writes its packed result. So the stage of pass q can
+    // live on top of the cells of passes <= q: the region is [extra][cells pass 0][cells pass 1]...
+    // and stage q = the stage_bytes that END where the cells of pass q end.
     p.stage_bytes = LANES * p.ostride;
     p.pass_cell_bytes = (LANES / n) * p.cstride * 4;
-    p.alias = unrolled_view && n <= LANES && LANES % n == 0 && p.pass_cell_bytes % 16 == 0;
-    const int spill = p.stage_bytes > p.pass_cell_bytes ? align16(p.stage_bytes - p.pass_cell_bytes) : 0;
+    p.alias = unrolled_view && n <= LANES && LANES % n == 0 && (G * n) % LANES == 0 &&
+              p.pass_cell_bytes % 16 == 0;
+    p.stage_extra = 0;
     int off = 0;
     if (p.alias) {
-        p.off_stage = off;              // = start of the region
-        off += spill;                   // front (B's first pass reaches back into it)
+        p.stage_extra = p.stage_bytes > p.pass_cell_bytes ? align16(p.stage_bytes - p.pass_cell_bytes) : 0;
+        p.off_stage = off; off += p.stage_extra;
         p.off_cells = off; off += align16(G * p.cstride * 4);
-        if (passes_a > 0) off += spill; // back (A's first pass, the last of the group, reaches into it)
     } else {
         p.off_cells = off; off += align16(G * p.cstride * 4);
-        p.off_stage = off; off += 2 * align16(p.stage_bytes);  // one stage per warp
+        p.off_stage = off; off += align16(p.stage_bytes);
     }
     p.off_keys = off;  off += n > 4 ? align16(G * n * 8) + align16(G * n) : 0;  // sort keys + order
     p.off_ag = off;    off += align16(G * n * 8);
     p.off_act = off;   off += align16(G * n);
     p.off_rk = off;    off += align16(G * 4);
     p.off_mbar = off;  off += 16;
-    p.pair_bytes = off;
+    p.warp_bytes = off;
     return off;
 }
 
-// Launch geometry: ppb pairs per block (2 or 1), whichever keeps more warps resident per SM.
-// Returns 0, or MG_ERR_TOO_LARGE when one group does not fit the shared memory of a block.
-inline int plan_launch(Params &p, int forced_ppb, int smem_per_block, int smem_per_sm) {
-    if (carve_smem(p) > smem_per_block) return MG_ERR_TOO_LARGE;
-    int best = 0, best_ppb = 1;
-    for (int ppb = 2; ppb >= 1; ppb--) {
-        const int bytes = ppb * p.pair_bytes;
+// Launch geometry: G envs per warp (16, or 32 when forced and it fits), wpb warps per block chosen
+// to maximise resident warps per SM. Returns 0, or MG_ERR_TOO_LARGE when 16 envs do not fit.
+inline int plan_launch(Params &p, int forced_G, int forced_wpb, int smem_per_block, int smem_per_sm) {
+    p.G = (forced_G == 32 || forced_G == 8) ? forced_G : 16;
+    if (carve_smem(p) > smem_per_block) {
+        p.G = 16;
+        if (carve_smem(p) > smem_per_block) return MG_ERR_TOO_LARGE;
+    }
+    int best = 0, best_wpb = 1;
+    for (int wpb = 4; wpb >= 1; wpb >>= 1) {
+        const int bytes = wpb * p.warp_bytes;
         if (bytes > smem_per_block) continue;
         int blocks = smem_per_sm / (bytes + 1024);  // 1 KB per block is reserved by the driver
         if (blocks > 32) blocks = 32;
-        int pairs = blocks * ppb;
-        if (pairs > 32) pairs = 32;
-        if (pairs > best) { best = pairs; best_ppb = ppb; }
+        int warps = blocks * wpb;
+        if (warps > 64) warps = 64;
+        if (warps > best) { best = warps; best_wpb = wpb; }
     }
-    p.ppb = best_ppb;
-    if (forced_ppb > 0 && forced_ppb <= 2 && forced_ppb * p.pair_bytes <= smem_per_block) p.ppb = forced_ppb;
+    p.wpb = best_wpb;
+    if (forced_wpb > 0 && forced_wpb <= 4 && forced_wpb * p.warp_bytes <= smem_per_block) p.wpb = forced_wpb;
     return 0;
 }
 
@@ -293,7 +283,7 @@ MG_HD void cell_words_x4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t out[4])
     out[3] = byte_perm(w2, O, 0x7321u);
 }
 
-// A pair's view of its group: e0 = first global env, ne = number of valid envs.
+// One warp's view of its group: e0 = first global env, ne = number of valid envs.
 struct Group {
     int e0, ne;
     uint32_t *cells; uint8_t *stage; uint32_t *ag; int8_t *act; int32_t *rk;
@@ -302,20 +292,31 @@ struct Group {
 
 MG_HD Group group_view(const Params &p, uint8_t *ws, int group) {
     Group g;
-    g.e0 = group * GROUP;
-    g.ne = p.num_envs - g.e0 < GROUP ? p.num_envs - g.e0 : GROUP;
+    g.e0 = group * p.G;
+    g.ne = p.num_envs - g.e0 < p.G ? p.num_envs - g.e0 : p.G;
     g.cells = (uint32_t *)(ws + p.off_cells);
     g.stage = ws + p.off_stage;  // pass 0's (see stage_of)
     g.ag = (uint32_t *)(ws + p.off_ag);
     g.act = (int8_t *)(ws + p.off_act);
     g.rk = (int32_t *)(ws + p.off_rk);
     g.keys = (uint64_t *)(ws + p.off_keys);
-    g.order = ws + p.off_keys + align16(GROUP * p.n * 8);
+    g.order = ws + p.off_keys + align16(p.G * p.n * 8);
     return g;
 }
 
-// The per-env phases (draw, reset decision, transition) run one lane per env.
-MG_HD int lane_env(const Params &p, const Group &g, int lane) { return lane < g.ne ? lane : -1; }
+// The per-env phases (reset decision, transition) run one lane per env. With G = 16 the upper half
+// warp SHADOWS the lower half on the GPU: lane l and lane l+16 do identical work on identical data
+// (duplicate stores of identical values), so the warp never splits into two half-warps that would
+// then run the observation phase twice at half width. The host simulator runs lanes one after the
+// other, so there only lanes < G act.
+MG_HD int lane_env(const Params &p, const Group &g, int lane) {
+#ifdef __CUDA_ARCH__
+    const int i = lane & (p.G - 1);
+#else
+    const int i = lane < p.G ? lane : p.G;
+#endif
+    return i < g.ne ? i : -1;
+}
 
 // Per-env scalars the env's lane keeps in registers from load to store.
 struct alignas(16) U128 { uint64_t lo, hi; };
@@ -414,7 +415,7 @@ MG_HD bool agent_at(const Params &p, const uint32_t *ag, uint32_t xy) {  // xy =
 // base.py:399: order = np_random.random(size=n).argsort(). Returns the order packed 4 bits per rank
 // (n <= 4, keys in registers) or writes g.order (n > 4, keys in the stage).
 MG_HD uint32_t draw_order(const Params &p, const Group &g, int i, EnvRegs &r) {
-    const int n = p.n, G = GROUP;
+    const int n = p.n, G = p.G;
     if (n == 1) return 0;  // base.py:396-397
     if (n <= 4) {
         uint64_t k[4];
@@ -449,7 +450,7 @@ MG_HD uint32_t draw_order(const Params &p, const Group &g, int i, EnvRegs &r) {
 // MultiGridEnv.handle_actions (base.py:378-476) for local env i; `ag` = this env's agent words.
 MG_HD void handle_actions(const Params &p, const Group &g, int i, uint32_t *cells, uint32_t *ag,
                           uint32_t ord, uint32_t &rewarded) {
-    const int n = p.n, G = GROUP, e = g.e0 + i;
+    const int n = p.n, G = p.G, e = g.e0 + i;
     const int8_t *act_e = g.act + i * n;
     for (int r = 0; r < n; r++) {
         const int k = n <= 4 ? (int)((ord >> (4 * r)) & 15u) : (int)g.order[r * G + i];
@@ -528,19 +529,6 @@ MG_HD void stamp_agents(const Params &p, uint32_t *cells, const uint32_t *ag, ui
 
 // The env's lane: transition, then every per-env output straight from registers to HBM
 // (lane <-> env, env-major arrays: the warp's accesses are contiguous).
-// The agent order of this step only needs the env's PCG64 registers, not the TMA-loaded state, so
-// it is drawn while the load is still in flight. `r` is advanced speculatively: phase_step keeps
-// the advanced state only if the env really steps (an env that auto-resets consumes no draw).
-struct OrderDraw { uint32_t ord; uint64_t lo0, hi0; };
-
-template <int MODE>
-MG_HD OrderDraw phase_draw(const Params &p, const Group &g, int i, EnvRegs &r) {
-    OrderDraw d;
-    d.ord = 0; d.lo0 = r.lo; d.hi0 = r.hi;
-    if (MODE != MODE_OBS && i >= 0) d.ord = draw_order(p, g, i, r);
-    return d;
-}
-
 MG_HD uint32_t terminated_mask(const Params &p, const uint32_t *ag) {
     uint32_t m = 0;
     for (int j = 0; j < p.n; j++) m |= (uint32_t)(((ag[j * 2] >> 24) & 0xff) != 0) << j;
@@ -549,8 +537,8 @@ MG_HD uint32_t terminated_mask(const Params &p, const uint32_t *ag) {
 
 // RedBlueDoorsEnv.step post-hook (envs/redbluedoors.py:170-187): for every agent whose action was
 // `toggle` (terminated or not), in agent order: if the cell in front of it is the (open) blue
-// door, then success if the red door is open, else failure and the blue door is closed again.
-// Runs on the un-stamped cells (before stamping).
+// door, then success if the red door is open, else failure and the blue door's OBJECT is closed
+// again. Runs on the un-stamped cells (before stamping).
 MG_HD void hook_red_blue_doors(const Params &p, const Group &g, int i, const uint32_t *cells, uint32_t *ag,
                                uint32_t &rewarded) {
     const int n = p.n, e = g.e0 + i;
@@ -579,6 +567,19 @@ MG_HD void hook_red_blue_doors(const Params &p, const Group &g, int i, const uin
             store_cell(p, e, idx, cw | DOOR_OBJ_CLOSED);
         }
     }
+}
+
+// The agent order of this step only needs the env's PCG64 registers, not the TMA-loaded state, so
+// it is drawn while the load is still in flight. `r` is advanced speculatively: phase_step keeps
+// the advanced state only if the env really steps (an env that auto-resets consumes no draw).
+struct OrderDraw { uint32_t ord; uint64_t lo0, hi0; };
+
+template <int MODE>
+MG_HD OrderDraw phase_draw(const Params &p, const Group &g, int i, EnvRegs &r) {
+    OrderDraw d;
+    d.ord = 0; d.lo0 = r.lo; d.hi0 = r.hi;
+    if (MODE != MODE_OBS && i >= 0) d.ord = draw_order(p, g, i, r);
+    return d;
 }
 
 template <int MODE>
@@ -805,21 +806,14 @@ MG_HD ObsTask obs_task(const Params &p, const Group &g, int pass, int lane) {
 
 MG_HD int obs_passes(const Params &p, const Group &g) { return (g.ne * p.n + LANES - 1) / LANES; }
 
-// Where pass `pass` packs its 32 observations (see carve_smem). role: 0 = warp A, 1 = warp B.
-MG_HD uint8_t *stage_of(const Params &p, const Group &g, int pass, int role) {
-    if (!p.alias) return g.stage + role * align16(p.stage_bytes);
-    uint8_t *cells = (uint8_t *)g.cells;
-    return role ? cells + (pass + 1) * p.pass_cell_bytes - p.stage_bytes : cells + pass * p.pass_cell_bytes;
+// Where pass `pass` packs its 32 observations (see carve_smem).
+MG_HD uint8_t *stage_of(const Params &p, const Group &g, int pass) {
+    return p.alias ? g.stage + (pass + 1) * p.pass_cell_bytes + p.stage_extra - p.stage_bytes : g.stage;
 }
-
-// Which warp of the pair runs pass q.
-MG_HD int pass_role(const Params &p, int pass) { return pass < p.passes_b ? 1 : 0; }
 
 MG_HD void phase_obs_store_plain(const Params &p, const Group &g, int pass, int lane) {
     const int cnt = g.ne * p.n - pass * LANES < LANES ? g.ne * p.n - pass * LANES : LANES;
-    if (cnt <= 0) return;
-    warp_copy(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride,
-              stage_of(p, g, pass, pass_role(p, pass)), cnt * p.ostride, lane);
+    warp_copy(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, stage_of(p, g, pass), cnt * p.ostride, lane);
 }
 
 // ---- P6 (plain path): agents back to HBM --------------------------------------------------------------
@@ -879,7 +873,7 @@ __device__ __forceinline__ void trace_mark(const Params &p, int group, int lane,
 template <int MODE>
 __device__ __forceinline__ void load_bulk(const Params &p, const Group &g, uint64_t *bar) {
     const size_t e0 = (size_t)g.e0;
-    const uint32_t G = (uint32_t)GROUP, n = (uint32_t)p.n;
+    const uint32_t G = (uint32_t)p.G, n = (uint32_t)p.n;
     uint32_t total = G * p.cstride * 4 + G * n * 8;
     if (MODE != MODE_OBS) total += G * n;
     mbar_expect_tx(bar, total);
@@ -916,125 +910,100 @@ __global__ void unpack_grid_kernel(int W, int H, int64_t total, const uint32_t *
     dst[0] = (uint8_t)w; dst[1] = (uint8_t)(w >> 8); dst[2] = (uint8_t)(w >> 16);
 }
 
-// 64-thread named barrier of one pair (id 0 is __syncthreads' barrier; ids 1.. = pairs of the block)
-// (literal ids: a register id would make ptxas reserve all 16 barriers and cap the blocks per SM)
-__device__ __forceinline__ void pair_sync(int pair_in_block) {
-    if (pair_in_block == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
-    else asm volatile("bar.sync 2, 64;" ::: "memory");
-}
-
-// One observation pass by one warp (see carve_smem / stage_of for where the stage lives).
-template <int VT>
-__device__ __forceinline__ void obs_pass(const Params &p, const Group &g, int pass, int role, int lane,
-                                         bool bulk, bool first_of_warp) {
-    const ObsTask t = obs_task(p, g, pass, lane);
-    uint8_t *stage = stage_of(p, g, pass, role), *out = stage + lane * p.ostride;
-    if constexpr (VT != 0) {
-        uint32_t cr[VT ? VT * VT : 1];
-        if (t.valid) obs_compute<VT>(p, t.cells, t.a0, t.a1, cr);
-        // this warp's previous TMA store must be done reading its stage, and (aliased stage) every
-        // lane must be done gathering before the cells under the stage are overwritten
-        if (bulk && !first_of_warp && lane == 0) bulk_wait_read();
-        __syncwarp();
-        if (t.valid) obs_pack_store<VT>(p, cr, out);
-    } else {
-        if (bulk && !first_of_warp && lane == 0) bulk_wait_read();
-        __syncwarp();
-        if (t.valid) obs_agent_generic(p, t.cells, t.a0, t.a1, out);
-    }
-    if (bulk) {
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-            bulk_s2g(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, stage,
-                     (uint32_t)(LANES * p.ostride));
-            bulk_commit();
-        }
-    } else {
-        __syncwarp();
-        phase_obs_store_plain(p, g, pass, lane);
-        __syncwarp();
-    }
-}
-
-// 2 or 4 warps per block; register cap: 72 (7 blocks x 128 threads per SM) up to V = 7, 128 for V = 9
+// <= 4 warps per block; register cap: 72 (7 blocks x 128 threads per SM) up to V = 7, 128 for V = 9
 template <int VT, int MODE>
 __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pib = warp >> 1, role = warp & 1;  // pair in block; role 0 = warp A, 1 = warp B
-    const int group = blockIdx.x * p.ppb + pib;
-    if (group * GROUP >= p.num_envs) return;     // whole pair
-    if (MODE == MODE_STEP && role) return;       // no observation: warp B has nothing to do
-    uint8_t *ws = smem + pib * p.pair_bytes;
+    const int group = blockIdx.x * p.wpb + warp;
+    if (group * p.G >= p.num_envs) return;  // whole warp
+    uint8_t *ws = smem + warp * p.warp_bytes;
     const Group g = group_view(p, ws, group);
     uint64_t *bar = (uint64_t *)(ws + p.off_mbar);
-    // TMA needs 16-byte multiples: full groups only (32 envs make every span aligned)
-    const bool bulk = p.use_bulk && g.ne == GROUP;
-    const int wid = group * 2 + role;
-    trace_mark(p, wid, lane, 0);
-    trace_mark(p, wid, lane, 7);
+    // TMA needs 16-byte multiples: full groups only (G % 16 == 0 makes every span aligned)
+    const bool bulk = p.use_bulk && g.ne == p.G;
+    const int env = lane_env(p, g, lane);
+    trace_mark(p, group, lane, 0);
+    trace_mark(p, group, lane, 7);
 
-    if (role == 0) {
-        const int env = lane_env(p, g, lane);
-        if (bulk) {
-            if (lane == 0) {
-                mbar_init(bar, 1);
-                load_bulk<MODE>(p, g, bar);
-            }
-        } else {
-            phase_load_plain<MODE>(p, g, lane);
+    if (bulk) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            load_bulk<MODE>(p, g, bar);
         }
-        EnvRegs er;
-        env_load<MODE>(p, g, env, er);  // the env's scalars, straight into its lane's registers
-        const OrderDraw draw = phase_draw<MODE>(p, g, env, er);
-        if (MODE != MODE_STEP) pair_sync(pib);  // B may now poll the mbarrier / see the plain loads
-        else __syncwarp();
-        if (bulk) mbar_wait(bar, 0);
-        trace_mark(p, wid, lane, 1);
-        if (MODE != MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
-            phase_reset(p, g, env, er);
-            const uint32_t pending = __ballot_sync(0xffffffffu, env >= 0 && g.rk[env] >= 0);
-            if (pending) {
-                __syncwarp();
-                phase_reset_grid(p, g, pending, lane);
-            }
+    } else {
+        phase_load_plain<MODE>(p, g, lane);
+    }
+    EnvRegs er;
+    env_load<MODE>(p, g, env, er);  // the env's scalars, straight into its lane's registers
+    const OrderDraw draw = phase_draw<MODE>(p, g, env, er);
+    __syncwarp();
+    if (bulk) mbar_wait(bar, 0);
+    trace_mark(p, group, lane, 1);
+    if (MODE != MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
+        phase_reset(p, g, env, er);
+        const uint32_t pending = __ballot_sync(0xffffffffu, env >= 0 && g.rk[env] >= 0) & (p.G == 32 ? 0xffffffffu : (1u << p.G) - 1u);
+        if (pending) {
             __syncwarp();
+            phase_reset_grid(p, g, pending, lane);
         }
-        phase_step<MODE>(p, g, env, er, draw);
-        if (MODE != MODE_STEP) pair_sync(pib);  // cells are stamped, agents final: B may observe
-        else __syncwarp();
-        trace_mark(p, wid, lane, 2);
-        if (MODE != MODE_OBS) {  // agents back to HBM
+        __syncwarp();
+    }
+    phase_step<MODE>(p, g, env, er, draw);
+    __syncwarp();
+    trace_mark(p, group, lane, 2);
+    if (MODE != MODE_STEP) {
+        const int passes = obs_passes(p, g);
+        for (int pass = 0; pass < passes; pass++) {
+            const ObsTask t = obs_task(p, g, pass, lane);
+            uint8_t *stage = stage_of(p, g, pass), *out = stage + lane * p.ostride;
+            if constexpr (VT != 0) {
+                uint32_t cr[VT ? VT * VT : 1];
+                if (t.valid) obs_compute<VT>(p, t.cells, t.a0, t.a1, cr);
+                // the previous pass's TMA store must be done reading its stage, and (aliased stage)
+                // every lane must be done gathering before the cells under the stage are overwritten
+                if (bulk && pass > 0 && lane == 0) bulk_wait_read();
+                __syncwarp();
+                if (t.valid) obs_pack_store<VT>(p, cr, out);
+            } else {
+                if (bulk && pass > 0) {
+                    if (lane == 0) bulk_wait_read();
+                    __syncwarp();
+                }
+                if (t.valid) obs_agent_generic(p, t.cells, t.a0, t.a1, out);
+            }
             if (bulk) {
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    bulk_s2g(p.agents + (size_t)g.e0 * p.n * 8, g.ag, (uint32_t)(GROUP * p.n * 8));
+                    const int left = g.ne * p.n - pass * LANES;
+                    const uint32_t cnt = left < LANES ? left : LANES;
+                    bulk_s2g(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, stage,
+                             cnt * p.ostride);
                     bulk_commit();
                 }
             } else {
-                phase_store_plain(p, g, lane);
+                __syncwarp();
+                phase_obs_store_plain(p, g, pass, lane);
+                __syncwarp();
             }
         }
-        if (MODE != MODE_STEP) {
-            const int passes = obs_passes(p, g);
-            bool first = true;
-            for (int pass = passes - 1; pass >= p.passes_b; pass--, first = false)
-                obs_pass<VT>(p, g, pass, 0, lane, bulk, first);
-        }
-    } else {
-        pair_sync(pib);
-        if (bulk) mbar_wait(bar, 0);
-        trace_mark(p, wid, lane, 1);
-        pair_sync(pib);
-        trace_mark(p, wid, lane, 2);
-        const int passes = obs_passes(p, g) < p.passes_b ? obs_passes(p, g) : p.passes_b;
-        for (int pass = 0; pass < passes; pass++) obs_pass<VT>(p, g, pass, 1, lane, bulk, pass == 0);
     }
-    trace_mark(p, wid, lane, 3);
+    trace_mark(p, group, lane, 3);
+    if (MODE != MODE_OBS) {
+        if (bulk) {
+            if (MODE == MODE_STEP) fence_async_smem();  // (the obs passes already fenced)
+            __syncwarp();
+            if (lane == 0) {
+                bulk_s2g(p.agents + (size_t)g.e0 * p.n * 8, g.ag, (uint32_t)(p.G * p.n * 8));
+                bulk_commit();
+            }
+        } else {
+            phase_store_plain(p, g, lane);
+        }
+    }
     if (bulk && lane == 0) bulk_wait_read();  // smem must stay valid until the TMA stores have read it
-    trace_mark(p, wid, lane, 4);
+    trace_mark(p, group, lane, 4);
 }
 #endif
 

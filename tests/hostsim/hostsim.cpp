@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE: runs the phase functions of multigrid_b200/csrc/mg_kernels.cuh on the CPU,
-// lane by lane and phase by phase (a phase boundary == __syncwarp / the pair barrier), so the kernel logic can be
+// lane by lane and phase by phase (a phase boundary == __syncwarp), so the kernel logic can be
 // checked against the oracle in a container without a GPU. The TMA bulk copies of the CUDA build
 // are replaced by the kernel's own plain-copy path. Never loaded by the product.
 #include <cstdlib>
@@ -15,7 +15,7 @@ namespace {
 template <int VT>
 void obs_pass(const mg::Params &p, const mg::Group &g, int pass) {
     static uint32_t cr[mg::LANES][VT ? VT * VT : 1];
-    uint8_t *stage = mg::stage_of(p, g, pass, mg::pass_role(p, pass));
+    uint8_t *stage = mg::stage_of(p, g, pass);
     mg::ObsTask t[mg::LANES];
     for (int l = 0; l < mg::LANES; l++) t[l] = mg::obs_task(p, g, pass, l);
     if constexpr (VT != 0) {
@@ -31,13 +31,13 @@ void obs_pass(const mg::Params &p, const mg::Group &g, int pass) {
 
 template <int VT, int MODE>
 void run_groups(const mg::Params &p) {
-    std::vector<uint8_t> smem_store(p.pair_bytes + 128);
+    std::vector<uint8_t> smem_store(p.warp_bytes + 128);
     uint8_t *ws = smem_store.data();
     ws += (128 - (reinterpret_cast<uintptr_t>(ws) & 127)) & 127;
-    const int groups = (p.num_envs + mg::GROUP - 1) / mg::GROUP;
+    const int groups = (p.num_envs + p.G - 1) / p.G;
     const int L = mg::LANES;
     for (int grp = 0; grp < groups; grp++) {
-        std::memset(ws, 0xCD, p.pair_bytes);  // poison: catches reads of unwritten smem
+        std::memset(ws, 0xCD, p.warp_bytes);  // poison: catches reads of unwritten smem
         const mg::Group g = mg::group_view(p, ws, grp);
         mg::EnvRegs er[mg::LANES];
         int env[mg::LANES];
@@ -53,12 +53,8 @@ void run_groups(const mg::Params &p) {
         }
         for (int l = 0; l < L; l++) mg::phase_step<MODE>(p, g, env[l], er[l], draw[l]);
         if (MODE != mg::MODE_STEP) {
-            // warp B: passes [0, passes_b) ascending; warp A: the rest, descending (stages alias cells)
             const int passes = mg::obs_passes(p, g);
-            std::vector<int> order;
-            for (int pass = 0; pass < passes && pass < p.passes_b; pass++) order.push_back(pass);
-            for (int pass = passes - 1; pass >= p.passes_b; pass--) order.push_back(pass);
-            for (int pass : order) {
+            for (int pass = 0; pass < passes; pass++) {
                 obs_pass<VT>(p, g, pass);
                 for (int l = 0; l < L; l++) mg::phase_obs_store_plain(p, g, pass, l);
             }
@@ -101,7 +97,7 @@ extern "C" int sim_run(int mode, const MgConfig *c, int64_t num_envs, const MgSt
     p.actions = actions;
     p.obs = o->obs; p.reward = o->reward; p.terminated = o->terminated; p.truncated = o->truncated;
     p.status = o->status;
-    int rc = mg::plan_launch(p, forced_group, 227 * 1024, 228 * 1024);
+    int rc = mg::plan_launch(p, forced_group, 0, 227 * 1024, 228 * 1024);
     if (rc) return rc;
     if (mode == mg::MODE_OBS) dispatch<mg::MODE_OBS>(p, generic);
     else if (mode == mg::MODE_STEP) dispatch<mg::MODE_STEP>(p, generic);

@@ -173,14 +173,14 @@ def test_full_size_configs_vs_c_oracle(label, size, n, V, E, hook):
     assert_same(g, ora, label)
 
 
-KNOBS = [dict(MG_NO_BULK="1"), dict(MG_PPB="1"), dict(MG_PPB="2"), dict(MG_PPB="1", MG_NO_BULK="1"),
-         dict(MG_GENERIC_VIEW="1")]
+KNOBS = [dict(MG_NO_BULK="1"), dict(MG_GROUP="8"), dict(MG_GROUP="32"), dict(MG_GROUP="32", MG_WPB="1"),
+         dict(MG_WPB="2"), dict(MG_WPB="1", MG_NO_BULK="1"), dict(MG_GENERIC_VIEW="1")]
 
 
 @pytest.mark.parametrize("knobs", KNOBS, ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
 @pytest.mark.parametrize("seed,B,kw", [SOUP[0], SOUP[1], SOUP[4], SOUP[6]])
 def test_launch_knobs_do_not_change_results(seed, B, kw, knobs, monkeypatch):
-    """Warp pairs per block, TMA-vs-plain copies and the rolled-loop view are implementation choices only."""
+    """Group size, warps per block, TMA-vs-plain copies and the rolled-loop view are implementation choices only."""
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     test_random_soup_vs_c_oracle(seed, B, kw)

@@ -12,7 +12,7 @@ from tests.test_oracle_golden import cfg_from_meta
 from tests.randstate import random_batch
 
 
-@pytest.mark.parametrize("variant", ["fused", "generic_view", "split"])
+@pytest.mark.parametrize("variant", ["fused", "generic_view", "group32", "split"])
 @pytest.mark.parametrize("name", ROLLOUT_CASES)
 def test_hostsim_rollout_matches_reference(name, variant):
     d, meta = load_case(name)
@@ -21,7 +21,7 @@ def test_hostsim_rollout_matches_reference(name, variant):
         pytest.skip("split step/gen_obs is only equivalent without post-hook / auto-reset")
     B, T, J = meta["B"], meta["T"], meta["pool_J"]
     T = min(T, 150)
-    kw = dict(fused={}, generic_view=dict(generic=1),
+    kw = dict(fused={}, generic_view=dict(generic=1), group32=dict(forced_group=32),
               split=dict(split=True))[variant]
     sim = SimEngine(cfg, d["init_grid"], O.pack_agents(d["init_agents"]), d["pcg_state"],
                     d["pcg_inc"], pool_grid=d["pool_grid"],

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel-only timing sweep of the fused step+observe kernel over the launch knobs
-(MG_PPB, MG_NO_BULK, ...) and over the BASELINE.json configurations.
+(MG_GROUP, MG_WPB, MG_NO_BULK, ...) and over the BASELINE.json configurations.
 
     python tools/kbench.py [--configs empty8,bup,empty16] [--steps 200]
 
@@ -56,25 +56,26 @@ def time_config(name, steps, knobs, replicas=8):
         eng.load_state(np.repeat(pg, E, 0), np.repeat(pa, E, 0), None, st, inc, None)
         engines.append(eng)
     gen = torch.Generator(device=dev).manual_seed(7)
-    tape = torch.randint(0, 7, (32, E, n), generator=gen, device=dev, dtype=torch.int32).to(torch.int8)
-    for k in range(64):
-        engines[k % replicas].step(tape[k % 32])
+    NT = 256  # long tape: a short action cycle keeps agents near their start cells and flatters the kernel
+    tape = torch.randint(0, 7, (NT, E, n), generator=gen, device=dev, dtype=torch.int32).to(torch.int8)
+    for k in range(NT):
+        engines[k % replicas].step(tape[k % NT])
     torch.cuda.synchronize()
     bpe = bench.algorithmic_bytes_per_env_step(W, H, n, V, mutable)
     out = []
     for knob in knobs:
-        for key in ("MG_PPB", "MG_NO_BULK", "MG_GENERIC_VIEW"):
+        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW"):
             os.environ.pop(key, None)
         os.environ.update({k: str(v) for k, v in knob.items()})
         stream = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(stream):
             for k in range(4):
-                engines[k % replicas].step(tape[k % 32])
+                engines[k % replicas].step(tape[k % NT])
             stream.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
                 for k in range(steps):
-                    engines[k % replicas].step(tape[k % 32])
+                    engines[k % replicas].step(tape[k % NT])
         torch.cuda.synchronize()
         best = 1e9
         for rep in range(3):
@@ -97,15 +98,18 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="empty8")
     ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--ppbs", default="0,1,2")
+    ap.add_argument("--groups", default="0")
+    ap.add_argument("--wpbs", default="0")
     ap.add_argument("--nobulk", default="0")
     ap.add_argument("--extra", default="", help="comma list of extra KEY=VAL knob sets to also try, e.g. MG_GENERIC_STEP=1")
     args = ap.parse_args()
     knobs = []
-    for w, nb in itertools.product(args.ppbs.split(","), args.nobulk.split(",")):
+    for g, w, nb in itertools.product(args.groups.split(","), args.wpbs.split(","), args.nobulk.split(",")):
         k = {}
+        if int(g):
+            k["MG_GROUP"] = int(g)
         if int(w):
-            k["MG_PPB"] = int(w)
+            k["MG_WPB"] = int(w)
         if int(nb):
             k["MG_NO_BULK"] = 1
         knobs.append(k)

@@ -19,7 +19,7 @@ import bench, kbench  # noqa: E402
 from multigrid_b200 import _cabi  # noqa: E402
 from multigrid_b200.engine import EngineConfig, StepEngine  # noqa: E402
 
-ap = argparse.ArgumentParser(); ap.add_argument("--config", default="empty8"); ap.add_argument("--group", type=int, default=32)
+ap = argparse.ArgumentParser(); ap.add_argument("--config", default="empty8"); ap.add_argument("--group", type=int, default=16)
 args = ap.parse_args()
 W, H, n, V, E, max_steps, _ = kbench.CONFIGS[args.config]
 dev = torch.device("cuda", 0); lib = _cabi.load()
@@ -35,17 +35,13 @@ tape = torch.randint(0, 7, (32, E, n), device=dev, dtype=torch.int32).to(torch.i
 for k in range(96):
     engines[k % 8].step(tape[k % 32])
 torch.cuda.synchronize()
-groups = 2 * ((E + args.group - 1) // args.group)  # one record per warp: A and B of every pair
+groups = (E + args.group - 1) // args.group
 buf = torch.zeros((groups, 8), dtype=torch.int64, device=dev)
 lib.mg_debug_set_trace(buf.data_ptr())
 engines[0].step(tape[0])
 torch.cuda.synchronize()
 lib.mg_debug_set_trace(None)
-t_all = buf.cpu().numpy().astype(np.float64)
-for role, nm_role in ((0, "warp A (transition + last passes)"), (1, "warp B (first passes)")):
-    tt = t_all[role::2]
-    print(f"-- {nm_role}: life mean {(tt[:, 4] - tt[:, 0]).mean() / 1e3:.2f} us, ends at p50 {(np.percentile(tt[:, 4], 50) - t_all[:, 0].min()) / 1e3:.2f} us")
-t = t_all
+t = buf.cpu().numpy().astype(np.float64)
 t0 = t[:, 0].min()
 rel = (t[:, :5] - t0) / 1e3  # us
 names = ["start", "loaded", "stepped", "observed", "end"]
