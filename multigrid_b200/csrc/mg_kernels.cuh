@@ -711,24 +711,29 @@ MG_HD void obs_compute(const Params &p, const uint32_t *cells, uint32_t a0, uint
         c = (unsigned)c < (unsigned)g.Ll ? c : g.Ll;
         colp[a] = cell_base(cells) + c * g.stl;
     }
-    // all V*V gathers first (independent loads in flight together) ...
+    // Row by row, nearest first. A row is only gathered while something in it can still be visible:
+    // once the visibility mask entering a row is empty (the view is walled off), that row and all
+    // further rows are UNSEEN whatever they contain, so their loads are skipped -- in small rooms
+    // that is ~40 % of the gathers, and the shared-memory wavefronts of the gather are what bounds
+    // this phase.
+    uint32_t vis = 1u << half;                          // vis_mask[V//2][V-1] = True (utils/obs.py:252)
 #pragma unroll
     for (int b = V - 1; b >= 0; b--) {
         int r = g.pf + g.sf * (V - 1 - b);
         r = (unsigned)r < (unsigned)g.Lf ? r : g.Lf;
         const int rowoff = r * g.stf;
+        if (stw || vis != 0) {
 #pragma unroll
-        for (int a = V - 1; a >= 0; a--) {
-            if (b == V - 1 && a == half) cr[a * V + b] = g.carry;
-            else if (b == V - 1 && a == V - 1) cr[a * V + b] = cell_load<true>(colp[a] + rowoff);
-            else cr[a * V + b] = cell_load<false>(colp[a] + rowoff);
+            for (int a = V - 1; a >= 0; a--) {
+                if (b == V - 1 && a == half) cr[a * V + b] = g.carry;
+                else if (a == V - 1) cr[a * V + b] = cell_load<true>(colp[a] + rowoff);
+                else cr[a * V + b] = cell_load<false>(colp[a] + rowoff);
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < V; a++) cr[a * V + b] = 0;
         }
-    }
-    // ... then the row-by-row visibility scan and masking, on registers only
-    if (!stw) {
-        uint32_t vis = 1u << half;                      // vis_mask[V//2][V-1] = True (utils/obs.py:252)
-#pragma unroll
-        for (int b = V - 1; b >= 0; b--) {
+        if (!stw) {
             uint32_t opq = 0;
 #pragma unroll
             for (int a = V - 1; a >= 0; a--) opq = shl1_in(opq, cr[a * V + b]);
