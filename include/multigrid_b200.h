@@ -35,6 +35,7 @@
  *   pcg_state   uint64[2]         {lo,hi} of numpy PCG64's 128-bit state (env.np_random)
  *   pcg_inc     uint64[2]         {lo,hi} of its increment (constant)
  *   layout_idx  int32             cursor into the reset-layout pool (auto-reset only)
+ *   hook_state  int32             post-hook state (LockedHallway: unlocked-door colour bits)
  * Outputs per env:
  *   obs         int8  [n][obs_agent_stride]  first 3*V*V bytes of each agent slot = image[V][V][3]
  *   reward      float64 [n]       bit-exact `1 - 0.9*(step_count/max_steps)` (base.py:598-602)
@@ -50,7 +51,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 2
+#define MG_ABI_VERSION 3
 
 /* MgConfig.flags */
 #define MG_FLAG_SEE_THROUGH_WALLS 0x01u /* agents[0].see_through_walls, base.py:364-365 */
@@ -64,6 +65,7 @@ extern "C" {
 #define MG_HOOK_NONE 0
 #define MG_HOOK_BLOCKED_UNLOCK_PICKUP 1 /* envs/blockedunlockpickup.py:166-175 */
 #define MG_HOOK_RED_BLUE_DOORS 2        /* envs/redbluedoors.py:170-187 */
+#define MG_HOOK_LOCKED_HALLWAY 3        /* envs/locked_hallway.py:203-227; hook_param = number of rooms */
 
 #define MG_ERR_BAD_ARG   (-1)
 #define MG_ERR_ALIGNMENT (-2)
@@ -82,6 +84,7 @@ typedef struct MgConfig {
     int32_t obs_agent_stride;  /* bytes between agents in `obs`; multiple of 4, >= 3*V*V */
     int32_t num_layouts;       /* K: size of the reset-layout pool (auto-reset) */
     int32_t layout_stride;     /* on reset: layout_idx = (layout_idx + layout_stride) % K */
+    int32_t hook_param;        /* hook-specific constant (MG_HOOK_LOCKED_HALLWAY: number of rooms) */
 } MgConfig;
 
 typedef struct MgState {
@@ -93,6 +96,8 @@ typedef struct MgState {
     int32_t *layout_idx;       /* [E]      (may be NULL without MG_FLAG_AUTO_RESET) */
     const uint32_t *pool_grid; /* [K][W+1][H+1] cell words (may be NULL without MG_FLAG_AUTO_RESET) */
     const int8_t *pool_agents; /* [K][n][8]    (may be NULL without MG_FLAG_AUTO_RESET) */
+    int32_t *hook_state;       /* [E] per-env state of the post-hook; only MG_HOOK_LOCKED_HALLWAY uses it
+                                  (bit per door colour already unlocked); may be NULL otherwise */
 } MgState;
 
 typedef struct MgStepOut {

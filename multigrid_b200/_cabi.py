@@ -22,8 +22,9 @@ FLAG_AUTO_RESET = 0x20
 HOOK_NONE = 0
 HOOK_BLOCKED_UNLOCK_PICKUP = 1
 HOOK_RED_BLUE_DOORS = 2
+HOOK_LOCKED_HALLWAY = 3
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_VIEW = 15
 MAX_AGENTS = 32
 
@@ -33,7 +34,7 @@ class MgConfig(C.Structure):
         ("width", C.c_int32), ("height", C.c_int32), ("num_agents", C.c_int32),
         ("view_size", C.c_int32), ("max_steps", C.c_int32), ("flags", C.c_uint32),
         ("hook", C.c_int32), ("obs_agent_stride", C.c_int32), ("num_layouts", C.c_int32),
-        ("layout_stride", C.c_int32),
+        ("layout_stride", C.c_int32), ("hook_param", C.c_int32),
     ]
 
 
@@ -41,7 +42,7 @@ class MgState(C.Structure):
     _fields_ = [
         ("grid", C.c_void_p), ("agents", C.c_void_p), ("step_count", C.c_void_p),
         ("pcg_state", C.c_void_p), ("pcg_inc", C.c_void_p), ("layout_idx", C.c_void_p),
-        ("pool_grid", C.c_void_p), ("pool_agents", C.c_void_p),
+        ("pool_grid", C.c_void_p), ("pool_agents", C.c_void_p), ("hook_state", C.c_void_p),
     ]
 
 

@@ -81,7 +81,7 @@ int dispatch(const mg::Params &p, cudaStream_t stream) {
 void fill_config(mg::Params &p, const MgConfig *c, int64_t num_envs) {
     std::memset(&p, 0, sizeof(p));
     p.W = c->width; p.H = c->height; p.n = c->num_agents; p.V = c->view_size;
-    p.max_steps = c->max_steps; p.flags = c->flags; p.hook = c->hook;
+    p.max_steps = c->max_steps; p.flags = c->flags; p.hook = c->hook; p.hook_param = c->hook_param;
     p.ostride = c->obs_agent_stride; p.K = c->num_layouts; p.lstride = c->layout_stride;
     p.num_envs = (int32_t)num_envs;
     p.trace = g_trace.load(std::memory_order_relaxed);
@@ -95,6 +95,8 @@ int fill_state(mg::Params &p, const MgState *s) {
     p.grid = s->grid; p.agents = s->agents; p.step_count = s->step_count;
     p.pcg_state = s->pcg_state; p.pcg_inc = s->pcg_inc; p.layout_idx = s->layout_idx;
     p.pool_grid = s->pool_grid; p.pool_agents = s->pool_agents;
+    if (p.hook == MG_HOOK_LOCKED_HALLWAY && !s->hook_state) return MG_ERR_BAD_ARG;
+    p.hook_state = s->hook_state;
     return 0;
 }
 

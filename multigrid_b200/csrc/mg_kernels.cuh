@@ -61,11 +61,11 @@ struct Params {
     // config
     int32_t W, H, n, V, max_steps;
     uint32_t flags;
-    int32_t hook, ostride, K, lstride;
+    int32_t hook, hook_param, ostride, K, lstride;
     int32_t num_envs, G, wpb, use_bulk, generic_view;
     // state (device)
     uint32_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;
-    int32_t *layout_idx; const uint32_t *pool_grid; const int8_t *pool_agents;
+    int32_t *layout_idx; const uint32_t *pool_grid; const int8_t *pool_agents; int32_t *hook_state;
     const int8_t *actions;
     // outputs (device)
     int8_t *obs; double *reward; uint8_t *terminated; uint8_t *truncated; int32_t *status;
@@ -322,13 +322,13 @@ MG_HD int lane_env(const Params &p, const Group &g, int lane) {
 struct alignas(16) U128 { uint64_t lo, hi; };
 struct EnvRegs {
     uint64_t lo, hi, ilo, ihi;  // numpy PCG64 state / increment
-    int32_t sc, lidx;           // step_count, layout cursor
+    int32_t sc, lidx, hs;       // step_count, layout cursor, post-hook state
 };
 
 // ---- P0: load ------------------------------------------------------------------------------------
 template <int MODE>
 MG_HD void env_load(const Params &p, const Group &g, int i, EnvRegs &r) {
-    r.lo = r.hi = r.ilo = r.ihi = 0; r.sc = 0; r.lidx = 0;
+    r.lo = r.hi = r.ilo = r.ihi = 0; r.sc = 0; r.lidx = 0; r.hs = 0;
     if (MODE == MODE_OBS || i < 0) return;
     const size_t e = (size_t)(g.e0 + i);
     r.sc = p.step_count[e];
@@ -337,6 +337,7 @@ MG_HD void env_load(const Params &p, const Group &g, int i, EnvRegs &r) {
         r.lo = s.lo; r.hi = s.hi; r.ilo = c.lo; r.ihi = c.hi;
     }
     if (p.flags & MG_FLAG_AUTO_RESET) r.lidx = p.layout_idx[e];
+    if (p.hook == MG_HOOK_LOCKED_HALLWAY) r.hs = p.hook_state[e];
 }
 
 template <int MODE>
@@ -353,10 +354,13 @@ MG_HD void phase_reset(const Params &p, const Group &g, int i, EnvRegs &r) {
     uint32_t all_term = 1;
     for (int j = 0; j < p.n; j++) all_term &= ((g.ag[(i * p.n + j) * 2] >> 24) & 0xff) != 0;
     int k = -1;
+    // LockedHallway terminates in the returned dict only (all doors unlocked), never in agent state
+    if (p.hook == MG_HOOK_LOCKED_HALLWAY && __builtin_popcount((unsigned)r.hs) == p.hook_param) all_term = 1;
     if (all_term || r.sc >= p.max_steps) {
         k = (int)(((uint32_t)r.lidx + (uint32_t)p.lstride) % (uint32_t)p.K);
         r.lidx = k;
         r.sc = 0;
+        r.hs = 0;
         const uint32_t *src = (const uint32_t *)(p.pool_agents + (size_t)k * p.n * 8);
         for (int j = 0; j < p.n * 2; j++) g.ag[i * p.n * 2 + j] = src[j];
     }
@@ -569,6 +573,29 @@ MG_HD void hook_red_blue_doors(const Params &p, const Group &g, int i, const uin
     }
 }
 
+// LockedHallwayEnv.step post-hook (envs/locked_hallway.py:203-227): every agent whose action was
+// `toggle`, in agent order: the door in front of it is not locked and was not counted before ->
+// remember it (bit per door colour; colours are distinct for <= 6 rooms, :156-158) and ADD the
+// step's reward to every agent (joint) or to this agent. `bonus_all` / `bonus` count the additions.
+MG_HD void hook_locked_hallway(const Params &p, const Group &g, int i, const uint32_t *cells, const uint32_t *ag,
+                               int32_t &hs, uint32_t &bonus_all, uint32_t &bonus) {
+    const int n = p.n;
+    for (int k = 0; k < n; k++) {
+        if (g.act[i * n + k] != ACT_TOGGLE) continue;
+        const uint32_t a0 = ag[k * 2], dir = a0 & 3u;
+        const int fx = (int)((a0 >> 8) & 0xff) + (dir == 0) - (dir == 2);
+        const int fy = (int)((a0 >> 16) & 0xff) + (dir == 1) - (dir == 3);
+        if ((unsigned)fx >= (unsigned)p.W || (unsigned)fy >= (unsigned)p.H) continue;
+        const uint32_t cw = cells[fx * p.Hp + fy];
+        if ((cw & 0xff) != T_DOOR || ((cw >> 16) & 0xff) == S_LOCKED) continue;
+        const int32_t bit = 1 << ((cw >> 8) & 0x1f);
+        if (hs & bit) continue;
+        hs |= bit;
+        if (p.flags & MG_FLAG_JOINT_REWARD) bonus_all += 1;
+        else bonus |= 1u << k;
+    }
+}
+
 // The agent order of this step only needs the env's PCG64 registers, not the TMA-loaded state, so
 // it is drawn while the load is still in flight. `r` is advanced speculatively: phase_step keeps
 // the advanced state only if the env really steps (an env that auto-resets consumes no draw).
@@ -608,21 +635,33 @@ MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const 
                 if ((ag[k * 2 + 1] & 0xff) == T_BOX) on_success(p, ag, rewarded, k);
         }
         if (!was_reset && p.hook == MG_HOOK_RED_BLUE_DOORS) hook_red_blue_doors(p, g, i, cells, ag, rewarded);
+        uint32_t bonus_all = 0, bonus = 0;
+        bool dict_terminated = false;  // LockedHallway: all doors unlocked -> terminations dict only
+        if (p.hook == MG_HOOK_LOCKED_HALLWAY) {
+            if (!was_reset) hook_locked_hallway(p, g, i, cells, ag, r.hs, bonus_all, bonus);
+            dict_terminated = !was_reset && __builtin_popcount((unsigned)r.hs) == p.hook_param;
+            p.hook_state[e] = r.hs;
+        }
         if (MODE == MODE_STEP_OBS) stamp_agents(p, cells, ag, pre_hook_terminated);  // obs sees pre-hook state
         p.step_count[e] = r.sc;
         if (n > 1) { U128 s; s.lo = r.lo; s.hi = r.hi; *(U128 *)(p.pcg_state + 2 * e) = s; }
         if (p.flags & MG_FLAG_AUTO_RESET) p.layout_idx[e] = r.lidx;
         p.truncated[e] = (uint8_t)truncated;
-        const double rv = rewarded ? reward_value(r.sc, p.max_steps) : 0.0;  // base.py:394, 598-602
+        const double rv = (rewarded | bonus_all | bonus) ? reward_value(r.sc, p.max_steps) : 0.0;  // base.py:394, 598-602
         if (n == 4) {
             uint32_t tw = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) tw |= (uint32_t)(((ag[j * 2] >> 24) & 0xff) != 0) << (8 * j);
-            *(uint32_t *)(p.terminated + e * 4) = tw;
+            *(uint32_t *)(p.terminated + e * 4) = dict_terminated ? 0x01010101u : tw;
         } else {
-            for (int j = 0; j < n; j++) p.terminated[e * n + j] = (uint8_t)(((ag[j * 2] >> 24) & 0xff) != 0);
+            for (int j = 0; j < n; j++)
+                p.terminated[e * n + j] = (uint8_t)(dict_terminated || ((ag[j * 2] >> 24) & 0xff) != 0);
         }
-        for (int j = 0; j < n; j++) p.reward[e * n + j] = ((rewarded >> j) & 1u) ? rv : 0.0;
+        for (int j = 0; j < n; j++) {
+            double rj = ((rewarded >> j) & 1u) ? rv : 0.0;
+            for (uint32_t c = bonus_all + ((bonus >> j) & 1u); c > 0; c--) rj = rj + rv;  // rewards[k] += _reward()
+            p.reward[e * n + j] = rj;
+        }
     }
 }
 

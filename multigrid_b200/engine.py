@@ -33,6 +33,7 @@ class EngineConfig:
     success_termination_mode: str = "any"
     failure_termination_mode: str = "all"
     hook: int = _cabi.HOOK_NONE
+    hook_param: int = 0  # LockedHallway: number of rooms
     auto_reset: bool = False
     layout_stride: int = 1
 
@@ -95,6 +96,7 @@ class StepEngine:
         self.pcg_state = z((E, 2), torch.int64)
         self.pcg_inc = z((E, 2), torch.int64)
         self.layout_idx = z((E,), torch.int32)
+        self.hook_state = z((E,), torch.int32)
         self.actions = z((E, n), torch.int8)
         self.obs_buf = z((E, n, self.obs_stride), torch.int8)
         self.reward = z((E, n), torch.float64)
@@ -145,7 +147,7 @@ class StepEngine:
         self._c = None
 
     def load_state(self, grid=None, agents=None, step_count=None, pcg_state=None, pcg_inc=None,
-                   layout_idx=None) -> None:
+                   layout_idx=None, hook_state=None) -> None:
         """Inject state (numpy or torch, host or device). uint64 PCG words are passed as numpy."""
         def put(dst, src, bits64=False):
             if src is None:
@@ -162,6 +164,7 @@ class StepEngine:
         put(self.pcg_state, pcg_state, bits64=True)
         put(self.pcg_inc, pcg_inc, bits64=True)
         put(self.layout_idx, layout_idx)
+        put(self.hook_state, hook_state)
 
     def reset_from_pool(self, layout_idx=None) -> None:
         """Host-driven reset of every env from the layout pool (step_count := 0)."""
@@ -171,6 +174,7 @@ class StepEngine:
         self.cells.copy_(self.pool_grid[idx])
         self.agents.copy_(self.pool_agents[idx])
         self.step_count.zero_()
+        self.hook_state.zero_()
 
     # -- C structs ---------------------------------------------------------------------------
     def _structs(self):
@@ -181,11 +185,11 @@ class StepEngine:
             K = 0 if self.pool_grid is None else int(self.pool_grid.shape[0])
             c = _cabi.MgConfig(cfg.width, cfg.height, cfg.num_agents, cfg.view_size,
                                cfg.max_steps, cfg.flags, cfg.hook, self.obs_stride, K,
-                               cfg.layout_stride)
+                               cfg.layout_stride, cfg.hook_param)
             p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
             st = _cabi.MgState(p(self.cells), p(self.agents), p(self.step_count), p(self.pcg_state),
                                p(self.pcg_inc), p(self.layout_idx), p(self.pool_grid),
-                               p(self.pool_agents))
+                               p(self.pool_agents), p(self.hook_state))
             out = _cabi.MgStepOut(p(self.obs_buf), p(self.reward), p(self.terminated),
                                   p(self.truncated), p(self.status))
             self._c = (c, st, out)

@@ -161,7 +161,7 @@ class BatchedMultiGridEnv:
             see_through_walls=see_through_walls, allow_agent_overlap=allow_agent_overlap,
             joint_reward=joint_reward, success_termination_mode=success_termination_mode,
             failure_termination_mode=failure_termination_mode, hook=layout.hook,
-            auto_reset=auto_reset)
+            hook_param=getattr(layout, "hook_param", 0), auto_reset=auto_reset)
         self.engine = StepEngine(cfg, self.num_envs, device)
         self.device = self.engine.device
         self.grid = BatchedGrid(self.engine)

@@ -70,6 +70,11 @@ class Canvas:
     def rand_color(self) -> Color:
         return self.rand_elem(_COLORS)
 
+    def rand_perm(self, items) -> list:
+        items = list(items)  # RandomMixin._rand_perm (utils/random.py:77-85): Generator.shuffle on a list
+        self.rng.shuffle(items)
+        return items
+
     # -- Grid drawing (core/grid.py:133-195) --------------------------------------------------
     def set(self, x: int, y: int, cell) -> None:
         self.grid[x, y] = EMPTY_CELL if cell is None else cell
@@ -350,6 +355,54 @@ class PlaygroundLayout(Layout):
             c.add_object(col, row)
         for k in range(self.num_agents):
             c.place_agent_in_room(k)
+        c.check()
+        return c.grid, c.agents, {}
+
+
+class LockedHallwayLayout(Layout):
+    """LockedHallwayEnv._gen_grid (envs/locked_hallway.py:150-194)."""
+    hook = 3  # MG_HOOK_LOCKED_HALLWAY
+    mission = "unlock all the doors"
+
+    def __init__(self, num_agents, num_rooms=6, room_size=5, max_hallway_keys=1, max_keys_per_room=2,
+                 max_steps=None):
+        assert room_size >= 4 and num_rooms % 2 == 0
+        assert num_rooms <= len(_COLORS), "door identity is tracked by colour: at most 6 rooms"
+        self.num_rooms, self.room_size = num_rooms, room_size
+        self.max_hallway_keys, self.max_keys_per_room = max_hallway_keys, max_keys_per_room
+        self.hook_param = num_rooms
+        super().__init__((room_size - 1) * 3 + 1, (room_size - 1) * (num_rooms // 2) + 1, num_agents,
+                         max_steps or 8 * num_rooms * room_size ** 2)
+
+    def generate(self, layout_rng, order_rng):
+        LEFT, HALLWAY, RIGHT = range(3)
+        num_rows = self.num_rooms // 2
+        c = RoomCanvas(self.room_size, num_rows, 3, self.num_agents, layout_rng, order_rng)
+        color_sequence = _COLORS * -(-self.num_rooms // len(_COLORS))
+        color_sequence = c.rand_perm(color_sequence)[:self.num_rooms]
+        for row in range(num_rows - 1):
+            c.remove_wall(HALLWAY, row, Direction.down)
+        rooms = {}
+        door_colors = c.rand_perm(color_sequence)
+        for row in range(num_rows):
+            for col, direction in ((LEFT, Direction.right), (RIGHT, Direction.left)):
+                color = door_colors.pop()
+                rooms[color] = c.room(col, row)
+                c.add_door(col, row, direction=direction, color=color, locked=True, rand_pos=False)
+        num_hallway_keys = c.rand_int(1, self.max_hallway_keys + 1)
+        hallway_top = c.room(HALLWAY, 0).top
+        hallway_size = (c.room(HALLWAY, 0).size[0], c.height)
+        for key_color in color_sequence[:num_hallway_keys]:
+            c.place_obj(encode(Type.key, key_color), hallway_top, hallway_size)
+        key_index = num_hallway_keys
+        while key_index < len(color_sequence):
+            room = rooms[color_sequence[key_index - 1]]
+            num_room_keys = c.rand_int(1, self.max_keys_per_room + 1)
+            for key_color in color_sequence[key_index:key_index + num_room_keys]:
+                c.place_obj(encode(Type.key, key_color), room.top, room.size)
+                key_index += 1
+        for k in range(self.num_agents):  # MultiGridEnv.place_agent, not RoomGrid's (:193-194)
+            c.place_agent(k, hallway_top, hallway_size)
         c.check()
         return c.grid, c.agents, {}
 

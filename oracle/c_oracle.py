@@ -21,7 +21,7 @@ class _Cfg(C.Structure):
     _fields_ = [(k, C.c_int32) for k in (
         "W", "H", "n", "V", "max_steps", "see_through_walls", "allow_overlap", "joint_reward",
         "success_any", "failure_any", "hook", "auto_reset", "layout_stride", "num_layouts",
-        "obs_agent_stride")]
+        "obs_agent_stride", "hook_param")]
 
 
 def build(force: bool = False) -> str:
@@ -70,12 +70,14 @@ class COracle:
         self.c = _Cfg(cfg.W, cfg.H, cfg.n, cfg.V, cfg.max_steps, int(cfg.see_through_walls),
                       int(cfg.allow_agent_overlap), int(cfg.joint_reward), int(cfg.success_any),
                       int(cfg.failure_any), int(cfg.hook), int(cfg.auto_reset),
-                      int(cfg.layout_stride), int(self.pool_grid.shape[0]), self.stride)
+                      int(cfg.layout_stride), int(self.pool_grid.shape[0]), self.stride,
+                      int(cfg.hook_param))
         self.obs = np.zeros((self.B, cfg.n, self.stride), np.int8)
         self.reward = np.zeros((self.B, cfg.n), np.float64)
         self.terminated = np.zeros((self.B, cfg.n), np.uint8)
         self.truncated = np.zeros((self.B,), np.uint8)
         self.cell_flags = np.zeros((self.B, cfg.W * cfg.H), np.uint8)  # see mg_oracle.c handle_actions
+        self.hook_state = np.zeros((self.B,), np.int32)
 
     def _obs_view(self):
         V = self.cfg.V
@@ -93,7 +95,8 @@ class COracle:
             C.byref(self.c), C.c_int64(self.B), _p(self.grid), _p(self.agents),
             _p(self.step_count), _p(self.pcg_state), _p(self.pcg_inc), _p(self.layout_idx),
             _p(self.pool_grid), _p(self.pool_agents), _p(actions), _p(self.obs), _p(self.reward),
-            _p(self.terminated), _p(self.truncated), _p(self.cell_flags), C.c_int(self.nthreads))
+            _p(self.terminated), _p(self.truncated), _p(self.cell_flags), _p(self.hook_state),
+            C.c_int(self.nthreads))
         if rc == 1:
             raise ValueError("Unknown action")
         assert rc == 0

@@ -26,7 +26,7 @@ enum { T_UNSEEN, T_EMPTY, T_WALL, T_FLOOR, T_DOOR, T_KEY, T_BALL, T_BOX, T_GOAL,
 enum { S_OPEN, S_CLOSED, S_LOCKED };
 enum { ACT_LEFT, ACT_RIGHT, ACT_FORWARD, ACT_PICKUP, ACT_DROP, ACT_TOGGLE, ACT_DONE };
 enum { A_DIR, A_X, A_Y, A_TERM, A_CT, A_CC, A_CS, A_COLOR, A_DIM };
-enum { HOOK_NONE, HOOK_BUP, HOOK_RBD };
+enum { HOOK_NONE, HOOK_BUP, HOOK_RBD, HOOK_LH };
 
 #define MGO_MAX_AGENTS 64
 #define MGO_MAX_VIEW 31
@@ -36,6 +36,7 @@ typedef struct {
     int32_t see_through_walls, allow_overlap, joint_reward, success_any, failure_any;
     int32_t hook, auto_reset, layout_stride, num_layouts;
     int32_t obs_agent_stride; /* bytes between agents in obs (>= 3*V*V) */
+    int32_t hook_param;       /* LockedHallway: number of rooms (= doors) */
 } mgo_config;
 
 static const int DIR_DX[4] = {1, 0, -1, 0}; /* core/constants.py:21-30 */
@@ -278,12 +279,35 @@ static void hook_red_blue_doors(const mgo_config *c, int8_t *grid, int8_t *agent
     }
 }
 
+/* LockedHallwayEnv.step post-hook (envs/locked_hallway.py:203-227). *hook_state = bit per door COLOUR
+ * already unlocked (distinct colours for num_rooms <= 6, :156-158) = the reference's unlocked_doors. */
+static void hook_locked_hallway(const mgo_config *c, const int8_t *grid, const int8_t *agents,
+                                const int8_t *actions, double *rew, uint8_t *term, int32_t step_count,
+                                int32_t *hook_state) {
+    for (int k = 0; k < c->n; k++) {
+        if (actions[k] != ACT_TOGGLE) continue;
+        const int8_t *ag = agents + k * A_DIM;
+        int fx = ag[A_X] + DIR_DX[ag[A_DIR] & 3], fy = ag[A_Y] + DIR_DY[ag[A_DIR] & 3];
+        if (fx < 0 || fx >= c->W || fy < 0 || fy >= c->H) continue;
+        const int8_t *cell = grid + ((size_t)fx * c->H + fy) * 3;
+        if (cell[0] != T_DOOR || cell[2] == S_LOCKED) continue;
+        if ((*hook_state >> cell[1]) & 1) continue;
+        *hook_state |= 1 << cell[1];
+        double r = reward_value(step_count, c->max_steps);
+        if (c->joint_reward) for (int j = 0; j < c->n; j++) rew[j] = rew[j] + r; /* rewards[k] += _reward() */
+        else rew[k] = rew[k] + r;
+    }
+    if (__builtin_popcount((unsigned)*hook_state) == c->hook_param) /* returned dict only, not agent state */
+        for (int j = 0; j < c->n; j++) term[j] = 1;
+}
+
 /* MultiGridEnv.step (base.py:303-346) + env post-hook, with the engine's "next-step" auto-reset */
 int mgo_step_obs(const mgo_config *c, int64_t num_envs, int8_t *grid, int8_t *agents,
                  int32_t *step_count, uint64_t *pcg_state, const uint64_t *pcg_inc,
                  int32_t *layout_idx, const int8_t *pool_grid, const int8_t *pool_agents,
                  const int8_t *actions, int8_t *obs, double *reward, uint8_t *terminated,
-                 uint8_t *truncated, uint8_t *cell_flags /* [E][W*H] */, int nthreads) {
+                 uint8_t *truncated, uint8_t *cell_flags /* [E][W*H] */, int32_t *hook_state /* [E] */,
+                 int nthreads) {
     if (c->n > MGO_MAX_AGENTS || c->V > MGO_MAX_VIEW) return -1;
     size_t gsz = (size_t)c->W * c->H * 3, asz = (size_t)c->n * A_DIM;
     size_t osz = (size_t)c->n * c->obs_agent_stride;
@@ -301,12 +325,15 @@ int mgo_step_obs(const mgo_config *c, int64_t num_envs, int8_t *grid, int8_t *ag
             if (c->auto_reset) {
                 int all_term = 1;
                 for (int j = 0; j < n; j++) all_term &= (ag[j * A_DIM + A_TERM] != 0);
+                if (c->hook == HOOK_LH && __builtin_popcount((unsigned)hook_state[e]) == c->hook_param)
+                    all_term = 1; /* LockedHallway terminates in the returned dict only */
                 if (all_term || step_count[e] >= c->max_steps) { /* is_done, base.py:534-539 */
                     int32_t k = (int32_t)(((int64_t)layout_idx[e] + c->layout_stride) % c->num_layouts);
                     layout_idx[e] = k;
                     memcpy(g, pool_grid + (size_t)k * gsz, gsz);
                     memcpy(ag, pool_agents + (size_t)k * asz, asz);
                     memset(cell_flags + e * (size_t)c->W * c->H, 0, (size_t)c->W * c->H);
+                    hook_state[e] = 0;
                     step_count[e] = 0;
                     gen_obs_env(c, g, ag, obs + e * osz, scratch);
                     for (int j = 0; j < n; j++) term[j] = 0;
@@ -326,6 +353,8 @@ int mgo_step_obs(const mgo_config *c, int64_t num_envs, int8_t *grid, int8_t *ag
                     if (ag[j * A_DIM + A_CT] == T_BOX) on_success(c, ag, j, rew, term, step_count[e]);
             if (c->hook == HOOK_RBD) /* envs/redbluedoors.py:170-187 */
                 hook_red_blue_doors(c, g, ag, actions + e * n, rew, term, step_count[e], cf);
+            if (c->hook == HOOK_LH)
+                hook_locked_hallway(c, g, ag, actions + e * n, rew, term, step_count[e], hook_state + e);
         }
         free(scratch);
     }

@@ -34,7 +34,7 @@ DIR_TO_VEC = ((1, 0), (0, 1), (-1, 0), (0, -1))  # core/constants.py:21-30
 WALL_ENCODING = (WALL, 5, 0)  # utils/obs.py:14  (grey wall)
 A_DIR, A_X, A_Y, A_TERM, A_CT, A_CC, A_CS, A_COLOR = range(8)
 
-HOOK_NONE, HOOK_BUP, HOOK_RBD = 0, 1, 2
+HOOK_NONE, HOOK_BUP, HOOK_RBD, HOOK_LH = 0, 1, 2, 3
 RED, BLUE = 0, 2  # core/constants.py:51-60
 
 M64 = (1 << 64) - 1
@@ -55,6 +55,7 @@ class OracleConfig:
     success_any: bool = True             # success_termination_mode == 'any' (base.py:97)
     failure_any: bool = False            # failure_termination_mode == 'any' (base.py:98)
     hook: int = HOOK_NONE                # env-specific step() post-hook
+    hook_param: int = 0                  # LockedHallway: number of rooms (= doors)
     auto_reset: bool = False             # engine extension ("next-step" reset), see DESIGN.md
     layout_stride: int = 1
 
@@ -252,7 +253,8 @@ def handle_actions_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, action
                 grid[fx, fy] = (EMPTY, 0, 0)
 
 
-def step_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions, cell_flags=None):
+def step_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions, cell_flags=None,
+             hook_state=None):
     """`MultiGridEnv.step` (base.py:303-346) + env post-hook for one env.
 
     Returns (obs, reward f64 (n,), terminated u8 (n,), truncated bool, new_step_count).
@@ -288,6 +290,28 @@ def step_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions, cell_fl
             else:
                 _on_failure(cfg, agents, k, terminated)
                 cell_flags[fx, fy] |= 1  # self.blue_door.is_open = False, WITHOUT grid.update()
+    if cfg.hook == HOOK_LH:  # envs/locked_hallway.py:203-227
+        # hook_state[0] = bit per door COLOUR already unlocked (doors have distinct colours for
+        # num_rooms <= 6, envs/locked_hallway.py:156-158): the reference's `unlocked_doors` list
+        for k in range(n):
+            if actions[k] != TOGGLE:
+                continue
+            dx, dy = DIR_TO_VEC[int(agents[k, A_DIR]) & 3]
+            fx, fy = int(agents[k, A_X]) + dx, int(agents[k, A_Y]) + dy
+            if not (0 <= fx < cfg.W and 0 <= fy < cfg.H):
+                continue
+            t, c, s = (int(v) for v in grid[fx, fy])
+            if t != DOOR or s == LOCKED:
+                continue
+            if not (int(hook_state[0]) >> c) & 1:
+                hook_state[0] = int(hook_state[0]) | (1 << c)
+                r = _reward(step_count, cfg.max_steps)
+                if cfg.joint_reward:
+                    rewards[:] = rewards + r  # rewards[k] += self._reward() for every k
+                else:
+                    rewards[k] = rewards[k] + r
+        if bin(int(hook_state[0])).count("1") == cfg.hook_param:  # all doors unlocked
+            terminated[:] = 1  # the returned dict only: agent state is NOT terminated
     return obs, rewards, terminated, truncated, step_count
 
 
@@ -338,6 +362,7 @@ class OracleBatch:
                            else np.array(layout_idx, dtype=np.int32))
         self.done = np.zeros(self.B, dtype=bool)
         self.cell_flags = np.zeros(self.grid.shape[:3], dtype=np.uint8)  # see handle_actions_env
+        self.hook_state = np.zeros((self.B, 1), dtype=np.int32)
 
     def gen_obs(self):
         return np.stack([gen_obs_env(self.cfg, self.grid[b], self.agents[b])
@@ -351,6 +376,8 @@ class OracleBatch:
         trunc = np.zeros((self.B,), np.uint8)
         for b in range(self.B):
             done = bool(self.agents[b, :, A_TERM].all()) or self.step_count[b] >= cfg.max_steps
+            if cfg.hook == HOOK_LH:  # its termination lives in the returned dict only (all doors unlocked)
+                done = done or bin(int(self.hook_state[b, 0])).count("1") == cfg.hook_param
             if cfg.auto_reset and done:
                 K = self.pool_grid.shape[0]
                 self.layout_idx[b] = (int(self.layout_idx[b]) + cfg.layout_stride) % K
@@ -358,11 +385,12 @@ class OracleBatch:
                 self.agents[b] = self.pool_agents[self.layout_idx[b]]
                 self.step_count[b] = 0
                 self.cell_flags[b] = 0
+                self.hook_state[b] = 0
                 obs[b] = gen_obs_env(cfg, self.grid[b], self.agents[b])
                 continue
             o, r, t, tr, sc = step_env(cfg, self.grid[b], self.agents[b], self.step_count[b],
                                        self.pcg_state[b], self.pcg_inc[b], actions[b],
-                                       self.cell_flags[b])
+                                       self.cell_flags[b], self.hook_state[b])
             obs[b], rew[b], term[b], trunc[b] = o, r, t, tr
             self.step_count[b] = sc
         return obs, rew, term, trunc

@@ -216,7 +216,9 @@ def run_case(name, env_id, kwargs, B, T, seed, p_absent=0.0, action_p=None, auto
         joint_reward=int(env0.joint_reward),
         success_any=int(env0.success_termination_mode == "any"),
         failure_any=int(env0.failure_termination_mode == "any"),
-        hook={"BlockedUnlockPickupEnv": 1, "RedBlueDoorsEnv": 2}.get(type(env0).__name__, 0),
+        hook={"BlockedUnlockPickupEnv": 1, "RedBlueDoorsEnv": 2, "LockedHallwayEnv": 3}.get(
+            type(env0).__name__, 0),
+        hook_param=getattr(env0, "num_rooms", 0),
         auto_reset=int(auto_reset), pool_J=J,
     )
     rec = dict(
@@ -323,6 +325,23 @@ def rbd_open_doors(env):
         env.agents[1].state.dir = 2
 
 
+def lh_keys_at_doors(env):
+    """Hand agent k the key of the k-th door and put it in the hallway cell in front of that door,
+    facing it, so that unlock rewards (joint and not), repeated toggles of an already unlocked
+    door and the all-doors-unlocked termination (envs/locked_hallway.py:203-227) occur under
+    random actions. State injection only."""
+    from multigrid.core.world_object import Door as _Door, Key as _Key
+    doors = [(x, y, env.grid.get(x, y)) for x in range(env.width) for y in range(env.height)
+             if isinstance(env.grid.get(x, y), _Door)]
+    hall_x0 = env.get_room(1, 0).top[0]
+    for k, agent in enumerate(env.agents):
+        x, y, door = doors[k % len(doors)]
+        left_door = x == hall_x0  # door in the hallway's left wall: stand right of it, face left
+        agent.state.pos = (x + 1, y) if left_door else (x - 1, y)
+        agent.state.dir = 2 if left_door else 0
+        agent.state.carrying = _Key(door.color)
+
+
 TOGGLE_HEAVY = [0.10, 0.10, 0.15, 0.05, 0.05, 0.50, 0.05]
 
 if __name__ == "__main__":
@@ -391,3 +410,12 @@ if __name__ == "__main__":
                   joint_reward=False), B=8, T=150, seed=41, action_p=TOGGLE_HEAVY, tweak=rbd_open_doors)
     run_case("rbd_n2_autoreset", "MultiGrid-RedBlueDoors-6x6-v0", dict(agents=2, max_steps=40),
              B=4, T=160, seed=42, action_p=TOGGLE_HEAVY, auto_reset=True)
+    # LockedHallway post-hook (first-unlock rewards that ADD UP, termination only in the returned dict)
+    run_case("lh2_n2", "MultiGrid-LockedHallway-2Rooms-v0", dict(agents=2), B=6, T=80, seed=50,
+             action_p=TOGGLE_HEAVY, tweak=lh_keys_at_doors)
+    run_case("lh4_n3_nojoint", "MultiGrid-LockedHallway-4Rooms-v0", dict(agents=3, joint_reward=False),
+             B=6, T=80, seed=51, action_p=TOGGLE_HEAVY, tweak=lh_keys_at_doors)
+    run_case("lh6_n4", "MultiGrid-LockedHallway-6Rooms-v0", dict(agents=4), B=4, T=100, seed=52,
+             action_p=FWD_HEAVY)
+    run_case("lh2_n2_autoreset", "MultiGrid-LockedHallway-2Rooms-v0", dict(agents=2, max_steps=30),
+             B=4, T=120, seed=53, action_p=TOGGLE_HEAVY, auto_reset=True, tweak=lh_keys_at_doors)

@@ -16,7 +16,8 @@ def engine_config(cfg) -> EngineConfig:
         joint_reward=cfg.joint_reward,
         success_termination_mode="any" if cfg.success_any else "all",
         failure_termination_mode="any" if cfg.failure_any else "all",
-        hook=cfg.hook, auto_reset=cfg.auto_reset, layout_stride=cfg.layout_stride)
+        hook=cfg.hook, hook_param=getattr(cfg, "hook_param", 0), auto_reset=cfg.auto_reset,
+        layout_stride=cfg.layout_stride)
 
 
 class GpuEngine:

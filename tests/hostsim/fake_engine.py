@@ -19,7 +19,7 @@ class HostSimStepEngine:
             W=W, H=H, n=n, V=cfg.view_size, max_steps=cfg.max_steps,
             see_through_walls=cfg.see_through_walls, allow_agent_overlap=cfg.allow_agent_overlap,
             joint_reward=cfg.joint_reward, success_any=cfg.success_termination_mode == "any",
-            failure_any=cfg.failure_termination_mode == "any", hook=cfg.hook,
+            failure_any=cfg.failure_termination_mode == "any", hook=cfg.hook, hook_param=cfg.hook_param,
             auto_reset=cfg.auto_reset, layout_stride=cfg.layout_stride)
         self._pending = dict(grid=np.zeros((E, W, H, 3), np.int8), agents=np.zeros((E, n, 8), np.int8),
                              pcg_state=np.zeros((E, 2), np.uint64), pcg_inc=np.zeros((E, 2), np.uint64),

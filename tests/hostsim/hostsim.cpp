@@ -86,14 +86,14 @@ extern "C" int sim_run(int mode, const MgConfig *c, int64_t num_envs, const MgSt
     mg::Params p;
     std::memset(&p, 0, sizeof(p));
     p.W = c->width; p.H = c->height; p.n = c->num_agents; p.V = c->view_size;
-    p.max_steps = c->max_steps; p.flags = c->flags; p.hook = c->hook;
+    p.max_steps = c->max_steps; p.flags = c->flags; p.hook = c->hook; p.hook_param = c->hook_param;
     p.ostride = c->obs_agent_stride; p.K = c->num_layouts; p.lstride = c->layout_stride;
     p.num_envs = (int32_t)num_envs;
     p.generic_view = generic & 1;
     if (mode == mg::MODE_OBS) p.flags &= ~MG_FLAG_AUTO_RESET;
     p.grid = s->grid; p.agents = s->agents; p.step_count = s->step_count;
     p.pcg_state = s->pcg_state; p.pcg_inc = s->pcg_inc; p.layout_idx = s->layout_idx;
-    p.pool_grid = s->pool_grid; p.pool_agents = s->pool_agents;
+    p.pool_grid = s->pool_grid; p.pool_agents = s->pool_agents; p.hook_state = s->hook_state;
     p.actions = actions;
     p.obs = o->obs; p.reward = o->reward; p.terminated = o->terminated; p.truncated = o->truncated;
     p.status = o->status;

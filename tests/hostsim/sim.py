@@ -104,17 +104,20 @@ class SimEngine:
                  | (_cabi.FLAG_FAILURE_ANY if cfg.failure_any else 0)
                  | (_cabi.FLAG_AUTO_RESET if cfg.auto_reset else 0))
         self.c = _cabi.MgConfig(cfg.W, cfg.H, cfg.n, cfg.V, cfg.max_steps, flags, cfg.hook,
-                                self.stride, self.pool_grid.shape[0], cfg.layout_stride)
+                                self.stride, self.pool_grid.shape[0], cfg.layout_stride,
+                                getattr(cfg, "hook_param", 0))
         self.obs = aligned((self.B, cfg.n, self.stride), np.int8)
         self.obs[...] = 0x55
         self.reward = aligned((self.B, cfg.n), np.float64)
         self.terminated = aligned((self.B, cfg.n), np.uint8)
         self.truncated = aligned((self.B,), np.uint8)
         self.status = aligned((1,), np.int32)
+        self.hook_state = aligned((self.B,), np.int32)
         self.state = _cabi.MgState(_p(self.cells).value, _p(self.agents).value,
                                    _p(self.step_count).value, _p(self.pcg_state).value,
                                    _p(self.pcg_inc).value, _p(self.layout_idx).value,
-                                   _p(self.pool_grid).value, _p(self.pool_agents).value)
+                                   _p(self.pool_grid).value, _p(self.pool_agents).value,
+                                   _p(self.hook_state).value)
         self.out = _cabi.MgStepOut(_p(self.obs).value, _p(self.reward).value,
                                    _p(self.terminated).value, _p(self.truncated).value,
                                    _p(self.status).value)

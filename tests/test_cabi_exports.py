@@ -42,8 +42,8 @@ def test_abi_version_and_pure_helpers(lib):
 
 
 def test_struct_sizes_match_header():
-    assert C.sizeof(_cabi.MgConfig) == 40
-    assert C.sizeof(_cabi.MgState) == 64
+    assert C.sizeof(_cabi.MgConfig) == 44
+    assert C.sizeof(_cabi.MgState) == 72
     assert C.sizeof(_cabi.MgStepOut) == 40
 
 

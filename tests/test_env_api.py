@@ -32,6 +32,7 @@ CASES = [
     ("empty8_n4_joint_stw", "MultiGrid-Empty-8x8-v0",
      dict(agents=4, joint_reward=True, see_through_walls=True, agent_view_size=5), 7),
     ("playground_n3", "MultiGrid-Playground-v0", dict(agents=3), 8),
+    ("lh6_n4", "MultiGrid-LockedHallway-6Rooms-v0", dict(agents=4), 52),
 ]
 # (fixtures whose initial state was tweaked after reset are covered at the engine level only)
 
@@ -40,8 +41,6 @@ def test_registry_covers_the_reference_ids():
     assert sorted(list(CONFIGURATIONS) + list(NOT_YET)) == sorted(REFERENCE_IDS)
     with pytest.raises(KeyError):
         make("MultiGrid-Nope-v0")
-    with pytest.raises(NotImplementedError):
-        make("MultiGrid-LockedHallway-2Rooms-v0")
 
 
 def test_pcg64_words_match_numpy_generators():

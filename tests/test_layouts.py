@@ -24,6 +24,7 @@ CASES = [
     ("bup_n2", 3, lambda n: L.BlockedUnlockPickupLayout(n)),
     ("playground_n3", 8, lambda n: L.PlaygroundLayout(n)),
     ("rbd_n2_autoreset", 42, lambda n: L.RedBlueDoorsLayout(n, size=6, max_steps=40)),
+    ("lh6_n4", 52, lambda n: L.LockedHallwayLayout(n, num_rooms=6)),
 ]
 
 

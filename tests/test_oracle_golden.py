@@ -14,6 +14,7 @@ def cfg_from_meta(meta):
         allow_agent_overlap=bool(meta["allow_agent_overlap"]),
         joint_reward=bool(meta["joint_reward"]), success_any=bool(meta["success_any"]),
         failure_any=bool(meta["failure_any"]), hook=int(meta["hook"]),
+        hook_param=int(meta.get("hook_param", 0)),
         auto_reset=bool(meta["auto_reset"]), layout_stride=1)
 
 
