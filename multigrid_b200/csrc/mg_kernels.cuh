@@ -648,19 +648,23 @@ MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const 
         if (p.flags & MG_FLAG_AUTO_RESET) p.layout_idx[e] = r.lidx;
         p.truncated[e] = (uint8_t)truncated;
         const double rv = (rewarded | bonus_all | bonus) ? reward_value(r.sc, p.max_steps) : 0.0;  // base.py:394, 598-602
+        const uint32_t term_force = dict_terminated ? 0x01010101u : 0u;
         if (n == 4) {
             uint32_t tw = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) tw |= (uint32_t)(((ag[j * 2] >> 24) & 0xff) != 0) << (8 * j);
-            *(uint32_t *)(p.terminated + e * 4) = dict_terminated ? 0x01010101u : tw;
+            *(uint32_t *)(p.terminated + e * 4) = tw | term_force;
         } else {
             for (int j = 0; j < n; j++)
-                p.terminated[e * n + j] = (uint8_t)(dict_terminated || ((ag[j * 2] >> 24) & 0xff) != 0);
+                p.terminated[e * n + j] = (uint8_t)((term_force & 1u) | (((ag[j * 2] >> 24) & 0xff) != 0));
         }
-        for (int j = 0; j < n; j++) {
-            double rj = ((rewarded >> j) & 1u) ? rv : 0.0;
-            for (uint32_t c = bonus_all + ((bonus >> j) & 1u); c > 0; c--) rj = rj + rv;  // rewards[k] += _reward()
-            p.reward[e * n + j] = rj;
+        for (int j = 0; j < n; j++) p.reward[e * n + j] = ((rewarded >> j) & 1u) ? rv : 0.0;
+        if (bonus_all | bonus) {  // LockedHallway only: rewards[k] += self._reward(), once per new door
+            for (int j = 0; j < n; j++) {
+                double rj = ((rewarded >> j) & 1u) ? rv : 0.0;
+                for (uint32_t c = bonus_all + ((bonus >> j) & 1u); c > 0; c--) rj = rj + rv;
+                p.reward[e * n + j] = rj;
+            }
         }
     }
 }
