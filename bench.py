@@ -32,6 +32,11 @@ MAX_STEPS = 4 * SIZE * SIZE  # envs/empty.py:145
 REPLICAS = 8   # state replicas rotated through so each launch finds its inputs in HBM, not L2
 BURN_IN = 64   # untimed steps that de-synchronise the envs before anything is measured
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used if MEASURED_PEAKS.json is absent
+# dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch of the fused kernel, from the
+# `ncu --set full` capture summarised in profiles/r01_summary.md (r01c): 26.30 MB read (= the layout's
+# 401 B/env of inputs) + 3.04 MB written; the other ~41.6 MB of outputs are still dirty in the 126 MB L2
+# when the kernel ends (ncu flushes before each replay) and reach HBM during later launches.
+NCU_DRAM_BYTES_PER_LAUNCH = 29_338_880
 
 
 def algorithmic_bytes_per_env_step(W, H, n, V, mutable_grid=False):
@@ -326,7 +331,10 @@ def run_engine(args):
                     "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_note": "ncu dram read+write bytes of one launch (profiles/r01_summary.md); "
+                                         "outputs still dirty in L2 at kernel end are not in it",
+                         "algorithmic_bytes_per_launch": bpe * E, "peak_source": peak_src,
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "algorithmic_bytes_per_env_step": bpe,
                          "actual_bytes_per_env_step": layout_bytes_per_env_step(SIZE, SIZE, n, VIEW),
