@@ -130,6 +130,16 @@ int mg_pack_grid(int32_t width, int32_t height, int64_t num_envs, const int8_t *
 int mg_unpack_grid(int32_t width, int32_t height, int64_t num_envs, const uint32_t *cells, int8_t *grid3,
                    void *stream);
 
+/*
+ * One-hot encoding of a batch of observations: obs int8 [A][obs_agent_stride] (A = all agents of all
+ * envs, images in the first 3*V*V bytes) -> out uint8 [A][V][V][21], channels = 11 type + 6 colour +
+ * 4 state/direction. Replaces: OneHotObsWrapper.one_hot (multigrid/wrappers.py:158-190), which the
+ * reference's RLlib registration always applies (multigrid/rllib/__init__.py:110-111).
+ */
+#define MG_ONE_HOT_CHANNELS 21
+int mg_one_hot(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
+               uint8_t *out, void *stream);
+
 /* Diagnostics: when set to a device buffer of 8 uint64 per warp (= per group of envs), every
  * following launch records %globaltimer at its phase boundaries (slots 0..4) and the SM id (slot 7).
  * NULL (the default) disables it. Used by tools/trace_timeline.py; not part of the hot path. */

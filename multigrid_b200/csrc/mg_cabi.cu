@@ -160,6 +160,20 @@ int mg_pack_grid(int32_t width, int32_t height, int64_t num_envs, const int8_t *
     return (int)cudaGetLastError();
 }
 
+int mg_one_hot(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
+               uint8_t *out, void *stream) {
+    if (view_size < 3 || view_size > MG_MAX_VIEW || num_agents_total < 0 ||
+        obs_agent_stride < 3 * view_size * view_size) return MG_ERR_BAD_ARG;
+    if (num_agents_total == 0) return 0;
+    if (!obs || !out) return MG_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(out) & 3u) return MG_ERR_ALIGNMENT;
+    const int64_t words = (num_agents_total * view_size * view_size * 21 + 3) / 4;
+    mg::one_hot_kernel<<<(unsigned)((words + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        view_size, num_agents_total, obs_agent_stride, obs, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 int mg_unpack_grid(int32_t width, int32_t height, int64_t num_envs, const uint32_t *cells, int8_t *grid3,
                    void *stream) {
     if (width < 1 || height < 1 || width > 127 || height > 127 || num_envs < 0) return MG_ERR_BAD_ARG;

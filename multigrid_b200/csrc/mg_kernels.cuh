@@ -959,6 +959,32 @@ __global__ void unpack_grid_kernel(int W, int H, int64_t total, const uint32_t *
 }
 
 // <= 4 warps per block; register cap: 72 (7 blocks x 128 threads per SM) up to V = 7, 128 for V = 9
+// OneHotObsWrapper.one_hot (multigrid/wrappers.py:158-190) over a whole observation batch:
+// image (type,color,state) -> 21 channels = 11 type + 6 colour + 4 state/direction, uint8.
+// The output [agents][V][V][21] is written as one flat stream of 32-bit words (4 channels each).
+__global__ void one_hot_kernel(int V, int64_t agents, int ostride, const int8_t *__restrict__ obs,
+                               uint8_t *__restrict__ out) {
+    const int64_t per_agent = (int64_t)V * V * 21, total = agents * per_agent;
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, p0 = 4 * w;
+    if (p0 >= total) return;
+    uint32_t word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const int64_t pos = p0 + b;
+        if (pos >= total) break;
+        const int64_t agent = pos / per_agent;
+        const int rem = (int)(pos - agent * per_agent), cell = rem / 21, ch = rem - cell * 21;
+        const int8_t *src = obs + agent * ostride + cell * 3;
+        const int hit = ch < 11 ? (src[0] == ch) : ch < 17 ? (src[1] == ch - 11) : (src[2] == ch - 17);
+        word |= (uint32_t)hit << (8 * b);
+    }
+    if (p0 + 4 <= total) {
+        *(uint32_t *)(out + p0) = word;
+    } else {
+        for (int b = 0; p0 + b < total; b++) out[p0 + b] = (uint8_t)(word >> (8 * b));
+    }
+}
+
 template <int VT, int MODE>
 __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem[];

@@ -1,0 +1,87 @@
+"""Batched counterparts of the reference's observation / agent wrappers (multigrid/wrappers.py).
+
+They wrap a `BatchedMultiGridEnv` and keep its batched, on-device conventions:
+  * `OneHotObsWrapper`  (wrappers.py:101-190): image -> uint8 (E, V, V, 21) one-hot, by the CUDA
+    kernel `mg_one_hot` (no torch fallback);
+  * `ImgObsWrapper`     (wrappers.py:61-98):  observations are the bare image tensors;
+  * `SingleAgentWrapper`(wrappers.py:193-233): agent 0's items instead of per-agent dicts.
+`FullyObsWrapper` (the whole grid as the image) is not built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi, spaces
+
+ONE_HOT_CHANNELS = 21  # len(Type) + len(Color) + max(len(State), len(Direction)), wrappers.py:140-141
+
+
+class _Wrapper:
+    def __init__(self, env):
+        self.env = env
+
+    def __getattr__(self, name):  # gym.Wrapper forwards unknown attributes to the wrapped env
+        return getattr(self.env, name)
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+    def observation(self, obs):
+        return obs
+
+    def reset(self, *args, **kwargs):
+        obs, infos = self.env.reset(*args, **kwargs)
+        return self.observation(obs), infos
+
+    def step(self, actions):
+        obs, rewards, terminations, truncations, infos = self.env.step(actions)
+        return self.observation(obs), rewards, terminations, truncations, infos
+
+
+class OneHotObsWrapper(_Wrapper):
+    """Images become one-hot: 11 type + 6 colour + 4 state/direction channels per cell."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        base = env.unwrapped
+        E, n, V = base.num_envs, base.num_agents, base.agent_view_size
+        self._out = torch.zeros((E, n, V, V, ONE_HOT_CHANNELS), dtype=torch.uint8, device=base.device)
+        for agent in base.agents:
+            agent.observation_space["image"] = spaces.Box(low=0, high=1, shape=(V, V, ONE_HOT_CHANNELS),
+                                                          dtype=np.uint8)
+
+    def observation(self, obs):
+        base = self.env.unwrapped
+        eng = base.engine
+        with torch.cuda.device(base.device):
+            _cabi.check(eng.lib.mg_one_hot(base.agent_view_size, base.num_envs * base.num_agents,
+                                           eng.obs_stride, eng.obs_buf.data_ptr(), self._out.data_ptr(),
+                                           C.c_void_p(torch.cuda.current_stream(base.device).cuda_stream)),
+                        "mg_one_hot")
+        for i in obs:
+            obs[i]["image"] = self._out[:, i]
+        return obs
+
+
+class ImgObsWrapper(_Wrapper):
+    def observation(self, obs):
+        return {i: o["image"] for i, o in obs.items()}
+
+
+class SingleAgentWrapper(_Wrapper):
+    """Agent 0's view of a (possibly multi-agent) env: `step(action)` acts for agent 0 only."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = env.unwrapped.agents[0].observation_space
+        self.action_space = env.unwrapped.agents[0].action_space
+
+    def reset(self, *args, **kwargs):
+        return tuple(item[0] for item in self.env.reset(*args, **kwargs))
+
+    def step(self, action):
+        return tuple(item[0] for item in self.env.step({0: action}))

@@ -315,6 +315,18 @@ def step_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions, cell_fl
     return obs, rewards, terminated, truncated, step_count
 
 
+def one_hot(x, dim_sizes=(11, 6, 4)):
+    """OneHotObsWrapper.one_hot (multigrid/wrappers.py:158-190): (..., h, w, 3) ints -> uint8
+    (..., h, w, sum(dim_sizes)); channel = offset of the dimension + value."""
+    x = np.asarray(x)
+    out = np.zeros(x.shape[:-1] + (sum(dim_sizes),), dtype=np.uint8)
+    offset = 0
+    for d, size in enumerate(dim_sizes):
+        np.put_along_axis(out, (offset + x[..., d:d + 1]).astype(np.int64), 1, axis=-1)
+        offset += size
+    return out
+
+
 # --- batched driver (mirrors the engine's fused mg_step_obs incl. its auto-reset extension) ---
 def pack_agents(ref_agents: np.ndarray) -> np.ndarray:
     """Reference AgentState (..., 9) -> packed (..., 8)."""

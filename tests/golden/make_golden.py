@@ -238,6 +238,24 @@ def run_case(name, env_id, kwargs, B, T, seed, p_absent=0.0, action_p=None, auto
           f"-> {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def one_hot_kat(name, seed=3, cases=24):
+    """OneHotObsWrapper.one_hot (wrappers.py:158-190, numba) on observation-shaped arrays."""
+    from multigrid.wrappers import OneHotObsWrapper
+    rng = np.random.default_rng(seed)
+    dim_sizes = np.array([11, 6, 4])
+    xs, outs = [], []
+    for c in range(cases):
+        V = (3, 5, 7, 9)[c % 4]
+        x = np.stack([rng.integers(0, 11, (V, V)), rng.integers(0, 6, (V, V)), rng.integers(0, 4, (V, V))], -1)
+        out = OneHotObsWrapper.one_hot(x.astype(np.int64), dim_sizes)
+        pad = np.zeros((9, 9, 3), np.int8); pad[:V, :V] = x
+        po = np.zeros((9, 9, 21), np.uint8); po[:V, :V] = out
+        xs.append(pad); outs.append(po)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), x=np.stack(xs), out=np.stack(outs),
+                        V=np.array([(3, 5, 7, 9)[c % 4] for c in range(cases)]))
+    print(f"{name}: ok")
+
+
 def random_obs_cases(name, seed, cases=400):
     """Pure-function golden vectors for utils/obs.py:66-102 on injected random states."""
     rng = np.random.default_rng(seed)
@@ -359,6 +377,9 @@ if __name__ == "__main__":
     def random_obs_cases(name, *a, **k):  # noqa: F811
         if not only or name in only:
             _random_obs_cases(name, *a, **k)
+
+    if not only or "one_hot_kat" in only:
+        one_hot_kat("one_hot_kat")
 
     pcg_kat("pcg64_kat")
     random_obs_cases("obs_random", seed=11)

@@ -224,3 +224,45 @@ def test_misaligned_pointer_is_rejected():
     assert rc == -2
     c.view_size = 4
     assert lib.mg_gen_obs(C.byref(c), 1, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), None) == -1
+
+
+@pytest.mark.parametrize("V,A", [(7, 1000), (3, 5), (9, 33), (5, 4096)])
+def test_one_hot_kernel_vs_oracle(V, A):
+    import ctypes as C
+    import torch
+    from multigrid_b200 import _cabi
+    lib = _cabi.load()
+    rng = np.random.default_rng(V * 100 + A)
+    stride = _cabi.obs_agent_stride(V)
+    img = np.stack([rng.integers(0, 11, (A, V, V)), rng.integers(0, 6, (A, V, V)), rng.integers(0, 4, (A, V, V))], -1)
+    buf = np.zeros((A, stride), np.int8)
+    buf[:, :3 * V * V] = img.reshape(A, -1)
+    obs = torch.from_numpy(buf).cuda()
+    out = torch.full((A, V, V, 21), 7, dtype=torch.uint8, device="cuda")
+    assert lib.mg_one_hot(V, A, stride, obs.data_ptr(), out.data_ptr(), None) == 0
+    np.testing.assert_array_equal(out.cpu().numpy(), O.one_hot(img))
+
+
+def test_wrappers_on_gpu():
+    import torch
+    from multigrid_b200.envs import make
+    from multigrid_b200.wrappers import ImgObsWrapper, OneHotObsWrapper, SingleAgentWrapper
+    env = make("MultiGrid-Empty-8x8-v0", agents=3, num_envs=50, device="cuda:0")
+    obs, _ = env.reset(seed=1)
+    plain = {i: obs[i]["image"].cpu().numpy().copy() for i in obs}
+    oh = OneHotObsWrapper(env)
+    obs, _ = oh.reset(seed=1)
+    for i in obs:
+        assert obs[i]["image"].shape == (50, 7, 7, 21) and obs[i]["image"].dtype == torch.uint8
+        np.testing.assert_array_equal(obs[i]["image"].cpu().numpy(), O.one_hot(plain[i]))
+    assert oh.agents[0].observation_space["image"].shape == (7, 7, 21)
+    obs, rew, term, trunc, _ = oh.step({0: 2, 1: 1, 2: 0})
+    np.testing.assert_array_equal(obs[1]["image"].cpu().numpy(), O.one_hot(env.engine.obs[:, 1].cpu().numpy()))
+    img = ImgObsWrapper(env)
+    o, _ = img.reset(seed=1)
+    assert o[0].shape == (50, 7, 7, 3)
+    single = SingleAgentWrapper(make("MultiGrid-Empty-5x5-v0", agents=1, num_envs=8, device="cuda:0"))
+    o, info = single.reset(seed=0)
+    assert set(o) == {"image", "direction", "mission"}
+    o, r, te, tr, info = single.step(2)
+    assert r.shape == (8,) and te.dtype == torch.bool

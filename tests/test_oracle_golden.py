@@ -67,3 +67,10 @@ def test_rollout_matches_reference(name, impl):
         np.testing.assert_array_equal(term, d["terminated"][t], err_msg=msg)
         np.testing.assert_array_equal(trunc, d["truncated"][t], err_msg=msg)
         np.testing.assert_array_equal(ob.step_count, d["step_count"][t], err_msg=msg)
+
+
+def test_one_hot_matches_reference_numba():
+    d = np.load(f"{GOLDEN_DIR}/one_hot_kat.npz")
+    for c in range(len(d["V"])):
+        V = int(d["V"][c])
+        np.testing.assert_array_equal(O.one_hot(d["x"][c, :V, :V]), d["out"][c, :V, :V])
