@@ -122,6 +122,13 @@ int step_common(const MgConfig *cfg, int64_t num_envs, const MgState *state, con
     if ((rc = fill_out(p, out, MODE == mg::MODE_STEP_OBS))) return rc;
     p.actions = actions;
     if ((rc = plan(p))) return rc;
+    // natural alignment of the per-env scalars (16-byte PCG words, 8-byte rewards, 4-byte counters and
+    // the packed 4-agent terminated word) is required; 16-byte alignment of everything enables TMA
+    auto misaligned = [](const void *ptr, uintptr_t a) { return (reinterpret_cast<uintptr_t>(ptr) & (a - 1)) != 0; };
+    if (misaligned(p.pcg_state, 16) || misaligned(p.pcg_inc, 16) || misaligned(p.reward, 8) ||
+        misaligned(p.step_count, 4) || misaligned(p.layout_idx, 4) || misaligned(p.hook_state, 4) ||
+        misaligned(p.terminated, 4) || misaligned(p.pool_grid, 4))
+        return MG_ERR_ALIGNMENT;
     // TMA bulk copies need 16-byte aligned spans; the small arrays may fall back to plain copies
     if (!aligned16(p.actions) || !aligned16(p.step_count) || !aligned16(p.pcg_state) || !aligned16(p.pcg_inc) ||
         !aligned16(p.layout_idx) || !aligned16(p.reward) || !aligned16(p.terminated) || !aligned16(p.truncated))
