@@ -131,6 +131,14 @@ int mg_unpack_grid(int32_t width, int32_t height, int64_t num_envs, const uint32
                    void *stream);
 
 /*
+ * Fully observable image: out int8 [E][W][H][3] = Grid.state with every agent (terminated or not)
+ * written over its cell as (agent, colour, dir), highest agent index last.
+ * Replaces: FullyObsWrapper.observation (multigrid/wrappers.py:50-58).
+ */
+int mg_full_obs(int32_t width, int32_t height, int32_t num_agents, int64_t num_envs, const uint32_t *cells,
+                const int8_t *agents, int8_t *out, void *stream);
+
+/*
  * One-hot encoding of a batch of observations: obs int8 [A][obs_agent_stride] (A = all agents of all
  * envs, images in the first 3*V*V bytes) -> out uint8 [A][V][V][21], channels = 11 type + 6 colour +
  * 4 state/direction. Replaces: OneHotObsWrapper.one_hot (multigrid/wrappers.py:158-190), which the

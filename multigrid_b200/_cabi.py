@@ -61,6 +61,8 @@ EXPORTS = {
     "mg_debug_set_trace": (None, [C.c_void_p]),
     "mg_cells_per_env": (C.c_int64, [C.c_int32, C.c_int32]),
     "mg_pack_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mg_full_obs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p]),
     "mg_one_hot": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_unpack_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_gen_obs": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,

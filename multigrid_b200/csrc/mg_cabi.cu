@@ -167,6 +167,19 @@ int mg_pack_grid(int32_t width, int32_t height, int64_t num_envs, const int8_t *
     return (int)cudaGetLastError();
 }
 
+int mg_full_obs(int32_t width, int32_t height, int32_t num_agents, int64_t num_envs, const uint32_t *cells,
+                const int8_t *agents, int8_t *out, void *stream) {
+    if (width < 1 || height < 1 || width > 127 || height > 127 || num_envs < 0 || num_agents < 1 ||
+        num_agents > MG_MAX_AGENTS) return MG_ERR_BAD_ARG;
+    if (num_envs == 0) return 0;
+    if (!cells || !agents || !out) return MG_ERR_BAD_ARG;
+    const int64_t total = num_envs * width * height;
+    mg::full_obs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        width, height, num_agents, total, cells, agents, out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 int mg_one_hot(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
                uint8_t *out, void *stream) {
     if (view_size < 3 || view_size > MG_MAX_VIEW || num_agents_total < 0 ||

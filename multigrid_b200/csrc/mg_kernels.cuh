@@ -959,6 +959,24 @@ __global__ void unpack_grid_kernel(int W, int H, int64_t total, const uint32_t *
 }
 
 // <= 4 warps per block; register cap: 72 (7 blocks x 128 threads per SM) up to V = 7, 128 for V = 9
+// FullyObsWrapper.observation (multigrid/wrappers.py:50-58): the whole grid as (W,H,3) bytes with
+// EVERY agent (terminated or not) written over its cell as (agent, colour, dir), ascending agent
+// index (the highest index wins). One thread per (env, cell).
+__global__ void full_obs_kernel(int W, int H, int n, int64_t total, const uint32_t *__restrict__ cells,
+                                const int8_t *__restrict__ agents, int8_t *__restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over E*W*H
+    if (idx >= total) return;
+    const int64_t e = idx / (W * H);
+    const int c = (int)(idx - e * (W * H)), x = c / H, y = c - x * H;
+    uint32_t w = cells[e * (int64_t)(W + 1) * (H + 1) + x * (H + 1) + y];
+    const int8_t *ag = agents + e * n * 8;
+    for (int j = 0; j < n; j++)
+        if (ag[j * 8 + 1] == x && ag[j * 8 + 2] == y)
+            w = T_AGENT | ((uint32_t)(uint8_t)ag[j * 8 + 7] << 8) | ((uint32_t)(uint8_t)ag[j * 8] << 16);
+    uint8_t *dst = (uint8_t *)out + idx * 3;
+    dst[0] = (uint8_t)w; dst[1] = (uint8_t)(w >> 8); dst[2] = (uint8_t)(w >> 16);
+}
+
 // OneHotObsWrapper.one_hot (multigrid/wrappers.py:158-190) over a whole observation batch:
 // image (type,color,state) -> 21 channels = 11 type + 6 colour + 4 state/direction, uint8.
 // The output [agents][V][V][21] is written as one flat stream of 32-bit words (4 channels each).

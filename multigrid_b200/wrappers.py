@@ -5,7 +5,8 @@ They wrap a `BatchedMultiGridEnv` and keep its batched, on-device conventions:
     kernel `mg_one_hot` (no torch fallback);
   * `ImgObsWrapper`     (wrappers.py:61-98):  observations are the bare image tensors;
   * `SingleAgentWrapper`(wrappers.py:193-233): agent 0's items instead of per-agent dicts.
-`FullyObsWrapper` (the whole grid as the image) is not built.
+  * `FullyObsWrapper`   (wrappers.py:17-58):  the whole grid with all agents drawn in, the same
+    (E, W, H, 3) int8 tensor for every agent, by the CUDA kernel `mg_full_obs`.
 """
 from __future__ import annotations
 
@@ -64,6 +65,31 @@ class OneHotObsWrapper(_Wrapper):
                         "mg_one_hot")
         for i in obs:
             obs[i]["image"] = self._out[:, i]
+        return obs
+
+
+class FullyObsWrapper(_Wrapper):
+    """Every agent observes the whole grid (Grid.encode + every agent's encoding on its cell)."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        base = env.unwrapped
+        self._out = torch.zeros((base.num_envs, base.width, base.height, 3), dtype=torch.int8,
+                                device=base.device)
+        for agent in base.agents:  # the reference declares (height, width, 3); the array is (W, H, 3)
+            agent.observation_space["image"] = spaces.Box(low=0, high=255, shape=(base.height, base.width, 3),
+                                                          dtype=np.int64)
+
+    def observation(self, obs):
+        base = self.env.unwrapped
+        eng = base.engine
+        with torch.cuda.device(base.device):
+            _cabi.check(eng.lib.mg_full_obs(base.width, base.height, base.num_agents, base.num_envs,
+                                            eng.cells.data_ptr(), eng.agents.data_ptr(), self._out.data_ptr(),
+                                            C.c_void_p(torch.cuda.current_stream(base.device).cuda_stream)),
+                        "mg_full_obs")
+        for i in obs:
+            obs[i]["image"] = self._out
         return obs
 
 

@@ -315,6 +315,15 @@ def step_env(cfg, grid, agents, step_count, pcg_state, pcg_inc, actions, cell_fl
     return obs, rewards, terminated, truncated, step_count
 
 
+def full_obs(grid, agents):
+    """FullyObsWrapper.observation (multigrid/wrappers.py:50-58) for one env: Grid.encode() with every
+    agent's (agent, colour, dir) on its cell, ascending agent index. `agents` = packed (n, 8)."""
+    img = np.array(grid, dtype=np.int8)
+    for k in range(agents.shape[0]):
+        img[agents[k, A_X], agents[k, A_Y]] = (AGENT, agents[k, A_COLOR], agents[k, A_DIR])
+    return img
+
+
 def one_hot(x, dim_sizes=(11, 6, 4)):
     """OneHotObsWrapper.one_hot (multigrid/wrappers.py:158-190): (..., h, w, 3) ints -> uint8
     (..., h, w, sum(dim_sizes)); channel = offset of the dimension + value."""

@@ -256,6 +256,33 @@ def one_hot_kat(name, seed=3, cases=24):
     print(f"{name}: ok")
 
 
+def full_obs_kat(name, seed=9):
+    """FullyObsWrapper (wrappers.py:17-58) images along short reference rollouts, with the state they
+    were made from (one agent is terminated by hand so that terminated agents are covered)."""
+    from multigrid.wrappers import FullyObsWrapper
+    rng = np.random.default_rng(seed)
+    grids, agents, imgs, dims = [], [], [], []
+    for env_id, kw in (("MultiGrid-Empty-8x8-v0", dict(agents=3)),
+                       ("MultiGrid-BlockedUnlockPickup-v0", dict(agents=2)),
+                       ("MultiGrid-Empty-Random-6x6-v0", dict(agents=4))):
+        env = FullyObsWrapper(make_env(env_id, kw, layout_seed=seed, order_seed=seed + 1))
+        obs, _ = env.reset()
+        base = env.unwrapped
+        for t in range(25):
+            if t == 10:
+                base.agents[0].state.terminated = True
+            act = {i: int(rng.integers(0, 7)) for i in range(base.num_agents)}
+            obs, *_ = env.step(act)
+            W, H = base.width, base.height
+            g = np.zeros((16, 16, 3), np.int8); g[:W, :H] = base.grid.state
+            im = np.zeros((16, 16, 3), np.int8); im[:W, :H] = obs[0]["image"]
+            a = np.zeros((4, 9), np.int8); a[:base.num_agents] = np.asarray(base.agent_states)
+            grids.append(g); imgs.append(im); agents.append(a); dims.append((W, H, base.num_agents))
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), grid=np.stack(grids), agents=np.stack(agents),
+                        img=np.stack(imgs), dims=np.array(dims))
+    print(f"{name}: {len(dims)} states")
+
+
 def random_obs_cases(name, seed, cases=400):
     """Pure-function golden vectors for utils/obs.py:66-102 on injected random states."""
     rng = np.random.default_rng(seed)
@@ -380,6 +407,8 @@ if __name__ == "__main__":
 
     if not only or "one_hot_kat" in only:
         one_hot_kat("one_hot_kat")
+    if not only or "full_obs_kat" in only:
+        full_obs_kat("full_obs_kat")
 
     pcg_kat("pcg64_kat")
     random_obs_cases("obs_random", seed=11)

@@ -10,7 +10,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ROLLOUT_CASES = sorted(
     os.path.splitext(os.path.basename(p))[0]
     for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-    if os.path.basename(p) not in ("obs_random.npz", "pcg64_kat.npz", "one_hot_kat.npz")
+    if os.path.basename(p) not in ("obs_random.npz", "pcg64_kat.npz", "one_hot_kat.npz", "full_obs_kat.npz")
 )
 
 

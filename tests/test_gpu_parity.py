@@ -266,3 +266,35 @@ def test_wrappers_on_gpu():
     assert set(o) == {"image", "direction", "mission"}
     o, r, te, tr, info = single.step(2)
     assert r.shape == (8,) and te.dtype == torch.bool
+
+
+def test_full_obs_kernel_vs_reference_wrapper():
+    import ctypes as C
+    import torch
+    from multigrid_b200 import _cabi
+    from tests.hostsim.sim import pack_cells
+    lib = _cabi.load()
+    d = np.load(f"{GOLDEN_DIR}/full_obs_kat.npz")
+    for c in range(len(d["dims"])):
+        W, H, n = (int(v) for v in d["dims"][c])
+        cells = torch.from_numpy(pack_cells(d["grid"][c:c + 1, :W, :H]).view(np.int32)).cuda()
+        agents = torch.from_numpy(O.pack_agents(d["agents"][c:c + 1, :n])).cuda()
+        out = torch.zeros((1, W, H, 3), dtype=torch.int8, device="cuda")
+        assert lib.mg_full_obs(W, H, n, 1, cells.data_ptr(), agents.data_ptr(), out.data_ptr(), None) == 0
+        np.testing.assert_array_equal(out.cpu().numpy()[0], d["img"][c, :W, :H], err_msg=f"state {c}")
+
+
+def test_fully_obs_wrapper_on_gpu():
+    from multigrid_b200.envs import make
+    from multigrid_b200.wrappers import FullyObsWrapper
+    env = FullyObsWrapper(make("MultiGrid-BlockedUnlockPickup-v0", agents=2, num_envs=40, device="cuda:0",
+                               layout_seed=3))
+    obs, _ = env.reset(seed=2)
+    rng = np.random.default_rng(0)
+    for t in range(20):
+        obs, *_ = env.step(rng.integers(0, 7, (40, 2)).astype(np.int8))
+        base = env.unwrapped
+        grid, agents = base.grid.state.cpu().numpy(), base.agent_states.cpu().numpy()
+        want = np.stack([O.full_obs(grid[e], agents[e]) for e in range(40)])
+        assert obs[0]["image"].shape == (40, 11, 6, 3) and obs[1]["image"] is obs[0]["image"]
+        np.testing.assert_array_equal(obs[0]["image"].cpu().numpy(), want)

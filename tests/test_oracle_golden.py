@@ -74,3 +74,11 @@ def test_one_hot_matches_reference_numba():
     for c in range(len(d["V"])):
         V = int(d["V"][c])
         np.testing.assert_array_equal(O.one_hot(d["x"][c, :V, :V]), d["out"][c, :V, :V])
+
+
+def test_full_obs_matches_reference_wrapper():
+    d = np.load(f"{GOLDEN_DIR}/full_obs_kat.npz")
+    for c in range(len(d["dims"])):
+        W, H, n = (int(v) for v in d["dims"][c])
+        got = O.full_obs(d["grid"][c, :W, :H], O.pack_agents(d["agents"][c, :n]))
+        np.testing.assert_array_equal(got, d["img"][c, :W, :H], err_msg=f"state {c}")
