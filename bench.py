@@ -36,7 +36,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used if MEASU
 # `ncu --set full` capture summarised in profiles/r01_summary.md (r01c): 26.30 MB read (= the layout's
 # 401 B/env of inputs) + 3.04 MB written; the other ~41.6 MB of outputs are still dirty in the 126 MB L2
 # when the kernel ends (ncu flushes before each replay) and reach HBM during later launches.
-NCU_DRAM_BYTES_PER_LAUNCH = 29_338_880
+NCU_DRAM_BYTES_PER_LAUNCH = 28382976  # profiles/r01d_ncu_details.txt: dram read 26 297 856 + write 2 085 120
 
 
 def algorithmic_bytes_per_env_step(W, H, n, V, mutable_grid=False):
@@ -211,7 +211,8 @@ def workload_config(n_gpus):
         "agents": N_AGENTS, "view_size": VIEW, "grid": f"{SIZE}x{SIZE}", "max_steps": MAX_STEPS,
         "sharding": f"env axis split over {n_gpus} GPU(s), no collective on the step path",
         "l2": f"{REPLICAS} state replicas rotated (each launch touches a batch last used "
-              f"{REPLICAS} launches ago; {REPLICAS}x61 MB > 126 MB L2), no explicit flush",
+              f"{REPLICAS} launches ago; {REPLICAS}x61 MB > 126 MB L2), no explicit flush; "
+              "MG_FLAG_STREAM_STATE (L2 evict_first on state loads / obs stores, cache policy only)",
     }
 
 
@@ -236,7 +237,7 @@ def run_engine(args):
     E, n = ENVS_PER_GPU, N_AGENTS
 
     cfg = EngineConfig(width=SIZE, height=SIZE, num_agents=n, view_size=VIEW, max_steps=MAX_STEPS,
-                       auto_reset=True)
+                       auto_reset=True, stream_state=True)
     pg, pa = empty_layout(SIZE, n)
     engines = []
     for r in range(REPLICAS):
@@ -288,6 +289,28 @@ def run_engine(args):
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
 
+    # ---- informational: the same K launches as TWO independent chains (even / odd replicas on two
+    # graph branches), i.e. two env batches in flight: one batch's load phase overlaps the other's
+    # compute tail. Reported under "two_chains", never as `value`.
+    side = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        graph2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph2, stream=stream):
+            side.wait_stream(stream)
+            for k in range(K):
+                with torch.cuda.stream(stream if k % 2 == 0 else side):
+                    launch(Wm + k)
+            stream.wait_stream(side)
+        graph2.replay()
+    torch.cuda.synchronize()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev2.record(stream)
+        graph2.replay()
+        ev3.record(stream)
+    torch.cuda.synchronize()
+    ms2 = ev2.elapsed_time(ev3)
+
     # ---- `e2e`: the host-buffer call (mg_step_obs_host): H2D actions, kernel, D2H results -------
     eng = engines[0]
     h = eng.host_buffers()
@@ -307,10 +330,10 @@ def run_engine(args):
     checksum = int(h["obs"].view(torch.uint8).sum()) + float(h["reward"].sum())
     clocks = sampler.stop()
 
-    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s, ms2], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_s = float(t[0]), float(t[1])
+    ms, e2e_s, ms2 = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         total_envs = E * world
@@ -341,6 +364,11 @@ def run_engine(args):
                          "kernel": "mg::step_obs_kernel<7, MODE_STEP_OBS> (one launch = 65536 env-steps)",
                          "avg_launch_us": 1e3 * ms / K},
         }
+        line["two_chains"] = {
+            "note": "informational, not `value`: the same K launches issued as two independent replica chains "
+                    "(two env batches in flight on two graph branches)",
+            "us_per_launch": 1e3 * ms2 / K, "value": total_envs * n * K / (ms2 * 1e-3),
+            "achieved_gbs": bpe * E / (ms2 * 1e-3 / K) / 1e9}
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
             v, done, dt = time_cpu_oracle(E, 10**9, 2, cores, budget_s=args.cpu_seconds)

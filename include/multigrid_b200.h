@@ -60,6 +60,11 @@ extern "C" {
 #define MG_FLAG_SUCCESS_ANY       0x08u /* success_termination_mode == 'any'          */
 #define MG_FLAG_FAILURE_ANY       0x10u /* failure_termination_mode == 'any'          */
 #define MG_FLAG_AUTO_RESET        0x20u /* engine extension: "next-step" auto reset   */
+#define MG_FLAG_STREAM_STATE      0x40u /* cache policy only (results unchanged): grid/action loads and
+                                           observation stores get L2 evict_first priority. For batches that
+                                           are NOT re-stepped while still L2-resident (state larger than L2,
+                                           or several engines interleaved); leave it off when one batch that
+                                           fits L2 is stepped back to back. */
 
 /* MgConfig.hook: env-specific step() post-hooks */
 #define MG_HOOK_NONE 0

@@ -18,6 +18,7 @@ FLAG_JOINT_REWARD = 0x04
 FLAG_SUCCESS_ANY = 0x08
 FLAG_FAILURE_ANY = 0x10
 FLAG_AUTO_RESET = 0x20
+FLAG_STREAM_STATE = 0x40
 
 HOOK_NONE = 0
 HOOK_BLOCKED_UNLOCK_PICKUP = 1

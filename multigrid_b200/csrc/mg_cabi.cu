@@ -35,10 +35,12 @@ int validate(const MgConfig *c, int64_t num_envs) {
 }
 
 // Tuning / test knobs (read per call): MG_GROUP = envs per warp (16|32), MG_WPB = warps per block,
-// MG_NO_BULK=1 = plain loads/stores instead of TMA bulk copies.
+// MG_NO_BULK=1 = plain loads/stores instead of TMA bulk copies, MG_PDL=0 = no programmatic dependent
+// launch, MG_L2HINT = override of the MG_FLAG_STREAM_STATE cache policy (bit 0 loads, bit 1 obs stores).
 int plan(mg::Params &p) {
     p.use_bulk = env_int("MG_NO_BULK", 0) ? 0 : 1;
     p.generic_view = env_int("MG_GENERIC_VIEW", 0) ? 1 : 0;
+    p.l2hint = env_int("MG_L2HINT", (p.flags & MG_FLAG_STREAM_STATE) ? 3 : 0);
     return mg::plan_launch(p, env_int("MG_GROUP", 0), env_int("MG_WPB", 0), kSmemPerBlock, kSmemPerSM);
 }
 
@@ -55,9 +57,20 @@ int launch(const mg::Params &p, cudaStream_t stream) {
     }
     const int groups = (p.num_envs + p.G - 1) / p.G;
     const int blocks = (groups + p.wpb - 1) / p.wpb;
-    kernel<<<blocks, p.wpb * mg::LANES, p.wpb * p.warp_bytes, stream>>>(p);
+    cudaLaunchConfig_t lc;
+    std::memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)blocks); lc.blockDim = dim3((unsigned)(p.wpb * mg::LANES));
+    lc.dynamicSmemBytes = (size_t)(p.wpb * p.warp_bytes); lc.stream = stream;
+    // Programmatic dependent launch: the grid may be scheduled while the previous kernel of the
+    // stream drains; the kernel executes griddepcontrol.wait before its first global access, so
+    // stream-order semantics are unchanged (MG_PDL=0 turns the attribute off).
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = env_int("MG_PDL", 1) ? 1 : 0;
+    const cudaError_t err = cudaLaunchKernelEx(&lc, kernel, p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    return (int)cudaGetLastError();
+    return (int)err;
 }
 
 template <int MODE>

@@ -63,6 +63,7 @@ struct Params {
     uint32_t flags;
     int32_t hook, hook_param, ostride, K, lstride;
     int32_t num_envs, G, wpb, use_bulk, generic_view;
+    int32_t l2hint;  // bit 0: state TMA loads L2 evict_first; bit 1: obs TMA stores L2 evict_first
     // state (device)
     uint32_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;
     int32_t *layout_idx; const uint32_t *pool_grid; const int8_t *pool_agents; int32_t *hook_state;
@@ -899,6 +900,25 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
+// L2 eviction-priority variants (createpolicy + .L2::cache_hint)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_hint(void *dst_gmem, const void *src_smem, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol) : "memory");
+}
+// Programmatic dependent launch (PDL): `launch_dependents` lets the next kernel of the stream be
+// scheduled onto SM resources as this grid's blocks retire; `wait` blocks until the previous grid
+// has completed and its writes are visible. Both are no-ops for a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -925,6 +945,13 @@ __device__ __forceinline__ void load_bulk(const Params &p, const Group &g, uint6
     uint32_t total = G * p.cstride * 4 + G * n * 8;
     if (MODE != MODE_OBS) total += G * n;
     mbar_expect_tx(bar, total);
+    if (p.l2hint & 1) {
+        const uint64_t pol = l2_policy_evict_first();
+        bulk_g2s_hint(g.cells, p.grid + e0 * p.cstride, G * p.cstride * 4, bar, pol);
+        bulk_g2s(g.ag, p.agents + e0 * n * 8, G * n * 8, bar);  // stored back by this launch: keep
+        if (MODE != MODE_OBS) bulk_g2s_hint(g.act, p.actions + e0 * n, G * n, bar, pol);
+        return;
+    }
     bulk_g2s(g.cells, p.grid + e0 * p.cstride, G * p.cstride * 4, bar);
     bulk_g2s(g.ag, p.agents + e0 * n * 8, G * n * 8, bar);
     if (MODE != MODE_OBS) bulk_g2s(g.act, p.actions + e0 * n, G * n, bar);
@@ -1008,6 +1035,7 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = blockIdx.x * p.wpb + warp;
+    pdl_launch_dependents();
     if (group * p.G >= p.num_envs) return;  // whole warp
     uint8_t *ws = smem + warp * p.warp_bytes;
     const Group g = group_view(p, ws, group);
@@ -1018,11 +1046,10 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
     trace_mark(p, group, lane, 0);
     trace_mark(p, group, lane, 7);
 
+    if (bulk && lane == 0) mbar_init(bar, 1);
+    pdl_wait();  // nothing of the previous launch is read or overwritten before this point
     if (bulk) {
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            load_bulk<MODE>(p, g, bar);
-        }
+        if (lane == 0) load_bulk<MODE>(p, g, bar);
     } else {
         phase_load_plain<MODE>(p, g, lane);
     }
@@ -1070,8 +1097,9 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
                 if (lane == 0) {
                     const int left = g.ne * p.n - pass * LANES;
                     const uint32_t cnt = left < LANES ? left : LANES;
-                    bulk_s2g(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, stage,
-                             cnt * p.ostride);
+                    int8_t *dst = p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride;
+                    if (p.l2hint & 2) bulk_s2g_hint(dst, stage, cnt * p.ostride, l2_policy_evict_first());
+                    else bulk_s2g(dst, stage, cnt * p.ostride);
                     bulk_commit();
                 }
             } else {

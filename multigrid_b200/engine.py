@@ -36,6 +36,7 @@ class EngineConfig:
     hook_param: int = 0  # LockedHallway: number of rooms
     auto_reset: bool = False
     layout_stride: int = 1
+    stream_state: bool = False  # MG_FLAG_STREAM_STATE: L2 evict_first for state loads / obs stores (cache policy only)
 
     def __post_init__(self):
         if self.view_size % 2 != 1 or self.view_size < 3:  # core/agent.py:78-79
@@ -55,7 +56,8 @@ class EngineConfig:
                 | (_cabi.FLAG_JOINT_REWARD if self.joint_reward else 0)
                 | (_cabi.FLAG_SUCCESS_ANY if self.success_termination_mode == "any" else 0)
                 | (_cabi.FLAG_FAILURE_ANY if self.failure_termination_mode == "any" else 0)
-                | (_cabi.FLAG_AUTO_RESET if self.auto_reset else 0))
+                | (_cabi.FLAG_AUTO_RESET if self.auto_reset else 0)
+                | (_cabi.FLAG_STREAM_STATE if self.stream_state else 0))
 
 
 def _as_i64_bits(a) -> np.ndarray:

@@ -174,7 +174,8 @@ def test_full_size_configs_vs_c_oracle(label, size, n, V, E, hook):
 
 
 KNOBS = [dict(MG_NO_BULK="1"), dict(MG_GROUP="8"), dict(MG_GROUP="32"), dict(MG_GROUP="32", MG_WPB="1"),
-         dict(MG_WPB="2"), dict(MG_WPB="1", MG_NO_BULK="1"), dict(MG_GENERIC_VIEW="1")]
+         dict(MG_WPB="2"), dict(MG_WPB="1", MG_NO_BULK="1"), dict(MG_GENERIC_VIEW="1"),
+         dict(MG_PDL="1"), dict(MG_PDL="0"), dict(MG_L2HINT="3"), dict(MG_PDL="1", MG_L2HINT="1")]
 
 
 @pytest.mark.parametrize("knobs", KNOBS, ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
@@ -184,6 +185,39 @@ def test_launch_knobs_do_not_change_results(seed, B, kw, knobs, monkeypatch):
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     test_random_soup_vs_c_oracle(seed, B, kw)
+
+
+@pytest.mark.parametrize("pdl", ["0", "1"])
+def test_back_to_back_launches_without_host_sync(pdl, monkeypatch):
+    """T dependent launches enqueued on one stream with no synchronisation in between (eager and as a
+    CUDA graph): with programmatic dependent launch every launch may be scheduled while its
+    predecessor drains, and must still see all of the predecessor's writes."""
+    import torch
+    monkeypatch.setenv("MG_PDL", pdl)
+    cfg = O.OracleConfig(W=8, H=8, n=4, V=7, max_steps=40, auto_reset=True)
+    B, T = 20000, 48
+    st = random_batch(cfg, B, 5)
+    ora, g = COracle(cfg, nthreads=NTHREADS, **st), GpuEngine(cfg, **st)
+    rng = np.random.default_rng(3)
+    actions = rng.integers(0, 7, size=(2 * T, B, cfg.n)).astype(np.int8)
+    tape = torch.from_numpy(actions).cuda()
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for t in range(T):
+            g.eng.step(tape[t])
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for t in range(T, 2 * T):
+                g.eng.step(tape[t])
+        graph.replay()
+    torch.cuda.synchronize()
+    for t in range(2 * T):
+        o1, r1, t1, tr1 = ora.step(actions[t])
+    np.testing.assert_array_equal(g._obs(g.eng.obs_buf), o1)
+    assert (g.eng.reward.cpu().numpy() == r1).all()
+    np.testing.assert_array_equal(g.eng.terminated.cpu().numpy(), t1)
+    assert_same(g, ora, f"pdl={pdl}")
 
 
 @pytest.mark.parametrize("B", [1, 15, 16, 17, 31, 32, 33, 129])

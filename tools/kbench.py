@@ -64,7 +64,7 @@ def time_config(name, steps, knobs, replicas=8):
     bpe = bench.algorithmic_bytes_per_env_step(W, H, n, V, mutable)
     out = []
     for knob in knobs:
-        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW"):
+        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_X"):
             os.environ.pop(key, None)
         os.environ.update({k: str(v) for k, v in knob.items()})
         stream = torch.cuda.Stream(device=dev)
@@ -101,7 +101,7 @@ def main():
     ap.add_argument("--groups", default="0")
     ap.add_argument("--wpbs", default="0")
     ap.add_argument("--nobulk", default="0")
-    ap.add_argument("--extra", default="", help="comma list of extra KEY=VAL knob sets to also try, e.g. MG_GENERIC_STEP=1")
+    ap.add_argument("--extra", default="", help="comma list of extra KEY=VAL knob sets to also try, e.g. MG_PDL=1,MG_PDL=1+MG_L2HINT=3")
     args = ap.parse_args()
     knobs = []
     for g, w, nb in itertools.product(args.groups.split(","), args.wpbs.split(","), args.nobulk.split(",")):
@@ -114,8 +114,7 @@ def main():
             k["MG_NO_BULK"] = 1
         knobs.append(k)
         for kv in [x for x in args.extra.split(",") if x]:
-            key, val = kv.split("=")
-            knobs.append({**k, key: val})
+            knobs.append({**k, **dict(item.split("=") for item in kv.split("+"))})
     for name in args.configs.split(","):
         time_config(name, args.steps, knobs)
 
