@@ -46,6 +46,12 @@ def algorithmic_bytes_per_env_step(W, H, n, V, mutable_grid=False):
     return reads + writes
 
 
+def rollout_bytes_per_env_step(n, V):
+    """SURVEY.md §8(d), in-kernel multi-step rollout: state stays on chip, so the per-env-step floor
+    is actions in + outputs out (obs, f64 reward, terminated, truncated, direction)."""
+    return n + 3 * n * V * V + 8 * n + n + 1 + n
+
+
 def layout_bytes_per_env_step(W, H, n, V, auto_reset=True):
     """Bytes the engine's HBM layout actually moves per env-step: padded 4-byte
     cell words, 8-byte agent records, int32 counters, 148-byte obs slots."""

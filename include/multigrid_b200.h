@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 3
+#define MG_ABI_VERSION 4
 
 /* MgConfig.flags */
 #define MG_FLAG_SEE_THROUGH_WALLS 0x01u /* agents[0].see_through_walls, base.py:364-365 */
@@ -182,6 +182,29 @@ int mg_step(const MgConfig *cfg, int64_t num_envs, const MgState *state, const i
  * Replaces: MultiGridEnv.step (base.py:303-346). This is what BASELINE.json's metric measures. */
 int mg_step_obs(const MgConfig *cfg, int64_t num_envs, const MgState *state,
                 const int8_t *actions, const MgStepOut *out, void *stream);
+
+/*
+ * T consecutive fused steps in ONE launch (engine extension; the reference has no counterpart: its
+ * rollouts are a Python loop over env.step, e.g. scripts/visualize.py). Bit-identical to T calls of
+ * mg_step_obs with actions[t] whose outputs go to slice t of the output arrays, but the agents and
+ * the per-env scalars stay on chip between steps, warps run ahead of each other (no launch
+ * boundary per step) and the cells are re-read from L2 instead of HBM. For open-loop action
+ * tapes: random-policy rollouts, scripted policies, replays.
+ *   actions     int8 [T][E][n]
+ *   out->obs    int8 [T][E][n][obs_agent_stride];  direction int8 [T][E][n] (may be NULL)
+ *   reward      float64 [T][E][n];  terminated uint8 [T][E][n];  truncated uint8 [T][E]
+ */
+typedef struct MgRolloutOut {
+    int8_t *obs;
+    int8_t *direction;
+    double *reward;
+    uint8_t *terminated;
+    uint8_t *truncated;
+    int32_t *status;
+} MgRolloutOut;
+
+int mg_rollout(const MgConfig *cfg, int64_t num_envs, int32_t num_steps, const MgState *state,
+               const int8_t *actions, const MgRolloutOut *out, void *stream);
 
 /*
  * Host-buffer variant of mg_step_obs (what a CPU-side caller of env.step() sees):

@@ -25,7 +25,7 @@ HOOK_BLOCKED_UNLOCK_PICKUP = 1
 HOOK_RED_BLUE_DOORS = 2
 HOOK_LOCKED_HALLWAY = 3
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_VIEW = 15
 MAX_AGENTS = 32
 
@@ -54,6 +54,13 @@ class MgStepOut(C.Structure):
     ]
 
 
+class MgRolloutOut(C.Structure):
+    _fields_ = [
+        ("obs", C.c_void_p), ("direction", C.c_void_p), ("reward", C.c_void_p),
+        ("terminated", C.c_void_p), ("truncated", C.c_void_p), ("status", C.c_void_p),
+    ]
+
+
 EXPORTS = {
     "mg_abi_version": (C.c_int, []),
     "mg_error_string": (C.c_char_p, [C.c_int]),
@@ -72,6 +79,8 @@ EXPORTS = {
                           C.POINTER(MgStepOut), C.c_void_p]),
     "mg_step_obs": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p,
                               C.POINTER(MgStepOut), C.c_void_p]),
+    "mg_rollout": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.c_int32, C.POINTER(MgState), C.c_void_p,
+                             C.POINTER(MgRolloutOut), C.c_void_p]),
     "mg_step_obs_host": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p,
                                    C.c_void_p, C.POINTER(MgStepOut), C.POINTER(MgStepOut),
                                    C.c_void_p]),

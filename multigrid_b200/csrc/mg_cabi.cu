@@ -40,13 +40,14 @@ int validate(const MgConfig *c, int64_t num_envs) {
 int plan(mg::Params &p) {
     p.use_bulk = env_int("MG_NO_BULK", 0) ? 0 : 1;
     p.generic_view = env_int("MG_GENERIC_VIEW", 0) ? 1 : 0;
+    p.xknob = env_int("MG_X", 0);
     p.l2hint = env_int("MG_L2HINT", (p.flags & MG_FLAG_STREAM_STATE) ? 3 : 0);
     return mg::plan_launch(p, env_int("MG_GROUP", 0), env_int("MG_WPB", 0), kSmemPerBlock, kSmemPerSM);
 }
 
-template <int VT, int MODE>
+template <int VT, int MODE, bool MULTI = false>
 int launch(const mg::Params &p, cudaStream_t stream) {
-    auto kernel = mg::step_obs_kernel<VT, MODE>;
+    auto kernel = mg::step_obs_kernel<VT, MODE, MULTI>;
     static thread_local bool configured_dev[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -73,21 +74,21 @@ int launch(const mg::Params &p, cudaStream_t stream) {
     return (int)err;
 }
 
-template <int MODE>
+template <int MODE, bool MULTI = false>
 int dispatch(const mg::Params &p, cudaStream_t stream) {
     if constexpr (MODE == mg::MODE_STEP) {
         return launch<0, MODE>(p, stream);  // no observation phase: view size is irrelevant
     } else {
         if (!p.generic_view) {
             switch (p.V) {
-                case 3: return launch<3, MODE>(p, stream);
-                case 5: return launch<5, MODE>(p, stream);
-                case 7: return launch<7, MODE>(p, stream);
-                case 9: return launch<9, MODE>(p, stream);
+                case 3: return launch<3, MODE, MULTI>(p, stream);
+                case 5: return launch<5, MODE, MULTI>(p, stream);
+                case 7: return launch<7, MODE, MULTI>(p, stream);
+                case 9: return launch<9, MODE, MULTI>(p, stream);
                 default: break;
             }
         }
-        return launch<0, MODE>(p, stream);
+        return launch<0, MODE, MULTI>(p, stream);
     }
 }
 
@@ -97,6 +98,7 @@ void fill_config(mg::Params &p, const MgConfig *c, int64_t num_envs) {
     p.max_steps = c->max_steps; p.flags = c->flags; p.hook = c->hook; p.hook_param = c->hook_param;
     p.ostride = c->obs_agent_stride; p.K = c->num_layouts; p.lstride = c->layout_stride;
     p.num_envs = (int32_t)num_envs;
+    p.T = 1;
     p.trace = g_trace.load(std::memory_order_relaxed);
 }
 
@@ -122,19 +124,26 @@ int fill_out(mg::Params &p, const MgStepOut *o, bool need_obs) {
     return 0;
 }
 
-template <int MODE>
+template <int MODE, bool MULTI = false>
 int step_common(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *actions,
-                const MgStepOut *out, void *stream) {
+                const MgStepOut *out, void *stream, int32_t num_steps = 1, int8_t *direction = nullptr) {
     int rc = validate(cfg, num_envs);
     if (rc) return rc;
-    if (num_envs == 0) return 0;
+    if (num_steps < 0 || (int64_t)num_steps * num_envs > (1ll << 40)) return MG_ERR_BAD_ARG;
+    if (num_envs == 0 || num_steps == 0) return 0;
     if (!actions) return MG_ERR_BAD_ARG;
     mg::Params p;
     fill_config(p, cfg, num_envs);
     if ((rc = fill_state(p, state))) return rc;
     if ((rc = fill_out(p, out, MODE == mg::MODE_STEP_OBS))) return rc;
     p.actions = actions;
+    p.T = num_steps;
+    p.direction = direction;
     if ((rc = plan(p))) return rc;
+    // a rollout re-reads its cells from L2 every step: never mark those loads evict_first
+    if (MULTI) p.l2hint &= ~1;
+    // TMA spans of step t start at t * E * n (actions) and t * E * n * stride (obs) bytes
+    if (MULTI && (((size_t)num_envs * p.n) & 15u)) p.use_bulk = 0;
     // natural alignment of the per-env scalars (16-byte PCG words, 8-byte rewards, 4-byte counters and
     // the packed 4-agent terminated word) is required; 16-byte alignment of everything enables TMA
     auto misaligned = [](const void *ptr, uintptr_t a) { return (reinterpret_cast<uintptr_t>(ptr) & (a - 1)) != 0; };
@@ -146,7 +155,7 @@ int step_common(const MgConfig *cfg, int64_t num_envs, const MgState *state, con
     if (!aligned16(p.actions) || !aligned16(p.step_count) || !aligned16(p.pcg_state) || !aligned16(p.pcg_inc) ||
         !aligned16(p.layout_idx) || !aligned16(p.reward) || !aligned16(p.terminated) || !aligned16(p.truncated))
         p.use_bulk = 0;
-    return dispatch<MODE>(p, (cudaStream_t)stream);
+    return dispatch<MODE, MULTI>(p, (cudaStream_t)stream);
 }
 
 }  // namespace
@@ -247,6 +256,14 @@ int mg_step(const MgConfig *cfg, int64_t num_envs, const MgState *state, const i
 int mg_step_obs(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *actions,
                 const MgStepOut *out, void *stream) {
     return step_common<mg::MODE_STEP_OBS>(cfg, num_envs, state, actions, out, stream);
+}
+
+int mg_rollout(const MgConfig *cfg, int64_t num_envs, int32_t num_steps, const MgState *state,
+               const int8_t *actions, const MgRolloutOut *out, void *stream) {
+    if (!out) return MG_ERR_BAD_ARG;
+    const MgStepOut so = {out->obs, out->reward, out->terminated, out->truncated, out->status};
+    return step_common<mg::MODE_STEP_OBS, true>(cfg, num_envs, state, actions, &so, stream, num_steps,
+                                                out->direction);
 }
 
 int mg_step_obs_host(const MgConfig *cfg, int64_t num_envs, const MgState *state,

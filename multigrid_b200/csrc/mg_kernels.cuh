@@ -64,6 +64,11 @@ struct Params {
     int32_t hook, hook_param, ostride, K, lstride;
     int32_t num_envs, G, wpb, use_bulk, generic_view;
     int32_t l2hint;  // bit 0: state TMA loads L2 evict_first; bit 1: obs TMA stores L2 evict_first
+    // mg_rollout: T consecutive steps in ONE launch. Step t reads actions[t][E][n] and writes slice t of
+    // every output array ([T][E]...); agents and the per-env scalars stay on chip between steps.
+    int32_t T;
+    int32_t xknob;  // experiments (MG_X), timing only
+    int8_t *direction;  // [T][E][n] per-step 'direction' observation (rollout only; NULL otherwise)
     // state (device)
     uint32_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;
     int32_t *layout_idx; const uint32_t *pool_grid; const int8_t *pool_agents; int32_t *hook_state;
@@ -341,12 +346,14 @@ MG_HD void env_load(const Params &p, const Group &g, int i, EnvRegs &r) {
     if (p.hook == MG_HOOK_LOCKED_HALLWAY) r.hs = p.hook_state[e];
 }
 
+// Step t of a launch (t > 0 only in mg_rollout): the cells are re-read every step (the observation
+// phase stamps agents into them and packs its stage on top of them), the agents only at t = 0.
 template <int MODE>
-MG_HD void phase_load_plain(const Params &p, const Group &g, int lane) {
+MG_HD void phase_load_plain(const Params &p, const Group &g, int lane, int t = 0) {
     const size_t e0 = (size_t)g.e0;
     warp_copy(g.cells, p.grid + e0 * p.cstride, g.ne * p.cstride * 4, lane);
-    warp_copy(g.ag, p.agents + e0 * p.n * 8, g.ne * p.n * 8, lane);
-    if (MODE != MODE_OBS) warp_copy(g.act, p.actions + e0 * p.n, g.ne * p.n, lane);
+    if (t == 0) warp_copy(g.ag, p.agents + e0 * p.n * 8, g.ne * p.n * 8, lane);
+    if (MODE != MODE_OBS) warp_copy(g.act, p.actions + ((size_t)t * p.num_envs + e0) * p.n, g.ne * p.n, lane);
 }
 
 // ---- P2: auto-reset decision ("next-step" mode; is_done = base.py:534-539) --------------------------
@@ -363,7 +370,7 @@ MG_HD void phase_reset(const Params &p, const Group &g, int i, EnvRegs &r) {
         r.sc = 0;
         r.hs = 0;
         const uint32_t *src = (const uint32_t *)(p.pool_agents + (size_t)k * p.n * 8);
-        for (int j = 0; j < p.n * 2; j++) g.ag[i * p.n * 2 + j] = src[j];
+            for (int j = 0; j < p.n * 2; j++) g.ag[i * p.n * 2 + j] = src[j];
     }
     g.rk[i] = k;
 }
@@ -396,7 +403,7 @@ MG_HD uint32_t all_agents(const Params &p) { return p.n >= 32 ? 0xffffffffu : (1
 // the step only records WHO is rewarded; `rewarded` = bit per agent.
 MG_HD void on_success(const Params &p, uint32_t *ag, uint32_t &rewarded, int k) {
     if (p.flags & MG_FLAG_SUCCESS_ANY) {
-        for (int j = 0; j < p.n; j++) ag[j * 2] |= 1u << 24;
+            for (int j = 0; j < p.n; j++) ag[j * 2] |= 1u << 24;
     } else {
         ag[k * 2] |= 1u << 24;
     }
@@ -405,7 +412,7 @@ MG_HD void on_success(const Params &p, uint32_t *ag, uint32_t &rewarded, int k) 
 
 MG_HD void on_failure(const Params &p, uint32_t *ag, int k) {  // base.py:509-532
     if (p.flags & MG_FLAG_FAILURE_ANY) {
-        for (int j = 0; j < p.n; j++) ag[j * 2] |= 1u << 24;
+            for (int j = 0; j < p.n; j++) ag[j * 2] |= 1u << 24;
     } else {
         ag[k * 2] |= 1u << 24;
     }
@@ -611,15 +618,15 @@ MG_HD OrderDraw phase_draw(const Params &p, const Group &g, int i, EnvRegs &r) {
 }
 
 template <int MODE>
-MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const OrderDraw &d) {
-    if (i < 0) return;
+MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const OrderDraw &d, size_t tE = 0) {
+    if (i < 0) return;  // tE = t * num_envs: slice t of the per-step output arrays (mg_rollout)
     const int n = p.n;
     uint32_t *cells = g.cells + i * p.cstride;
     uint32_t *ag = g.ag + i * n * 2;
     if constexpr (MODE == MODE_OBS) {
         stamp_agents(p, cells, ag, terminated_mask(p, ag));
     } else {
-        const size_t e = (size_t)(g.e0 + i);
+        const size_t e = (size_t)(g.e0 + i), eo = e + tE;
         const bool was_reset = (p.flags & MG_FLAG_AUTO_RESET) && g.rk[i] >= 0;
         uint32_t rewarded = 0;
         bool truncated = false;
@@ -647,24 +654,27 @@ MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const 
         p.step_count[e] = r.sc;
         if (n > 1) { U128 s; s.lo = r.lo; s.hi = r.hi; *(U128 *)(p.pcg_state + 2 * e) = s; }
         if (p.flags & MG_FLAG_AUTO_RESET) p.layout_idx[e] = r.lidx;
-        p.truncated[e] = (uint8_t)truncated;
+        p.truncated[eo] = (uint8_t)truncated;
         const double rv = (rewarded | bonus_all | bonus) ? reward_value(r.sc, p.max_steps) : 0.0;  // base.py:394, 598-602
         const uint32_t term_force = dict_terminated ? 0x01010101u : 0u;
         if (n == 4) {
             uint32_t tw = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) tw |= (uint32_t)(((ag[j * 2] >> 24) & 0xff) != 0) << (8 * j);
-            *(uint32_t *)(p.terminated + e * 4) = tw | term_force;
+            *(uint32_t *)(p.terminated + eo * 4) = tw | term_force;
         } else {
-            for (int j = 0; j < n; j++)
-                p.terminated[e * n + j] = (uint8_t)((term_force & 1u) | (((ag[j * 2] >> 24) & 0xff) != 0));
+                    for (int j = 0; j < n; j++)
+                p.terminated[eo * n + j] = (uint8_t)((term_force & 1u) | (((ag[j * 2] >> 24) & 0xff) != 0));
         }
-        for (int j = 0; j < n; j++) p.reward[e * n + j] = ((rewarded >> j) & 1u) ? rv : 0.0;
+        if (p.direction) {  // rollout: the 'direction' observation of this step (base.py:371)
+                    for (int j = 0; j < n; j++) p.direction[eo * n + j] = (int8_t)(ag[j * 2] & 0xff);
+        }
+            for (int j = 0; j < n; j++) p.reward[eo * n + j] = ((rewarded >> j) & 1u) ? rv : 0.0;
         if (bonus_all | bonus) {  // LockedHallway only: rewards[k] += self._reward(), once per new door
             for (int j = 0; j < n; j++) {
                 double rj = ((rewarded >> j) & 1u) ? rv : 0.0;
                 for (uint32_t c = bonus_all + ((bonus >> j) & 1u); c > 0; c--) rj = rj + rv;
-                p.reward[e * n + j] = rj;
+                p.reward[eo * n + j] = rj;
             }
         }
     }
@@ -860,9 +870,9 @@ MG_HD uint8_t *stage_of(const Params &p, const Group &g, int pass) {
     return p.alias ? g.stage + (pass + 1) * p.pass_cell_bytes + p.stage_extra - p.stage_bytes : g.stage;
 }
 
-MG_HD void phase_obs_store_plain(const Params &p, const Group &g, int pass, int lane) {
+MG_HD void phase_obs_store_plain(const Params &p, const Group &g, int pass, int lane, size_t tE = 0) {
     const int cnt = g.ne * p.n - pass * LANES < LANES ? g.ne * p.n - pass * LANES : LANES;
-    warp_copy(p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride, stage_of(p, g, pass), cnt * p.ostride, lane);
+    warp_copy(p.obs + ((tE + (size_t)g.e0) * p.n + (size_t)pass * LANES) * p.ostride, stage_of(p, g, pass), cnt * p.ostride, lane);
 }
 
 // ---- P6 (plain path): agents back to HBM --------------------------------------------------------------
@@ -923,6 +933,8 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (TMA) reads that follow
+// generic-proxy global writes (dirty cells, reset layouts) -> visible to later TMA loads
+__device__ __forceinline__ void fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Compiled in only with -DMG_TRACE (python -m multigrid_b200.build --trace): the product build has
@@ -939,22 +951,24 @@ __device__ __forceinline__ void trace_mark(const Params &p, int group, int lane,
 }
 
 template <int MODE>
-__device__ __forceinline__ void load_bulk(const Params &p, const Group &g, uint64_t *bar) {
+__device__ __forceinline__ void load_bulk(const Params &p, const Group &g, uint64_t *bar, int t) {
     const size_t e0 = (size_t)g.e0;
     const uint32_t G = (uint32_t)p.G, n = (uint32_t)p.n;
-    uint32_t total = G * p.cstride * 4 + G * n * 8;
+    uint32_t total = G * p.cstride * 4;
+    if (t == 0) total += G * n * 8;
     if (MODE != MODE_OBS) total += G * n;
     mbar_expect_tx(bar, total);
+    const int8_t *act = p.actions + ((size_t)t * p.num_envs + e0) * n;
     if (p.l2hint & 1) {
         const uint64_t pol = l2_policy_evict_first();
         bulk_g2s_hint(g.cells, p.grid + e0 * p.cstride, G * p.cstride * 4, bar, pol);
-        bulk_g2s(g.ag, p.agents + e0 * n * 8, G * n * 8, bar);  // stored back by this launch: keep
-        if (MODE != MODE_OBS) bulk_g2s_hint(g.act, p.actions + e0 * n, G * n, bar, pol);
+        if (t == 0) bulk_g2s(g.ag, p.agents + e0 * n * 8, G * n * 8, bar);  // stored back by this launch: keep
+        if (MODE != MODE_OBS) bulk_g2s_hint(g.act, act, G * n, bar, pol);
         return;
     }
     bulk_g2s(g.cells, p.grid + e0 * p.cstride, G * p.cstride * 4, bar);
-    bulk_g2s(g.ag, p.agents + e0 * n * 8, G * n * 8, bar);
-    if (MODE != MODE_OBS) bulk_g2s(g.act, p.actions + e0 * n, G * n, bar);
+    if (t == 0) bulk_g2s(g.ag, p.agents + e0 * n * 8, G * n * 8, bar);
+    if (MODE != MODE_OBS) bulk_g2s(g.act, act, G * n, bar);
 }
 
 // ---- layout conversion kernels (API utilities, not on the hot path) -----------------------------------
@@ -1030,7 +1044,8 @@ __global__ void one_hot_kernel(int V, int64_t agents, int ostride, const int8_t 
     }
 }
 
-template <int VT, int MODE>
+// MULTI = mg_rollout (p.T steps per launch); the single-step kernels compile with T == 1 and no loop.
+template <int VT, int MODE, bool MULTI = false>
 __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1048,68 +1063,84 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
 
     if (bulk && lane == 0) mbar_init(bar, 1);
     pdl_wait();  // nothing of the previous launch is read or overwritten before this point
-    if (bulk) {
-        if (lane == 0) load_bulk<MODE>(p, g, bar);
-    } else {
-        phase_load_plain<MODE>(p, g, lane);
-    }
     EnvRegs er;
-    env_load<MODE>(p, g, env, er);  // the env's scalars, straight into its lane's registers
-    const OrderDraw draw = phase_draw<MODE>(p, g, env, er);
-    __syncwarp();
-    if (bulk) mbar_wait(bar, 0);
-    trace_mark(p, group, lane, 1);
-    if (MODE != MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
-        phase_reset(p, g, env, er);
-        const uint32_t pending = __ballot_sync(0xffffffffu, env >= 0 && g.rk[env] >= 0) & (p.G == 32 ? 0xffffffffu : (1u << p.G) - 1u);
-        if (pending) {
-            __syncwarp();
-            phase_reset_grid(p, g, pending, lane);
+    const int T = MULTI ? p.T : 1;
+#pragma unroll 1
+    for (int t = 0; t < T; t++) {
+        const size_t tE = (size_t)t * (size_t)p.num_envs;
+        trace_mark(p, group, lane, 5);
+        if (bulk) {
+            if (lane == 0) {
+                if (t > 0) bulk_wait_read();  // the last obs store has read its stage (which lies on the cells)
+                load_bulk<MODE>(p, g, bar, t);
+            }
+        } else {
+            phase_load_plain<MODE>(p, g, lane, t);
         }
+        if (t == 0) env_load<MODE>(p, g, env, er);  // the env's scalars, straight into its lane's registers
+        const OrderDraw draw = phase_draw<MODE>(p, g, env, er);
         __syncwarp();
-    }
-    phase_step<MODE>(p, g, env, er, draw);
-    __syncwarp();
-    trace_mark(p, group, lane, 2);
-    if (MODE != MODE_STEP) {
-        const int passes = obs_passes(p, g);
-        for (int pass = 0; pass < passes; pass++) {
-            const ObsTask t = obs_task(p, g, pass, lane);
-            uint8_t *stage = stage_of(p, g, pass), *out = stage + lane * p.ostride;
-            if constexpr (VT != 0) {
-                uint32_t cr[VT ? VT * VT : 1];
-                if (t.valid) obs_compute<VT>(p, t.cells, t.a0, t.a1, cr);
-                // the previous pass's TMA store must be done reading its stage, and (aliased stage)
-                // every lane must be done gathering before the cells under the stage are overwritten
-                if (bulk && pass > 0 && lane == 0) bulk_wait_read();
+        if (bulk) mbar_wait(bar, (uint32_t)(t & 1));
+        trace_mark(p, group, lane, 1);
+        if (MODE != MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
+            phase_reset(p, g, env, er);
+            const uint32_t pending = __ballot_sync(0xffffffffu, env >= 0 && g.rk[env] >= 0) & (p.G == 32 ? 0xffffffffu : (1u << p.G) - 1u);
+            if (pending) {
                 __syncwarp();
-                if (t.valid) obs_pack_store<VT>(p, cr, out);
-            } else {
-                if (bulk && pass > 0) {
-                    if (lane == 0) bulk_wait_read();
+                phase_reset_grid(p, g, pending, lane);
+            }
+            __syncwarp();
+        }
+        phase_step<MODE>(p, g, env, er, draw, tE);
+        __syncwarp();
+        trace_mark(p, group, lane, 2);
+        if (MODE != MODE_STEP) {
+            const int passes = obs_passes(p, g);
+            for (int pass = 0; pass < passes; pass++) {
+                const ObsTask tk = obs_task(p, g, pass, lane);
+                uint8_t *stage = stage_of(p, g, pass), *out = stage + lane * p.ostride;
+                if constexpr (VT != 0) {
+                    uint32_t cr[VT ? VT * VT : 1];
+                    if (tk.valid) obs_compute<VT>(p, tk.cells, tk.a0, tk.a1, cr);
+                    // the previous pass's TMA store must be done reading its stage, and (aliased stage)
+                    // every lane must be done gathering before the cells under the stage are overwritten
+                    if (bulk && pass > 0 && lane == 0) bulk_wait_read();
+                    __syncwarp();
+                    if (tk.valid) obs_pack_store<VT>(p, cr, out);
+                } else {
+                    if (bulk && pass > 0) {
+                        if (lane == 0) bulk_wait_read();
+                        __syncwarp();
+                    }
+                    if (tk.valid) obs_agent_generic(p, tk.cells, tk.a0, tk.a1, out);
+                }
+                if (bulk) {
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int left = g.ne * p.n - pass * LANES;
+                        const uint32_t cnt = left < LANES ? left : LANES;
+                        int8_t *dst = p.obs + ((tE + (size_t)g.e0) * p.n + (size_t)pass * LANES) * p.ostride;
+                        if (p.l2hint & 2) bulk_s2g_hint(dst, stage, cnt * p.ostride, l2_policy_evict_first());
+                        else bulk_s2g(dst, stage, cnt * p.ostride);
+                        bulk_commit();
+                    }
+                } else {
+                    __syncwarp();
+                    phase_obs_store_plain(p, g, pass, lane, tE);
                     __syncwarp();
                 }
-                if (t.valid) obs_agent_generic(p, t.cells, t.a0, t.a1, out);
-            }
-            if (bulk) {
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    const int left = g.ne * p.n - pass * LANES;
-                    const uint32_t cnt = left < LANES ? left : LANES;
-                    int8_t *dst = p.obs + ((size_t)g.e0 * p.n + (size_t)pass * LANES) * p.ostride;
-                    if (p.l2hint & 2) bulk_s2g_hint(dst, stage, cnt * p.ostride, l2_policy_evict_first());
-                    else bulk_s2g(dst, stage, cnt * p.ostride);
-                    bulk_commit();
-                }
-            } else {
-                __syncwarp();
-                phase_obs_store_plain(p, g, pass, lane);
-                __syncwarp();
             }
         }
+        trace_mark(p, group, lane, 3);
+        if (t + 1 < T) {
+            // this step's writes to the grid in HBM (dirty cells, reset layouts: generic proxy) must be
+            // visible to the next step's TMA load of the cells (async proxy)
+            if (bulk && !(p.xknob & 1)) fence_async_global();
+            __syncwarp();
+            trace_mark(p, group, lane, 6);
+        }
     }
-    trace_mark(p, group, lane, 3);
     if (MODE != MODE_OBS) {
         if (bulk) {
             if (MODE == MODE_STEP) fence_async_smem();  // (the obs passes already fenced)

@@ -238,6 +238,31 @@ class StepEngine:
                            self._stream()), "mg_step_obs" if fused else "mg_step")
         return self.obs, self.reward, self.terminated, self.truncated
 
+    def rollout(self, actions: torch.Tensor, out: dict | None = None) -> dict:
+        """mg_rollout: T = actions.shape[0] consecutive fused steps in ONE launch on an open-loop
+        action tape (T, E, n) int8. Bit-identical to T calls of `step(actions[t])`; returns (and
+        optionally reuses, `out=`) a dict of device tensors with a leading T axis: obs
+        (T,E,n,V,V,3) view of obs_buf (T,E,n,stride), direction (T,E,n), reward, terminated,
+        truncated (T,E). Asynchronous on the current CUDA stream."""
+        if (actions.dtype != torch.int8 or not actions.is_contiguous() or actions.device != self.device
+                or actions.dim() != 3 or tuple(actions.shape[1:]) != (self.num_envs, self.cfg.num_agents)):
+            raise TypeError("actions must be a contiguous int8 CUDA tensor of shape (T, num_envs, n)")
+        T, E, n, V = int(actions.shape[0]), self.num_envs, self.cfg.num_agents, self.cfg.view_size
+        if out is None:
+            e = lambda shape, dt: torch.empty(shape, dtype=dt, device=self.device)  # noqa: E731
+            out = dict(obs_buf=e((T, E, n, self.obs_stride), torch.int8), direction=e((T, E, n), torch.int8),
+                       reward=e((T, E, n), torch.float64), terminated=e((T, E, n), torch.uint8),
+                       truncated=e((T, E), torch.uint8))
+        assert out["obs_buf"].shape[0] == T and out["obs_buf"].is_contiguous()
+        c, st, _ = self._structs()
+        ro = _cabi.MgRolloutOut(out["obs_buf"].data_ptr(), out["direction"].data_ptr(), out["reward"].data_ptr(),
+                                out["terminated"].data_ptr(), out["truncated"].data_ptr(), self.status.data_ptr())
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.mg_rollout(C.byref(c), E, T, C.byref(st), actions.data_ptr(), C.byref(ro),
+                                            self._stream()), "mg_rollout")
+        out["obs"] = out["obs_buf"][..., :3 * V * V].unflatten(-1, (V, V, 3))
+        return out
+
     def host_buffers(self):
         """Pinned host mirrors used by `step_host` (allocated on first use)."""
         if self._host is None:

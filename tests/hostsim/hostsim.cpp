@@ -42,21 +42,25 @@ void run_groups(const mg::Params &p) {
         mg::EnvRegs er[mg::LANES];
         int env[mg::LANES];
         for (int l = 0; l < L; l++) env[l] = mg::lane_env(p, g, l);
-        for (int l = 0; l < L; l++) mg::phase_load_plain<MODE>(p, g, l);
-        for (int l = 0; l < L; l++) mg::env_load<MODE>(p, g, env[l], er[l]);
-        mg::OrderDraw draw[mg::LANES];
-        for (int l = 0; l < L; l++) draw[l] = mg::phase_draw<MODE>(p, g, env[l], er[l]);
-        if (MODE != mg::MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
-            for (int l = 0; l < L; l++) mg::phase_reset(p, g, env[l], er[l]);
-            const uint32_t pending = mg::reset_mask_host(g);
-            for (int l = 0; l < L; l++) mg::phase_reset_grid(p, g, pending, l);
-        }
-        for (int l = 0; l < L; l++) mg::phase_step<MODE>(p, g, env[l], er[l], draw[l]);
-        if (MODE != mg::MODE_STEP) {
-            const int passes = mg::obs_passes(p, g);
-            for (int pass = 0; pass < passes; pass++) {
-                obs_pass<VT>(p, g, pass);
-                for (int l = 0; l < L; l++) mg::phase_obs_store_plain(p, g, pass, l);
+        for (int t = 0; t < p.T; t++) {  // same loop as the kernel's (T > 1: mg_rollout)
+            const size_t tE = (size_t)t * (size_t)p.num_envs;
+            for (int l = 0; l < L; l++) mg::phase_load_plain<MODE>(p, g, l, t);
+            if (t == 0)
+                for (int l = 0; l < L; l++) mg::env_load<MODE>(p, g, env[l], er[l]);
+            mg::OrderDraw draw[mg::LANES];
+            for (int l = 0; l < L; l++) draw[l] = mg::phase_draw<MODE>(p, g, env[l], er[l]);
+            if (MODE != mg::MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
+                for (int l = 0; l < L; l++) mg::phase_reset(p, g, env[l], er[l]);
+                const uint32_t pending = mg::reset_mask_host(g);
+                for (int l = 0; l < L; l++) mg::phase_reset_grid(p, g, pending, l);
+            }
+            for (int l = 0; l < L; l++) mg::phase_step<MODE>(p, g, env[l], er[l], draw[l], tE);
+            if (MODE != mg::MODE_STEP) {
+                const int passes = mg::obs_passes(p, g);
+                for (int pass = 0; pass < passes; pass++) {
+                    obs_pass<VT>(p, g, pass);
+                    for (int l = 0; l < L; l++) mg::phase_obs_store_plain(p, g, pass, l, tE);
+                }
             }
         }
         if (MODE != mg::MODE_OBS)
@@ -82,7 +86,8 @@ void dispatch(const mg::Params &p, int generic) {
 }  // namespace
 
 extern "C" int sim_run(int mode, const MgConfig *c, int64_t num_envs, const MgState *s,
-                       const int8_t *actions, const MgStepOut *o, int forced_group, int generic) {
+                       const int8_t *actions, const MgStepOut *o, int forced_group, int generic,
+                       int num_steps, int8_t *direction) {
     mg::Params p;
     std::memset(&p, 0, sizeof(p));
     p.W = c->width; p.H = c->height; p.n = c->num_agents; p.V = c->view_size;
@@ -90,6 +95,7 @@ extern "C" int sim_run(int mode, const MgConfig *c, int64_t num_envs, const MgSt
     p.ostride = c->obs_agent_stride; p.K = c->num_layouts; p.lstride = c->layout_stride;
     p.num_envs = (int32_t)num_envs;
     p.generic_view = generic & 1;
+    p.T = num_steps; p.direction = direction;
     if (mode == mg::MODE_OBS) p.flags &= ~MG_FLAG_AUTO_RESET;
     p.grid = s->grid; p.agents = s->agents; p.step_count = s->step_count;
     p.pcg_state = s->pcg_state; p.pcg_inc = s->pcg_inc; p.layout_idx = s->layout_idx;

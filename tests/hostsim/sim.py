@@ -126,11 +126,27 @@ class SimEngine:
     def grid(self):
         return unpack_cells(self.cells, self.cfg.W, self.cfg.H)
 
-    def _run(self, mode, actions=None):
+    def _run(self, mode, actions=None, out=None, T=1, direction=None):
         rc = lib().sim_run(C.c_int(mode), C.byref(self.c), C.c_int64(self.B), C.byref(self.state),
-                           _p(actions), C.byref(self.out), C.c_int(self.forced_group),
-                           C.c_int(self.generic))
+                           _p(actions), C.byref(self.out if out is None else out), C.c_int(self.forced_group),
+                           C.c_int(self.generic), C.c_int(T), _p(direction))
         assert rc == 0, rc
+
+    def rollout(self, actions):
+        """T steps in one run of the kernel's step loop (mg_rollout). actions (T,B,n)."""
+        actions = aligned_copy(actions, np.int8)
+        T, cfg, V = actions.shape[0], self.cfg, self.cfg.V
+        obs = aligned((T, self.B, cfg.n, self.stride), np.int8)
+        obs[...] = 0x55
+        rew, term = aligned((T, self.B, cfg.n), np.float64), aligned((T, self.B, cfg.n), np.uint8)
+        trunc, dirs = aligned((T, self.B), np.uint8), aligned((T, self.B, cfg.n), np.int8)
+        out = _cabi.MgStepOut(_p(obs).value, _p(rew).value, _p(term).value, _p(trunc).value,
+                              _p(self.status).value)
+        self._run(MODE_STEP_OBS, actions, out=out, T=T, direction=dirs)
+        if self.status[0] & 1:
+            raise ValueError("Unknown action")
+        assert (obs[..., 3 * V * V:] == 0).all(), "padding bytes must be zero"
+        return obs[..., :3 * V * V].reshape(T, self.B, cfg.n, V, V, 3), dirs, rew, term, trunc
 
     def _obs_view(self):
         V = self.cfg.V

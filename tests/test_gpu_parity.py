@@ -220,6 +220,65 @@ def test_back_to_back_launches_without_host_sync(pdl, monkeypatch):
     assert_same(g, ora, f"pdl={pdl}")
 
 
+@pytest.mark.parametrize("seed,B,T,kw", [
+    (0, 4096, 40, dict(W=8, H=8, n=4, V=7, auto_reset=True, max_steps=9)),
+    (1, 2048, 50, dict(W=11, H=6, n=2, V=7, hook=1, joint_reward=True, auto_reset=True, max_steps=14)),
+    (2, 300, 30, dict(W=9, H=13, n=5, V=9, allow_agent_overlap=False, failure_any=True)),
+    (6, 203, 25, dict(W=10, H=6, n=12, V=11, max_steps=30, auto_reset=True, layout_stride=3)),
+    (7, 77, 25, dict(W=6, H=9, n=2, V=13, allow_agent_overlap=False)),
+    (8, 1024, 30, dict(W=16, H=16, n=8, V=9, joint_reward=True, auto_reset=True, max_steps=11)),
+])
+@pytest.mark.parametrize("knobs", [{}, dict(MG_NO_BULK="1"), dict(MG_GROUP="32")], ids=["default", "nobulk", "g32"])
+def test_rollout_equals_single_steps(seed, B, T, kw, knobs, monkeypatch):
+    """mg_rollout (T steps in one launch, dense random soups where cells change and envs reset):
+    slice t of every output == step t of the C oracle; final state == the oracle's after T steps."""
+    import torch
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    kw = dict(kw)
+    cfg = O.OracleConfig(max_steps=kw.pop("max_steps", 40), **kw)
+    st = random_batch(cfg, B, seed)
+    ora, g = COracle(cfg, nthreads=NTHREADS, **st), GpuEngine(cfg, **st)
+    rng = np.random.default_rng(seed + 7)
+    actions = rng.integers(-1, 7, size=(T, B, cfg.n)).astype(np.int8)
+    out = g.eng.rollout(torch.from_numpy(actions).cuda())
+    g.eng.check_status()
+    obs = out["obs"].cpu().numpy()
+    assert (out["obs_buf"][..., 3 * cfg.V * cfg.V:] == 0).all()
+    dirs, rew = out["direction"].cpu().numpy(), out["reward"].cpu().numpy()
+    term, trunc = out["terminated"].cpu().numpy(), out["truncated"].cpu().numpy()
+    for t in range(T):
+        o1, r1, t1, tr1 = ora.step(actions[t])
+        msg = f"step {t}"
+        np.testing.assert_array_equal(obs[t], o1, err_msg=msg)
+        np.testing.assert_array_equal(dirs[t], ora.agents[..., O.A_DIR], err_msg=msg)
+        assert (rew[t] == r1).all(), msg
+        np.testing.assert_array_equal(term[t], t1, err_msg=msg)
+        np.testing.assert_array_equal(trunc[t], tr1, err_msg=msg)
+    assert_same(g, ora, "rollout")
+
+
+@pytest.mark.parametrize("name", ROLLOUT_CASES)
+def test_rollout_matches_reference_fixtures(name):
+    """mg_rollout against the rollouts recorded from the unmodified reference."""
+    import torch
+    d, meta = load_case(name)
+    cfg = cfg_from_meta(meta)
+    B, T, J = meta["B"], meta["T"], meta["pool_J"]
+    g = GpuEngine(cfg, d["init_grid"], O.pack_agents(d["init_agents"]), d["pcg_state"],
+                  d["pcg_inc"], pool_grid=d["pool_grid"],
+                  pool_agents=O.pack_agents(d["pool_agents"]), layout_idx=np.arange(B) * J)
+    out = g.eng.rollout(torch.from_numpy(np.ascontiguousarray(d["actions"][:T], dtype=np.int8)).cuda())
+    g.eng.check_status()
+    np.testing.assert_array_equal(out["obs"].cpu().numpy(), d["obs"][:T])
+    assert (out["reward"].cpu().numpy() == d["reward"][:T]).all()
+    np.testing.assert_array_equal(out["terminated"].cpu().numpy(), d["terminated"][:T])
+    np.testing.assert_array_equal(out["truncated"].cpu().numpy(), d["truncated"][:T])
+    np.testing.assert_array_equal(out["direction"].cpu().numpy(), d["direction"][:T])
+    np.testing.assert_array_equal(g.grid, d["grid"][T - 1])
+    np.testing.assert_array_equal(O.unpack_agents(g.agents), d["agents"][T - 1])
+
+
 @pytest.mark.parametrize("B", [1, 15, 16, 17, 31, 32, 33, 129])
 def test_ragged_batch_sizes(B):
     cfg = O.OracleConfig(W=8, H=8, n=4, V=7, max_steps=20, auto_reset=True)

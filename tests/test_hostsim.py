@@ -85,3 +85,34 @@ def test_hostsim_random_soup_vs_c_oracle(seed, kw):
         np.testing.assert_array_equal(sim.step_count, ora.step_count, err_msg=msg)
         np.testing.assert_array_equal(sim.pcg_state, ora.pcg_state, err_msg=msg)
         np.testing.assert_array_equal(sim.layout_idx, ora.layout_idx, err_msg=msg)
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (0, dict(W=8, H=8, n=4, V=7, auto_reset=True, max_steps=9)),
+    (1, dict(W=11, H=6, n=2, V=7, hook=1, joint_reward=True, auto_reset=True, max_steps=14)),
+    (6, dict(W=10, H=6, n=12, V=11, max_steps=30, auto_reset=True, layout_stride=3)),
+    (7, dict(W=6, H=9, n=2, V=13, allow_agent_overlap=False)),
+])
+def test_hostsim_rollout_equals_single_steps(seed, kw):
+    """The kernel's in-launch step loop (mg_rollout): slice t of every output == step t of the
+    C oracle, final state == state after T oracle steps."""
+    cfg = O.OracleConfig(max_steps=kw.pop("max_steps", 40), **kw)
+    B, T = 75, 33
+    st = random_batch(cfg, B, seed)
+    ora, sim = COracle(cfg, **st), SimEngine(cfg, **st)
+    rng = np.random.default_rng(seed + 7)
+    actions = rng.integers(-1, 7, size=(T, B, cfg.n)).astype(np.int8)
+    obs, dirs, rew, term, trunc = sim.rollout(actions)
+    for t in range(T):
+        o1, r1, t1, tr1 = ora.step(actions[t])
+        msg = f"step {t}"
+        np.testing.assert_array_equal(obs[t], o1, err_msg=msg)
+        np.testing.assert_array_equal(dirs[t], ora.agents[..., O.A_DIR], err_msg=msg)
+        assert (rew[t] == r1).all(), msg
+        np.testing.assert_array_equal(term[t], t1, err_msg=msg)
+        np.testing.assert_array_equal(trunc[t], tr1, err_msg=msg)
+    np.testing.assert_array_equal(sim.grid, ora.grid)
+    np.testing.assert_array_equal(sim.agents, ora.agents)
+    np.testing.assert_array_equal(sim.step_count, ora.step_count)
+    np.testing.assert_array_equal(sim.pcg_state, ora.pcg_state)
+    np.testing.assert_array_equal(sim.layout_idx, ora.layout_idx)

@@ -94,6 +94,42 @@ def time_config(name, steps, knobs, replicas=8):
     return out
 
 
+def time_rollout(name, T, knobs):
+    """mg_rollout: T steps in one launch on one engine (state stays L2/on-chip resident)."""
+    W, H, n, V, E, max_steps, mutable = CONFIGS[name]
+    dev = torch.device("cuda", 0)
+    cfg = EngineConfig(width=W, height=H, num_agents=n, view_size=V, max_steps=max_steps, auto_reset=True,
+                       stream_state=True)
+    pg, pa = layout(W, H, n)
+    eng = StepEngine(cfg, E, dev, pg, pa)
+    st, inc = bench.pcg_words(0, E)
+    eng.load_state(np.repeat(pg, E, 0), np.repeat(pa, E, 0), None, st, inc, None)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    tape = torch.randint(0, 7, (T, E, n), generator=gen, device=dev, dtype=torch.int32).to(torch.int8)
+    out = eng.rollout(tape)  # warm-up: spreads the agents, allocates the outputs
+    for _ in range(max(1, 256 // T)):
+        eng.rollout(tape, out)
+    torch.cuda.synchronize()
+    bpe = bench.rollout_bytes_per_env_step(n, V)
+    for knob in knobs:
+        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_X"):
+            os.environ.pop(key, None)
+        os.environ.update({k: str(v) for k, v in knob.items()})
+        eng.rollout(tape, out)
+        torch.cuda.synchronize()
+        best = 1e9
+        for rep in range(3):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            eng.rollout(tape, out)
+            ev1.record()
+            torch.cuda.synchronize()
+            best = min(best, ev0.elapsed_time(ev1))
+        us = 1e3 * best / T
+        print(json.dumps(dict(config=name, rollout_T=T, **knob, us_per_step=round(us, 2),
+                              gagent_steps_s=round(E * n / us / 1e3, 2), gbs=round(bpe * E / us / 1e3, 1))), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="empty8")
@@ -102,6 +138,7 @@ def main():
     ap.add_argument("--wpbs", default="0")
     ap.add_argument("--nobulk", default="0")
     ap.add_argument("--extra", default="", help="comma list of extra KEY=VAL knob sets to also try, e.g. MG_PDL=1,MG_PDL=1+MG_L2HINT=3")
+    ap.add_argument("--rollout", type=int, default=0, help="also time mg_rollout with this many steps per launch")
     args = ap.parse_args()
     knobs = []
     for g, w, nb in itertools.product(args.groups.split(","), args.wpbs.split(","), args.nobulk.split(",")):
@@ -116,7 +153,10 @@ def main():
         for kv in [x for x in args.extra.split(",") if x]:
             knobs.append({**k, **dict(item.split("=") for item in kv.split("+"))})
     for name in args.configs.split(","):
-        time_config(name, args.steps, knobs)
+        if args.steps > 0:
+            time_config(name, args.steps, knobs)
+        if args.rollout:
+            time_rollout(name, args.rollout, knobs)
 
 
 if __name__ == "__main__":

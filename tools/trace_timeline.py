@@ -20,6 +20,7 @@ from multigrid_b200 import _cabi  # noqa: E402
 from multigrid_b200.engine import EngineConfig, StepEngine  # noqa: E402
 
 ap = argparse.ArgumentParser(); ap.add_argument("--config", default="empty8"); ap.add_argument("--group", type=int, default=16)
+ap.add_argument("--rollout", type=int, default=0, help="trace one mg_rollout launch of this many steps instead")
 args = ap.parse_args()
 W, H, n, V, E, max_steps, _ = kbench.CONFIGS[args.config]
 dev = torch.device("cuda", 0); lib = _cabi.load()
@@ -37,6 +38,25 @@ for k in range(96):
 torch.cuda.synchronize()
 groups = (E + args.group - 1) // args.group
 buf = torch.zeros((groups, 8), dtype=torch.int64, device=dev)
+if args.rollout:
+    T = args.rollout
+    rt = torch.randint(0, 7, (T, E, n), device=dev, dtype=torch.int32).to(torch.int8)
+    out = engines[0].rollout(rt)
+    torch.cuda.synchronize()
+    lib.mg_debug_set_trace(buf.data_ptr())
+    engines[0].rollout(rt, out)
+    torch.cuda.synchronize()
+    lib.mg_debug_set_trace(None)
+    t = buf.cpu().numpy().astype(np.float64)
+    print(f"rollout T={T}: launch span {(t[:, 4].max() - t[:, 0].min()) / 1e3:.2f} us = {(t[:, 4].max() - t[:, 0].min()) / 1e3 / T:.2f} us/step")
+    print("last iteration of every warp (slots: 5 iteration start, 1 loaded, 2 stepped, 3 observed; 6 = fence after the previous iteration):")
+    for a, b, nm in [(5, 1, "load wait"), (1, 2, "reset+step"), (2, 3, "obs"), (6, 5, "loop edge"), (5, 3, "iteration"), (3, 4, "store+drain")]:
+        d = (t[:, b] - t[:, a]) / 1e3
+        q = np.percentile(d, [0, 10, 50, 90, 100])
+        print(f"{nm:11s} dur(us) min/p10/p50/p90/max = " + " ".join(f"{v:7.2f}" for v in q) + f"  mean {d.mean():.2f}")
+    life = (t[:, 4] - t[:, 0]) / 1e3
+    print("warp life us min/p50/max:", life.min(), np.median(life), life.max())
+    sys.exit(0)
 lib.mg_debug_set_trace(buf.data_ptr())
 engines[0].step(tape[0])
 torch.cuda.synchronize()
