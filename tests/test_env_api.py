@@ -142,3 +142,87 @@ def test_env_seed_int_matches_per_env_seeds():
         for i in range(4):
             assert torch.equal(oa[0][i]["image"][32:], ob[0][i]["image"])
             assert torch.equal(oa[1][i][32:], ob[1][i])
+
+
+def _to_goal(env, agent):
+    """Empty-5x5 from (1,1) facing right to the goal at (3,3): forward x2, right, forward x2."""
+    out = None
+    for a in (2, 2, 1, 2, 2):
+        out = env.step({agent: a})
+    return out
+
+
+def test_rllib_adapter_surface(monkeypatch):
+    """multigrid/rllib/__init__.py:44-105: agents / possible_agents, '__all__' = all() over agents, spaces."""
+    from tests.hostsim.fake_engine import HostSimStepEngine
+    from multigrid_b200.rllib import RLlibWrapper, to_rllib_env
+    monkeypatch.setattr(env_mod, "StepEngine", HostSimStepEngine)
+    cls = to_rllib_env("MultiGrid-Empty-5x5-v0", default_config=dict(agents=2, success_termination_mode="all"))
+    assert cls.__name__ == "RLlib_MultiGrid-Empty-5x5-v0"
+    env = cls(dict(num_envs=3, device="cpu", max_steps=9))
+    assert isinstance(env, RLlibWrapper) and env.agents == [0, 1] == env.possible_agents
+    assert env.get_observation_space(1)["image"].shape == (7, 7, 3) and env.get_action_space(0).n == 7
+    obs, infos = env.reset(seed=3)
+    assert sorted(obs) == [0, 1]
+    obs, rew, term, trunc, infos = _to_goal(env, 0)
+    assert term[0].all() and not term[1].any() and not term["__all__"].any() and term["__all__"].shape == (3,)
+    assert not trunc["__all__"].any() and (rew[0] > 0).all() and (rew[1] == 0).all()
+    obs, rew, term, trunc, infos = _to_goal(env, 1)  # step 10 > max_steps 9
+    assert term["__all__"].all() and trunc["__all__"].all() and sorted(obs) == [0, 1]
+
+
+def test_pettingzoo_adapter_surface(monkeypatch):
+    """multigrid/pettingzoo/__init__.py:38-115: live-agent list, possible_agents, spaces by id."""
+    from tests.hostsim.fake_engine import HostSimStepEngine
+    from multigrid_b200.pettingzoo import PettingZooWrapper, to_pettingzoo_env
+    monkeypatch.setattr(env_mod, "StepEngine", HostSimStepEngine)
+    cls = to_pettingzoo_env("MultiGrid-Empty-5x5-v0", metadata={"name": "empty_v0"})
+    env = cls(agents=2, num_envs=4, device="cpu", success_termination_mode="all", max_steps=50)
+    assert isinstance(env, PettingZooWrapper) and cls.metadata == {"name": "empty_v0"}
+    assert env.possible_agents == [0, 1] and sorted(env.observation_spaces) == [0, 1]
+    assert env.action_space(1).n == 7 and env.observation_space(0)["direction"].n == 4
+    env.reset(seed=0)
+    assert env.agents == [0, 1] and env.agent_mask.all()
+    _to_goal(env, 0)
+    assert env.agents == [1] and not env.agent_mask[:, 0].any() and env.agent_mask[:, 1].all()
+    _to_goal(env, 1)
+    assert env.agents == [] and not env.agent_mask.any()  # every env is done
+    assert env.render_mode is None
+
+
+def test_wrappers_compose_with_adapters(monkeypatch):
+    """ImgObs / SingleAgent wrappers under the adapters (the RLlib registration wraps with a
+    wrapper before adapting, rllib/__init__.py:110-111)."""
+    from tests.hostsim.fake_engine import HostSimStepEngine
+    from multigrid_b200.rllib import to_rllib_env
+    from multigrid_b200.wrappers import ImgObsWrapper
+    monkeypatch.setattr(env_mod, "StepEngine", HostSimStepEngine)
+    env = to_rllib_env("MultiGrid-Empty-6x6-v0", ImgObsWrapper)(dict(agents=3, num_envs=2, device="cpu"))
+    obs, _ = env.reset(seed=1)
+    assert obs[2].shape == (2, 7, 7, 3)
+    obs, rew, term, trunc, _ = env.step({0: 2, 1: 0, 2: 1})
+    assert obs[0].shape == (2, 7, 7, 3) and "__all__" in term and "__all__" in trunc
+
+
+@pytest.mark.gpu
+def test_adapters_on_gpu():
+    """The RLlib registration path of the reference (OneHotObsWrapper under the adapter) and the
+    PettingZoo adapter over the real CUDA engine."""
+    from multigrid_b200.pettingzoo import to_pettingzoo_env
+    from multigrid_b200.rllib import to_rllib_env
+    from multigrid_b200.wrappers import OneHotObsWrapper
+    env = to_rllib_env("MultiGrid-Empty-5x5-v0", OneHotObsWrapper,
+                       default_config=dict(agents=2, success_termination_mode="all"))(
+        dict(num_envs=100, device="cuda:0"))
+    obs, _ = env.reset(seed=0)
+    assert obs[1]["image"].shape == (100, 7, 7, 21) and obs[1]["image"].dtype == torch.uint8
+    assert env.get_observation_space(0)["image"].shape == (7, 7, 21)
+    obs, rew, term, trunc, _ = _to_goal(env, 0)
+    assert term[0].all() and not term["__all__"].any()
+    plain = env.env.unwrapped.engine.obs[:, 1].cpu().numpy()
+    np.testing.assert_array_equal(obs[1]["image"].cpu().numpy(), O.one_hot(plain))
+    pz = to_pettingzoo_env("MultiGrid-Empty-5x5-v0")(agents=2, num_envs=64, device="cuda:0",
+                                                     success_termination_mode="all")
+    pz.reset(seed=1)
+    _to_goal(pz, 1)
+    assert pz.agents == [0] and pz.possible_agents == [0, 1]
