@@ -209,6 +209,12 @@ int mg_one_hot(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_st
     if (num_agents_total == 0) return 0;
     if (!obs || !out) return MG_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(out) & 3u) return MG_ERR_ALIGNMENT;
+    if ((reinterpret_cast<uintptr_t>(out) & 15u) == 0 && !env_int("MG_ONE_HOT_W32", 0)) {
+        mg::one_hot_kernel_v16<<<(unsigned)((num_agents_total + 15) / 16), 256, 0, (cudaStream_t)stream>>>(
+            view_size, num_agents_total, obs_agent_stride, mg::rcp32(view_size * view_size), obs, (uint4 *)out);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return (int)cudaGetLastError();
+    }
     const int64_t words = (num_agents_total * view_size * view_size * 21 + 3) / 4;
     mg::one_hot_kernel<<<(unsigned)((words + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         view_size, num_agents_total, obs_agent_stride, obs, out);

@@ -1045,6 +1045,47 @@ __global__ void one_hot_kernel(int V, int64_t agents, int ostride, const int8_t 
 }
 
 // MULTI = mg_rollout (p.T steps per launch); the single-step kernels compile with T == 1 and no loop.
+// Same result, 16 output bytes per thread (one 128-bit store): the 16 bytes [p0, p0+16) of the flat
+// [A][V][V][21] stream lie in at most two consecutive cells, i.e. hold at most six 1-bytes; each is
+// placed with one shift into a 16-bit mask that a multiply spreads into bytes. The output is 7x the
+// observation (270 MB for the 65 536 x 4 x 7 x 7 bench batch): HBM writes are the floor.
+// One block = 16 consecutive agents = VV*21 16-byte vectors: every index below is a small 32-bit number.
+__global__ void __launch_bounds__(256) one_hot_kernel_v16(int V, int64_t agents, int ostride, uint32_t rcp_vv,
+                                                          const int8_t *__restrict__ obs, uint4 *__restrict__ out) {
+    const uint32_t VV = (uint32_t)(V * V), nvec = VV * 21u;          // vectors per full block
+    const int64_t a0 = (int64_t)blockIdx.x * 16;
+    const uint32_t na = (uint32_t)(agents - a0 < 16 ? agents - a0 : 16);
+    const uint32_t nbytes = na * VV * 21u;                            // bytes of this block (tail block: fewer)
+    const uint8_t *obs_b = (const uint8_t *)obs + a0 * ostride;
+    uint4 *out_b = out + (int64_t)blockIdx.x * nvec;
+    auto shl = [](uint32_t q) { uint32_t r; asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(q)); return r; };
+    for (uint32_t v = threadIdx.x; 16u * v < nbytes; v += 256u) {
+        const uint32_t rel = 16u * v, c = mulhi32(rel, 204522253u), off = rel - c * 21u;  // rel / 21, rel < 2^21
+        uint32_t a = fastdiv(c, rcp_vv), cia = c - a * VV;
+        // bit q of `mask` <=> output byte q is 1; shifts by >= 32 (positions outside the window, including
+        // "negative" ones that wrapped) give 0 in PTX, positions 16..31 are masked off by the spread below
+        const uint8_t *src = obs_b + a * (uint32_t)ostride + cia * 3u;
+        uint32_t base = 0u - off;
+        uint32_t mask = shl(base + src[0]) | shl(base + 11u + src[1]) | shl(base + 17u + src[2]);
+        if (off > 5u && rel + (21u - off) < nbytes) {  // the window reaches into the next cell
+            if (++cia == VV) { cia = 0; a++; }
+            src = obs_b + a * (uint32_t)ostride + cia * 3u;
+            base = 21u - off;
+            mask |= shl(base + src[0]) | shl(base + 11u + src[1]) | shl(base + 17u + src[2]);
+        }
+        if (rel + 16u <= nbytes) {
+            // 4 mask bits -> 4 bytes of 0/1: the multiply puts bit i at bit 8*i (no two products collide)
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[k] = (((mask >> (4 * k)) & 15u) * 0x00204081u) & 0x01010101u;
+            out_b[v] = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            uint8_t *o = (uint8_t *)out_b + rel;
+            for (uint32_t b = 0; rel + b < nbytes; b++) o[b] = (uint8_t)((mask >> b) & 1u);
+        }
+    }
+}
+
 template <int VT, int MODE, bool MULTI = false>
 __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem[];

@@ -319,21 +319,28 @@ def test_misaligned_pointer_is_rejected():
     assert lib.mg_gen_obs(C.byref(c), 1, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), None) == -1
 
 
-@pytest.mark.parametrize("V,A", [(7, 1000), (3, 5), (9, 33), (5, 4096)])
-def test_one_hot_kernel_vs_oracle(V, A):
+@pytest.mark.parametrize("path", ["v16", "w32", "w32_unaligned"])
+@pytest.mark.parametrize("V,A", [(7, 1000), (3, 5), (9, 33), (5, 4096), (7, 1)])
+def test_one_hot_kernel_vs_oracle(V, A, path, monkeypatch):
+    """Both one-hot kernels: 16 bytes per thread (16-byte aligned output) and the 4-byte fallback."""
     import ctypes as C
     import torch
     from multigrid_b200 import _cabi
     lib = _cabi.load()
+    if path == "w32":
+        monkeypatch.setenv("MG_ONE_HOT_W32", "1")
     rng = np.random.default_rng(V * 100 + A)
     stride = _cabi.obs_agent_stride(V)
     img = np.stack([rng.integers(0, 11, (A, V, V)), rng.integers(0, 6, (A, V, V)), rng.integers(0, 4, (A, V, V))], -1)
     buf = np.zeros((A, stride), np.int8)
     buf[:, :3 * V * V] = img.reshape(A, -1)
     obs = torch.from_numpy(buf).cuda()
-    out = torch.full((A, V, V, 21), 7, dtype=torch.uint8, device="cuda")
+    raw = torch.full((A * V * V * 21 + 32,), 7, dtype=torch.uint8, device="cuda")
+    shift = 4 if path == "w32_unaligned" else 0
+    out = raw[shift:shift + A * V * V * 21].view(A, V, V, 21)
     assert lib.mg_one_hot(V, A, stride, obs.data_ptr(), out.data_ptr(), None) == 0
     np.testing.assert_array_equal(out.cpu().numpy(), O.one_hot(img))
+    assert (raw[:shift] == 7).all() and (raw[shift + A * V * V * 21:] == 7).all()  # nothing written outside
 
 
 def test_wrappers_on_gpu():

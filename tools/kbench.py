@@ -130,6 +130,32 @@ def time_rollout(name, T, knobs):
                               gagent_steps_s=round(E * n / us / 1e3, 2), gbs=round(bpe * E / us / 1e3, 1))), flush=True)
 
 
+def time_one_hot(V=7, A=262144):
+    """mg_one_hot on the bench batch's observations: output 21 B per cell, HBM-write-bound at best."""
+    import ctypes as C
+    from multigrid_b200 import _cabi
+    lib = _cabi.load()
+    stride = _cabi.obs_agent_stride(V)
+    obs = torch.randint(0, 4, (A, stride), device="cuda", dtype=torch.int32).to(torch.int8)
+    outs = [torch.empty((A, V, V, 21), dtype=torch.uint8, device="cuda") for _ in range(3)]  # 3 x 270 MB > L2
+    for name, env in (("v16", "0"), ("w32", "1")):
+        os.environ["MG_ONE_HOT_W32"] = env
+        for o in outs:
+            lib.mg_one_hot(V, A, stride, obs.data_ptr(), o.data_ptr(), None)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for k in range(30):
+            lib.mg_one_hot(V, A, stride, obs.data_ptr(), outs[k % 3].data_ptr(), None)
+        ev1.record()
+        torch.cuda.synchronize()
+        us = 1e3 * ev0.elapsed_time(ev1) / 30
+        nbytes = A * V * V * 21 + A * stride
+        print(json.dumps(dict(kernel=f"one_hot_{name}", agents=A, V=V, us=round(us, 2),
+                              gbs=round(nbytes / us / 1e3, 1))), flush=True)
+    os.environ.pop("MG_ONE_HOT_W32", None)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="empty8")
@@ -138,6 +164,7 @@ def main():
     ap.add_argument("--wpbs", default="0")
     ap.add_argument("--nobulk", default="0")
     ap.add_argument("--extra", default="", help="comma list of extra KEY=VAL knob sets to also try, e.g. MG_PDL=1,MG_PDL=1+MG_L2HINT=3")
+    ap.add_argument("--one-hot", action="store_true", help="time the one-hot kernels on the bench batch")
     ap.add_argument("--rollout", type=int, default=0, help="also time mg_rollout with this many steps per launch")
     args = ap.parse_args()
     knobs = []
@@ -152,6 +179,8 @@ def main():
         knobs.append(k)
         for kv in [x for x in args.extra.split(",") if x]:
             knobs.append({**k, **dict(item.split("=") for item in kv.split("+"))})
+    if args.one_hot:
+        time_one_hot()
     for name in args.configs.split(","):
         if args.steps > 0:
             time_config(name, args.steps, knobs)
