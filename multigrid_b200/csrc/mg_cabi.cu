@@ -42,7 +42,15 @@ int plan(mg::Params &p) {
     p.generic_view = env_int("MG_GENERIC_VIEW", 0) ? 1 : 0;
     p.xknob = env_int("MG_X", 0);
     p.l2hint = env_int("MG_L2HINT", (p.flags & MG_FLAG_STREAM_STATE) ? 3 : 0);
-    return mg::plan_launch(p, env_int("MG_GROUP", 0), env_int("MG_WPB", 0), kSmemPerBlock, kSmemPerSM);
+    static thread_local int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n_sm = 148;
+    if (dev >= 0 && dev < 64) {
+        if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (sms[dev] > 0) n_sm = sms[dev];
+    }
+    return mg::plan_launch(p, env_int("MG_GROUP", 0), env_int("MG_WPB", 0), kSmemPerBlock, kSmemPerSM, n_sm);
 }
 
 template <int VT, int MODE, bool MULTI = false>

@@ -27,6 +27,8 @@ CONFIGS = {
     "empty8": (8, 8, 4, 7, 65536, 256, False),
     "bup": (11, 6, 2, 7, 32768, 576, True),
     "empty16": (16, 16, 8, 9, 16384, 1024, False),
+    "empty8h": (8, 8, 4, 7, 32768, 256, False),   # half batch: launch-plan heuristics
+    "empty8q": (8, 8, 4, 7, 8192, 256, False),
 }
 
 
@@ -63,10 +65,18 @@ def time_config(name, steps, knobs, replicas=8):
     torch.cuda.synchronize()
     bpe = bench.algorithmic_bytes_per_env_step(W, H, n, V, mutable)
     out = []
+    # every knob set is timed from the SAME state (all envs of a fixed-start layout share their episode
+    # phase: how far the agents have spread, and with it the cost of a launch, drifts with the step count)
+    names = ("cells", "agents", "step_count", "pcg_state", "layout_idx", "hook_state")
+    snap = [{k: getattr(e, k).clone() for k in names} for e in engines]
     for knob in knobs:
         for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_X"):
             os.environ.pop(key, None)
         os.environ.update({k: str(v) for k, v in knob.items()})
+        for e, sn in zip(engines, snap):
+            for k in names:
+                getattr(e, k).copy_(sn[k])
+        torch.cuda.synchronize()
         stream = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(stream):
             for k in range(4):
