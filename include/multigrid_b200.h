@@ -136,6 +136,23 @@ int mg_unpack_grid(int32_t width, int32_t height, int64_t num_envs, const uint32
                    void *stream);
 
 /*
+ * On-device layout generation for EmptyEnv with random agent placement (the 'MultiGrid-Empty-Random-*'
+ * ids and any EmptyEnv with agent_start_pos/agent_start_dir = None): one layout per generator.
+ * Replaces: EmptyEnv._gen_grid (envs/empty.py:151-170) -> MultiGridEnv.place_agent / place_obj
+ * (base.py:604-697) -> RandomMixin._rand_int (utils/random.py:23-38) -> numpy Generator(PCG64).integers
+ * (bounded Lemire draw on the buffered 32-bit stream), bit-exactly: given the generator the reference's
+ * RandomMixin holds, the layout and the generator's state afterwards are the reference's.
+ *   rng_state  uint64 [K][2] {lo,hi} PCG64 state, advanced in place;  rng_inc uint64 [K][2] (constant)
+ *   rng_buf    uint64 [K]: bit 32 = has_uint32, low word = uinteger of numpy's pcg64 state (may be NULL:
+ *              starts empty, the leftover half is dropped)
+ *   cells      uint32 [K][W+1][H+1] cell words (out);  agents int8 [K][n][8] (out)
+ *   status     device word OR-ed with 2 if a placement gave up after 65 536 tries (may be NULL)
+ */
+int mg_gen_layouts_empty_random(int32_t width, int32_t height, int32_t num_agents, int64_t num_layouts,
+                                uint64_t *rng_state, const uint64_t *rng_inc, uint64_t *rng_buf, uint32_t *cells,
+                                int8_t *agents, int32_t *status, void *stream);
+
+/*
  * Fully observable image: out int8 [E][W][H][3] = Grid.state with every agent (terminated or not)
  * written over its cell as (agent, colour, dir), highest agent index last.
  * Replaces: FullyObsWrapper.observation (multigrid/wrappers.py:50-58).

@@ -242,6 +242,87 @@ MG_HD uint64_t pcg64_next53(uint64_t &lo, uint64_t &hi, uint64_t inc_lo, uint64_
     return out >> 11;
 }
 
+// ---- numpy Generator(PCG64).integers(low, high) as RandomMixin._rand_int calls it -----------------
+// (utils/random.py:23-38 -> numpy/random/_bounded_integers.pyx _rand_int64 -> distributions.c
+// random_bounded_uint64_fill: ranges below 2^32 take buffered_bounded_lemire_uint32 on the bit
+// generator's 32-bit stream). numpy is a third-party dependency of the reference (pyproject.toml:30,
+// unpinned; 2.3.5 here): restated from its published algorithm and pinned against numpy itself.
+struct LayoutRng {
+    uint64_t lo, hi, ilo, ihi;  // PCG64 state / increment
+    uint32_t has32, buf32;      // pcg64_next32's buffered upper half (numpy/random/src/pcg64/pcg64.h)
+};
+
+MG_HD uint64_t pcg64_next64(LayoutRng &g) {
+    const uint64_t M_HI = 0x2360ED051FC65DA4ull, M_LO = 0x4385DF649FCCF645ull;
+    uint64_t nlo = g.lo * M_LO;
+    uint64_t nhi = mulhi64(g.lo, M_LO) + g.lo * M_HI + g.hi * M_LO;
+    uint64_t slo = nlo + g.ilo;
+    nhi += g.ihi + (slo < nlo ? 1ull : 0ull);
+    g.lo = slo; g.hi = nhi;
+    const uint64_t x = g.hi ^ g.lo;
+    const unsigned rot = (unsigned)(g.hi >> 58);
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+
+MG_HD uint32_t pcg64_next32(LayoutRng &g) {  // low half first, the high half is kept for the next call
+    if (g.has32) { g.has32 = 0; return g.buf32; }
+    const uint64_t v = pcg64_next64(g);
+    g.has32 = 1; g.buf32 = (uint32_t)(v >> 32);
+    return (uint32_t)v;
+}
+
+// Generator.integers(low, high) for 0 < high - low <= 2^32 (Lemire's nearly divisionless bounded draw)
+MG_HD int32_t rng_integers(LayoutRng &g, int32_t low, int32_t high) {
+    const uint32_t rng = (uint32_t)(high - low - 1);
+    if (rng == 0) return low;  // no draw (random_bounded_uint64_fill, rng == 0)
+    if (rng == 0xffffffffu) return low + (int32_t)pcg64_next32(g);
+    const uint32_t rng_excl = rng + 1u;
+    uint64_t m = (uint64_t)pcg64_next32(g) * rng_excl;
+    uint32_t leftover = (uint32_t)m;
+    if (leftover < rng_excl) {
+        const uint32_t threshold = (0xffffffffu - rng) % rng_excl;
+        while (leftover < threshold) {
+            m = (uint64_t)pcg64_next32(g) * rng_excl;
+            leftover = (uint32_t)m;
+        }
+    }
+    return low + (int32_t)(m >> 32);
+}
+
+// EmptyEnv._gen_grid with random agent placement (envs/empty.py:151-170): wall ring, goal at (W-2,H-2),
+// then per agent place_agent (base.py:672-697) = place_obj's rejection sampling (base.py:604-655: a cell
+// is taken when it is empty and NO agent record -- placed or not -- has that position) followed by
+// dir = _rand_int(0, 4). Writes one layout: padded cell words and packed agent records.
+// Returns false when the sampling gave up (the reference would loop forever).
+MG_HD bool gen_layout_empty_random(int W, int H, int n, LayoutRng &g, uint32_t *cells, int8_t *agents) {
+    const int Hp = H + 1;
+    for (int x = 0; x <= W; x++)
+        for (int y = 0; y <= H; y++) {
+            const bool wall = x == 0 || y == 0 || x >= W - 1 || y >= H - 1;
+            cells[x * Hp + y] = wall ? CELL_WALL : CELL_EMPTY;
+        }
+    if (W >= 3 && H >= 3) cells[(W - 2) * Hp + (H - 2)] = T_GOAL | (1u << 8);  // Goal() is green
+    for (int j = 0; j < n; j++) {
+        int8_t *a = agents + j * 8;
+        a[0] = -1; a[1] = -1; a[2] = -1; a[3] = 0; a[4] = T_EMPTY; a[5] = 0; a[6] = 0; a[7] = (int8_t)(j % 6);
+    }
+    for (int j = 0; j < n; j++) {
+        int x = -1, y = -1;
+        for (int tries = 0;; tries++) {
+            if (tries >= (1 << 16)) return false;
+            x = rng_integers(g, 0, W);
+            y = rng_integers(g, 0, H);
+            if ((cells[x * Hp + y] & 0xffu) != T_EMPTY) continue;   // grid.get(*pos) is not None
+            bool taken = false;
+            for (int q = 0; q < n; q++) taken |= agents[q * 8 + 1] == x && agents[q * 8 + 2] == y;
+            if (!taken) break;
+        }
+        agents[j * 8 + 1] = (int8_t)x; agents[j * 8 + 2] = (int8_t)y;
+        agents[j * 8 + 0] = (int8_t)rng_integers(g, 0, 4);
+    }
+    return true;
+}
+
 // base.py:598-602: `1 - 0.9 * (step_count / max_steps)` in float64, round-to-nearest at every
 // operation, never contracted into an FMA.
 MG_HD double reward_value(int32_t step_count, int32_t max_steps) {
@@ -1026,6 +1107,23 @@ __global__ void unpack_grid_kernel(int W, int H, int64_t total, const uint32_t *
     const uint32_t w = cells[e * (int64_t)(W + 1) * (H + 1) + x * (H + 1) + y];
     uint8_t *dst = (uint8_t *)grid3 + idx * 3;
     dst[0] = (uint8_t)w; dst[1] = (uint8_t)(w >> 8); dst[2] = (uint8_t)(w >> 16);
+}
+
+// One thread per layout; the generator state is advanced in place (rng_buf: bit 32 = has_uint32,
+// low word = the buffered upper half). Not on the step path: it fills the reset-layout pool.
+__global__ void gen_layouts_empty_random_kernel(int W, int H, int n, int64_t K, uint64_t *rng_state,
+                                                const uint64_t *rng_inc, uint64_t *rng_buf, uint32_t *cells,
+                                                int8_t *agents, int32_t *status) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    LayoutRng g;
+    g.lo = rng_state[2 * k]; g.hi = rng_state[2 * k + 1]; g.ilo = rng_inc[2 * k]; g.ihi = rng_inc[2 * k + 1];
+    const uint64_t b = rng_buf ? rng_buf[k] : 0ull;
+    g.has32 = (uint32_t)(b >> 32) & 1u; g.buf32 = (uint32_t)b;
+    const bool ok = gen_layout_empty_random(W, H, n, g, cells + k * (int64_t)(W + 1) * (H + 1), agents + k * n * 8);
+    if (!ok) status_or(status, 2);
+    rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
+    if (rng_buf) rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
 }
 
 // <= 4 warps per block; register cap: 72 (7 blocks x 128 threads per SM) up to V = 7, 128 for V = 9

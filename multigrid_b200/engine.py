@@ -148,6 +148,31 @@ class StepEngine:
         self.pool_agents = pa.to(self.device)
         self._c = None
 
+    def gen_layout_pool_empty_random(self, rng_state, rng_inc, rng_buf=None):
+        """mg_gen_layouts_empty_random: fill the reset-layout pool ON THE DEVICE with K =
+        len(rng_state) EmptyEnv layouts with random agent placement (envs/empty.py:151-170), one per
+        numpy PCG64 generator given as uint64 words (state [K,2], inc [K,2], optional buffered-uint32
+        word [K]). Returns the advanced (state, buf) as numpy uint64 arrays."""
+        cfg = self.cfg
+        K = len(rng_state)
+        dev = self.device
+        st = torch.as_tensor(_as_i64_bits(rng_state)).to(dev).reshape(K, 2).contiguous()
+        inc = torch.as_tensor(_as_i64_bits(rng_inc)).to(dev).reshape(K, 2).contiguous()
+        buf = torch.as_tensor(_as_i64_bits(np.zeros(K, np.uint64) if rng_buf is None else rng_buf)).to(dev)
+        cells = torch.empty((K, cfg.width + 1, cfg.height + 1), dtype=torch.int32, device=dev)
+        agents = torch.empty((K, cfg.num_agents, 8), dtype=torch.int8, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.check(self.lib.mg_gen_layouts_empty_random(
+                cfg.width, cfg.height, cfg.num_agents, K, st.data_ptr(), inc.data_ptr(), buf.data_ptr(),
+                cells.data_ptr(), agents.data_ptr(), self.status.data_ptr(), self._stream()),
+                "mg_gen_layouts_empty_random")
+        if int(self.status.item()) & 2:
+            self.status.zero_()
+            raise RecursionError("rejection sampling failed in place_obj")  # base.py:640-641
+        self.pool_grid, self.pool_agents = cells, agents
+        self._c = None
+        return st.cpu().numpy().view(np.uint64), buf.cpu().numpy().view(np.uint64)
+
     def load_state(self, grid=None, agents=None, step_count=None, pcg_state=None, pcg_inc=None,
                    layout_idx=None, hook_state=None) -> None:
         """Inject state (numpy or torch, host or device). uint64 PCG words are passed as numpy."""

@@ -25,7 +25,7 @@ import torch
 from . import _cabi, spaces
 from .core.constants import Action, Color, Direction, Type
 from .engine import EngineConfig, StepEngine
-from .layouts import A_COLOR, A_CC, A_CS, A_CT, A_DIR, A_TERM, A_X, A_Y, Layout
+from .layouts import A_COLOR, A_CC, A_CS, A_CT, A_DIR, A_TERM, A_X, A_Y, EmptyLayout, Layout
 
 _M64 = (1 << 64) - 1
 
@@ -45,6 +45,19 @@ def pcg64_words(seeds: Sequence[int]) -> tuple[np.ndarray, np.ndarray]:
 def generator_words(gen: np.random.Generator) -> tuple[tuple[int, int], tuple[int, int]]:
     d = gen.bit_generator.state["state"]
     return (d["state"] & _M64, d["state"] >> 64), (d["inc"] & _M64, d["inc"] >> 64)
+
+
+def layout_generator_words(gens) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(state [K,2], inc [K,2], buf [K]) uint64 words of numpy PCG64 generators, including the buffered
+    upper half of the 32-bit stream (bit 32 of buf = has_uint32, low word = uinteger)."""
+    K = len(gens)
+    st, inc, buf = np.empty((K, 2), np.uint64), np.empty((K, 2), np.uint64), np.empty(K, np.uint64)
+    for k, g in enumerate(gens):
+        d = g.bit_generator.state
+        st[k] = (d["state"]["state"] & _M64, d["state"]["state"] >> 64)
+        inc[k] = (d["state"]["inc"] & _M64, d["state"]["inc"] >> 64)
+        buf[k] = (int(d["has_uint32"]) << 32) | int(d["uinteger"])
+    return st, inc, buf
 
 
 def entropy_words(count: int) -> tuple[np.ndarray, np.ndarray]:
@@ -139,7 +152,7 @@ class BatchedMultiGridEnv:
                  joint_reward: bool = False, success_termination_mode: str = "any",
                  failure_termination_mode: str = "all", auto_reset: bool = False,
                  pool_size: int | None = None, layout_seed: int | None = None,
-                 first_env: int = 0, render_mode: str | None = None):
+                 first_env: int = 0, render_mode: str | None = None, device_layouts: bool = True):
         if render_mode is not None:
             raise NotImplementedError("rendering is out of scope of the batched engine")
         self.layout = layout
@@ -154,6 +167,9 @@ class BatchedMultiGridEnv:
         self.auto_reset = auto_reset
         self.first_env = int(first_env)  # global id of local env 0 (multi-GPU sharding)
         self.layout_seed = layout_seed
+        # EmptyEnv layouts with random agent placement are generated by a CUDA kernel (bit-exact with the
+        # host generator, tests/test_layouts.py); device_layouts=False forces the host path
+        self.device_layouts = bool(device_layouts) and isinstance(layout, EmptyLayout) and not layout.deterministic
         self.pool_size = 1 if layout.deterministic else min(self.num_envs, pool_size or 4096)
         cfg = EngineConfig(
             width=self.width, height=self.height, num_agents=self.num_agents,
@@ -212,14 +228,34 @@ class BatchedMultiGridEnv:
         seeds = self._seeds(seed)
         st, inc = entropy_words(E) if seeds is None else pcg64_words(seeds)
         layout_rngs = options.get("layout_rngs")
+
+        def layout_rng(k):
+            if layout_rngs is not None:
+                return layout_rngs[k]
+            if self.layout_seed is not None:
+                return np.random.default_rng([int(self.layout_seed), self.first_env + k])
+            return np.random.default_rng()
+
+        if self.device_layouts:
+            gens = [layout_rng(k) for k in range(K)]
+            lst, linc, lbuf = layout_generator_words(gens)
+            lst, lbuf = self.engine.gen_layout_pool_empty_random(lst, linc, lbuf)
+            if layout_rngs is not None:  # the caller's generators advance as the reference's would
+                for k, g in enumerate(gens):
+                    d = g.bit_generator.state
+                    d["state"]["state"] = int(lst[k, 0]) | (int(lst[k, 1]) << 64)
+                    d["has_uint32"], d["uinteger"] = int(lbuf[k] >> np.uint64(32)) & 1, int(lbuf[k] & np.uint64(0xffffffff))
+                    g.bit_generator.state = d
+            idx = np.arange(E, dtype=np.int32) % K
+            self.engine.load_state(layout_idx=idx, pcg_state=st, pcg_inc=inc)
+            self.engine.reset_from_pool()
+            self.missions = Missions([self.layout.mission], None)
+            self._needs_reset = False
+            return self._obs(self.engine.gen_obs()), defaultdict(dict)
+
         grids, agents, infos = [], [], []
         for k in range(K):
-            if layout_rngs is not None:
-                lrng = layout_rngs[k]
-            elif self.layout_seed is not None:
-                lrng = np.random.default_rng([int(self.layout_seed), self.first_env + k])
-            else:
-                lrng = np.random.default_rng()
+            lrng = layout_rng(k)
             if self.layout.deterministic:
                 orng = None
             else:  # env k's own order stream: reset-time draws (door positions) advance it

@@ -31,6 +31,14 @@ class HostSimStepEngine:
         self._pool = (np.asarray(pool_grid, np.int8), np.asarray(pool_agents, np.int8))
         self._sim = None
 
+    def gen_layout_pool_empty_random(self, rng_state, rng_inc, rng_buf=None):
+        from tests.hostsim.sim import gen_layouts_empty_random
+        cfg = self.cfg
+        buf = np.zeros(len(rng_state), np.uint64) if rng_buf is None else rng_buf
+        grid, agents, st, buf = gen_layouts_empty_random(cfg.width, cfg.height, cfg.num_agents, rng_state, rng_inc, buf)
+        self.set_layout_pool(grid, agents)
+        return np.array(st), np.array(buf)
+
     def load_state(self, grid=None, agents=None, step_count=None, pcg_state=None, pcg_inc=None,
                    layout_idx=None):
         self._snapshot()

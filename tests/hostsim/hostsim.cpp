@@ -110,3 +110,19 @@ extern "C" int sim_run(int mode, const MgConfig *c, int64_t num_envs, const MgSt
     else dispatch<mg::MODE_STEP_OBS>(p, generic);
     return 0;
 }
+
+// mg_gen_layouts_empty_random on the CPU: the same gen_layout_empty_random() the CUDA kernel calls.
+extern "C" int sim_gen_layouts_empty_random(int W, int H, int n, int64_t K, uint64_t *rng_state,
+                                            const uint64_t *rng_inc, uint64_t *rng_buf, uint32_t *cells,
+                                            int8_t *agents) {
+    int bad = 0;
+    for (int64_t k = 0; k < K; k++) {
+        mg::LayoutRng g;
+        g.lo = rng_state[2 * k]; g.hi = rng_state[2 * k + 1]; g.ilo = rng_inc[2 * k]; g.ihi = rng_inc[2 * k + 1];
+        g.has32 = (uint32_t)(rng_buf[k] >> 32) & 1u; g.buf32 = (uint32_t)rng_buf[k];
+        if (!mg::gen_layout_empty_random(W, H, n, g, cells + k * (int64_t)(W + 1) * (H + 1), agents + k * n * 8)) bad = 1;
+        rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
+        rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
+    }
+    return bad;
+}

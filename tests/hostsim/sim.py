@@ -77,6 +77,19 @@ def unpack_cells(cells, W, H):
     return np.stack([w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff], -1).astype(np.int8)
 
 
+def gen_layouts_empty_random(W, H, n, rng_state, rng_inc, rng_buf):
+    """CPU run of the layout kernel's function. Returns (grid (K,W,H,3) int8, agents (K,n,8), state, buf)."""
+    K = len(rng_state)
+    st, inc = aligned_copy(rng_state, np.uint64), aligned_copy(rng_inc, np.uint64)
+    buf = aligned_copy(rng_buf, np.uint64)
+    cells, agents = aligned((K, W + 1, H + 1), np.uint32), aligned((K, n, 8), np.int8)
+    rc = lib().sim_gen_layouts_empty_random(C.c_int(W), C.c_int(H), C.c_int(n), C.c_int64(K), _p(st), _p(inc),
+                                            _p(buf), _p(cells), _p(agents))
+    assert rc == 0, rc
+    assert (cells[:, W, :] == cells[:, 0, :]).all() and (cells[:, :, H] == cells[:, :, 0]).all()  # sentinels = walls
+    return unpack_cells(cells, W, H), agents, st, buf
+
+
 class SimEngine:
     """Mirror of oracle.OracleBatch's interface on top of the host-simulated kernels."""
 

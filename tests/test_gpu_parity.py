@@ -398,3 +398,55 @@ def test_fully_obs_wrapper_on_gpu():
         want = np.stack([O.full_obs(grid[e], agents[e]) for e in range(40)])
         assert obs[0]["image"].shape == (40, 11, 6, 3) and obs[1]["image"] is obs[0]["image"]
         np.testing.assert_array_equal(obs[0]["image"].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("size,n", [(5, 2), (6, 3), (8, 8), (16, 12), (9, 30)])
+def test_layout_kernel_matches_host_generator(size, n):
+    """mg_gen_layouts_empty_random on the GPU vs EmptyLayout.generate driven by numpy generators (which
+    tests/test_layouts.py pins to the reference's post-reset states): grids, agents, generator state."""
+    import torch
+    from multigrid_b200 import layouts as L
+    from multigrid_b200.engine import EngineConfig, StepEngine
+    from multigrid_b200.env import layout_generator_words
+    K = 1500
+    mk = lambda: [np.random.default_rng([size, n, k]) for k in range(K)]  # noqa: E731
+    gens = mk()
+    for g in gens[::3]:
+        g.integers(0, 10)  # a buffered 32-bit half in every third generator
+    st, inc, buf = layout_generator_words(gens)
+    eng = StepEngine(EngineConfig(width=size, height=size, num_agents=n), 4, "cuda:0")
+    st2, buf2 = eng.gen_layout_pool_empty_random(st, inc, buf)
+    W = size
+    grid = eng.pool_grid.view(torch.int8).view(K, W + 1, W + 1, 4)[:, :W, :W, :3].cpu().numpy()
+    agents = eng.pool_agents.cpu().numpy()
+    layout = L.EmptyLayout(n, size=size, agent_start_pos=None, agent_start_dir=None)
+    for k in range(K):
+        g, a, _ = layout.generate(gens[k], None)
+        np.testing.assert_array_equal(grid[k], g, err_msg=f"layout {k}")
+        np.testing.assert_array_equal(agents[k], a, err_msg=f"layout {k}")
+    st_h, _, buf_h = layout_generator_words(gens)
+    np.testing.assert_array_equal(st2, st_h)
+    np.testing.assert_array_equal(buf2, buf_h)
+
+
+def test_env_reset_device_layouts_equal_host_layouts():
+    """'MultiGrid-Empty-Random-6x6-v0': reset() with the pool generated on the device == generated in Python."""
+    from multigrid_b200.envs import make
+    kw = dict(agents=3, num_envs=2000, device="cuda:0", layout_seed=11, pool_size=2000, allow_agent_overlap=False)
+    a = make("MultiGrid-Empty-Random-6x6-v0", **kw)
+    b = make("MultiGrid-Empty-Random-6x6-v0", device_layouts=False, **kw)
+    assert a.device_layouts and not b.device_layouts
+    oa, _ = a.reset(seed=5)
+    ob, _ = b.reset(seed=5)
+    np.testing.assert_array_equal(a.grid.state.cpu().numpy(), b.grid.state.cpu().numpy())
+    np.testing.assert_array_equal(a.agent_states.cpu().numpy(), b.agent_states.cpu().numpy())
+    for i in range(3):
+        np.testing.assert_array_equal(oa[i]["image"].cpu().numpy(), ob[i]["image"].cpu().numpy())
+    assert len({x.tobytes() for x in a.agent_states.cpu().numpy()}) > 1000
+    rng = np.random.default_rng(0)
+    for t in range(30):
+        acts = rng.integers(0, 7, (2000, 3)).astype(np.int8)
+        ra, rb = a.step(acts), b.step(acts)
+        for i in range(3):
+            np.testing.assert_array_equal(ra[0][i]["image"].cpu().numpy(), rb[0][i]["image"].cpu().numpy())
+            assert (ra[1][i].cpu().numpy() == rb[1][i].cpu().numpy()).all()

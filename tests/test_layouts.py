@@ -56,3 +56,52 @@ def test_generate_pool_shapes_and_determinism():
     assert len({g.tobytes() for g in g1}) > 1
     g, a, _ = L.generate_pool(L.EmptyLayout(4), 100, seed=0)
     assert g.shape[0] == 1 and (a[0, :, 1:3] == 1).all() and (a[0, :, 0] == int(Direction.right)).all()
+
+
+def _numpy_rngs(K, seed, odd_buffer):
+    gens = [np.random.default_rng([seed, k]) for k in range(K)]
+    if odd_buffer:  # leave a buffered upper half in every second generator (numpy's has_uint32 state)
+        for g in gens[::2]:
+            g.integers(0, 10)
+    return gens
+
+
+@pytest.mark.parametrize("size,n,seed", [(5, 1, 0), (5, 4, 1), (6, 3, 2), (8, 8, 3), (16, 12, 4), (7, 20, 5), (3, 1, 6)])
+@pytest.mark.parametrize("odd_buffer", [False, True])
+def test_device_layout_function_matches_host_generator(size, n, seed, odd_buffer):
+    """gen_layout_empty_random (the function the CUDA layout kernel runs; here compiled for the CPU by
+    tests/hostsim) against EmptyLayout.generate driven by real numpy generators: same grids, same agent
+    records, same generator state afterwards (PCG64 state AND the buffered 32-bit half) -- i.e. the
+    in-kernel Generator.integers (Lemire + pcg64_next32 buffering) is numpy's."""
+    from multigrid_b200.env import layout_generator_words
+    from tests.hostsim.sim import gen_layouts_empty_random
+    if n > (size - 2) ** 2 - 1:
+        pytest.skip("more agents than free cells")
+    K = 300
+    layout = L.EmptyLayout(n, size=size, agent_start_pos=None, agent_start_dir=None)
+    st, inc, buf = layout_generator_words(_numpy_rngs(K, seed, odd_buffer))
+    grid, agents, st2, buf2 = gen_layouts_empty_random(size, size, n, st, inc, buf)
+    host = _numpy_rngs(K, seed, odd_buffer)
+    for k in range(K):
+        g, a, _ = layout.generate(host[k], None)
+        np.testing.assert_array_equal(grid[k], g, err_msg=f"layout {k}")
+        np.testing.assert_array_equal(agents[k], a, err_msg=f"layout {k}")
+    st_h, _, buf_h = layout_generator_words(host)
+    np.testing.assert_array_equal(st2, st_h)
+    np.testing.assert_array_equal(buf2, buf_h)
+    assert len({a.tobytes() for a in agents}) > 1
+
+
+def test_in_kernel_integers_matches_numpy_for_awkward_ranges():
+    """Ranges whose Lemire threshold is non-zero (3, 5, 6, 7, 14 cells ...) exercise the rejection loop."""
+    from multigrid_b200.env import layout_generator_words
+    from tests.hostsim.sim import gen_layouts_empty_random
+    for size in (5, 7, 9, 16, 100):  # integers(0, size): thresholds (2^32 - size) % size
+        K = 2000
+        gens = [np.random.default_rng([99, size, k]) for k in range(K)]
+        st, inc, buf = layout_generator_words(gens)
+        grid, agents, st2, buf2 = gen_layouts_empty_random(size, size, 1, st, inc, buf)
+        layout = L.EmptyLayout(1, size=size, agent_start_pos=None, agent_start_dir=None)
+        for k in range(0, K, 7):
+            g, a, _ = layout.generate(gens[k], None)
+            np.testing.assert_array_equal(agents[k], a)
