@@ -107,6 +107,7 @@ class StepEngine:
         self.status = z((1,), torch.int32)
         self.pool_grid = None
         self.pool_agents = None
+        self._pool_rng = None
         if pool_grid is not None:
             self.set_layout_pool(pool_grid, pool_agents)
         self._host = None
@@ -146,6 +147,7 @@ class StepEngine:
                                      device=self.device)
         self._pack(pg, self.pool_grid)
         self.pool_agents = pa.to(self.device)
+        self._pool_rng = None
         self._c = None
 
     def gen_layout_pool_empty_random(self, rng_state, rng_inc, rng_buf=None):
@@ -161,17 +163,28 @@ class StepEngine:
         buf = torch.as_tensor(_as_i64_bits(np.zeros(K, np.uint64) if rng_buf is None else rng_buf)).to(dev)
         cells = torch.empty((K, cfg.width + 1, cfg.height + 1), dtype=torch.int32, device=dev)
         agents = torch.empty((K, cfg.num_agents, 8), dtype=torch.int8, device=dev)
-        with torch.cuda.device(dev):
-            _cabi.check(self.lib.mg_gen_layouts_empty_random(
-                cfg.width, cfg.height, cfg.num_agents, K, st.data_ptr(), inc.data_ptr(), buf.data_ptr(),
-                cells.data_ptr(), agents.data_ptr(), self.status.data_ptr(), self._stream()),
-                "mg_gen_layouts_empty_random")
+        self.pool_grid, self.pool_agents = cells, agents
+        self._pool_rng = (st, inc, buf)  # stays on the device: refresh_layout_pool() continues these streams
+        self._c = None
+        self.refresh_layout_pool()
         if int(self.status.item()) & 2:
             self.status.zero_()
             raise RecursionError("rejection sampling failed in place_obj")  # base.py:640-641
-        self.pool_grid, self.pool_agents = cells, agents
-        self._c = None
         return st.cpu().numpy().view(np.uint64), buf.cpu().numpy().view(np.uint64)
+
+    def refresh_layout_pool(self) -> None:
+        """Overwrite the pool with the NEXT layout of every pool generator (one kernel launch, no host
+        work, asynchronous): with auto_reset, envs that reset after this draw from fresh layouts
+        instead of cycling the first K. Only after gen_layout_pool_empty_random."""
+        if getattr(self, "_pool_rng", None) is None:
+            raise RuntimeError("the layout pool was not generated on the device")
+        cfg = self.cfg
+        st, inc, buf = self._pool_rng
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.mg_gen_layouts_empty_random(
+                cfg.width, cfg.height, cfg.num_agents, st.shape[0], st.data_ptr(), inc.data_ptr(), buf.data_ptr(),
+                self.pool_grid.data_ptr(), self.pool_agents.data_ptr(), self.status.data_ptr(), self._stream()),
+                "mg_gen_layouts_empty_random")
 
     def load_state(self, grid=None, agents=None, step_count=None, pcg_state=None, pcg_inc=None,
                    layout_idx=None, hook_state=None) -> None:

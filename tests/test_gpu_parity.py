@@ -427,6 +427,11 @@ def test_layout_kernel_matches_host_generator(size, n):
     st_h, _, buf_h = layout_generator_words(gens)
     np.testing.assert_array_equal(st2, st_h)
     np.testing.assert_array_equal(buf2, buf_h)
+    eng.refresh_layout_pool()  # the NEXT layout of every generator, in place, no host work
+    agents2 = eng.pool_agents.cpu().numpy()
+    for k in range(0, K, 5):
+        g, a, _ = layout.generate(gens[k], None)
+        np.testing.assert_array_equal(agents2[k], a, err_msg=f"refreshed layout {k}")
 
 
 def test_env_reset_device_layouts_equal_host_layouts():
