@@ -466,11 +466,50 @@ MG_HD void phase_load_plain(const Params &p, const Group &g, int lane, int t = 0
     if (MODE != MODE_OBS) warp_copy(g.act, p.actions + ((size_t)t * p.num_envs + e0) * p.n, g.ne * p.n, lane);
 }
 
+// n == 4 (the headline configuration): the env's four agent records in registers -- two 16-byte
+// shared-memory loads instead of one 4/8-byte load per agent in each of the epilogue's loops.
+struct Ag4 { uint32_t a0[4], a1[4]; };
+
+MG_HD Ag4 load_ag4(const uint32_t *ag) {
+    Ag4 a;
+#ifdef __CUDA_ARCH__
+    const uint4 q0 = *(const uint4 *)ag, q1 = *(const uint4 *)(ag + 4);
+    a.a0[0] = q0.x; a.a1[0] = q0.y; a.a0[1] = q0.z; a.a1[1] = q0.w;
+    a.a0[2] = q1.x; a.a1[2] = q1.y; a.a0[3] = q1.z; a.a1[3] = q1.w;
+#else
+    for (int j = 0; j < 4; j++) { a.a0[j] = ag[2 * j]; a.a1[j] = ag[2 * j + 1]; }
+#endif
+    return a;
+}
+
+MG_HD uint32_t terminated_mask4(const Ag4 &a) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) m |= (uint32_t)((a.a0[j] & 0xff000000u) != 0) << j;
+    return m;
+}
+
+// 4 mask bits -> 4 bytes of 0/1 (bit i lands on bit 8*i; no two partial products collide)
+MG_HD uint32_t bits_to_bytes4(uint32_t bits) { return ((bits & 15u) * 0x00204081u) & 0x01010101u; }
+
+MG_HD void stamp_agents4(const Params &p, uint32_t *cells, const Ag4 &a, uint32_t terminated) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t x = (a.a0[j] >> 8) & 0xff, y = (a.a0[j] >> 16) & 0xff;
+        const bool on = !((terminated >> j) & 1u) && x < (uint32_t)p.W && y < (uint32_t)p.H;
+        if (on) cells[x * p.Hp + y] = T_AGENT | ((a.a1[j] >> 24) << 8) | ((a.a0[j] & 0xff) << 16);
+    }
+}
+
 // ---- P2: auto-reset decision ("next-step" mode; is_done = base.py:534-539) --------------------------
 MG_HD void phase_reset(const Params &p, const Group &g, int i, EnvRegs &r) {
     if (i < 0) return;
     uint32_t all_term = 1;
-    for (int j = 0; j < p.n; j++) all_term &= ((g.ag[(i * p.n + j) * 2] >> 24) & 0xff) != 0;
+    if (p.n == 4) {
+        all_term = terminated_mask4(load_ag4(g.ag + i * 8)) == 15u;
+    } else {
+        for (int j = 0; j < p.n; j++) all_term &= ((g.ag[(i * p.n + j) * 2] >> 24) & 0xff) != 0;
+    }
     int k = -1;
     // LockedHallway terminates in the returned dict only (all doors unlocked), never in agent state
     if (p.hook == MG_HOOK_LOCKED_HALLWAY && __builtin_popcount((unsigned)r.hs) == p.hook_param) all_term = 1;
@@ -747,7 +786,9 @@ MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const 
         } else {
             r.lo = d.lo0; r.hi = d.hi0;  // no step, no draw
         }
-        const uint32_t pre_hook_terminated = terminated_mask(p, ag);
+        Ag4 a4;
+        if (n == 4) a4 = load_ag4(ag);
+        const uint32_t pre_hook_terminated = n == 4 ? terminated_mask4(a4) : terminated_mask(p, ag);
         if (!was_reset && p.hook == MG_HOOK_BLOCKED_UNLOCK_PICKUP) {  // envs/blockedunlockpickup.py:166-175
             for (int k = 0; k < n; k++)
                 if ((ag[k * 2 + 1] & 0xff) == T_BOX) on_success(p, ag, rewarded, k);
@@ -760,7 +801,10 @@ MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const 
             dict_terminated = !was_reset && __builtin_popcount((unsigned)r.hs) == p.hook_param;
             p.hook_state[e] = r.hs;
         }
-        if (MODE == MODE_STEP_OBS) stamp_agents(p, cells, ag, pre_hook_terminated);  // obs sees pre-hook state
+        if (MODE == MODE_STEP_OBS) {  // obs sees pre-hook state (the hooks only touch the terminated bytes)
+            if (n == 4) stamp_agents4(p, cells, a4, pre_hook_terminated);
+            else stamp_agents(p, cells, ag, pre_hook_terminated);
+        }
         p.step_count[e] = r.sc;
         if (n > 1) { U128 s; s.lo = r.lo; s.hi = r.hi; *(U128 *)(p.pcg_state + 2 * e) = s; }
         if (p.flags & MG_FLAG_AUTO_RESET) p.layout_idx[e] = r.lidx;
@@ -768,18 +812,28 @@ MG_HD void phase_step(const Params &p, const Group &g, int i, EnvRegs &r, const 
         const double rv = (rewarded | bonus_all | bonus) ? reward_value(r.sc, p.max_steps) : 0.0;  // base.py:394, 598-602
         const uint32_t term_force = dict_terminated ? 0x01010101u : 0u;
         if (n == 4) {
-            uint32_t tw = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) tw |= (uint32_t)(((ag[j * 2] >> 24) & 0xff) != 0) << (8 * j);
-            *(uint32_t *)(p.terminated + eo * 4) = tw | term_force;
+            const uint32_t post = p.hook == MG_HOOK_NONE ? pre_hook_terminated : terminated_mask(p, ag);
+            *(uint32_t *)(p.terminated + eo * 4) = bits_to_bytes4(post) | term_force;
+            if (p.direction)  // rollout: the 'direction' observation of this step (base.py:371)
+                *(uint32_t *)(p.direction + eo * 4) = (a4.a0[0] & 0xff) | ((a4.a0[1] & 0xff) << 8) |
+                                                      ((a4.a0[2] & 0xff) << 16) | ((a4.a0[3] & 0xff) << 24);
+#ifdef __CUDA_ARCH__
+            if (((uintptr_t)p.reward & 15u) == 0) {  // (the ABI only requires 8-byte alignment)
+                double2 *rw = (double2 *)(p.reward + eo * 4);
+                rw[0] = make_double2((rewarded & 1u) ? rv : 0.0, (rewarded & 2u) ? rv : 0.0);
+                rw[1] = make_double2((rewarded & 4u) ? rv : 0.0, (rewarded & 8u) ? rv : 0.0);
+            } else
+#endif
+            {
+                for (int j = 0; j < 4; j++) p.reward[eo * 4 + j] = ((rewarded >> j) & 1u) ? rv : 0.0;
+            }
         } else {
-                    for (int j = 0; j < n; j++)
+            for (int j = 0; j < n; j++)
                 p.terminated[eo * n + j] = (uint8_t)((term_force & 1u) | (((ag[j * 2] >> 24) & 0xff) != 0));
-        }
-        if (p.direction) {  // rollout: the 'direction' observation of this step (base.py:371)
-                    for (int j = 0; j < n; j++) p.direction[eo * n + j] = (int8_t)(ag[j * 2] & 0xff);
-        }
+            if (p.direction)
+                for (int j = 0; j < n; j++) p.direction[eo * n + j] = (int8_t)(ag[j * 2] & 0xff);
             for (int j = 0; j < n; j++) p.reward[eo * n + j] = ((rewarded >> j) & 1u) ? rv : 0.0;
+        }
         if (bonus_all | bonus) {  // LockedHallway only: rewards[k] += self._reward(), once per new door
             for (int j = 0; j < n; j++) {
                 double rj = ((rewarded >> j) & 1u) ? rv : 0.0;
