@@ -226,3 +226,39 @@ def test_adapters_on_gpu():
     pz.reset(seed=1)
     _to_goal(pz, 1)
     assert pz.agents == [0] and pz.possible_agents == [0, 1]
+
+
+def test_vectorised_seeding_matches_numpy():
+    """seed_sequence_pcg64_words == PCG64(SeedSequence(...)) for int seeds (1 and 2 words) and list entropy."""
+    seeds = [0, 1, 7, 123456789, 2 ** 32 - 1, 2 ** 32, 2 ** 40 + 5, 2 ** 62 + 11]
+    st, inc = env_mod.pcg64_words(seeds)
+    for r, s in enumerate(seeds):
+        ref = np.random.Generator(np.random.PCG64(np.random.SeedSequence(s)))
+        assert env_mod.generator_words(ref) == (tuple(int(v) for v in st[r]), tuple(int(v) for v in inc[r]))
+    ent = np.array([[5, 3], [11, 4096], [0, 0], [2 ** 32 - 1, 17]], np.uint32)
+    st, inc = env_mod.seed_sequence_pcg64_words(ent)
+    for r in range(len(ent)):
+        ref = np.random.default_rng([int(ent[r, 0]), int(ent[r, 1])])
+        assert env_mod.generator_words(ref) == (tuple(int(v) for v in st[r]), tuple(int(v) for v in inc[r]))
+    ent = (np.arange(12, dtype=np.uint32).reshape(2, 6) + 1) * np.uint32(2654435761)
+    st, inc = env_mod.seed_sequence_pcg64_words(ent)
+    for r in range(2):
+        ref = np.random.default_rng([int(x) for x in ent[r]])
+        assert env_mod.generator_words(ref) == (tuple(int(v) for v in st[r]), tuple(int(v) for v in inc[r]))
+
+
+def test_reset_device_layout_path_equals_host_path(monkeypatch):
+    """Empty-Random reset with the pool from the layout kernel's function (hostsim) and vectorised seeding
+    == the Python generator path with one numpy Generator per layout."""
+    from tests.hostsim.fake_engine import HostSimStepEngine
+    monkeypatch.setattr(env_mod, "StepEngine", HostSimStepEngine)
+    kw = dict(agents=3, num_envs=300, device="cpu", layout_seed=11, pool_size=300, first_env=1000)
+    a = make("MultiGrid-Empty-Random-5x5-v0", **kw)
+    b = make("MultiGrid-Empty-Random-5x5-v0", device_layouts=False, **kw)
+    assert a.device_layouts and not b.device_layouts
+    oa, _ = a.reset(seed=5)
+    ob, _ = b.reset(seed=5)
+    np.testing.assert_array_equal(a.grid.state.numpy(), b.grid.state.numpy())
+    np.testing.assert_array_equal(a.agent_states.numpy(), b.agent_states.numpy())
+    np.testing.assert_array_equal(oa[2]["image"].numpy(), ob[2]["image"].numpy())
+    assert len({x.tobytes() for x in a.agent_states.numpy()}) > 100
