@@ -153,6 +153,19 @@ int mg_gen_layouts_empty_random(int32_t width, int32_t height, int32_t num_agent
                                 int8_t *agents, int32_t *status, void *stream);
 
 /*
+ * On-device layouts of BlockedUnlockPickupEnv (envs/blockedunlockpickup.py:142-164 over
+ * core/roomgrid.py:203-404: add_object, add_door, place_in_room on a 1 x 2 RoomGrid of `room_size`), same
+ * generator conventions as mg_gen_layouts_empty_random plus the ORDER generator of each layout
+ * (env.np_random: the door height is drawn from it, roomgrid.py:324): order_state [K][2] is advanced in
+ * place, order_inc [K][2]. info [K] (may be NULL) receives the box colour index (the mission names it).
+ * Grid is (2*(room_size-1)+1) x room_size. status |= 2 when a placement exceeded the reference's
+ * max_tries = 1000 (the reference raises RecursionError).
+ */
+int mg_gen_layouts_bup(int32_t room_size, int32_t num_agents, int64_t num_layouts, uint64_t *rng_state,
+                       const uint64_t *rng_inc, uint64_t *rng_buf, uint64_t *order_state, const uint64_t *order_inc,
+                       uint32_t *cells, int8_t *agents, int32_t *info, int32_t *status, void *stream);
+
+/*
  * Fully observable image: out int8 [E][W][H][3] = Grid.state with every agent (terminated or not)
  * written over its cell as (agent, colour, dir), highest agent index last.
  * Replaces: FullyObsWrapper.observation (multigrid/wrappers.py:50-58).

@@ -242,6 +242,18 @@ MG_HD uint64_t pcg64_next53(uint64_t &lo, uint64_t &hi, uint64_t inc_lo, uint64_
     return out >> 11;
 }
 
+MG_HD uint32_t cell_word(uint32_t t, uint32_t c, uint32_t s) {
+    // see_behind (utils/obs.py:47-63): walls and non-open doors block the view
+    const uint32_t opaque = (uint32_t)(t == T_WALL) | (uint32_t)((t == T_DOOR) & (s != S_OPEN));
+    return t | (c << 8) | (s << 16) | (opaque << 31);
+}
+
+MG_HD uint32_t cell_word24(uint32_t c) {  // c = type | color<<8 | state<<16
+    const uint32_t t = c & 0xffu;
+    const uint32_t opaque = (uint32_t)(t == T_WALL) | (uint32_t)((t == T_DOOR) & ((c >> 16) != S_OPEN));
+    return c | (opaque << 31);
+}
+
 // ---- numpy Generator(PCG64).integers(low, high) as RandomMixin._rand_int calls it -----------------
 // (utils/random.py:23-38 -> numpy/random/_bounded_integers.pyx _rand_int64 -> distributions.c
 // random_bounded_uint64_fill: ranges below 2^32 take buffered_bounded_lemire_uint32 on the bit
@@ -323,6 +335,78 @@ MG_HD bool gen_layout_empty_random(int W, int H, int n, LayoutRng &g, uint32_t *
     return true;
 }
 
+// ---- RoomGrid pieces (core/roomgrid.py) for on-device layouts ---------------------------------------
+// place_obj (base.py:604-655) inside the rectangle [tx, tx+sx) x [ty, ty+sy) clipped to the grid, with
+// max_tries = 1000 as every RoomGrid caller passes (roomgrid.py:365, 398): -1 = gave up (the reference
+// raises RecursionError). `next_to_agents` = reject_next_to (roomgrid.py:46-51): no agent within
+// Euclidean distance 1 of the position. Returns x | y << 8.
+MG_HD int place_in_rect(int W, int H, int n, LayoutRng &g, const uint32_t *cells, const int8_t *agents,
+                        int tx, int ty, int sx, int sy, bool next_to_agents) {
+    const int Hp = H + 1;
+    const int hx = tx + sx < W ? tx + sx : W, hy = ty + sy < H ? ty + sy : H;
+    for (int tries = 0;; tries++) {
+        if (tries > 1000) return -1;
+        const int x = rng_integers(g, tx, hx), y = rng_integers(g, ty, hy);
+        if ((cells[x * Hp + y] & 0xffu) != T_EMPTY) continue;
+        bool bad = false;
+        for (int q = 0; q < n; q++) {
+            const int dx = agents[q * 8 + 1] - x, dy = agents[q * 8 + 2] - y;
+            bad |= (dx == 0 && dy == 0) || (next_to_agents && dx * dx + dy * dy <= 1);
+        }
+        if (!bad) return x | (y << 8);
+    }
+}
+
+// BlockedUnlockPickupEnv._gen_grid (envs/blockedunlockpickup.py:142-164) on a 1 x 2 RoomGrid
+// (core/roomgrid.py:203-236: rooms share walls, agents start in the middle of room (1,0) facing right):
+// box of a random colour in the right room, locked door of a random colour in the shared wall at a height
+// drawn from the ORDER generator (env.np_random, roomgrid.py:324 -> :106-124), a ball of a random colour
+// in front of it, the door's key in the left room, then every agent in the left room, not facing an object
+// (place_in_room, roomgrid.py:387-404). Returns the box colour (the mission names it), -1 = gave up.
+MG_HD int gen_layout_bup(int S, int n, LayoutRng &g, LayoutRng &order, uint32_t *cells, int8_t *agents) {
+    const int W = 2 * (S - 1) + 1, H = S, Hp = H + 1, step = S - 1;
+    for (int x = 0; x <= W; x++)
+        for (int y = 0; y <= H; y++) {
+            const bool wall = x >= W || y >= H || y == 0 || y == H - 1 || x % step == 0;
+            cells[x * Hp + y] = wall ? CELL_WALL : CELL_EMPTY;
+        }
+    for (int j = 0; j < n; j++) {
+        int8_t *a = agents + j * 8;
+        a[0] = 0; a[1] = (int8_t)(step + S / 2); a[2] = (int8_t)(S / 2); a[3] = 0;
+        a[4] = T_EMPTY; a[5] = 0; a[6] = 0; a[7] = (int8_t)(j % 6);
+    }
+    // add_object(1, 0, kind=box): colour, then position (roomgrid.py:338-368)
+    const uint32_t box_color = (uint32_t)rng_integers(g, 0, 6);
+    int pos = place_in_rect(W, H, n, g, cells, agents, step, 0, S, S, true);
+    if (pos < 0) return -1;
+    cells[(pos & 0xff) * Hp + (pos >> 8)] = cell_word(T_BOX, box_color, 0);
+    // add_door(0, 0, right, locked=True): colour from the layout generator, height from the order generator
+    const uint32_t door_color = (uint32_t)rng_integers(g, 0, 6);
+    const int door_y = rng_integers(order, 1, S - 1);
+    cells[step * Hp + door_y] = cell_word(T_DOOR, door_color, S_LOCKED);
+    // a ball blocks the door (blockedunlockpickup.py:155)
+    const uint32_t ball_color = (uint32_t)rng_integers(g, 0, 6);
+    cells[(step - 1) * Hp + door_y] = cell_word(T_BALL, ball_color, 0);
+    // add_object(0, 0, key, door colour)
+    pos = place_in_rect(W, H, n, g, cells, agents, 0, 0, S, S, true);
+    if (pos < 0) return -1;
+    cells[(pos & 0xff) * Hp + (pos >> 8)] = cell_word(T_KEY, door_color, 0);
+    // place_agent(top, size) until the agent does not face an object
+    for (int j = 0; j < n; j++) {
+        for (;;) {
+            agents[j * 8 + 1] = -1; agents[j * 8 + 2] = -1;
+            pos = place_in_rect(W, H, n, g, cells, agents, 0, 0, S, S, false);
+            if (pos < 0) return -1;
+            const int x = pos & 0xff, y = pos >> 8, dir = rng_integers(g, 0, 4);
+            agents[j * 8 + 1] = (int8_t)x; agents[j * 8 + 2] = (int8_t)y; agents[j * 8] = (int8_t)dir;
+            const int fx = x + (dir == 0) - (dir == 2), fy = y + (dir == 1) - (dir == 3);
+            const uint32_t t = cells[fx * Hp + fy] & 0xffu;
+            if (t == T_EMPTY || t == T_WALL) break;
+        }
+    }
+    return (int)box_color;
+}
+
 // base.py:598-602: `1 - 0.9 * (step_count / max_steps)` in float64, round-to-nearest at every
 // operation, never contracted into an FMA.
 MG_HD double reward_value(int32_t step_count, int32_t max_steps) {
@@ -370,18 +454,6 @@ MG_HD_COLD void warp_copy(void *dst, const void *src, int nbytes, int lane) {
 #pragma unroll 1
         for (int b = lane; b < nbytes; b += LANES) ((uint8_t *)dst)[b] = ((const uint8_t *)src)[b];
     }
-}
-
-MG_HD uint32_t cell_word(uint32_t t, uint32_t c, uint32_t s) {
-    // see_behind (utils/obs.py:47-63): walls and non-open doors block the view
-    const uint32_t opaque = (uint32_t)(t == T_WALL) | (uint32_t)((t == T_DOOR) & (s != S_OPEN));
-    return t | (c << 8) | (s << 16) | (opaque << 31);
-}
-
-MG_HD uint32_t cell_word24(uint32_t c) {  // c = type | color<<8 | state<<16
-    const uint32_t t = c & 0xffu;
-    const uint32_t opaque = (uint32_t)(t == T_WALL) | (uint32_t)((t == T_DOOR) & ((c >> 16) != S_OPEN));
-    return c | (opaque << 31);
 }
 
 // 4 consecutive 3-byte cells (12 bytes = words w0,w1,w2) -> 4 cell words. The opaque test runs on
@@ -1178,6 +1250,29 @@ __global__ void gen_layouts_empty_random_kernel(int W, int H, int n, int64_t K, 
     if (!ok) status_or(status, 2);
     rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
     if (rng_buf) rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
+}
+
+// BlockedUnlockPickup layouts, one thread per layout. order_state/order_inc: the env's own generator
+// (env.np_random), advanced by the door-height draw; its buffered 32-bit half starts empty and is dropped,
+// like the host path. info[k] = box colour.
+__global__ void gen_layouts_bup_kernel(int S, int n, int64_t K, uint64_t *rng_state, const uint64_t *rng_inc,
+                                       uint64_t *rng_buf, uint64_t *order_state, const uint64_t *order_inc,
+                                       uint32_t *cells, int8_t *agents, int32_t *info, int32_t *status) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    LayoutRng g, o;
+    g.lo = rng_state[2 * k]; g.hi = rng_state[2 * k + 1]; g.ilo = rng_inc[2 * k]; g.ihi = rng_inc[2 * k + 1];
+    const uint64_t b = rng_buf ? rng_buf[k] : 0ull;
+    g.has32 = (uint32_t)(b >> 32) & 1u; g.buf32 = (uint32_t)b;
+    o.lo = order_state[2 * k]; o.hi = order_state[2 * k + 1]; o.ilo = order_inc[2 * k]; o.ihi = order_inc[2 * k + 1];
+    o.has32 = 0; o.buf32 = 0;
+    const int W = 2 * (S - 1) + 1;
+    const int color = gen_layout_bup(S, n, g, o, cells + k * (int64_t)(W + 1) * (S + 1), agents + k * n * 8);
+    if (color < 0) status_or(status, 2);
+    if (info) info[k] = color;
+    rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
+    if (rng_buf) rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
+    order_state[2 * k] = o.lo; order_state[2 * k + 1] = o.hi;
 }
 
 // <= 4 warps per block; register cap: 72 (7 blocks x 128 threads per SM) up to V = 7, 128 for V = 9

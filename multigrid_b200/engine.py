@@ -172,6 +172,35 @@ class StepEngine:
             raise RecursionError("rejection sampling failed in place_obj")  # base.py:640-641
         return st.cpu().numpy().view(np.uint64), buf.cpu().numpy().view(np.uint64)
 
+    def gen_layout_pool_bup(self, room_size, rng_state, rng_inc, rng_buf, order_state, order_inc):
+        """mg_gen_layouts_bup: fill the pool on the device with K BlockedUnlockPickup layouts
+        (envs/blockedunlockpickup.py:142-164). Layout generators as in gen_layout_pool_empty_random; the
+        ORDER generators (env.np_random of the K envs, uint64 words state/inc [K,2]) give the door heights.
+        Returns (order_state [K,2], box colour index [K] int32, rng_state [K,2], rng_buf [K]) after the draws."""
+        cfg = self.cfg
+        K, dev = len(rng_state), self.device
+        t64 = lambda a: torch.as_tensor(_as_i64_bits(a)).to(dev).contiguous()  # noqa: E731
+        st, inc = t64(rng_state).reshape(K, 2), t64(rng_inc).reshape(K, 2)
+        buf = t64(np.zeros(K, np.uint64) if rng_buf is None else rng_buf)
+        ost, oinc = t64(order_state).reshape(K, 2), t64(order_inc).reshape(K, 2)
+        assert (cfg.width, cfg.height) == (2 * (room_size - 1) + 1, room_size)
+        cells = torch.empty((K, cfg.width + 1, cfg.height + 1), dtype=torch.int32, device=dev)
+        agents = torch.empty((K, cfg.num_agents, 8), dtype=torch.int8, device=dev)
+        info = torch.empty((K,), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.check(self.lib.mg_gen_layouts_bup(
+                room_size, cfg.num_agents, K, st.data_ptr(), inc.data_ptr(), buf.data_ptr(), ost.data_ptr(),
+                oinc.data_ptr(), cells.data_ptr(), agents.data_ptr(), info.data_ptr(), self.status.data_ptr(),
+                self._stream()), "mg_gen_layouts_bup")
+        if int(self.status.item()) & 2:
+            self.status.zero_()
+            raise RecursionError("rejection sampling failed in place_obj")  # base.py:640-641
+        self.pool_grid, self.pool_agents = cells, agents
+        self._pool_rng = None
+        self._c = None
+        u64 = lambda t: t.cpu().numpy().view(np.uint64)  # noqa: E731
+        return u64(ost), info.cpu().numpy(), u64(st), u64(buf)
+
     def refresh_layout_pool(self) -> None:
         """Overwrite the pool with the NEXT layout of every pool generator (one kernel launch, no host
         work, asynchronous): with auto_reset, envs that reset after this draw from fresh layouts

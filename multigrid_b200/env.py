@@ -25,7 +25,8 @@ import torch
 from . import _cabi, spaces
 from .core.constants import Action, Color, Direction, Type
 from .engine import EngineConfig, StepEngine
-from .layouts import A_COLOR, A_CC, A_CS, A_CT, A_DIR, A_TERM, A_X, A_Y, EmptyLayout, Layout
+from .layouts import (A_COLOR, A_CC, A_CS, A_CT, A_DIR, A_TERM, A_X, A_Y, BlockedUnlockPickupLayout, EmptyLayout,
+                      Layout)
 
 _M64 = (1 << 64) - 1
 
@@ -255,7 +256,8 @@ class BatchedMultiGridEnv:
         self.layout_seed = layout_seed
         # EmptyEnv layouts with random agent placement are generated by a CUDA kernel (bit-exact with the
         # host generator, tests/test_layouts.py); device_layouts=False forces the host path
-        self.device_layouts = bool(device_layouts) and isinstance(layout, EmptyLayout) and not layout.deterministic
+        self.device_layouts = bool(device_layouts) and (
+            (isinstance(layout, EmptyLayout) and not layout.deterministic) or isinstance(layout, BlockedUnlockPickupLayout))
         self.pool_size = 1 if layout.deterministic else min(self.num_envs, pool_size or 4096)
         cfg = EngineConfig(
             width=self.width, height=self.height, num_agents=self.num_agents,
@@ -338,7 +340,16 @@ class BatchedMultiGridEnv:
             else:
                 lst, linc = entropy_words(K)
                 lbuf = np.zeros(K, np.uint64)
-            lst, lbuf = self.engine.gen_layout_pool_empty_random(lst, linc, lbuf)
+            table = [self.layout.mission]
+            if isinstance(self.layout, BlockedUnlockPickupLayout):
+                # env k's own order stream gives layout k's door height and is advanced by that draw
+                ost, box_color, lst, lbuf = self.engine.gen_layout_pool_bup(
+                    self.layout.room_size, lst, linc, lbuf, st[:K], inc[:K])
+                st[:K] = ost
+                names = [c.value for c in Color]
+                table = [f"pick up the {names[int(c)]} box" for c in box_color]  # blockedunlockpickup.py:139-140
+            else:
+                lst, lbuf = self.engine.gen_layout_pool_empty_random(lst, linc, lbuf)
             if gens is not None:  # the caller's generators advance as the reference's would
                 for k, g in enumerate(gens):
                     d = g.bit_generator.state
@@ -348,7 +359,7 @@ class BatchedMultiGridEnv:
             idx = np.arange(E, dtype=np.int32) % K
             self.engine.load_state(layout_idx=idx, pcg_state=st, pcg_inc=inc)
             self.engine.reset_from_pool()
-            self.missions = Missions([self.layout.mission], None)
+            self.missions = Missions(table, None if len(set(table)) == 1 else self.engine.layout_idx)
             self._needs_reset = False
             return self._obs(self.engine.gen_obs()), defaultdict(dict)
 

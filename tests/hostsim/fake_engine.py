@@ -39,6 +39,14 @@ class HostSimStepEngine:
         self.set_layout_pool(grid, agents)
         return np.array(st), np.array(buf)
 
+    def gen_layout_pool_bup(self, room_size, rng_state, rng_inc, rng_buf, order_state, order_inc):
+        from tests.hostsim.sim import gen_layouts_bup
+        buf = np.zeros(len(rng_state), np.uint64) if rng_buf is None else rng_buf
+        grid, agents, st, buf, ost, info = gen_layouts_bup(room_size, self.cfg.num_agents, rng_state, rng_inc, buf,
+                                                           order_state, order_inc)
+        self.set_layout_pool(grid, agents)
+        return np.array(ost), np.array(info), np.array(st), np.array(buf)
+
     def load_state(self, grid=None, agents=None, step_count=None, pcg_state=None, pcg_inc=None,
                    layout_idx=None):
         self._snapshot()

@@ -126,3 +126,23 @@ extern "C" int sim_gen_layouts_empty_random(int W, int H, int n, int64_t K, uint
     }
     return bad;
 }
+
+extern "C" int sim_gen_layouts_bup(int S, int n, int64_t K, uint64_t *rng_state, const uint64_t *rng_inc,
+                                   uint64_t *rng_buf, uint64_t *order_state, const uint64_t *order_inc,
+                                   uint32_t *cells, int8_t *agents, int32_t *info) {
+    int bad = 0;
+    const int W = 2 * (S - 1) + 1;
+    for (int64_t k = 0; k < K; k++) {
+        mg::LayoutRng g, o;
+        g.lo = rng_state[2 * k]; g.hi = rng_state[2 * k + 1]; g.ilo = rng_inc[2 * k]; g.ihi = rng_inc[2 * k + 1];
+        g.has32 = (uint32_t)(rng_buf[k] >> 32) & 1u; g.buf32 = (uint32_t)rng_buf[k];
+        o.lo = order_state[2 * k]; o.hi = order_state[2 * k + 1]; o.ilo = order_inc[2 * k]; o.ihi = order_inc[2 * k + 1];
+        o.has32 = 0; o.buf32 = 0;
+        info[k] = mg::gen_layout_bup(S, n, g, o, cells + k * (int64_t)(W + 1) * (S + 1), agents + k * n * 8);
+        if (info[k] < 0) bad = 1;
+        rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
+        rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
+        order_state[2 * k] = o.lo; order_state[2 * k + 1] = o.hi;
+    }
+    return bad;
+}

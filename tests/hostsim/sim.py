@@ -90,6 +90,18 @@ def gen_layouts_empty_random(W, H, n, rng_state, rng_inc, rng_buf):
     return unpack_cells(cells, W, H), agents, st, buf
 
 
+def gen_layouts_bup(S, n, rng_state, rng_inc, rng_buf, order_state, order_inc):
+    """CPU run of the BUP layout function. Returns (grid, agents, rng_state, rng_buf, order_state, box colours)."""
+    K, W, H = len(rng_state), 2 * (S - 1) + 1, S
+    st, inc, buf = aligned_copy(rng_state, np.uint64), aligned_copy(rng_inc, np.uint64), aligned_copy(rng_buf, np.uint64)
+    ost, oinc = aligned_copy(order_state, np.uint64), aligned_copy(order_inc, np.uint64)
+    cells, agents, info = aligned((K, W + 1, H + 1), np.uint32), aligned((K, n, 8), np.int8), aligned((K,), np.int32)
+    rc = lib().sim_gen_layouts_bup(C.c_int(S), C.c_int(n), C.c_int64(K), _p(st), _p(inc), _p(buf), _p(ost), _p(oinc),
+                                   _p(cells), _p(agents), _p(info))
+    assert rc == 0, rc
+    return unpack_cells(cells, W, H), agents, st, buf, ost, info
+
+
 class SimEngine:
     """Mirror of oracle.OracleBatch's interface on top of the host-simulated kernels."""
 

@@ -262,3 +262,27 @@ def test_reset_device_layout_path_equals_host_path(monkeypatch):
     np.testing.assert_array_equal(a.agent_states.numpy(), b.agent_states.numpy())
     np.testing.assert_array_equal(oa[2]["image"].numpy(), ob[2]["image"].numpy())
     assert len({x.tobytes() for x in a.agent_states.numpy()}) > 100
+
+
+def test_bup_reset_device_layout_path_equals_host_path(monkeypatch):
+    """BlockedUnlockPickup reset with the pool from the BUP layout function (hostsim) == the Python
+    generator path: grids, agents, missions, per-env order streams (advanced by the door-height draw)."""
+    from tests.hostsim.fake_engine import HostSimStepEngine
+    monkeypatch.setattr(env_mod, "StepEngine", HostSimStepEngine)
+    kw = dict(agents=2, num_envs=60, device="cpu", layout_seed=4, pool_size=40)
+    a = make("MultiGrid-BlockedUnlockPickup-v0", **kw)
+    b = make("MultiGrid-BlockedUnlockPickup-v0", device_layouts=False, **kw)
+    assert a.device_layouts and not b.device_layouts
+    oa, _ = a.reset(seed=9)
+    ob, _ = b.reset(seed=9)
+    np.testing.assert_array_equal(a.grid.state.numpy(), b.grid.state.numpy())
+    np.testing.assert_array_equal(a.agent_states.numpy(), b.agent_states.numpy())
+    np.testing.assert_array_equal(oa[1]["image"].numpy(), ob[1]["image"].numpy())
+    assert [a.missions[e] for e in range(60)] == [b.missions[e] for e in range(60)]
+    assert len({a.missions[e] for e in range(60)}) > 1
+    rng = np.random.default_rng(0)
+    for t in range(25):  # the order streams must agree too: same agent order every step
+        acts = rng.integers(0, 7, (60, 2)).astype(np.int8)
+        ra, rb = a.step(acts), b.step(acts)
+        np.testing.assert_array_equal(ra[0][0]["image"].numpy(), rb[0][0]["image"].numpy())
+        np.testing.assert_array_equal(a.agent_states.numpy(), b.agent_states.numpy())

@@ -455,3 +455,55 @@ def test_env_reset_device_layouts_equal_host_layouts():
         for i in range(3):
             np.testing.assert_array_equal(ra[0][i]["image"].cpu().numpy(), rb[0][i]["image"].cpu().numpy())
             assert (ra[1][i].cpu().numpy() == rb[1][i].cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("S,n", [(6, 2), (4, 1), (7, 6)])
+def test_bup_layout_kernel_matches_host_generator(S, n):
+    """mg_gen_layouts_bup on the GPU vs BlockedUnlockPickupLayout.generate with numpy generators."""
+    import torch
+    from multigrid_b200 import layouts as L
+    from multigrid_b200.engine import EngineConfig, StepEngine
+    from multigrid_b200.env import layout_generator_words
+    K, W = 1200, 2 * (S - 1) + 1
+    lg = [np.random.default_rng([S, n, k]) for k in range(K)]
+    og = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(77 * S + k))) for k in range(K)]
+    for g in lg[::3]:
+        g.integers(0, 10)
+    st, inc, buf = layout_generator_words(lg)
+    ost, oinc, _ = layout_generator_words(og)
+    eng = StepEngine(EngineConfig(width=W, height=S, num_agents=n, hook=1), 4, "cuda:0")
+    ost2, info, st2, buf2 = eng.gen_layout_pool_bup(S, st, inc, buf, ost, oinc)
+    grid = eng.pool_grid.view(torch.int8).view(K, W + 1, S + 1, 4)[:, :W, :S, :3].cpu().numpy()
+    agents = eng.pool_agents.cpu().numpy()
+    layout = L.BlockedUnlockPickupLayout(n, room_size=S)
+    colors = [c.value for c in L._COLORS]
+    for k in range(K):
+        g, a, inf = layout.generate(lg[k], og[k])
+        np.testing.assert_array_equal(grid[k], g, err_msg=f"layout {k}")
+        np.testing.assert_array_equal(agents[k], a, err_msg=f"layout {k}")
+        assert inf["mission"] == f"pick up the {colors[info[k]]} box"
+    st_h, _, buf_h = layout_generator_words(lg)
+    ost_h, _, _ = layout_generator_words(og)
+    np.testing.assert_array_equal(st2, st_h)
+    np.testing.assert_array_equal(buf2, buf_h)
+    np.testing.assert_array_equal(ost2, ost_h)
+
+
+def test_bup_env_reset_device_layouts_equal_host_layouts():
+    from multigrid_b200.envs import make
+    kw = dict(agents=2, num_envs=3000, device="cuda:0", layout_seed=3, pool_size=1000, auto_reset=True, max_steps=12)
+    a = make("MultiGrid-BlockedUnlockPickup-v0", **kw)
+    b = make("MultiGrid-BlockedUnlockPickup-v0", device_layouts=False, **kw)
+    a.reset(seed=21)
+    b.reset(seed=21)
+    np.testing.assert_array_equal(a.grid.state.cpu().numpy(), b.grid.state.cpu().numpy())
+    np.testing.assert_array_equal(a.agent_states.cpu().numpy(), b.agent_states.cpu().numpy())
+    assert [a.missions[e] for e in range(0, 3000, 37)] == [b.missions[e] for e in range(0, 3000, 37)]
+    rng = np.random.default_rng(0)
+    for t in range(40):  # through auto-resets from the pool
+        acts = rng.integers(0, 7, (3000, 2)).astype(np.int8)
+        ra, rb = a.step(acts), b.step(acts)
+        for i in range(2):
+            np.testing.assert_array_equal(ra[0][i]["image"].cpu().numpy(), rb[0][i]["image"].cpu().numpy())
+            assert (ra[1][i].cpu().numpy() == rb[1][i].cpu().numpy()).all()
+    np.testing.assert_array_equal(a.grid.state.cpu().numpy(), b.grid.state.cpu().numpy())

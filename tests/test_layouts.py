@@ -105,3 +105,33 @@ def test_in_kernel_integers_matches_numpy_for_awkward_ranges():
         for k in range(0, K, 7):
             g, a, _ = layout.generate(gens[k], None)
             np.testing.assert_array_equal(agents[k], a)
+
+
+@pytest.mark.parametrize("S,n,seed", [(6, 2, 0), (6, 5, 1), (4, 1, 2), (5, 3, 3), (9, 8, 4)])
+def test_device_bup_layout_function_matches_host_generator(S, n, seed):
+    """gen_layout_bup (the function of the BUP layout kernel, CPU build) against
+    BlockedUnlockPickupLayout.generate (pinned to the reference's reset by the fixtures above) with real
+    numpy generators: grid, agents, box colour, both generators' states afterwards."""
+    from multigrid_b200.env import layout_generator_words
+    from tests.hostsim.sim import gen_layouts_bup
+    K = 400
+    mk_l = lambda: [np.random.default_rng([seed, k]) for k in range(K)]                      # noqa: E731
+    mk_o = lambda: [np.random.Generator(np.random.PCG64(np.random.SeedSequence(1000 * seed + k))) for k in range(K)]  # noqa: E731
+    lg, og = mk_l(), mk_o()
+    for g in lg[::2]:
+        g.integers(0, 10)  # a buffered 32-bit half in every second layout generator
+    st, inc, buf = layout_generator_words(lg)
+    ost, oinc, _ = layout_generator_words(og)
+    grid, agents, st2, buf2, ost2, info = gen_layouts_bup(S, n, st, inc, buf, ost, oinc)
+    layout = L.BlockedUnlockPickupLayout(n, room_size=S)
+    colors = [c.value for c in L._COLORS]
+    for k in range(K):
+        g, a, inf = layout.generate(lg[k], og[k])
+        np.testing.assert_array_equal(grid[k], g, err_msg=f"layout {k}")
+        np.testing.assert_array_equal(agents[k], a, err_msg=f"layout {k}")
+        assert inf["mission"] == f"pick up the {colors[info[k]]} box"
+    st_h, _, buf_h = layout_generator_words(lg)
+    ost_h, _, _ = layout_generator_words(og)
+    np.testing.assert_array_equal(st2, st_h)
+    np.testing.assert_array_equal(buf2, buf_h)
+    np.testing.assert_array_equal(ost2, ost_h)

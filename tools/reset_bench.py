@@ -11,13 +11,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=65536)
 ap.add_argument("--pool", type=int, default=4096)
 args = ap.parse_args()
-for dl in (True, False):
-    env = make("MultiGrid-Empty-Random-6x6-v0", agents=4, num_envs=args.envs, device="cuda:0", layout_seed=1,
+ap2 = [("MultiGrid-Empty-Random-6x6-v0", 4), ("MultiGrid-BlockedUnlockPickup-v0", 2)]
+for env_id, n, dl in [(i, n, d) for i, n in ap2 for d in (True, False)]:
+    env = make(env_id, agents=n, num_envs=args.envs, device="cuda:0", layout_seed=1,
                pool_size=args.pool, device_layouts=dl)
     env.reset(seed=0)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     env.reset(seed=1)
     torch.cuda.synchronize()
-    print(json.dumps(dict(device_layouts=dl, envs=args.envs, pool=args.pool,
+    print(json.dumps(dict(env=env_id, device_layouts=dl, envs=args.envs, pool=args.pool,
                           reset_s=round(time.perf_counter() - t0, 4))), flush=True)
