@@ -153,6 +153,15 @@ int mg_gen_layouts_empty_random(int32_t width, int32_t height, int32_t num_agent
                                 int8_t *agents, int32_t *status, void *stream);
 
 /*
+ * On-device layouts of RedBlueDoorsEnv (envs/redbluedoors.py:142-168): grid (2*size) x size, agents placed in
+ * the middle room, red / blue door heights from the layout generator. Arguments as
+ * mg_gen_layouts_empty_random.
+ */
+int mg_gen_layouts_red_blue_doors(int32_t size, int32_t num_agents, int64_t num_layouts, uint64_t *rng_state,
+                                  const uint64_t *rng_inc, uint64_t *rng_buf, uint32_t *cells, int8_t *agents,
+                                  int32_t *status, void *stream);
+
+/*
  * On-device layouts of BlockedUnlockPickupEnv (envs/blockedunlockpickup.py:142-164 over
  * core/roomgrid.py:203-404: add_object, add_door, place_in_room on a 1 x 2 RoomGrid of `room_size`), same
  * generator conventions as mg_gen_layouts_empty_random plus the ORDER generator of each layout

@@ -244,6 +244,19 @@ int mg_gen_layouts_empty_random(int32_t width, int32_t height, int32_t num_agent
     return (int)cudaGetLastError();
 }
 
+int mg_gen_layouts_red_blue_doors(int32_t size, int32_t num_agents, int64_t num_layouts, uint64_t *rng_state,
+                                  const uint64_t *rng_inc, uint64_t *rng_buf, uint32_t *cells, int8_t *agents,
+                                  int32_t *status, void *stream) {
+    if (size < 4 || size > 63 || num_layouts < 0 || num_agents < 1 || num_agents > MG_MAX_AGENTS) return MG_ERR_BAD_ARG;
+    if (num_agents > (size - 2) * (size - 2)) return MG_ERR_BAD_ARG;  // more agents than cells in the room
+    if (num_layouts == 0) return 0;
+    if (!rng_state || !rng_inc || !cells || !agents) return MG_ERR_BAD_ARG;
+    mg::gen_layouts_red_blue_doors_kernel<<<(unsigned)((num_layouts + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        size, num_agents, num_layouts, rng_state, rng_inc, rng_buf, cells, agents, status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 int mg_gen_layouts_bup(int32_t room_size, int32_t num_agents, int64_t num_layouts, uint64_t *rng_state,
                        const uint64_t *rng_inc, uint64_t *rng_buf, uint64_t *order_state, const uint64_t *order_inc,
                        uint32_t *cells, int8_t *agents, int32_t *info, int32_t *status, void *stream) {

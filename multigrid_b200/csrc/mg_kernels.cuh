@@ -341,11 +341,11 @@ MG_HD bool gen_layout_empty_random(int W, int H, int n, LayoutRng &g, uint32_t *
 // raises RecursionError). `next_to_agents` = reject_next_to (roomgrid.py:46-51): no agent within
 // Euclidean distance 1 of the position. Returns x | y << 8.
 MG_HD int place_in_rect(int W, int H, int n, LayoutRng &g, const uint32_t *cells, const int8_t *agents,
-                        int tx, int ty, int sx, int sy, bool next_to_agents) {
+                        int tx, int ty, int sx, int sy, bool next_to_agents, int max_tries = 1000) {
     const int Hp = H + 1;
     const int hx = tx + sx < W ? tx + sx : W, hy = ty + sy < H ? ty + sy : H;
     for (int tries = 0;; tries++) {
-        if (tries > 1000) return -1;
+        if (tries > max_tries) return -1;
         const int x = rng_integers(g, tx, hx), y = rng_integers(g, ty, hy);
         if ((cells[x * Hp + y] & 0xffu) != T_EMPTY) continue;
         bool bad = false;
@@ -405,6 +405,34 @@ MG_HD int gen_layout_bup(int S, int n, LayoutRng &g, LayoutRng &order, uint32_t 
         }
     }
     return (int)box_color;
+}
+
+// RedBlueDoorsEnv._gen_grid (envs/redbluedoors.py:142-168): a (2*size) x size grid, a walled room in the
+// middle half, every agent placed in it (place_agent with the default unlimited tries; capped at 65 536
+// here), then a closed red door in the room's left wall and a closed blue door in its right wall at
+// heights drawn from the layout generator. false = a placement gave up.
+MG_HD bool gen_layout_red_blue_doors(int size, int n, LayoutRng &g, uint32_t *cells, int8_t *agents) {
+    const int W = 2 * size, H = size, Hp = H + 1, rx = W / 4, rw = W / 2;
+    for (int x = 0; x <= W; x++)
+        for (int y = 0; y <= H; y++) {
+            const bool wall = x >= W - 1 || y >= H - 1 || x == 0 || y == 0 || x == rx || x == rx + rw - 1;
+            cells[x * Hp + y] = wall ? CELL_WALL : CELL_EMPTY;
+        }
+    for (int j = 0; j < n; j++) {
+        int8_t *a = agents + j * 8;
+        a[0] = -1; a[1] = -1; a[2] = -1; a[3] = 0; a[4] = T_EMPTY; a[5] = 0; a[6] = 0; a[7] = (int8_t)(j % 6);
+    }
+    for (int j = 0; j < n; j++) {
+        const int pos = place_in_rect(W, H, n, g, cells, agents, rx, 0, rw, H, false, 1 << 16);
+        if (pos < 0) return false;
+        agents[j * 8 + 1] = (int8_t)(pos & 0xff); agents[j * 8 + 2] = (int8_t)(pos >> 8);
+        agents[j * 8] = (int8_t)rng_integers(g, 0, 4);
+    }
+    int y = rng_integers(g, 1, H - 1);
+    cells[rx * Hp + y] = cell_word(T_DOOR, 0, S_CLOSED);             // red
+    y = rng_integers(g, 1, H - 1);
+    cells[(rx + rw - 1) * Hp + y] = cell_word(T_DOOR, 2, S_CLOSED);  // blue
+    return true;
 }
 
 // base.py:598-602: `1 - 0.9 * (step_count / max_steps)` in float64, round-to-nearest at every
@@ -1247,6 +1275,21 @@ __global__ void gen_layouts_empty_random_kernel(int W, int H, int n, int64_t K, 
     const uint64_t b = rng_buf ? rng_buf[k] : 0ull;
     g.has32 = (uint32_t)(b >> 32) & 1u; g.buf32 = (uint32_t)b;
     const bool ok = gen_layout_empty_random(W, H, n, g, cells + k * (int64_t)(W + 1) * (H + 1), agents + k * n * 8);
+    if (!ok) status_or(status, 2);
+    rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
+    if (rng_buf) rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
+}
+
+__global__ void gen_layouts_red_blue_doors_kernel(int size, int n, int64_t K, uint64_t *rng_state,
+                                                  const uint64_t *rng_inc, uint64_t *rng_buf, uint32_t *cells,
+                                                  int8_t *agents, int32_t *status) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    LayoutRng g;
+    g.lo = rng_state[2 * k]; g.hi = rng_state[2 * k + 1]; g.ilo = rng_inc[2 * k]; g.ihi = rng_inc[2 * k + 1];
+    const uint64_t b = rng_buf ? rng_buf[k] : 0ull;
+    g.has32 = (uint32_t)(b >> 32) & 1u; g.buf32 = (uint32_t)b;
+    const bool ok = gen_layout_red_blue_doors(size, n, g, cells + k * (int64_t)(2 * size + 1) * (size + 1), agents + k * n * 8);
     if (!ok) status_or(status, 2);
     rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
     if (rng_buf) rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;

@@ -150,7 +150,13 @@ class StepEngine:
         self._pool_rng = None
         self._c = None
 
-    def gen_layout_pool_empty_random(self, rng_state, rng_inc, rng_buf=None):
+    def gen_layout_pool_red_blue_doors(self, size, rng_state, rng_inc, rng_buf=None):
+        """mg_gen_layouts_red_blue_doors (envs/redbluedoors.py:142-168); arguments and result as
+        gen_layout_pool_empty_random. refresh_layout_pool() continues the same generators."""
+        assert (self.cfg.width, self.cfg.height) == (2 * size, size)
+        return self.gen_layout_pool_empty_random(rng_state, rng_inc, rng_buf, _family=("rbd", size))
+
+    def gen_layout_pool_empty_random(self, rng_state, rng_inc, rng_buf=None, _family=("empty", 0)):
         """mg_gen_layouts_empty_random: fill the reset-layout pool ON THE DEVICE with K =
         len(rng_state) EmptyEnv layouts with random agent placement (envs/empty.py:151-170), one per
         numpy PCG64 generator given as uint64 words (state [K,2], inc [K,2], optional buffered-uint32
@@ -165,6 +171,7 @@ class StepEngine:
         agents = torch.empty((K, cfg.num_agents, 8), dtype=torch.int8, device=dev)
         self.pool_grid, self.pool_agents = cells, agents
         self._pool_rng = (st, inc, buf)  # stays on the device: refresh_layout_pool() continues these streams
+        self._pool_family = _family
         self._c = None
         self.refresh_layout_pool()
         if int(self.status.item()) & 2:
@@ -209,11 +216,15 @@ class StepEngine:
             raise RuntimeError("the layout pool was not generated on the device")
         cfg = self.cfg
         st, inc, buf = self._pool_rng
+        tail = (st.shape[0], st.data_ptr(), inc.data_ptr(), buf.data_ptr(), self.pool_grid.data_ptr(),
+                self.pool_agents.data_ptr(), self.status.data_ptr(), self._stream())
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.mg_gen_layouts_empty_random(
-                cfg.width, cfg.height, cfg.num_agents, st.shape[0], st.data_ptr(), inc.data_ptr(), buf.data_ptr(),
-                self.pool_grid.data_ptr(), self.pool_agents.data_ptr(), self.status.data_ptr(), self._stream()),
-                "mg_gen_layouts_empty_random")
+            if self._pool_family[0] == "rbd":
+                _cabi.check(self.lib.mg_gen_layouts_red_blue_doors(self._pool_family[1], cfg.num_agents, *tail),
+                            "mg_gen_layouts_red_blue_doors")
+            else:
+                _cabi.check(self.lib.mg_gen_layouts_empty_random(cfg.width, cfg.height, cfg.num_agents, *tail),
+                            "mg_gen_layouts_empty_random")
 
     def load_state(self, grid=None, agents=None, step_count=None, pcg_state=None, pcg_inc=None,
                    layout_idx=None, hook_state=None) -> None:

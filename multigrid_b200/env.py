@@ -26,7 +26,7 @@ from . import _cabi, spaces
 from .core.constants import Action, Color, Direction, Type
 from .engine import EngineConfig, StepEngine
 from .layouts import (A_COLOR, A_CC, A_CS, A_CT, A_DIR, A_TERM, A_X, A_Y, BlockedUnlockPickupLayout, EmptyLayout,
-                      Layout)
+                      Layout, RedBlueDoorsLayout)
 
 _M64 = (1 << 64) - 1
 
@@ -257,7 +257,8 @@ class BatchedMultiGridEnv:
         # EmptyEnv layouts with random agent placement are generated by a CUDA kernel (bit-exact with the
         # host generator, tests/test_layouts.py); device_layouts=False forces the host path
         self.device_layouts = bool(device_layouts) and (
-            (isinstance(layout, EmptyLayout) and not layout.deterministic) or isinstance(layout, BlockedUnlockPickupLayout))
+            (isinstance(layout, EmptyLayout) and not layout.deterministic)
+            or isinstance(layout, (BlockedUnlockPickupLayout, RedBlueDoorsLayout)))
         self.pool_size = 1 if layout.deterministic else min(self.num_envs, pool_size or 4096)
         cfg = EngineConfig(
             width=self.width, height=self.height, num_agents=self.num_agents,
@@ -348,6 +349,8 @@ class BatchedMultiGridEnv:
                 st[:K] = ost
                 names = [c.value for c in Color]
                 table = [f"pick up the {names[int(c)]} box" for c in box_color]  # blockedunlockpickup.py:139-140
+            elif isinstance(self.layout, RedBlueDoorsLayout):
+                lst, lbuf = self.engine.gen_layout_pool_red_blue_doors(self.layout.size, lst, linc, lbuf)
             else:
                 lst, lbuf = self.engine.gen_layout_pool_empty_random(lst, linc, lbuf)
             if gens is not None:  # the caller's generators advance as the reference's would

@@ -507,3 +507,33 @@ def test_bup_env_reset_device_layouts_equal_host_layouts():
             np.testing.assert_array_equal(ra[0][i]["image"].cpu().numpy(), rb[0][i]["image"].cpu().numpy())
             assert (ra[1][i].cpu().numpy() == rb[1][i].cpu().numpy()).all()
     np.testing.assert_array_equal(a.grid.state.cpu().numpy(), b.grid.state.cpu().numpy())
+
+
+def test_rbd_env_reset_device_layouts_equal_host_layouts():
+    """'MultiGrid-RedBlueDoors-6x6-v0': pool from mg_gen_layouts_red_blue_doors == pool generated in Python,
+    and refresh_layout_pool() continues the same generators."""
+    from multigrid_b200 import layouts as L
+    from multigrid_b200.envs import make
+    kw = dict(agents=3, num_envs=1500, device="cuda:0", layout_seed=8, pool_size=1500)
+    a = make("MultiGrid-RedBlueDoors-6x6-v0", **kw)
+    b = make("MultiGrid-RedBlueDoors-6x6-v0", device_layouts=False, **kw)
+    assert a.device_layouts and not b.device_layouts
+    oa, _ = a.reset(seed=2)
+    ob, _ = b.reset(seed=2)
+    np.testing.assert_array_equal(a.grid.state.cpu().numpy(), b.grid.state.cpu().numpy())
+    np.testing.assert_array_equal(a.agent_states.cpu().numpy(), b.agent_states.cpu().numpy())
+    np.testing.assert_array_equal(oa[2]["image"].cpu().numpy(), ob[2]["image"].cpu().numpy())
+    rng = np.random.default_rng(1)
+    for t in range(30):
+        acts = rng.integers(0, 7, (1500, 3)).astype(np.int8)
+        ra, rb = a.step(acts), b.step(acts)
+        np.testing.assert_array_equal(ra[0][0]["image"].cpu().numpy(), rb[0][0]["image"].cpu().numpy())
+        assert (ra[1][1].cpu().numpy() == rb[1][1].cpu().numpy()).all()
+    a.engine.refresh_layout_pool()  # second layout of generator k == the host generator's second draw
+    pool2 = a.engine.pool_agents.cpu().numpy()
+    layout = L.RedBlueDoorsLayout(3, size=6)
+    for k in range(0, 1500, 50):
+        g = np.random.default_rng([8, k])
+        layout.generate(g, None)
+        _, a2, _ = layout.generate(g, None)
+        np.testing.assert_array_equal(pool2[k], a2)

@@ -135,3 +135,24 @@ def test_device_bup_layout_function_matches_host_generator(S, n, seed):
     np.testing.assert_array_equal(st2, st_h)
     np.testing.assert_array_equal(buf2, buf_h)
     np.testing.assert_array_equal(ost2, ost_h)
+
+
+@pytest.mark.parametrize("size,n,seed", [(6, 2, 0), (8, 3, 1), (4, 4, 2), (11, 7, 3)])
+def test_device_rbd_layout_function_matches_host_generator(size, n, seed):
+    """gen_layout_red_blue_doors (CPU build of the kernel's function) vs RedBlueDoorsLayout.generate."""
+    from multigrid_b200.env import layout_generator_words
+    from tests.hostsim.sim import gen_layouts_red_blue_doors
+    K = 400
+    lg = [np.random.default_rng([seed, k, 5]) for k in range(K)]
+    for g in lg[1::2]:
+        g.integers(0, 3)
+    st, inc, buf = layout_generator_words(lg)
+    grid, agents, st2, buf2 = gen_layouts_red_blue_doors(size, n, st, inc, buf)
+    layout = L.RedBlueDoorsLayout(n, size=size)
+    for k in range(K):
+        g, a, _ = layout.generate(lg[k], None)
+        np.testing.assert_array_equal(grid[k], g, err_msg=f"layout {k}")
+        np.testing.assert_array_equal(agents[k], a, err_msg=f"layout {k}")
+    st_h, _, buf_h = layout_generator_words(lg)
+    np.testing.assert_array_equal(st2, st_h)
+    np.testing.assert_array_equal(buf2, buf_h)
