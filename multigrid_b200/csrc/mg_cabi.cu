@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 
 #include "mg_kernels.cuh"
 
@@ -16,7 +17,17 @@ std::atomic<unsigned long long *> g_trace{nullptr};  // diagnostics only (mg_deb
 constexpr int kSmemPerBlock = 227 * 1024;  // B200 opt-in maximum per block
 constexpr int kSmemPerSM = 228 * 1024;
 
-int env_int(const char *name, int dflt) {
+// Tuning / test knobs are environment variables named MG_*, read on every call (tests flip them between
+// launches). One pass over `environ` finds out whether any exists at all -- normally none does, and the
+// seven lookups of a launch then cost nothing.
+bool any_mg_knob() {
+    for (char **e = environ; e && *e; ++e)
+        if ((*e)[0] == 'M' && (*e)[1] == 'G' && (*e)[2] == '_') return true;
+    return false;
+}
+
+int env_int(const char *name, int dflt, bool present = true) {
+    if (!present) return dflt;
     const char *s = std::getenv(name);
     return (s && *s) ? std::atoi(s) : dflt;
 }
@@ -38,10 +49,12 @@ int validate(const MgConfig *c, int64_t num_envs) {
 // MG_NO_BULK=1 = plain loads/stores instead of TMA bulk copies, MG_PDL=0 = no programmatic dependent
 // launch, MG_L2HINT = override of the MG_FLAG_STREAM_STATE cache policy (bit 0 loads, bit 1 obs stores).
 int plan(mg::Params &p) {
-    p.use_bulk = env_int("MG_NO_BULK", 0) ? 0 : 1;
-    p.generic_view = env_int("MG_GENERIC_VIEW", 0) ? 1 : 0;
-    p.xknob = env_int("MG_X", 0);
-    p.l2hint = env_int("MG_L2HINT", (p.flags & MG_FLAG_STREAM_STATE) ? 3 : 0);
+    const bool k = any_mg_knob();
+    p.use_bulk = env_int("MG_NO_BULK", 0, k) ? 0 : 1;
+    p.generic_view = env_int("MG_GENERIC_VIEW", 0, k) ? 1 : 0;
+    p.xknob = env_int("MG_X", 0, k);
+    p.pdl = env_int("MG_PDL", 1, k) ? 1 : 0;
+    p.l2hint = env_int("MG_L2HINT", (p.flags & MG_FLAG_STREAM_STATE) ? 3 : 0, k);
     static thread_local int sms[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -50,7 +63,7 @@ int plan(mg::Params &p) {
         if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (sms[dev] > 0) n_sm = sms[dev];
     }
-    return mg::plan_launch(p, env_int("MG_GROUP", 0), env_int("MG_WPB", 0), kSmemPerBlock, kSmemPerSM, n_sm);
+    return mg::plan_launch(p, env_int("MG_GROUP", 0, k), env_int("MG_WPB", 0, k), kSmemPerBlock, kSmemPerSM, n_sm);
 }
 
 template <int VT, int MODE, bool MULTI = false>
@@ -76,7 +89,7 @@ int launch(const mg::Params &p, cudaStream_t stream) {
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = attr; lc.numAttrs = env_int("MG_PDL", 1) ? 1 : 0;
+    lc.attrs = attr; lc.numAttrs = p.pdl ? 1 : 0;
     const cudaError_t err = cudaLaunchKernelEx(&lc, kernel, p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)err;

@@ -68,6 +68,7 @@ struct Params {
     // every output array ([T][E]...); agents and the per-env scalars stay on chip between steps.
     int32_t T;
     int32_t xknob;  // experiments (MG_X), timing only
+    int32_t pdl;    // host side only: launch with programmatic stream serialization
     int8_t *direction;  // [T][E][n] per-step 'direction' observation (rollout only; NULL otherwise)
     // state (device)
     uint32_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;

@@ -112,6 +112,9 @@ class StepEngine:
             self.set_layout_pool(pool_grid, pool_agents)
         self._host = None
         self._c = None
+        self._views = None  # (obs, reward, terminated, truncated): views of fixed buffers, built once
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
 
     # -- grid layout ---------------------------------------------------------------------------
     @property
@@ -273,6 +276,7 @@ class StepEngine:
             out = _cabi.MgStepOut(p(self.obs_buf), p(self.reward), p(self.terminated),
                                   p(self.truncated), p(self.status))
             self._c = (c, st, out)
+            self._refs = (C.byref(c), C.byref(st), C.byref(out))
         return self._c
 
     def _stream(self) -> C.c_void_p:
@@ -309,12 +313,21 @@ class StepEngine:
             actions = self.actions
         if actions.dtype != torch.int8 or not actions.is_contiguous() or actions.device != self.device:
             raise TypeError("actions must be a contiguous int8 CUDA tensor of shape (num_envs, n)")
-        c, st, out = self._structs()
+        if self._c is None:
+            self._structs()
+        rc, rst, rout = self._refs
         fn = self.lib.mg_step_obs if fused else self.lib.mg_step
-        with torch.cuda.device(self.device):
-            _cabi.check(fn(C.byref(c), self.num_envs, C.byref(st), actions.data_ptr(), C.byref(out),
-                           self._stream()), "mg_step_obs" if fused else "mg_step")
-        return self.obs, self.reward, self.terminated, self.truncated
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        if torch.cuda.current_device() == self.device.index:  # (a device guard costs more than the launch)
+            rc_ = fn(rc, self.num_envs, rst, actions.data_ptr(), rout, stream)
+        else:
+            with torch.cuda.device(self.device):
+                rc_ = fn(rc, self.num_envs, rst, actions.data_ptr(), rout, stream)
+        if rc_:
+            _cabi.check(rc_, "mg_step_obs" if fused else "mg_step")
+        if self._views is None:
+            self._views = (self.obs, self.reward, self.terminated, self.truncated)
+        return self._views
 
     def rollout(self, actions: torch.Tensor, out: dict | None = None) -> dict:
         """mg_rollout: T = actions.shape[0] consecutive fused steps in ONE launch on an open-loop

@@ -277,6 +277,7 @@ class BatchedMultiGridEnv:
         self._actions = torch.full((self.num_envs, self.num_agents), -1, dtype=torch.int8,
                                    device=self.device)
         self._needs_reset = True
+        self._step_views = None
 
     # -- reference attributes -------------------------------------------------------------------
     @property
@@ -412,6 +413,14 @@ class BatchedMultiGridEnv:
             self._actions.copy_(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.int8)).reshape(E, n))
             return self._actions
         # dict {agent_id: action}; ids missing from the dict do not act (base.py:403-404)
+        if len(actions) == n and all(isinstance(actions.get(i), torch.Tensor) and actions[i].device == self.device
+                                     and actions[i].shape == (E,) for i in range(n)):
+            cols = [actions[i] for i in range(n)]  # one kernel instead of a fill and n column copies
+            if all(c.dtype == torch.int8 for c in cols):
+                torch.stack(cols, dim=1, out=self._actions)
+            else:
+                self._actions.copy_(torch.stack(cols, dim=1))
+            return self._actions
         self._actions.fill_(-1)
         for i, a in actions.items():
             if not 0 <= int(i) < n:
@@ -434,12 +443,19 @@ class BatchedMultiGridEnv:
         if self._needs_reset:
             raise RuntimeError("call reset() before step()")
         image, reward, terminated, truncated = self.engine.step(self._action_tensor(actions))
-        term_b, trunc_b = terminated.view(torch.bool), truncated.view(torch.bool)
-        n = self.num_agents
-        return (self._obs(image),
-                {i: reward[:, i] for i in range(n)},
-                {i: term_b[:, i] for i in range(n)},
-                {i: trunc_b for i in range(n)},
+        if self._step_views is None or self._step_views[0] is not image:
+            # every item is a view of a fixed engine buffer: build the per-agent views once (some 20 tensor
+            # ops, twice the cost of the kernel launch) and hand out fresh dicts around them every step
+            term_b, trunc_b = terminated.view(torch.bool), truncated.view(torch.bool)
+            n, direction = self.num_agents, self.engine.direction
+            self._step_views = (image,
+                                [(image[:, i], direction[:, i]) for i in range(n)],
+                                [reward[:, i] for i in range(n)],
+                                [term_b[:, i] for i in range(n)], trunc_b)
+        _, obs_v, rew_v, term_v, trunc_b = self._step_views
+        missions = self.missions
+        return ({i: {"image": v[0], "direction": v[1], "mission": missions} for i, v in enumerate(obs_v)},
+                dict(enumerate(rew_v)), dict(enumerate(term_v)), dict.fromkeys(range(len(rew_v)), trunc_b),
                 defaultdict(dict))
 
     def check(self) -> None:
