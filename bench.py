@@ -36,7 +36,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used if MEASU
 # `ncu --set full` capture summarised in profiles/r01_summary.md (r01c): 26.30 MB read (= the layout's
 # 401 B/env of inputs) + 3.04 MB written; the other ~41.6 MB of outputs are still dirty in the 126 MB L2
 # when the kernel ends (ncu flushes before each replay) and reach HBM during later launches.
-NCU_DRAM_BYTES_PER_LAUNCH = 28382976  # profiles/r01d_ncu_details.txt: dram read 26 297 856 + write 2 085 120
+NCU_DRAM_BYTES_PER_LAUNCH = 28722432  # profiles/r01e_ncu_details.txt: dram read 26 292 480 + write 2 429 952
 
 
 def algorithmic_bytes_per_env_step(W, H, n, V, mutable_grid=False):
@@ -334,6 +334,21 @@ def run_engine(args):
         eng.step_host(synchronize=True)       # results are in pinned host memory on return
     e2e_s = time.perf_counter() - t0
     checksum = int(h["obs"].view(torch.uint8).sum()) + float(h["reward"].sum())
+
+    # ---- informational: the public Python env API, eager (no graph), device-resident actions: one
+    # BatchedMultiGridEnv stepped back to back (its 61 MB of state + outputs stay L2-resident)
+    from multigrid_b200.envs import make
+    api_env = make("MultiGrid-Empty-8x8-v0", agents=n, num_envs=E, device=dev, auto_reset=True, first_env=rank * E)
+    api_env.reset(seed=1234)
+    K3 = 2000
+    for k in range(64):
+        api_env.step(tape[k % n_tape])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(K3):
+        api_env.step(tape[k % n_tape])
+    torch.cuda.synchronize()
+    api_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
     t = torch.tensor([ms, e2e_s, ms2], dtype=torch.float64, device=dev)
@@ -375,6 +390,10 @@ def run_engine(args):
                     "(two env batches in flight on two graph branches)",
             "us_per_launch": 1e3 * ms2 / K, "value": total_envs * n * K / (ms2 * 1e-3),
             "achieved_gbs": bpe * E / (ms2 * 1e-3 / K) / 1e9}
+        line["api_device_resident"] = {
+            "note": "informational: env.step(actions_on_device) of the public Python API, eager launches, per-agent "
+                    "dict results left on the device, one batch stepped back to back (state stays in L2), this rank",
+            "us_per_step": 1e6 * api_s / K3, "value": E * n * K3 / api_s, "steps": K3}
         if world == 1 and not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0))
             v, done, dt = time_cpu_oracle(E, 10**9, 2, cores, budget_s=args.cpu_seconds)
