@@ -162,6 +162,17 @@ int mg_gen_layouts_red_blue_doors(int32_t size, int32_t num_agents, int64_t num_
                                   int32_t *status, void *stream);
 
 /*
+ * On-device layouts of LockedHallwayEnv (envs/locked_hallway.py:150-194; RandomMixin._rand_perm =
+ * Generator.shuffle of a list = Fisher-Yates on numpy's random_interval): grid (3*(room_size-1)+1) x
+ * ((num_rooms/2)*(room_size-1)+1); num_rooms even, 2..6 (door identity is its colour). Other arguments as
+ * mg_gen_layouts_empty_random.
+ */
+int mg_gen_layouts_locked_hallway(int32_t num_rooms, int32_t room_size, int32_t max_hallway_keys,
+                                  int32_t max_keys_per_room, int32_t num_agents, int64_t num_layouts,
+                                  uint64_t *rng_state, const uint64_t *rng_inc, uint64_t *rng_buf, uint32_t *cells,
+                                  int8_t *agents, int32_t *status, void *stream);
+
+/*
  * On-device layouts of BlockedUnlockPickupEnv (envs/blockedunlockpickup.py:142-164 over
  * core/roomgrid.py:203-404: add_object, add_door, place_in_room on a 1 x 2 RoomGrid of `room_size`), same
  * generator conventions as mg_gen_layouts_empty_random plus the ORDER generator of each layout

@@ -75,6 +75,7 @@ EXPORTS = {
     "mg_gen_layouts_empty_random": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_gen_layouts_red_blue_doors": (C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
+    "mg_gen_layouts_locked_hallway": (C.c_int, [C.c_int32] * 5 + [C.c_int64] + [C.c_void_p] * 7),
     "mg_gen_layouts_bup": (C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 10),
     "mg_unpack_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_gen_obs": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -270,6 +270,21 @@ int mg_gen_layouts_red_blue_doors(int32_t size, int32_t num_agents, int64_t num_
     return (int)cudaGetLastError();
 }
 
+int mg_gen_layouts_locked_hallway(int32_t num_rooms, int32_t room_size, int32_t max_hallway_keys,
+                                  int32_t max_keys_per_room, int32_t num_agents, int64_t num_layouts,
+                                  uint64_t *rng_state, const uint64_t *rng_inc, uint64_t *rng_buf, uint32_t *cells,
+                                  int8_t *agents, int32_t *status, void *stream) {
+    if (num_rooms < 2 || num_rooms > 6 || (num_rooms & 1) || room_size < 4 || room_size > 40 || max_hallway_keys < 1 ||
+        max_keys_per_room < 1 || num_layouts < 0 || num_agents < 1 || num_agents > MG_MAX_AGENTS) return MG_ERR_BAD_ARG;
+    if (num_layouts == 0) return 0;
+    if (!rng_state || !rng_inc || !cells || !agents) return MG_ERR_BAD_ARG;
+    mg::gen_layouts_locked_hallway_kernel<<<(unsigned)((num_layouts + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        num_rooms, room_size, max_hallway_keys, max_keys_per_room, num_agents, num_layouts, rng_state, rng_inc,
+        rng_buf, cells, agents, status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 int mg_gen_layouts_bup(int32_t room_size, int32_t num_agents, int64_t num_layouts, uint64_t *rng_state,
                        const uint64_t *rng_inc, uint64_t *rng_buf, uint64_t *order_state, const uint64_t *order_inc,
                        uint32_t *cells, int8_t *agents, int32_t *info, int32_t *status, void *stream) {

@@ -302,6 +302,25 @@ MG_HD int32_t rng_integers(LayoutRng &g, int32_t low, int32_t high) {
     return low + (int32_t)(m >> 32);
 }
 
+// numpy's random_interval (distributions.c): uniform in [0, max] by masked rejection on the 32-bit stream;
+// Generator.shuffle of a Python list (the untyped path of _generator.pyx) is Fisher-Yates with it:
+// for i = n-1 .. 1: j = random_interval(i); swap(x[i], x[j]). RandomMixin._rand_perm (utils/random.py:77-85).
+MG_HD uint32_t rng_interval(LayoutRng &g, uint32_t max) {
+    if (max == 0) return 0;
+    uint32_t mask = max;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    uint32_t v;
+    do { v = pcg64_next32(g) & mask; } while (v > max);
+    return v;
+}
+
+MG_HD void rng_shuffle(LayoutRng &g, uint8_t *x, int n) {
+    for (int i = n - 1; i >= 1; i--) {
+        const uint32_t j = rng_interval(g, (uint32_t)i);
+        const uint8_t t = x[i]; x[i] = x[j]; x[j] = t;
+    }
+}
+
 // EmptyEnv._gen_grid with random agent placement (envs/empty.py:151-170): wall ring, goal at (W-2,H-2),
 // then per agent place_agent (base.py:672-697) = place_obj's rejection sampling (base.py:604-655: a cell
 // is taken when it is empty and NO agent record -- placed or not -- has that position) followed by
@@ -433,6 +452,68 @@ MG_HD bool gen_layout_red_blue_doors(int size, int n, LayoutRng &g, uint32_t *ce
     cells[rx * Hp + y] = cell_word(T_DOOR, 0, S_CLOSED);             // red
     y = rng_integers(g, 1, H - 1);
     cells[(rx + rw - 1) * Hp + y] = cell_word(T_DOOR, 2, S_CLOSED);  // blue
+    return true;
+}
+
+// LockedHallwayEnv._gen_grid (envs/locked_hallway.py:150-194) on a (num_rooms/2) x 3 RoomGrid: a shuffled
+// colour sequence, the hallway column opened vertically, one locked door per side room (colours from a second
+// shuffle, popped from the end; doors sit in the middle of the wall), 1..max_hallway_keys keys in the hallway,
+// then for every further key 1..max_keys_per_room keys inside the room the previous key opens, and every agent
+// in the hallway (MultiGridEnv.place_agent: unlimited tries; capped at 65 536 here). num_rooms even, <= 6.
+MG_HD bool gen_layout_locked_hallway(int num_rooms, int S, int max_hallway_keys, int max_keys_per_room, int n,
+                                     LayoutRng &g, uint32_t *cells, int8_t *agents) {
+    const int step = S - 1, num_rows = num_rooms / 2, W = 3 * step + 1, H = num_rows * step + 1, Hp = H + 1;
+    const int INF = 1 << 16;
+    for (int x = 0; x <= W; x++)
+        for (int y = 0; y <= H; y++) {
+            const bool wall = x >= W || y >= H || x % step == 0 || y % step == 0;
+            cells[x * Hp + y] = wall ? CELL_WALL : CELL_EMPTY;
+        }
+    for (int j = 0; j < n; j++) {  // RoomGrid: agents start in the middle room facing right (roomgrid.py:231-236)
+        int8_t *a = agents + j * 8;
+        a[0] = 0; a[1] = (int8_t)(step + S / 2); a[2] = (int8_t)((num_rows / 2) * step + S / 2); a[3] = 0;
+        a[4] = T_EMPTY; a[5] = 0; a[6] = 0; a[7] = (int8_t)(j % 6);
+    }
+    uint8_t seq[6] = {0, 1, 2, 3, 4, 5}, doors[6];   // list(Color) * ceil(num_rooms / 6), num_rooms <= 6
+    rng_shuffle(g, seq, 6);                            // color_sequence = _rand_perm(...)[:num_rooms]
+    for (int row = 0; row + 1 < num_rows; row++)       // remove_wall(HALLWAY, row, down)
+        for (int x = step + 1; x <= 2 * step - 1; x++) cells[x * Hp + (row + 1) * step] = CELL_EMPTY;
+    for (int q = 0; q < num_rooms; q++) doors[q] = seq[q];
+    rng_shuffle(g, doors, num_rooms);                  // door_colors = _rand_perm(color_sequence)
+    int room_of_color[6] = {0, 0, 0, 0, 0, 0};         // colour -> (col, row) packed col | row << 4
+    int left = num_rooms;
+    for (int row = 0; row < num_rows; row++)
+        for (int side = 0; side < 2; side++) {         // (LEFT, right) then (RIGHT, left)
+            const uint32_t color = doors[--left];      // door_colors.pop()
+            const int col = side == 0 ? 0 : 2;
+            room_of_color[color] = col | (row << 4);
+            const int dx = side == 0 ? step : 2 * step, dy = row * step + (S - 1) / 2;
+            cells[dx * Hp + dy] = cell_word(T_DOOR, color, S_LOCKED);
+        }
+    const int hallway_keys = rng_integers(g, 1, max_hallway_keys + 1);
+    for (int q = 0; q < hallway_keys && q < num_rooms; q++) {
+        const int pos = place_in_rect(W, H, n, g, cells, agents, step, 0, S, H, false, INF);
+        if (pos < 0) return false;
+        cells[(pos & 0xff) * Hp + (pos >> 8)] = cell_word(T_KEY, seq[q], 0);
+    }
+    int key_index = hallway_keys;
+    while (key_index < num_rooms) {
+        const int room = room_of_color[seq[key_index - 1]], tx = (room & 15) * step, ty = (room >> 4) * step;
+        const int room_keys = rng_integers(g, 1, max_keys_per_room + 1);
+        for (int q = 0; q < room_keys && key_index < num_rooms; q++) {  // color_sequence[key_index : key_index + k]
+            const int pos = place_in_rect(W, H, n, g, cells, agents, tx, ty, S, S, false, INF);
+            if (pos < 0) return false;
+            cells[(pos & 0xff) * Hp + (pos >> 8)] = cell_word(T_KEY, seq[key_index], 0);
+            key_index++;
+        }
+    }
+    for (int j = 0; j < n; j++) {
+        agents[j * 8 + 1] = -1; agents[j * 8 + 2] = -1;
+        const int pos = place_in_rect(W, H, n, g, cells, agents, step, 0, S, H, false, INF);
+        if (pos < 0) return false;
+        agents[j * 8 + 1] = (int8_t)(pos & 0xff); agents[j * 8 + 2] = (int8_t)(pos >> 8);
+        agents[j * 8] = (int8_t)rng_integers(g, 0, 4);
+    }
     return true;
 }
 
@@ -1291,6 +1372,22 @@ __global__ void gen_layouts_red_blue_doors_kernel(int size, int n, int64_t K, ui
     const uint64_t b = rng_buf ? rng_buf[k] : 0ull;
     g.has32 = (uint32_t)(b >> 32) & 1u; g.buf32 = (uint32_t)b;
     const bool ok = gen_layout_red_blue_doors(size, n, g, cells + k * (int64_t)(2 * size + 1) * (size + 1), agents + k * n * 8);
+    if (!ok) status_or(status, 2);
+    rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
+    if (rng_buf) rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
+}
+
+__global__ void gen_layouts_locked_hallway_kernel(int num_rooms, int S, int mhk, int mkpr, int n, int64_t K,
+                                                  uint64_t *rng_state, const uint64_t *rng_inc, uint64_t *rng_buf,
+                                                  uint32_t *cells, int8_t *agents, int32_t *status) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    LayoutRng g;
+    g.lo = rng_state[2 * k]; g.hi = rng_state[2 * k + 1]; g.ilo = rng_inc[2 * k]; g.ihi = rng_inc[2 * k + 1];
+    const uint64_t b = rng_buf ? rng_buf[k] : 0ull;
+    g.has32 = (uint32_t)(b >> 32) & 1u; g.buf32 = (uint32_t)b;
+    const int64_t cs = (int64_t)(3 * (S - 1) + 2) * ((num_rooms / 2) * (S - 1) + 2);
+    const bool ok = gen_layout_locked_hallway(num_rooms, S, mhk, mkpr, n, g, cells + k * cs, agents + k * n * 8);
     if (!ok) status_or(status, 2);
     rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
     if (rng_buf) rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;

@@ -159,6 +159,13 @@ class StepEngine:
         assert (self.cfg.width, self.cfg.height) == (2 * size, size)
         return self.gen_layout_pool_empty_random(rng_state, rng_inc, rng_buf, _family=("rbd", size))
 
+    def gen_layout_pool_locked_hallway(self, num_rooms, room_size, max_hallway_keys, max_keys_per_room,
+                                       rng_state, rng_inc, rng_buf=None):
+        """mg_gen_layouts_locked_hallway (envs/locked_hallway.py:150-194); result as
+        gen_layout_pool_empty_random."""
+        return self.gen_layout_pool_empty_random(
+            rng_state, rng_inc, rng_buf, _family=("lh", num_rooms, room_size, max_hallway_keys, max_keys_per_room))
+
     def gen_layout_pool_empty_random(self, rng_state, rng_inc, rng_buf=None, _family=("empty", 0)):
         """mg_gen_layouts_empty_random: fill the reset-layout pool ON THE DEVICE with K =
         len(rng_state) EmptyEnv layouts with random agent placement (envs/empty.py:151-170), one per
@@ -222,7 +229,10 @@ class StepEngine:
         tail = (st.shape[0], st.data_ptr(), inc.data_ptr(), buf.data_ptr(), self.pool_grid.data_ptr(),
                 self.pool_agents.data_ptr(), self.status.data_ptr(), self._stream())
         with torch.cuda.device(self.device):
-            if self._pool_family[0] == "rbd":
+            if self._pool_family[0] == "lh":
+                _cabi.check(self.lib.mg_gen_layouts_locked_hallway(*self._pool_family[1:], cfg.num_agents, *tail),
+                            "mg_gen_layouts_locked_hallway")
+            elif self._pool_family[0] == "rbd":
                 _cabi.check(self.lib.mg_gen_layouts_red_blue_doors(self._pool_family[1], cfg.num_agents, *tail),
                             "mg_gen_layouts_red_blue_doors")
             else:

@@ -46,6 +46,14 @@ class HostSimStepEngine:
         self.set_layout_pool(grid, agents)
         return np.array(st), np.array(buf)
 
+    def gen_layout_pool_locked_hallway(self, num_rooms, room_size, mhk, mkpr, rng_state, rng_inc, rng_buf=None):
+        from tests.hostsim.sim import gen_layouts_locked_hallway
+        buf = np.zeros(len(rng_state), np.uint64) if rng_buf is None else rng_buf
+        grid, agents, st, buf = gen_layouts_locked_hallway(num_rooms, room_size, mhk, mkpr, self.cfg.num_agents,
+                                                           rng_state, rng_inc, buf)
+        self.set_layout_pool(grid, agents)
+        return np.array(st), np.array(buf)
+
     def gen_layout_pool_bup(self, room_size, rng_state, rng_inc, rng_buf, order_state, order_inc):
         from tests.hostsim.sim import gen_layouts_bup
         buf = np.zeros(len(rng_state), np.uint64) if rng_buf is None else rng_buf

@@ -160,3 +160,19 @@ extern "C" int sim_gen_layouts_red_blue_doors(int size, int n, int64_t K, uint64
     }
     return bad;
 }
+
+extern "C" int sim_gen_layouts_locked_hallway(int num_rooms, int S, int mhk, int mkpr, int n, int64_t K,
+                                              uint64_t *rng_state, const uint64_t *rng_inc, uint64_t *rng_buf,
+                                              uint32_t *cells, int8_t *agents) {
+    int bad = 0;
+    const int64_t cs = (int64_t)(3 * (S - 1) + 2) * ((num_rooms / 2) * (S - 1) + 2);
+    for (int64_t k = 0; k < K; k++) {
+        mg::LayoutRng g;
+        g.lo = rng_state[2 * k]; g.hi = rng_state[2 * k + 1]; g.ilo = rng_inc[2 * k]; g.ihi = rng_inc[2 * k + 1];
+        g.has32 = (uint32_t)(rng_buf[k] >> 32) & 1u; g.buf32 = (uint32_t)rng_buf[k];
+        if (!mg::gen_layout_locked_hallway(num_rooms, S, mhk, mkpr, n, g, cells + k * cs, agents + k * n * 8)) bad = 1;
+        rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
+        rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
+    }
+    return bad;
+}

@@ -156,3 +156,26 @@ def test_device_rbd_layout_function_matches_host_generator(size, n, seed):
     st_h, _, buf_h = layout_generator_words(lg)
     np.testing.assert_array_equal(st2, st_h)
     np.testing.assert_array_equal(buf2, buf_h)
+
+
+@pytest.mark.parametrize("rooms,S,mhk,mkpr,n,seed", [(6, 5, 1, 2, 4, 0), (2, 5, 1, 2, 2, 1), (4, 4, 2, 1, 3, 2),
+                                                      (6, 6, 3, 3, 8, 3), (4, 7, 1, 4, 1, 4)])
+def test_device_locked_hallway_layout_function_matches_host_generator(rooms, S, mhk, mkpr, n, seed):
+    """gen_layout_locked_hallway (CPU build of the kernel's function; in-kernel Generator.shuffle) vs
+    LockedHallwayLayout.generate with real numpy generators."""
+    from multigrid_b200.env import layout_generator_words
+    from tests.hostsim.sim import gen_layouts_locked_hallway
+    K = 400
+    lg = [np.random.default_rng([seed, k, 9]) for k in range(K)]
+    for g in lg[1::2]:
+        g.integers(0, 3)
+    st, inc, buf = layout_generator_words(lg)
+    grid, agents, st2, buf2 = gen_layouts_locked_hallway(rooms, S, mhk, mkpr, n, st, inc, buf)
+    layout = L.LockedHallwayLayout(n, num_rooms=rooms, room_size=S, max_hallway_keys=mhk, max_keys_per_room=mkpr)
+    for k in range(K):
+        g, a, _ = layout.generate(lg[k], None)
+        np.testing.assert_array_equal(grid[k], g, err_msg=f"layout {k}")
+        np.testing.assert_array_equal(agents[k], a, err_msg=f"layout {k}")
+    st_h, _, buf_h = layout_generator_words(lg)
+    np.testing.assert_array_equal(st2, st_h)
+    np.testing.assert_array_equal(buf2, buf_h)
