@@ -173,6 +173,16 @@ int mg_gen_layouts_locked_hallway(int32_t num_rooms, int32_t room_size, int32_t 
                                   int8_t *agents, int32_t *status, void *stream);
 
 /*
+ * On-device layouts of PlaygroundEnv (envs/playground.py:122-137 over core/roomgrid.py: connect_all,
+ * add_object, place_agent in a random room) on a num_rows x num_cols RoomGrid (at most 16 rooms). Generator
+ * arguments as mg_gen_layouts_bup (door positions come from the ORDER generator, roomgrid.py:324).
+ */
+int mg_gen_layouts_playground(int32_t room_size, int32_t num_rows, int32_t num_cols, int32_t num_agents,
+                              int64_t num_layouts, uint64_t *rng_state, const uint64_t *rng_inc, uint64_t *rng_buf,
+                              uint64_t *order_state, const uint64_t *order_inc, uint32_t *cells, int8_t *agents,
+                              int32_t *status, void *stream);
+
+/*
  * On-device layouts of BlockedUnlockPickupEnv (envs/blockedunlockpickup.py:142-164 over
  * core/roomgrid.py:203-404: add_object, add_door, place_in_room on a 1 x 2 RoomGrid of `room_size`), same
  * generator conventions as mg_gen_layouts_empty_random plus the ORDER generator of each layout

@@ -285,6 +285,22 @@ int mg_gen_layouts_locked_hallway(int32_t num_rooms, int32_t room_size, int32_t 
     return (int)cudaGetLastError();
 }
 
+int mg_gen_layouts_playground(int32_t room_size, int32_t num_rows, int32_t num_cols, int32_t num_agents,
+                              int64_t num_layouts, uint64_t *rng_state, const uint64_t *rng_inc, uint64_t *rng_buf,
+                              uint64_t *order_state, const uint64_t *order_inc, uint32_t *cells, int8_t *agents,
+                              int32_t *status, void *stream) {
+    if (room_size < 4 || num_rows < 1 || num_cols < 1 || num_rows * num_cols > 16 || num_layouts < 0 ||
+        num_cols * (room_size - 1) + 1 > 127 || num_rows * (room_size - 1) + 1 > 127 || num_agents < 1 ||
+        num_agents > MG_MAX_AGENTS) return MG_ERR_BAD_ARG;
+    if (num_layouts == 0) return 0;
+    if (!rng_state || !rng_inc || !order_state || !order_inc || !cells || !agents) return MG_ERR_BAD_ARG;
+    mg::gen_layouts_playground_kernel<<<(unsigned)((num_layouts + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        room_size, num_rows, num_cols, num_agents, num_layouts, rng_state, rng_inc, rng_buf, order_state, order_inc,
+        cells, agents, status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 int mg_gen_layouts_bup(int32_t room_size, int32_t num_agents, int64_t num_layouts, uint64_t *rng_state,
                        const uint64_t *rng_inc, uint64_t *rng_buf, uint64_t *order_state, const uint64_t *order_inc,
                        uint32_t *cells, int8_t *agents, int32_t *info, int32_t *status, void *stream) {

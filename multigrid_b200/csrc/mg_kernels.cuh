@@ -517,6 +517,79 @@ MG_HD bool gen_layout_locked_hallway(int num_rooms, int S, int max_hallway_keys,
     return true;
 }
 
+// PlaygroundEnv._gen_grid (envs/playground.py:122-137) on a rows x cols RoomGrid (3 x 3 rooms of 7):
+// connect_all (roomgrid.py:406-452: until a search from room (0,0) over rooms joined by doors reaches every
+// room, draw a room and a direction and, if there is a neighbour without a door, add an unlocked door of a
+// random colour at a position drawn from the ORDER generator), 12 x add_object in a random room with random
+// kind (key, ball, box) and colour, then every agent in a random room, not facing an object.
+// rows * cols <= 16. false = a placement or connect_all gave up.
+MG_HD bool gen_layout_playground(int S, int rows, int cols, int n, LayoutRng &g, LayoutRng &order,
+                                 uint32_t *cells, int8_t *agents) {
+    const int step = S - 1, W = cols * step + 1, H = rows * step + 1, Hp = H + 1, total = rows * cols;
+    for (int x = 0; x <= W; x++)
+        for (int y = 0; y <= H; y++) {
+            const bool wall = x >= W || y >= H || x % step == 0 || y % step == 0;
+            cells[x * Hp + y] = wall ? CELL_WALL : CELL_EMPTY;
+        }
+    for (int j = 0; j < n; j++) {
+        int8_t *a = agents + j * 8;
+        a[0] = 0; a[1] = (int8_t)((cols / 2) * step + S / 2); a[2] = (int8_t)((rows / 2) * step + S / 2); a[3] = 0;
+        a[4] = T_EMPTY; a[5] = 0; a[6] = 0; a[7] = (int8_t)(j % 6);
+    }
+    uint8_t doors[16];  // per room (index row * cols + col): bit d = a door in direction d (right, down, left, up)
+    for (int q = 0; q < total; q++) doors[q] = 0;
+    const int DC[4] = {1, 0, -1, 0}, DR[4] = {0, 1, 0, -1};
+    bool connected = false;
+    for (int it = 0; it < 5000; it++) {
+        uint32_t seen = 1u, frontier = 1u;  // reachability from room (0,0) through doors
+        while (frontier) {
+            uint32_t next = 0;
+            for (int q = 0; q < total; q++)
+                if ((frontier >> q) & 1u)
+                    for (int d = 0; d < 4; d++)
+                        if ((doors[q] >> d) & 1u) next |= 1u << (q + DR[d] * cols + DC[d]);
+            frontier = next & ~seen;
+            seen |= next;
+        }
+        if (seen == (total >= 32 ? 0xffffffffu : (1u << total) - 1u)) { connected = true; break; }
+        const int col = rng_integers(g, 0, cols), row = rng_integers(g, 0, rows), d = rng_integers(g, 0, 4);
+        const int oc = col + DC[d], orow = row + DR[d];
+        if (oc < 0 || oc >= cols || orow < 0 || orow >= rows) continue;  // no neighbour
+        if ((doors[row * cols + col] >> d) & 1u) continue;                // door already there
+        const uint32_t color = (uint32_t)rng_integers(g, 0, 6);           // rand_elem(door_colors)
+        const int left = col * step, top = row * step, right = left + S - 1, bottom = top + S - 1;
+        int dx, dy;                                                       // Room.set_door_pos, roomgrid.py:87-124
+        if (d == 0) { dx = right; dy = rng_integers(order, top + 1, bottom); }
+        else if (d == 1) { dx = rng_integers(order, left + 1, right); dy = bottom; }
+        else if (d == 2) { dx = left; dy = rng_integers(order, top + 1, bottom); }
+        else { dx = rng_integers(order, left + 1, right); dy = top; }
+        cells[dx * Hp + dy] = cell_word(T_DOOR, color, S_CLOSED);
+        doors[row * cols + col] |= (uint8_t)(1u << d);
+        doors[orow * cols + oc] |= (uint8_t)(1u << ((d + 2) & 3));
+    }
+    if (!connected) return false;
+    for (int q = 0; q < 12; q++) {  // playground.py:128-131
+        const int col = rng_integers(g, 0, cols), row = rng_integers(g, 0, rows);
+        const uint32_t kind = (uint32_t)(T_KEY + rng_integers(g, 0, 3)), color = (uint32_t)rng_integers(g, 0, 6);
+        const int pos = place_in_rect(W, H, n, g, cells, agents, col * step, row * step, S, S, true);
+        if (pos < 0) return false;
+        cells[(pos & 0xff) * Hp + (pos >> 8)] = cell_word(kind, color, 0);
+    }
+    for (int j = 0; j < n; j++) {   // place_agent() -> place_in_room in a random room (roomgrid.py:370-404)
+        const int col = rng_integers(g, 0, cols), row = rng_integers(g, 0, rows);
+        for (;;) {
+            agents[j * 8 + 1] = -1; agents[j * 8 + 2] = -1;
+            const int pos = place_in_rect(W, H, n, g, cells, agents, col * step, row * step, S, S, false);
+            if (pos < 0) return false;
+            const int x = pos & 0xff, y = pos >> 8, dir = rng_integers(g, 0, 4);
+            agents[j * 8 + 1] = (int8_t)x; agents[j * 8 + 2] = (int8_t)y; agents[j * 8] = (int8_t)dir;
+            const uint32_t t = cells[(x + (dir == 0) - (dir == 2)) * Hp + y + (dir == 1) - (dir == 3)] & 0xffu;
+            if (t == T_EMPTY || t == T_WALL) break;
+        }
+    }
+    return true;
+}
+
 // base.py:598-602: `1 - 0.9 * (step_count / max_steps)` in float64, round-to-nearest at every
 // operation, never contracted into an FMA.
 MG_HD double reward_value(int32_t step_count, int32_t max_steps) {
@@ -1391,6 +1464,26 @@ __global__ void gen_layouts_locked_hallway_kernel(int num_rooms, int S, int mhk,
     if (!ok) status_or(status, 2);
     rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
     if (rng_buf) rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
+}
+
+// Playground layouts (two generators, like BUP below).
+__global__ void gen_layouts_playground_kernel(int S, int rows, int cols, int n, int64_t K, uint64_t *rng_state,
+                                              const uint64_t *rng_inc, uint64_t *rng_buf, uint64_t *order_state,
+                                              const uint64_t *order_inc, uint32_t *cells, int8_t *agents,
+                                              int32_t *status) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    LayoutRng g, o;
+    g.lo = rng_state[2 * k]; g.hi = rng_state[2 * k + 1]; g.ilo = rng_inc[2 * k]; g.ihi = rng_inc[2 * k + 1];
+    const uint64_t b = rng_buf ? rng_buf[k] : 0ull;
+    g.has32 = (uint32_t)(b >> 32) & 1u; g.buf32 = (uint32_t)b;
+    o.lo = order_state[2 * k]; o.hi = order_state[2 * k + 1]; o.ilo = order_inc[2 * k]; o.ihi = order_inc[2 * k + 1];
+    o.has32 = 0; o.buf32 = 0;
+    const int64_t cs = (int64_t)(cols * (S - 1) + 2) * (rows * (S - 1) + 2);
+    if (!gen_layout_playground(S, rows, cols, n, g, o, cells + k * cs, agents + k * n * 8)) status_or(status, 2);
+    rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
+    if (rng_buf) rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
+    order_state[2 * k] = o.lo; order_state[2 * k + 1] = o.hi;
 }
 
 // BlockedUnlockPickup layouts, one thread per layout. order_state/order_inc: the env's own generator

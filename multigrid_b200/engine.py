@@ -189,7 +189,14 @@ class StepEngine:
             raise RecursionError("rejection sampling failed in place_obj")  # base.py:640-641
         return st.cpu().numpy().view(np.uint64), buf.cpu().numpy().view(np.uint64)
 
-    def gen_layout_pool_bup(self, room_size, rng_state, rng_inc, rng_buf, order_state, order_inc):
+    def gen_layout_pool_playground(self, room_size, num_rows, num_cols, rng_state, rng_inc, rng_buf, order_state,
+                                   order_inc):
+        """mg_gen_layouts_playground (envs/playground.py:122-137); arguments / result as gen_layout_pool_bup
+        (the info array is all zero: the mission is constant)."""
+        return self.gen_layout_pool_bup(room_size, rng_state, rng_inc, rng_buf, order_state, order_inc,
+                                        _grid=(num_rows, num_cols))
+
+    def gen_layout_pool_bup(self, room_size, rng_state, rng_inc, rng_buf, order_state, order_inc, _grid=None):
         """mg_gen_layouts_bup: fill the pool on the device with K BlockedUnlockPickup layouts
         (envs/blockedunlockpickup.py:142-164). Layout generators as in gen_layout_pool_empty_random; the
         ORDER generators (env.np_random of the K envs, uint64 words state/inc [K,2]) give the door heights.
@@ -200,15 +207,22 @@ class StepEngine:
         st, inc = t64(rng_state).reshape(K, 2), t64(rng_inc).reshape(K, 2)
         buf = t64(np.zeros(K, np.uint64) if rng_buf is None else rng_buf)
         ost, oinc = t64(order_state).reshape(K, 2), t64(order_inc).reshape(K, 2)
-        assert (cfg.width, cfg.height) == (2 * (room_size - 1) + 1, room_size)
+        rows, cols = _grid or (1, 2)
+        assert (cfg.width, cfg.height) == (cols * (room_size - 1) + 1, rows * (room_size - 1) + 1)
         cells = torch.empty((K, cfg.width + 1, cfg.height + 1), dtype=torch.int32, device=dev)
         agents = torch.empty((K, cfg.num_agents, 8), dtype=torch.int8, device=dev)
-        info = torch.empty((K,), dtype=torch.int32, device=dev)
+        info = torch.zeros((K,), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
-            _cabi.check(self.lib.mg_gen_layouts_bup(
-                room_size, cfg.num_agents, K, st.data_ptr(), inc.data_ptr(), buf.data_ptr(), ost.data_ptr(),
-                oinc.data_ptr(), cells.data_ptr(), agents.data_ptr(), info.data_ptr(), self.status.data_ptr(),
-                self._stream()), "mg_gen_layouts_bup")
+            if _grid is not None:
+                _cabi.check(self.lib.mg_gen_layouts_playground(
+                    room_size, rows, cols, cfg.num_agents, K, st.data_ptr(), inc.data_ptr(), buf.data_ptr(),
+                    ost.data_ptr(), oinc.data_ptr(), cells.data_ptr(), agents.data_ptr(), self.status.data_ptr(),
+                    self._stream()), "mg_gen_layouts_playground")
+            else:
+                _cabi.check(self.lib.mg_gen_layouts_bup(
+                    room_size, cfg.num_agents, K, st.data_ptr(), inc.data_ptr(), buf.data_ptr(), ost.data_ptr(),
+                    oinc.data_ptr(), cells.data_ptr(), agents.data_ptr(), info.data_ptr(), self.status.data_ptr(),
+                    self._stream()), "mg_gen_layouts_bup")
         if int(self.status.item()) & 2:
             self.status.zero_()
             raise RecursionError("rejection sampling failed in place_obj")  # base.py:640-641

@@ -26,7 +26,7 @@ from . import _cabi, spaces
 from .core.constants import Action, Color, Direction, Type
 from .engine import EngineConfig, StepEngine
 from .layouts import (A_COLOR, A_CC, A_CS, A_CT, A_DIR, A_TERM, A_X, A_Y, BlockedUnlockPickupLayout, EmptyLayout,
-                      Layout, LockedHallwayLayout, RedBlueDoorsLayout)
+                      Layout, LockedHallwayLayout, PlaygroundLayout, RedBlueDoorsLayout)
 
 _M64 = (1 << 64) - 1
 
@@ -258,7 +258,7 @@ class BatchedMultiGridEnv:
         # host generator, tests/test_layouts.py); device_layouts=False forces the host path
         self.device_layouts = bool(device_layouts) and (
             (isinstance(layout, EmptyLayout) and not layout.deterministic)
-            or isinstance(layout, (BlockedUnlockPickupLayout, RedBlueDoorsLayout, LockedHallwayLayout)))
+            or isinstance(layout, (BlockedUnlockPickupLayout, RedBlueDoorsLayout, LockedHallwayLayout, PlaygroundLayout)))
         self.pool_size = 1 if layout.deterministic else min(self.num_envs, pool_size or 4096)
         cfg = EngineConfig(
             width=self.width, height=self.height, num_agents=self.num_agents,
@@ -350,6 +350,11 @@ class BatchedMultiGridEnv:
                 st[:K] = ost
                 names = [c.value for c in Color]
                 table = [f"pick up the {names[int(c)]} box" for c in box_color]  # blockedunlockpickup.py:139-140
+            elif isinstance(self.layout, PlaygroundLayout):
+                lo = self.layout
+                ost, _, lst, lbuf = self.engine.gen_layout_pool_playground(
+                    lo.room_size, lo.num_rows, lo.num_cols, lst, linc, lbuf, st[:K], inc[:K])
+                st[:K] = ost
             elif isinstance(self.layout, LockedHallwayLayout):
                 lo = self.layout
                 lst, lbuf = self.engine.gen_layout_pool_locked_hallway(

@@ -54,6 +54,15 @@ class HostSimStepEngine:
         self.set_layout_pool(grid, agents)
         return np.array(st), np.array(buf)
 
+    def gen_layout_pool_playground(self, room_size, num_rows, num_cols, rng_state, rng_inc, rng_buf, order_state,
+                                   order_inc):
+        from tests.hostsim.sim import gen_layouts_playground
+        buf = np.zeros(len(rng_state), np.uint64) if rng_buf is None else rng_buf
+        grid, agents, st, buf, ost = gen_layouts_playground(room_size, num_rows, num_cols, self.cfg.num_agents,
+                                                            rng_state, rng_inc, buf, order_state, order_inc)
+        self.set_layout_pool(grid, agents)
+        return np.array(ost), np.zeros(len(rng_state), np.int32), np.array(st), np.array(buf)
+
     def gen_layout_pool_bup(self, room_size, rng_state, rng_inc, rng_buf, order_state, order_inc):
         from tests.hostsim.sim import gen_layouts_bup
         buf = np.zeros(len(rng_state), np.uint64) if rng_buf is None else rng_buf

@@ -176,3 +176,22 @@ extern "C" int sim_gen_layouts_locked_hallway(int num_rooms, int S, int mhk, int
     }
     return bad;
 }
+
+extern "C" int sim_gen_layouts_playground(int S, int rows, int cols, int n, int64_t K, uint64_t *rng_state,
+                                          const uint64_t *rng_inc, uint64_t *rng_buf, uint64_t *order_state,
+                                          const uint64_t *order_inc, uint32_t *cells, int8_t *agents) {
+    int bad = 0;
+    const int64_t cs = (int64_t)(cols * (S - 1) + 2) * (rows * (S - 1) + 2);
+    for (int64_t k = 0; k < K; k++) {
+        mg::LayoutRng g, o;
+        g.lo = rng_state[2 * k]; g.hi = rng_state[2 * k + 1]; g.ilo = rng_inc[2 * k]; g.ihi = rng_inc[2 * k + 1];
+        g.has32 = (uint32_t)(rng_buf[k] >> 32) & 1u; g.buf32 = (uint32_t)rng_buf[k];
+        o.lo = order_state[2 * k]; o.hi = order_state[2 * k + 1]; o.ilo = order_inc[2 * k]; o.ihi = order_inc[2 * k + 1];
+        o.has32 = 0; o.buf32 = 0;
+        if (!mg::gen_layout_playground(S, rows, cols, n, g, o, cells + k * cs, agents + k * n * 8)) bad = 1;
+        rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
+        rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
+        order_state[2 * k] = o.lo; order_state[2 * k + 1] = o.hi;
+    }
+    return bad;
+}

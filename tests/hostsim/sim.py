@@ -110,6 +110,17 @@ def gen_layouts_locked_hallway(num_rooms, S, mhk, mkpr, n, rng_state, rng_inc, r
     return unpack_cells(cells, W, H), agents, st, buf
 
 
+def gen_layouts_playground(S, rows, cols, n, rng_state, rng_inc, rng_buf, order_state, order_inc):
+    K, W, H = len(rng_state), cols * (S - 1) + 1, rows * (S - 1) + 1
+    st, inc, buf = aligned_copy(rng_state, np.uint64), aligned_copy(rng_inc, np.uint64), aligned_copy(rng_buf, np.uint64)
+    ost, oinc = aligned_copy(order_state, np.uint64), aligned_copy(order_inc, np.uint64)
+    cells, agents = aligned((K, W + 1, H + 1), np.uint32), aligned((K, n, 8), np.int8)
+    rc = lib().sim_gen_layouts_playground(C.c_int(S), C.c_int(rows), C.c_int(cols), C.c_int(n), C.c_int64(K), _p(st),
+                                          _p(inc), _p(buf), _p(ost), _p(oinc), _p(cells), _p(agents))
+    assert rc == 0, rc
+    return unpack_cells(cells, W, H), agents, st, buf, ost
+
+
 def gen_layouts_bup(S, n, rng_state, rng_inc, rng_buf, order_state, order_inc):
     """CPU run of the BUP layout function. Returns (grid, agents, rng_state, rng_buf, order_state, box colours)."""
     K, W, H = len(rng_state), 2 * (S - 1) + 1, S

@@ -537,3 +537,28 @@ def test_rbd_env_reset_device_layouts_equal_host_layouts():
         layout.generate(g, None)
         _, a2, _ = layout.generate(g, None)
         np.testing.assert_array_equal(pool2[k], a2)
+
+
+@pytest.mark.parametrize("env_id,n", [("MultiGrid-LockedHallway-6Rooms-v0", 4), ("MultiGrid-LockedHallway-2Rooms-v0", 2),
+                                      ("MultiGrid-Playground-v0", 3)])
+def test_roomgrid_env_reset_device_layouts_equal_host_layouts(env_id, n):
+    """Pools from mg_gen_layouts_locked_hallway / mg_gen_layouts_playground == pools generated in Python
+    (which tests/test_layouts.py pins to the reference's post-reset states), then identical rollouts."""
+    from multigrid_b200.envs import make
+    kw = dict(agents=n, num_envs=600, device="cuda:0", layout_seed=6, pool_size=600)
+    a = make(env_id, **kw)
+    b = make(env_id, device_layouts=False, **kw)
+    assert a.device_layouts and not b.device_layouts
+    oa, _ = a.reset(seed=4)
+    ob, _ = b.reset(seed=4)
+    np.testing.assert_array_equal(a.grid.state.cpu().numpy(), b.grid.state.cpu().numpy())
+    np.testing.assert_array_equal(a.agent_states.cpu().numpy(), b.agent_states.cpu().numpy())
+    assert len({x.tobytes() for x in a.grid.state.cpu().numpy()}) > 300
+    rng = np.random.default_rng(2)
+    for t in range(25):
+        acts = rng.integers(0, 7, (600, n)).astype(np.int8)
+        ra, rb = a.step(acts), b.step(acts)
+        for i in range(n):
+            np.testing.assert_array_equal(ra[0][i]["image"].cpu().numpy(), rb[0][i]["image"].cpu().numpy())
+            assert (ra[1][i].cpu().numpy() == rb[1][i].cpu().numpy()).all()
+    np.testing.assert_array_equal(a.agent_states.cpu().numpy(), b.agent_states.cpu().numpy())

@@ -179,3 +179,29 @@ def test_device_locked_hallway_layout_function_matches_host_generator(rooms, S, 
     st_h, _, buf_h = layout_generator_words(lg)
     np.testing.assert_array_equal(st2, st_h)
     np.testing.assert_array_equal(buf2, buf_h)
+
+
+@pytest.mark.parametrize("S,rows,cols,n,seed", [(7, 3, 3, 3, 0), (7, 3, 3, 8, 1), (7, 2, 4, 2, 2), (6, 4, 4, 5, 3), (8, 1, 2, 1, 4)])
+def test_device_playground_layout_function_matches_host_generator(S, rows, cols, n, seed):
+    """gen_layout_playground (CPU build of the kernel's function: connect_all, add_object, place_in_room with
+    both generators) vs PlaygroundLayout.generate with real numpy generators."""
+    from multigrid_b200.env import layout_generator_words
+    from tests.hostsim.sim import gen_layouts_playground
+    K = 250
+    lg = [np.random.default_rng([seed, k, 3]) for k in range(K)]
+    og = [np.random.Generator(np.random.PCG64(np.random.SeedSequence(500 * seed + k))) for k in range(K)]
+    for g in lg[::2]:
+        g.integers(0, 10)
+    st, inc, buf = layout_generator_words(lg)
+    ost, oinc, _ = layout_generator_words(og)
+    grid, agents, st2, buf2, ost2 = gen_layouts_playground(S, rows, cols, n, st, inc, buf, ost, oinc)
+    layout = L.PlaygroundLayout(n, room_size=S, num_rows=rows, num_cols=cols)
+    for k in range(K):
+        g, a, _ = layout.generate(lg[k], og[k])
+        np.testing.assert_array_equal(grid[k], g, err_msg=f"layout {k}")
+        np.testing.assert_array_equal(agents[k], a, err_msg=f"layout {k}")
+    st_h, _, buf_h = layout_generator_words(lg)
+    ost_h, _, _ = layout_generator_words(og)
+    np.testing.assert_array_equal(st2, st_h)
+    np.testing.assert_array_equal(buf2, buf_h)
+    np.testing.assert_array_equal(ost2, ost_h)
