@@ -267,6 +267,15 @@ int mg_rollout(const MgConfig *cfg, int64_t num_envs, int32_t num_steps, const M
                const int8_t *actions, const MgRolloutOut *out, void *stream);
 
 /*
+ * Host-driven reset of the envs whose mask byte is non-zero (mask: uint8 [E], device): each takes the NEXT
+ * layout of the pool (layout_idx = (layout_idx + layout_stride) % num_layouts), step_count = 0, hook state = 0;
+ * the env's PCG64 stream continues. Identical to what the step kernels do to an env under MG_FLAG_AUTO_RESET,
+ * for callers that decide about resets themselves (RLlib resets sub-envs from outside).
+ * Replaces: MultiGridEnv.reset (base.py:250-301) for selected envs of a batch.
+ */
+int mg_reset_where(const MgConfig *cfg, int64_t num_envs, const MgState *state, const uint8_t *mask, void *stream);
+
+/*
  * Host-buffer variant of mg_step_obs (what a CPU-side caller of env.step() sees):
  * copies h_actions -> d_actions, runs the fused kernel, copies the outputs in `d_out` to the
  * matching pointers in `h_out` (obs, reward, terminated, truncated; status is not copied).

@@ -87,6 +87,7 @@ EXPORTS = {
                               C.POINTER(MgStepOut), C.c_void_p]),
     "mg_rollout": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.c_int32, C.POINTER(MgState), C.c_void_p,
                              C.POINTER(MgRolloutOut), C.c_void_p]),
+    "mg_reset_where": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p, C.c_void_p]),
     "mg_step_obs_host": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p,
                                    C.c_void_p, C.POINTER(MgStepOut), C.POINTER(MgStepOut),
                                    C.c_void_p]),

@@ -365,6 +365,23 @@ int mg_rollout(const MgConfig *cfg, int64_t num_envs, int32_t num_steps, const M
                                                 out->direction);
 }
 
+int mg_reset_where(const MgConfig *cfg, int64_t num_envs, const MgState *state, const uint8_t *mask, void *stream) {
+    int rc = validate(cfg, num_envs);
+    if (rc) return rc;
+    if (num_envs == 0) return 0;
+    if (!mask || !state || !state->layout_idx || !state->pool_grid || !state->pool_agents || cfg->num_layouts < 1 ||
+        cfg->layout_stride < 0) return MG_ERR_BAD_ARG;
+    mg::Params p;
+    fill_config(p, cfg, num_envs);
+    if ((rc = fill_state(p, state))) return rc;
+    p.G = 16;
+    mg::carve_smem(p);  // derived geometry (cstride)
+    const int64_t threads = num_envs * 32;
+    mg::reset_where_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, mask);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 int mg_step_obs_host(const MgConfig *cfg, int64_t num_envs, const MgState *state,
                      const int8_t *h_actions, int8_t *d_actions, const MgStepOut *d_out,
                      const MgStepOut *h_out, void *stream) {

@@ -1509,6 +1509,29 @@ __global__ void gen_layouts_bup_kernel(int S, int n, int64_t K, uint64_t *rng_st
     order_state[2 * k] = o.lo; order_state[2 * k + 1] = o.hi;
 }
 
+// Host-driven reset of selected envs from the layout pool, one warp per env: exactly what the step
+// kernel's auto-reset does to an env (phase_reset / phase_reset_grid) -- next layout of the pool, step_count
+// and hook state zeroed, the env's PCG64 stream untouched.
+__global__ void reset_where_kernel(const __grid_constant__ Params p, const uint8_t *__restrict__ mask) {
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (e >= p.num_envs || !mask[e]) return;  // whole warp
+    int k = 0;
+    if (lane == 0) k = (int)(((uint32_t)p.layout_idx[e] + (uint32_t)p.lstride) % (uint32_t)p.K);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    const uint32_t *src = p.pool_grid + (size_t)k * p.cstride;
+    uint32_t *dst = p.grid + (size_t)e * p.cstride;
+    for (int w = lane; w < p.cstride; w += LANES) dst[w] = src[w];
+    const uint32_t *asrc = (const uint32_t *)(p.pool_agents + (size_t)k * p.n * 8);
+    uint32_t *adst = (uint32_t *)(p.agents + (size_t)e * p.n * 8);
+    for (int w = lane; w < p.n * 2; w += LANES) adst[w] = asrc[w];
+    if (lane == 0) {
+        p.layout_idx[e] = k;
+        p.step_count[e] = 0;
+        if (p.hook_state) p.hook_state[e] = 0;
+    }
+}
+
 // <= 4 warps per block; register cap: 72 (7 blocks x 128 threads per SM) up to V = 7, 128 for V = 9
 // FullyObsWrapper.observation (multigrid/wrappers.py:50-58): the whole grid as (W,H,3) bytes with
 // EVERY agent (terminated or not) written over its cell as (agent, colour, dir), ascending agent

@@ -283,6 +283,20 @@ class StepEngine:
         self.step_count.zero_()
         self.hook_state.zero_()
 
+    def reset_where(self, mask: torch.Tensor) -> None:
+        """mg_reset_where: envs with a non-zero mask entry ((E,) bool / uint8 on the device) take the next
+        layout of the pool, like the kernel's auto-reset does. Asynchronous."""
+        if mask.shape != (self.num_envs,) or mask.device != self.device:
+            raise TypeError("mask must be a (num_envs,) tensor on the engine's device")
+        m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
+        m = m.contiguous()
+        c, st, _ = self._structs()
+        if self.pool_grid is None:
+            raise RuntimeError("reset_where needs a layout pool (set_layout_pool)")
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.mg_reset_where(C.byref(c), self.num_envs, C.byref(st), m.data_ptr(), self._stream()),
+                        "mg_reset_where")
+
     # -- C structs ---------------------------------------------------------------------------
     def _structs(self):
         if self._c is None:

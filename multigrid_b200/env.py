@@ -467,6 +467,17 @@ class BatchedMultiGridEnv:
                 dict(enumerate(rew_v)), dict(enumerate(term_v)), dict.fromkeys(range(len(rew_v)), trunc_b),
                 defaultdict(dict))
 
+    def reset_where(self, mask):
+        """Reset only the envs selected by `mask` ((E,) bool tensor / array): each takes the next layout of
+        the pool (what `auto_reset=True` does inside the kernel, driven from outside, as RLlib does with its
+        sub-envs). Returns the observations of the whole batch after the reset."""
+        if self._needs_reset:
+            raise RuntimeError("call reset() before reset_where()")
+        if not isinstance(mask, torch.Tensor):
+            mask = torch.as_tensor(np.asarray(mask, dtype=bool))
+        self.engine.reset_where(mask.to(self.device))
+        return self._obs(self.engine.gen_obs())
+
     def check(self) -> None:
         """Synchronise and raise ValueError if a kernel saw an unknown action (base.py:473-474)."""
         self.engine.check_status()

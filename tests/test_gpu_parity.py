@@ -562,3 +562,37 @@ def test_roomgrid_env_reset_device_layouts_equal_host_layouts(env_id, n):
             np.testing.assert_array_equal(ra[0][i]["image"].cpu().numpy(), rb[0][i]["image"].cpu().numpy())
             assert (ra[1][i].cpu().numpy() == rb[1][i].cpu().numpy()).all()
     np.testing.assert_array_equal(a.agent_states.cpu().numpy(), b.agent_states.cpu().numpy())
+
+
+def test_reset_where_matches_auto_reset_semantics():
+    """mg_reset_where == what the kernel's auto-reset does to an env: next pool layout, counters zeroed,
+    PCG stream untouched; unselected envs untouched."""
+    import torch
+    cfg = O.OracleConfig(W=11, H=6, n=2, V=7, hook=1, auto_reset=True, layout_stride=3, max_steps=50)
+    B = 777
+    st = random_batch(cfg, B, 12)
+    g = GpuEngine(cfg, **st)
+    rng = np.random.default_rng(5)
+    for t in range(5):
+        g.step(rng.integers(0, 7, size=(B, cfg.n)).astype(np.int8))
+    before = dict(grid=g.grid, agents=g.agents, sc=g.step_count, pcg=g.pcg_state, idx=g.layout_idx)
+    mask = rng.random(B) < 0.3
+    g.eng.reset_where(torch.from_numpy(mask).cuda())
+    K = st["pool_grid"].shape[0]
+    new_idx = np.where(mask, (before["idx"] + 3) % K, before["idx"])
+    np.testing.assert_array_equal(g.layout_idx, new_idx)
+    np.testing.assert_array_equal(g.step_count, np.where(mask, 0, before["sc"]))
+    np.testing.assert_array_equal(g.pcg_state, before["pcg"])
+    np.testing.assert_array_equal(g.grid, np.where(mask[:, None, None, None], st["pool_grid"][new_idx], before["grid"]))
+    np.testing.assert_array_equal(g.agents, np.where(mask[:, None, None], st["pool_agents"][new_idx], before["agents"]))
+    obs = g.gen_obs()  # and the engine keeps stepping consistently with an oracle given the same state
+    ora = COracle(cfg, grid=g.grid, agents=g.agents, pcg_state=g.pcg_state, pcg_inc=st["pcg_inc"],
+                  pool_grid=st["pool_grid"], pool_agents=st["pool_agents"], layout_idx=g.layout_idx,
+                  step_count=g.step_count, nthreads=NTHREADS)
+    np.testing.assert_array_equal(obs, ora.gen_obs())
+    for t in range(10):
+        a = rng.integers(0, 7, size=(B, cfg.n)).astype(np.int8)
+        o1, r1, t1, tr1 = ora.step(a)
+        o2, r2, t2, tr2 = g.step(a)
+        np.testing.assert_array_equal(o2, o1)
+        assert (r1 == r2).all()
