@@ -596,3 +596,50 @@ def test_reset_where_matches_auto_reset_semantics():
         o2, r2, t2, tr2 = g.step(a)
         np.testing.assert_array_equal(o2, o1)
         assert (r1 == r2).all()
+
+
+def _random_config(rng):
+    """A random engine configuration: grid 3..24 per side, 1..12 agents, any odd view 3..15, any flag set,
+    hooks none / BlockedUnlockPickup / RedBlueDoors / LockedHallway."""
+    hook = int(rng.choice([0, 0, 0, 1, 2, 3]))
+    kw = dict(W=int(rng.integers(3, 25)), H=int(rng.integers(3, 25)), n=int(rng.integers(1, 13)),
+              V=int(rng.choice([3, 5, 7, 9, 11, 13, 15])), max_steps=int(rng.integers(3, 40)),
+              see_through_walls=bool(rng.random() < 0.25), allow_agent_overlap=bool(rng.random() < 0.6),
+              joint_reward=bool(rng.random() < 0.5), success_any=bool(rng.random() < 0.5),
+              failure_any=bool(rng.random() < 0.5), auto_reset=bool(rng.random() < 0.6),
+              layout_stride=int(rng.integers(0, 5)), hook=hook)
+    if hook == 3:
+        kw["hook_param"] = int(rng.integers(1, 5))
+    return kw
+
+
+@pytest.mark.parametrize("case", range(48))
+def test_random_configurations_vs_c_oracle(case):
+    """Differential sweep over the configuration space (sizes, agent counts, views, flags, hooks):
+    the kernel (fused path; every sixth case also through mg_rollout) vs the C oracle on dense random soups."""
+    import torch
+    rng = np.random.default_rng(10_000 + case)
+    kw = _random_config(rng)
+    cfg = O.OracleConfig(**kw)
+    B, T = int(rng.integers(1, 400)), 14
+    st = random_batch(cfg, B, 20_000 + case)
+    ora, g = COracle(cfg, nthreads=NTHREADS, **st), GpuEngine(cfg, **st)
+    msg = f"case {case}: {kw} B={B}"
+    np.testing.assert_array_equal(g.gen_obs(), ora.gen_obs(), err_msg=msg)
+    actions = rng.integers(-1, 7, size=(T, B, cfg.n)).astype(np.int8)
+    if case % 6 == 5:
+        out = g.eng.rollout(torch.from_numpy(actions).cuda())
+        g.eng.check_status()
+        obs, rew = out["obs"].cpu().numpy(), out["reward"].cpu().numpy()
+        term, trunc = out["terminated"].cpu().numpy(), out["truncated"].cpu().numpy()
+    for t in range(T):
+        o1, r1, t1, tr1 = ora.step(actions[t])
+        if case % 6 == 5:
+            o2, r2, t2, tr2 = obs[t], rew[t], term[t], trunc[t]
+        else:
+            o2, r2, t2, tr2 = g.step(actions[t])
+        np.testing.assert_array_equal(o2, o1, err_msg=f"{msg} step {t}")
+        assert (r1 == r2).all(), f"{msg} step {t}"
+        np.testing.assert_array_equal(t2, t1, err_msg=f"{msg} step {t}")
+        np.testing.assert_array_equal(tr2, tr1, err_msg=f"{msg} step {t}")
+    assert_same(g, ora, msg)

@@ -116,3 +116,29 @@ def test_hostsim_rollout_equals_single_steps(seed, kw):
     np.testing.assert_array_equal(sim.step_count, ora.step_count)
     np.testing.assert_array_equal(sim.pcg_state, ora.pcg_state)
     np.testing.assert_array_equal(sim.layout_idx, ora.layout_idx)
+
+
+@pytest.mark.parametrize("case", range(16))
+def test_hostsim_random_configurations_vs_c_oracle(case):
+    """The configuration sweep of tests/test_gpu_parity.py::test_random_configurations_vs_c_oracle on the
+    CPU build of the kernel's phase functions (smaller batches)."""
+    from tests.test_gpu_parity import _random_config
+    rng = np.random.default_rng(10_000 + case)
+    kw = _random_config(rng)
+    cfg = O.OracleConfig(**kw)
+    B, T = int(rng.integers(1, 400)) % 60 + 1, 10
+    st = random_batch(cfg, B, 20_000 + case)
+    ora, sim = COracle(cfg, **st), SimEngine(cfg, **st)
+    msg = f"case {case}: {kw} B={B}"
+    np.testing.assert_array_equal(sim.gen_obs(), ora.gen_obs(), err_msg=msg)
+    for t in range(T):
+        actions = rng.integers(-1, 7, size=(B, cfg.n)).astype(np.int8)
+        o1, r1, t1, tr1 = ora.step(actions)
+        o2, r2, t2, tr2 = sim.step(actions)
+        np.testing.assert_array_equal(o2, o1, err_msg=f"{msg} step {t}")
+        assert (r1 == r2).all(), f"{msg} step {t}"
+        np.testing.assert_array_equal(t2, t1, err_msg=f"{msg} step {t}")
+        np.testing.assert_array_equal(tr2, tr1, err_msg=f"{msg} step {t}")
+    np.testing.assert_array_equal(sim.grid, ora.grid, err_msg=msg)
+    np.testing.assert_array_equal(sim.agents, ora.agents, err_msg=msg)
+    np.testing.assert_array_equal(sim.pcg_state, ora.pcg_state, err_msg=msg)
