@@ -868,8 +868,11 @@ MG_HD void handle_actions(const Params &p, const Group &g, int i, uint32_t *cell
                           uint32_t ord, uint32_t &rewarded) {
     const int n = p.n, G = p.G, e = g.e0 + i;
     const int8_t *act_e = g.act + i * n;
+    const bool packed_order = n <= 4;  // (hoisted: the order of <= 4 agents travels in a register)
+    const uint8_t *order_e = g.order + i;
     for (int r = 0; r < n; r++) {
-        const int k = n <= 4 ? (int)((ord >> (4 * r)) & 15u) : (int)g.order[r * G + i];
+        const int k = packed_order ? (int)(ord & 15u) : (int)order_e[r * G];
+        ord >>= 4;
         const int act = act_e[k];
         uint32_t a0 = ag[k * 2], a1 = ag[k * 2 + 1];
         if (act < 0) continue;            // id not in the action dict (base.py:403-404)
