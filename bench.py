@@ -36,7 +36,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used if MEASU
 # `ncu --set full` capture summarised in profiles/r01_summary.md (r01c): 26.30 MB read (= the layout's
 # 401 B/env of inputs) + 3.04 MB written; the other ~41.6 MB of outputs are still dirty in the 126 MB L2
 # when the kernel ends (ncu flushes before each replay) and reach HBM during later launches.
-NCU_DRAM_BYTES_PER_LAUNCH = 28722432  # profiles/r01e_ncu_details.txt: dram read 26 292 480 + write 2 429 952
+NCU_DRAM_BYTES_PER_LAUNCH = 30447104  # profiles/r01f_ncu_details.txt: dram read 26 817 536 + write 3 629 568
 
 
 def algorithmic_bytes_per_env_step(W, H, n, V, mutable_grid=False):
@@ -219,6 +219,9 @@ def workload_config(n_gpus):
         "l2": f"{REPLICAS} state replicas rotated (each launch touches a batch last used "
               f"{REPLICAS} launches ago; {REPLICAS}x61 MB > 126 MB L2), no explicit flush; "
               "MG_FLAG_STREAM_STATE (L2 evict_first on state loads / obs stores, cache policy only)",
+        "launches": "chained (MG_FLAG_CHAINED): each launch is ordered after the previous launch on the same replica env by "
+                    "env through chain tickets, not by a kernel-boundary barrier, so it loads while its predecessor drains; "
+                    "`unchained` in this line is the same graph with plain launches",
     }
 
 
@@ -258,8 +261,10 @@ def run_engine(args):
                          # near their start cells, which flatters the kernel by ~15 %)
     tape = torch.randint(0, 7, (n_tape, E, n), generator=gen, device=dev, dtype=torch.int32).to(torch.int8)
 
-    def launch(k):
-        engines[k % REPLICAS].step(tape[k % n_tape])
+    def launch(k, chained=True):
+        # MG_FLAG_CHAINED: consecutive launches are ordered per env by the engine's chain tickets instead of a
+        # kernel-boundary barrier (the action tape is staged before the timed region, nothing else runs on the stream)
+        engines[k % REPLICAS].step(tape[k % n_tape], chained=chained)
 
     for k in range(BURN_IN):
         launch(k)
@@ -295,18 +300,12 @@ def run_engine(args):
         dist.barrier()
     ms = ev0.elapsed_time(ev1)
 
-    # ---- informational: the same K launches as TWO independent chains (even / odd replicas on two
-    # graph branches), i.e. two env batches in flight: one batch's load phase overlaps the other's
-    # compute tail. Reported under "two_chains", never as `value`.
-    side = torch.cuda.Stream(device=dev)
+    # ---- informational: the same K launches as PLAIN launches (every launch waits for the whole previous grid)
     with torch.cuda.stream(stream):
         graph2 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph2, stream=stream):
-            side.wait_stream(stream)
             for k in range(K):
-                with torch.cuda.stream(stream if k % 2 == 0 else side):
-                    launch(Wm + k)
-            stream.wait_stream(side)
+                launch(Wm + k, chained=False)
         graph2.replay()
     torch.cuda.synchronize()
     ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -376,18 +375,20 @@ def run_engine(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_note": "ncu dram read+write bytes of one launch (profiles/r01_summary.md); "
+                         "traffic_note": "ncu dram read+write bytes of one launch (profiles/r01f_ncu_details.txt); "
                                          "outputs still dirty in L2 at kernel end are not in it",
                          "algorithmic_bytes_per_launch": bpe * E, "peak_source": peak_src,
                          "frac_of_8TBs_nominal": achieved / 8000.0,
                          "algorithmic_bytes_per_env_step": bpe,
                          "actual_bytes_per_env_step": layout_bytes_per_env_step(SIZE, SIZE, n, VIEW),
-                         "kernel": "mg::step_obs_kernel<7, MODE_STEP_OBS> (one launch = 65536 env-steps)",
+                         "kernel": "mg::step_obs_kernel<7, MODE_STEP_OBS, MULTI=false, CHAIN=true> (one launch = 65536 env-steps)",
+                         "launch_time_note": "avg_launch_us = timed region / launches; chained launches overlap (a launch "
+                                             "loads while its predecessor drains), so this is the throughput time per "
+                                             "launch, not the latency of one launch (see `unchained`)",
                          "avg_launch_us": 1e3 * ms / K},
         }
-        line["two_chains"] = {
-            "note": "informational, not `value`: the same K launches issued as two independent replica chains "
-                    "(two env batches in flight on two graph branches)",
+        line["unchained"] = {
+            "note": "informational: the same K launches as plain launches (kernel-boundary barrier between them)",
             "us_per_launch": 1e3 * ms2 / K, "value": total_envs * n * K / (ms2 * 1e-3),
             "achieved_gbs": bpe * E / (ms2 * 1e-3 / K) / 1e9}
         line["api_device_resident"] = {

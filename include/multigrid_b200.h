@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 4
+#define MG_ABI_VERSION 5
 
 /* MgConfig.flags */
 #define MG_FLAG_SEE_THROUGH_WALLS 0x01u /* agents[0].see_through_walls, base.py:364-365 */
@@ -65,6 +65,18 @@ extern "C" {
                                            are NOT re-stepped while still L2-resident (state larger than L2,
                                            or several engines interleaved); leave it off when one batch that
                                            fits L2 is stepped back to back. */
+
+#define MG_FLAG_CHAINED           0x80u /* scheduling only (results unchanged), needs MgState.chain_next/chain_done:
+                                           this step launch is ordered after the previous CHAINED step launch on the
+                                           same state env by env (tickets) instead of waiting for that whole grid,
+                                           so its blocks load and compute while the previous launch drains. The
+                                           caller promises that since that previous launch nothing else was enqueued
+                                           on the stream that writes this launch's inputs (the actions!) or reads or
+                                           writes the state / the outputs. Completion stays in stream order. */
+#define MG_FLAG_CHAIN_HEAD        0x100u /* with MG_FLAG_CHAINED: first launch of a chain (the previous operation on
+                                           the state was not a chained step launch): takes tickets and also waits for
+                                           the whole previous grid of the stream, like a plain launch. Launches
+                                           without MG_FLAG_CHAINED never touch the tickets. */
 
 /* MgConfig.hook: env-specific step() post-hooks */
 #define MG_HOOK_NONE 0
@@ -103,6 +115,8 @@ typedef struct MgState {
     const int8_t *pool_agents; /* [K][n][8]    (may be NULL without MG_FLAG_AUTO_RESET) */
     int32_t *hook_state;       /* [E] per-env state of the post-hook; only MG_HOOK_LOCKED_HALLWAY uses it
                                   (bit per door colour already unlocked); may be NULL otherwise */
+    uint32_t *chain_next;      /* [E] chain tickets (may be NULL without MG_FLAG_CHAINED; zero-initialised): a chained */
+    uint32_t *chain_done;      /* [E] launch takes chain_next[e]++ and publishes chain_done[e] = ticket + 1 when done with e */
 } MgState;
 
 typedef struct MgStepOut {

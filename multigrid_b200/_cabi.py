@@ -19,13 +19,15 @@ FLAG_SUCCESS_ANY = 0x08
 FLAG_FAILURE_ANY = 0x10
 FLAG_AUTO_RESET = 0x20
 FLAG_STREAM_STATE = 0x40
+FLAG_CHAINED = 0x80
+FLAG_CHAIN_HEAD = 0x100
 
 HOOK_NONE = 0
 HOOK_BLOCKED_UNLOCK_PICKUP = 1
 HOOK_RED_BLUE_DOORS = 2
 HOOK_LOCKED_HALLWAY = 3
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_VIEW = 15
 MAX_AGENTS = 32
 
@@ -44,6 +46,7 @@ class MgState(C.Structure):
         ("grid", C.c_void_p), ("agents", C.c_void_p), ("step_count", C.c_void_p),
         ("pcg_state", C.c_void_p), ("pcg_inc", C.c_void_p), ("layout_idx", C.c_void_p),
         ("pool_grid", C.c_void_p), ("pool_agents", C.c_void_p), ("hook_state", C.c_void_p),
+        ("chain_next", C.c_void_p), ("chain_done", C.c_void_p),
     ]
 
 

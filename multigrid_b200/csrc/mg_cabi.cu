@@ -66,9 +66,9 @@ int plan(mg::Params &p) {
     return mg::plan_launch(p, env_int("MG_GROUP", 0, k), env_int("MG_WPB", 0, k), kSmemPerBlock, kSmemPerSM, n_sm);
 }
 
-template <int VT, int MODE, bool MULTI = false>
+template <int VT, int MODE, bool MULTI = false, bool CHAIN = false>
 int launch(const mg::Params &p, cudaStream_t stream) {
-    auto kernel = mg::step_obs_kernel<VT, MODE, MULTI>;
+    auto kernel = mg::step_obs_kernel<VT, MODE, MULTI, CHAIN>;
     static thread_local bool configured_dev[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -100,6 +100,20 @@ int dispatch(const mg::Params &p, cudaStream_t stream) {
     if constexpr (MODE == mg::MODE_STEP) {
         return launch<0, MODE>(p, stream);  // no observation phase: view size is irrelevant
     } else {
+        if constexpr (MODE == mg::MODE_STEP_OBS && !MULTI) {
+            if (p.chained) {
+                if (!p.generic_view) {
+                    switch (p.V) {
+                        case 3: return launch<3, MODE, false, true>(p, stream);
+                        case 5: return launch<5, MODE, false, true>(p, stream);
+                        case 7: return launch<7, MODE, false, true>(p, stream);
+                        case 9: return launch<9, MODE, false, true>(p, stream);
+                        default: break;
+                    }
+                }
+                return launch<0, MODE, false, true>(p, stream);
+            }
+        }
         if (!p.generic_view) {
             switch (p.V) {
                 case 3: return launch<3, MODE, MULTI>(p, stream);
@@ -133,6 +147,11 @@ int fill_state(mg::Params &p, const MgState *s) {
     p.pool_grid = s->pool_grid; p.pool_agents = s->pool_agents;
     if (p.hook == MG_HOOK_LOCKED_HALLWAY && !s->hook_state) return MG_ERR_BAD_ARG;
     p.hook_state = s->hook_state;
+    if ((s->chain_next == nullptr) != (s->chain_done == nullptr)) return MG_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(s->chain_next) | reinterpret_cast<uintptr_t>(s->chain_done)) & 3u) return MG_ERR_ALIGNMENT;
+    p.chain_next = s->chain_next; p.chain_done = s->chain_done;
+    if ((p.flags & MG_FLAG_CHAINED) && !s->chain_next) return MG_ERR_BAD_ARG;
+    p.chained = (p.flags & MG_FLAG_CHAINED) ? ((p.flags & MG_FLAG_CHAIN_HEAD) ? 2 : 1) : 0;
     return 0;
 }
 
@@ -163,6 +182,9 @@ int step_common(const MgConfig *cfg, int64_t num_envs, const MgState *state, con
     if ((rc = plan(p))) return rc;
     // a rollout re-reads its cells from L2 every step: never mark those loads evict_first
     if (MULTI) p.l2hint &= ~1;
+    if (MULTI || MODE != mg::MODE_STEP_OBS) p.chained = 0;  // only the fused single-step launch chains; a rollout
+                                                            // or mg_step is a plain launch and leaves the tickets alone
+    if (p.chained && !p.pdl) p.chained = 2;  // without programmatic launch every launch waits like a chain head
     // TMA spans of step t start at t * E * n (actions) and t * E * n * stride (obs) bytes
     if (MULTI && (((size_t)num_envs * p.n) & 15u)) p.use_bulk = 0;
     // natural alignment of the per-env scalars (16-byte PCG words, 8-byte rewards, 4-byte counters and

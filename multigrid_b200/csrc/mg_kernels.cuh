@@ -69,6 +69,12 @@ struct Params {
     int32_t T;
     int32_t xknob;  // experiments (MG_X), timing only
     int32_t pdl;    // host side only: launch with programmatic stream serialization
+    // Chained launches (MG_FLAG_CHAINED, MgState.chain_next / chain_done, see include/multigrid_b200.h):
+    // per-env tickets order consecutive chained step launches on the same state env by env, so a launch need
+    // not wait for the whole previous grid. chained: 0 = plain launch (tickets untouched), 1 = chained,
+    // 2 = head of a chain (takes tickets AND waits for the whole previous grid of the stream).
+    uint32_t *chain_next, *chain_done;
+    int32_t chained;
     int8_t *direction;  // [T][E][n] per-step 'direction' observation (rollout only; NULL otherwise)
     // state (device)
     uint32_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;
@@ -1351,6 +1357,19 @@ __device__ __forceinline__ void bulk_s2g_hint(void *dst_gmem, const void *src_sm
 // has completed and its writes are visible. Both are no-ops for a launch without the attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -1622,13 +1641,17 @@ __global__ void __launch_bounds__(256) one_hot_kernel_v16(int V, int64_t agents,
     }
 }
 
-template <int VT, int MODE, bool MULTI = false>
+// CHAIN = the launch takes part in the chain tickets (MG_FLAG_CHAINED); plain launches compile without them.
+template <int VT, int MODE, bool MULTI = false, bool CHAIN = false>
 __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __grid_constant__ Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = blockIdx.x * p.wpb + warp;
-    pdl_launch_dependents();
-    if (group * p.G >= p.num_envs) return;  // whole warp
+    constexpr bool tickets = CHAIN;
+    if (group * p.G >= p.num_envs) {  // whole warp
+        pdl_launch_dependents();
+        return;
+    }
     uint8_t *ws = smem + warp * p.warp_bytes;
     const Group g = group_view(p, ws, group);
     uint64_t *bar = (uint64_t *)(ws + p.off_mbar);
@@ -1638,8 +1661,32 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
     trace_mark(p, group, lane, 0);
     trace_mark(p, group, lane, 7);
 
+    // Chain tickets. Every step launch on this state takes, per env, the next ticket (chain_next) BEFORE it
+    // lets its dependents launch, so tickets follow launch order: the dependent grid's blocks only start once
+    // all blocks of this grid have passed launch_dependents. An env may be touched once chain_done equals the
+    // ticket, i.e. once the previous launch has finished THAT env (its stores complete, then a release store).
+    uint32_t ticket = 0;
+    if (tickets) {
+        if (env >= 0) {
+            ticket = ld_relaxed_gpu(p.chain_next + g.e0 + env);
+            p.chain_next[g.e0 + env] = ticket + 1u;  // (shadow lanes write the same value)
+        }
+        __threadfence();  // the claim is performed device-wide before the dependents may launch
+    }
+    pdl_launch_dependents();
     if (bulk && lane == 0) mbar_init(bar, 1);
-    pdl_wait();  // nothing of the previous launch is read or overwritten before this point
+    // Plain launch or head of a chain: wait for the whole previous grid, nothing of it is read or overwritten
+    // before this point. Chained: only the per-env tickets order this launch after its predecessor on the state.
+    if (!tickets || p.chained == 2) pdl_wait();
+    if (tickets) {
+        for (;;) {
+            const bool ready = env < 0 || ld_acquire_gpu(p.chain_done + g.e0 + env) == ticket;
+            if (__all_sync(0xffffffffu, ready)) break;
+            __nanosleep(64);
+        }
+        fence_async_global();  // what the acquire made visible is also visible to the TMA loads below
+        __syncwarp();
+    }
     EnvRegs er;
     const int T = MULTI ? p.T : 1;
 #pragma unroll 1
@@ -1730,7 +1777,19 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
             phase_store_plain(p, g, lane);
         }
     }
-    if (bulk && lane == 0) bulk_wait_read();  // smem must stay valid until the TMA stores have read it
+    if (tickets) {
+        // publish: this launch is done with its envs once every store of the warp is complete -- the TMA stores
+        // (full completion, not only their shared-memory reads) and the lanes' own global stores
+        if (bulk && lane == 0) bulk_wait_all();
+        __syncwarp();
+        __threadfence();
+        if (env >= 0) st_release_gpu(p.chain_done + g.e0 + env, ticket + 1u);
+        // completion order: a chained launch did not wait for its predecessor when it started; it must not
+        // COMPLETE before it either, or the next unchained operation of the stream could overtake that grid
+        if (p.chained == 1) pdl_wait();
+    } else if (bulk && lane == 0) {
+        bulk_wait_read();  // smem must stay valid until the TMA stores have read it
+    }
     trace_mark(p, group, lane, 4);
 }
 #endif

@@ -105,6 +105,10 @@ class StepEngine:
         self.terminated = z((E, n), torch.uint8)
         self.truncated = z((E,), torch.uint8)
         self.status = z((1,), torch.int32)
+        # chain tickets (include/multigrid_b200.h, MG_FLAG_CHAINED): maintained by chained step launches
+        self.chain_next = z((E,), torch.int32)
+        self.chain_done = z((E,), torch.int32)
+        self._chain_armed = None  # the stream whose last operation on this engine was a step launch
         self.pool_grid = None
         self.pool_agents = None
         self._pool_rng = None
@@ -127,6 +131,7 @@ class StepEngine:
 
     def _pack(self, grid3, out_cells: torch.Tensor) -> None:
         """mg_pack_grid: (K,W,H,3) bytes (numpy / torch, host / device) -> cell words in `out_cells`."""
+        self._chain_armed = None
         W, H = self.cfg.width, self.cfg.height
         if isinstance(grid3, torch.Tensor):
             g = grid3.to(self.device, torch.int8).contiguous()
@@ -141,6 +146,7 @@ class StepEngine:
     # -- configuration / state injection ------------------------------------------------------
     def set_layout_pool(self, pool_grid, pool_agents) -> None:
         """Reset layouts: grid (K,W,H,3) int8 and packed agents (K,n,8) int8."""
+        self._chain_armed = None
         cfg = self.cfg
         pg = np.ascontiguousarray(pool_grid, dtype=np.int8)
         pa = torch.as_tensor(np.ascontiguousarray(pool_agents, dtype=np.int8))
@@ -156,6 +162,7 @@ class StepEngine:
     def gen_layout_pool_red_blue_doors(self, size, rng_state, rng_inc, rng_buf=None):
         """mg_gen_layouts_red_blue_doors (envs/redbluedoors.py:142-168); arguments and result as
         gen_layout_pool_empty_random. refresh_layout_pool() continues the same generators."""
+        self._chain_armed = None
         assert (self.cfg.width, self.cfg.height) == (2 * size, size)
         return self.gen_layout_pool_empty_random(rng_state, rng_inc, rng_buf, _family=("rbd", size))
 
@@ -163,6 +170,7 @@ class StepEngine:
                                        rng_state, rng_inc, rng_buf=None):
         """mg_gen_layouts_locked_hallway (envs/locked_hallway.py:150-194); result as
         gen_layout_pool_empty_random."""
+        self._chain_armed = None
         return self.gen_layout_pool_empty_random(
             rng_state, rng_inc, rng_buf, _family=("lh", num_rooms, room_size, max_hallway_keys, max_keys_per_room))
 
@@ -171,6 +179,7 @@ class StepEngine:
         len(rng_state) EmptyEnv layouts with random agent placement (envs/empty.py:151-170), one per
         numpy PCG64 generator given as uint64 words (state [K,2], inc [K,2], optional buffered-uint32
         word [K]). Returns the advanced (state, buf) as numpy uint64 arrays."""
+        self._chain_armed = None
         cfg = self.cfg
         K = len(rng_state)
         dev = self.device
@@ -193,6 +202,7 @@ class StepEngine:
                                    order_inc):
         """mg_gen_layouts_playground (envs/playground.py:122-137); arguments / result as gen_layout_pool_bup
         (the info array is all zero: the mission is constant)."""
+        self._chain_armed = None
         return self.gen_layout_pool_bup(room_size, rng_state, rng_inc, rng_buf, order_state, order_inc,
                                         _grid=(num_rows, num_cols))
 
@@ -201,6 +211,7 @@ class StepEngine:
         (envs/blockedunlockpickup.py:142-164). Layout generators as in gen_layout_pool_empty_random; the
         ORDER generators (env.np_random of the K envs, uint64 words state/inc [K,2]) give the door heights.
         Returns (order_state [K,2], box colour index [K] int32, rng_state [K,2], rng_buf [K]) after the draws."""
+        self._chain_armed = None
         cfg = self.cfg
         K, dev = len(rng_state), self.device
         t64 = lambda a: torch.as_tensor(_as_i64_bits(a)).to(dev).contiguous()  # noqa: E731
@@ -236,6 +247,7 @@ class StepEngine:
         """Overwrite the pool with the NEXT layout of every pool generator (one kernel launch, no host
         work, asynchronous): with auto_reset, envs that reset after this draw from fresh layouts
         instead of cycling the first K. Only after gen_layout_pool_empty_random."""
+        self._chain_armed = None
         if getattr(self, "_pool_rng", None) is None:
             raise RuntimeError("the layout pool was not generated on the device")
         cfg = self.cfg
@@ -256,6 +268,7 @@ class StepEngine:
     def load_state(self, grid=None, agents=None, step_count=None, pcg_state=None, pcg_inc=None,
                    layout_idx=None, hook_state=None) -> None:
         """Inject state (numpy or torch, host or device). uint64 PCG words are passed as numpy."""
+        self._chain_armed = None
         def put(dst, src, bits64=False):
             if src is None:
                 return
@@ -275,6 +288,7 @@ class StepEngine:
 
     def reset_from_pool(self, layout_idx=None) -> None:
         """Host-driven reset of every env from the layout pool (step_count := 0)."""
+        self._chain_armed = None
         if layout_idx is not None:
             self.load_state(layout_idx=layout_idx)
         idx = self.layout_idx.long()
@@ -286,6 +300,7 @@ class StepEngine:
     def reset_where(self, mask: torch.Tensor) -> None:
         """mg_reset_where: envs with a non-zero mask entry ((E,) bool / uint8 on the device) take the next
         layout of the pool, like the kernel's auto-reset does. Asynchronous."""
+        self._chain_armed = None
         if mask.shape != (self.num_envs,) or mask.device != self.device:
             raise TypeError("mask must be a (num_envs,) tensor on the engine's device")
         m = mask.view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8)
@@ -310,11 +325,16 @@ class StepEngine:
             p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
             st = _cabi.MgState(p(self.cells), p(self.agents), p(self.step_count), p(self.pcg_state),
                                p(self.pcg_inc), p(self.layout_idx), p(self.pool_grid),
-                               p(self.pool_agents), p(self.hook_state))
+                               p(self.pool_agents), p(self.hook_state), p(self.chain_next), p(self.chain_done))
             out = _cabi.MgStepOut(p(self.obs_buf), p(self.reward), p(self.terminated),
                                   p(self.truncated), p(self.status))
+            mk = lambda extra: _cabi.MgConfig(cfg.width, cfg.height, cfg.num_agents, cfg.view_size,  # noqa: E731
+                                              cfg.max_steps, cfg.flags | extra, cfg.hook, self.obs_stride, K,
+                                              cfg.layout_stride, cfg.hook_param)
+            cc, ch = mk(_cabi.FLAG_CHAINED), mk(_cabi.FLAG_CHAINED | _cabi.FLAG_CHAIN_HEAD)
             self._c = (c, st, out)
             self._refs = (C.byref(c), C.byref(st), C.byref(out))
+            self._chained_cfg = (cc, C.byref(cc), ch, C.byref(ch))
         return self._c
 
     def _stream(self) -> C.c_void_p:
@@ -334,6 +354,7 @@ class StepEngine:
     # -- launches ------------------------------------------------------------------------------
     def gen_obs(self) -> torch.Tensor:
         """mg_gen_obs: observations of the current state (used after reset)."""
+        self._chain_armed = None
         c, st, out = self._structs()
         with torch.cuda.device(self.device):
             _cabi.check(self.lib.mg_gen_obs(C.byref(c), self.num_envs, self.cells.data_ptr(),
@@ -341,11 +362,18 @@ class StepEngine:
                                             self._stream()), "mg_gen_obs")
         return self.obs
 
-    def step(self, actions: torch.Tensor | None = None, fused: bool = True):
+    def step(self, actions: torch.Tensor | None = None, fused: bool = True, chained: bool = False):
         """mg_step_obs on device-resident int8 actions (E,n); -1 = agent absent.
 
         Returns device views (obs, reward, terminated, truncated); they are overwritten by the
         next call. Asynchronous on the current CUDA stream.
+
+        chained=True (MG_FLAG_CHAINED, scheduling only): this launch is ordered after the previous step
+        launch of this engine env by env instead of waiting for that whole grid. The caller promises that
+        since that launch nothing else on the stream wrote `actions` or touched this engine's state or
+        outputs (open-loop action tapes). The first chained launch after any other operation of the engine
+        (plain step, load_state, gen_obs, reset_where, ...) is the head of a new chain and waits like a
+        plain launch; plain launches never touch the tickets.
         """
         if actions is None:
             actions = self.actions
@@ -356,6 +384,11 @@ class StepEngine:
         rc, rst, rout = self._refs
         fn = self.lib.mg_step_obs if fused else self.lib.mg_step
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if chained and fused:  # head of a chain unless the engine's previous operation was a chained step on this stream
+            rc = self._chained_cfg[1] if self._chain_armed == stream else self._chained_cfg[3]
+            self._chain_armed = stream
+        else:
+            self._chain_armed = None
         if torch.cuda.current_device() == self.device.index:  # (a device guard costs more than the launch)
             rc_ = fn(rc, self.num_envs, rst, actions.data_ptr(), rout, stream)
         else:
@@ -373,6 +406,7 @@ class StepEngine:
         optionally reuses, `out=`) a dict of device tensors with a leading T axis: obs
         (T,E,n,V,V,3) view of obs_buf (T,E,n,stride), direction (T,E,n), reward, terminated,
         truncated (T,E). Asynchronous on the current CUDA stream."""
+        self._chain_armed = None
         if (actions.dtype != torch.int8 or not actions.is_contiguous() or actions.device != self.device
                 or actions.dim() != 3 or tuple(actions.shape[1:]) != (self.num_envs, self.cfg.num_agents)):
             raise TypeError("actions must be a contiguous int8 CUDA tensor of shape (T, num_envs, n)")
@@ -407,6 +441,7 @@ class StepEngine:
         Fill `host_buffers()['actions']` first. This is the end-to-end path a CPU-side caller of
         `env.step()` sees: H2D actions + kernel + D2H (obs, reward, terminated, truncated).
         """
+        self._chain_armed = None
         h = self.host_buffers()
         c, st, out = self._structs()
         hout = _cabi.MgStepOut(h["obs"].data_ptr(), h["reward"].data_ptr(),

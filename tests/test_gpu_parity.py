@@ -187,11 +187,13 @@ def test_launch_knobs_do_not_change_results(seed, B, kw, knobs, monkeypatch):
     test_random_soup_vs_c_oracle(seed, B, kw)
 
 
-@pytest.mark.parametrize("pdl", ["0", "1"])
-def test_back_to_back_launches_without_host_sync(pdl, monkeypatch):
+@pytest.mark.parametrize("pdl,chained", [("0", False), ("1", False), ("1", True), ("0", True)])
+def test_back_to_back_launches_without_host_sync(pdl, chained, monkeypatch):
     """T dependent launches enqueued on one stream with no synchronisation in between (eager and as a
     CUDA graph): with programmatic dependent launch every launch may be scheduled while its
-    predecessor drains, and must still see all of the predecessor's writes."""
+    predecessor drains, and must still see all of the predecessor's writes. chained=True
+    (MG_FLAG_CHAINED): launches are ordered env by env through the chain tickets instead of waiting
+    for the whole previous grid -- every warp of launch k+1 races the other warps of launch k."""
     import torch
     monkeypatch.setenv("MG_PDL", pdl)
     cfg = O.OracleConfig(W=8, H=8, n=4, V=7, max_steps=40, auto_reset=True)
@@ -202,14 +204,15 @@ def test_back_to_back_launches_without_host_sync(pdl, monkeypatch):
     actions = rng.integers(0, 7, size=(2 * T, B, cfg.n)).astype(np.int8)
     tape = torch.from_numpy(actions).cuda()
     stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
     with torch.cuda.stream(stream):
         for t in range(T):
-            g.eng.step(tape[t])
+            g.eng.step(tape[t], chained=chained)
         stream.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
             for t in range(T, 2 * T):
-                g.eng.step(tape[t])
+                g.eng.step(tape[t], chained=chained)
         graph.replay()
     torch.cuda.synchronize()
     for t in range(2 * T):
@@ -217,7 +220,55 @@ def test_back_to_back_launches_without_host_sync(pdl, monkeypatch):
     np.testing.assert_array_equal(g._obs(g.eng.obs_buf), o1)
     assert (g.eng.reward.cpu().numpy() == r1).all()
     np.testing.assert_array_equal(g.eng.terminated.cpu().numpy(), t1)
-    assert_same(g, ora, f"pdl={pdl}")
+    assert_same(g, ora, f"pdl={pdl} chained={chained}")
+    want = 2 * T if chained else 0  # plain launches never touch the tickets
+    assert (g.eng.chain_next.cpu().numpy() == want).all() and (g.eng.chain_done.cpu().numpy() == want).all()
+
+
+@pytest.mark.parametrize("kw,B", [(dict(W=8, H=8, n=4, V=7, max_steps=30, auto_reset=True), 65536),
+                                  (dict(W=11, H=6, n=2, V=7, hook=1, joint_reward=True, auto_reset=True, max_steps=14), 9000),
+                                  (dict(W=16, H=16, n=8, V=9, auto_reset=True, max_steps=11), 3000)])
+def test_chained_launches_rotating_engines(kw, B):
+    """The bench's launch pattern: several engines (replicas) rotated on one stream, every launch chained, as
+    one CUDA graph replayed twice, with unchained operations (gen_obs, a plain step, mg_rollout) in between.
+    Every engine must end in the oracle's state."""
+    import torch
+    kw = dict(kw)
+    cfg = O.OracleConfig(**kw)
+    R, T = 3, 30
+    sts = [random_batch(cfg, B, 50 + r) for r in range(R)]
+    oras = [COracle(cfg, nthreads=NTHREADS, **st) for st in sts]
+    gs = [GpuEngine(cfg, **st) for st in sts]
+    rng = np.random.default_rng(9)
+    actions = rng.integers(0, 7, size=(T, B, cfg.n)).astype(np.int8)
+    tape = torch.from_numpy(actions).cuda()
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    done = [[] for _ in range(R)]  # action indices applied to each engine, in order
+    with torch.cuda.stream(stream):
+        for k in range(8):
+            gs[k % R].eng.step(tape[k % T], chained=True)
+            done[k % R].append(k % T)
+        stream.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for k in range(8, 8 + 2 * T):
+                gs[k % R].eng.step(tape[k % T], chained=True)
+        for rep in range(2):
+            graph.replay()
+            for k in range(8, 8 + 2 * T):
+                done[k % R].append(k % T)
+            gs[0].eng.gen_obs()                                   # unchained reader of engine 0's state
+            gs[1].eng.step(tape[rep]); done[1].append(rep)        # a plain (unchained) step
+            gs[2].eng.rollout(tape[:3]); done[2].extend(range(3))  # three steps in one launch
+    torch.cuda.synchronize()
+    for r in range(R):
+        for a in done[r]:
+            oras[r].step(actions[a])
+        assert_same(gs[r], oras[r], f"engine {r}")
+        n_launch_steps = len(done[r])
+        assert (gs[r].eng.chain_next.cpu().numpy() == gs[r].eng.chain_done.cpu().numpy()).all()
+    np.testing.assert_array_equal(gs[0].gen_obs(), oras[0].gen_obs())
 
 
 @pytest.mark.parametrize("seed,B,T,kw", [

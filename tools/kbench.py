@@ -70,9 +70,10 @@ def time_config(name, steps, knobs, replicas=8):
     names = ("cells", "agents", "step_count", "pcg_state", "layout_idx", "hook_state")
     snap = [{k: getattr(e, k).clone() for k in names} for e in engines]
     for knob in knobs:
-        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_X"):
+        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_X", "CHAINED"):
             os.environ.pop(key, None)
         os.environ.update({k: str(v) for k, v in knob.items()})
+        chained = bool(int(os.environ.get("CHAINED", "0")))  # (a kbench knob, not a library one)
         for e, sn in zip(engines, snap):
             for k in names:
                 getattr(e, k).copy_(sn[k])
@@ -85,7 +86,7 @@ def time_config(name, steps, knobs, replicas=8):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
                 for k in range(steps):
-                    engines[k % replicas].step(tape[k % NT])
+                    engines[k % replicas].step(tape[k % NT], chained=chained)
         torch.cuda.synchronize()
         best = 1e9
         for rep in range(3):
