@@ -66,7 +66,7 @@ extern "C" {
                                            or several engines interleaved); leave it off when one batch that
                                            fits L2 is stepped back to back. */
 
-#define MG_FLAG_CHAINED           0x80u /* scheduling only (results unchanged), needs MgState.chain_next/chain_done:
+#define MG_FLAG_CHAINED           0x80u /* scheduling only (results unchanged), needs MgState.chain:
                                            this step launch is ordered after the previous CHAINED step launch on the
                                            same state env by env (tickets) instead of waiting for that whole grid,
                                            so its blocks load and compute while the previous launch drains. The
@@ -115,8 +115,9 @@ typedef struct MgState {
     const int8_t *pool_agents; /* [K][n][8]    (may be NULL without MG_FLAG_AUTO_RESET) */
     int32_t *hook_state;       /* [E] per-env state of the post-hook; only MG_HOOK_LOCKED_HALLWAY uses it
                                   (bit per door colour already unlocked); may be NULL otherwise */
-    uint32_t *chain_next;      /* [E] chain tickets (may be NULL without MG_FLAG_CHAINED; zero-initialised): a chained */
-    uint32_t *chain_done;      /* [E] launch takes chain_next[e]++ and publishes chain_done[e] = ticket + 1 when done with e */
+    uint32_t *chain;           /* [E][2] chain tickets {next, done} (may be NULL without MG_FLAG_CHAINED; zero-
+                                  initialised, 8-byte aligned): a chained launch takes ticket next[e]++ and publishes
+                                  done[e] = ticket + 1 when it is done with env e */
 } MgState;
 
 typedef struct MgStepOut {

@@ -46,7 +46,7 @@ class MgState(C.Structure):
         ("grid", C.c_void_p), ("agents", C.c_void_p), ("step_count", C.c_void_p),
         ("pcg_state", C.c_void_p), ("pcg_inc", C.c_void_p), ("layout_idx", C.c_void_p),
         ("pool_grid", C.c_void_p), ("pool_agents", C.c_void_p), ("hook_state", C.c_void_p),
-        ("chain_next", C.c_void_p), ("chain_done", C.c_void_p),
+        ("chain", C.c_void_p),
     ]
 
 

@@ -147,10 +147,9 @@ int fill_state(mg::Params &p, const MgState *s) {
     p.pool_grid = s->pool_grid; p.pool_agents = s->pool_agents;
     if (p.hook == MG_HOOK_LOCKED_HALLWAY && !s->hook_state) return MG_ERR_BAD_ARG;
     p.hook_state = s->hook_state;
-    if ((s->chain_next == nullptr) != (s->chain_done == nullptr)) return MG_ERR_BAD_ARG;
-    if ((reinterpret_cast<uintptr_t>(s->chain_next) | reinterpret_cast<uintptr_t>(s->chain_done)) & 3u) return MG_ERR_ALIGNMENT;
-    p.chain_next = s->chain_next; p.chain_done = s->chain_done;
-    if ((p.flags & MG_FLAG_CHAINED) && !s->chain_next) return MG_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(s->chain) & 7u) return MG_ERR_ALIGNMENT;
+    p.chain = s->chain;
+    if ((p.flags & MG_FLAG_CHAINED) && !s->chain) return MG_ERR_BAD_ARG;
     p.chained = (p.flags & MG_FLAG_CHAINED) ? ((p.flags & MG_FLAG_CHAIN_HEAD) ? 2 : 1) : 0;
     return 0;
 }
@@ -179,11 +178,11 @@ int step_common(const MgConfig *cfg, int64_t num_envs, const MgState *state, con
     p.actions = actions;
     p.T = num_steps;
     p.direction = direction;
+    if (MULTI || MODE != mg::MODE_STEP_OBS) p.chained = 0;  // only the fused single-step launch chains; a rollout
+                                                            // or mg_step is a plain launch and leaves the tickets alone
     if ((rc = plan(p))) return rc;
     // a rollout re-reads its cells from L2 every step: never mark those loads evict_first
     if (MULTI) p.l2hint &= ~1;
-    if (MULTI || MODE != mg::MODE_STEP_OBS) p.chained = 0;  // only the fused single-step launch chains; a rollout
-                                                            // or mg_step is a plain launch and leaves the tickets alone
     if (p.chained && !p.pdl) p.chained = 2;  // without programmatic launch every launch waits like a chain head
     // TMA spans of step t start at t * E * n (actions) and t * E * n * stride (obs) bytes
     if (MULTI && (((size_t)num_envs * p.n) & 15u)) p.use_bulk = 0;

@@ -73,7 +73,7 @@ struct Params {
     // per-env tickets order consecutive chained step launches on the same state env by env, so a launch need
     // not wait for the whole previous grid. chained: 0 = plain launch (tickets untouched), 1 = chained,
     // 2 = head of a chain (takes tickets AND waits for the whole previous grid of the stream).
-    uint32_t *chain_next, *chain_done;
+    uint32_t *chain;  // [E][2] {next ticket, tickets done}
     int32_t chained;
     int8_t *direction;  // [T][E][n] per-step 'direction' observation (rollout only; NULL otherwise)
     // state (device)
@@ -159,6 +159,21 @@ inline int plan_launch(Params &p, int forced_G, int forced_wpb, int smem_per_blo
     }
     int best_wpb = 1;
     const int warps16 = best_warps_per_sm(p, smem_per_block, smem_per_sm, &best_wpb);
+    // Chained launches overlap two launches on the chip, so half the warps per launch (32 envs each, the
+    // transition at full lane width: -20 % instructions) still fill it: 17.0 -> 16.7 us on the bench. Only for
+    // batches of about a wave or more; smaller ones want the warps.
+    if (forced_G == 0 && p.chained) {
+        p.G = 32;
+        int wpb32 = 1;
+        const int warps32 = carve_smem(p) <= smem_per_block ? best_warps_per_sm(p, smem_per_block, smem_per_sm, &wpb32) : 0;
+        if (warps32 >= 12 && (p.num_envs + 31) / 32 >= (3 * num_sms * warps32) / 4) {
+            p.wpb = wpb32;
+            if (forced_wpb > 0 && forced_wpb <= 4 && forced_wpb * p.warp_bytes <= smem_per_block) p.wpb = forced_wpb;
+            return 0;
+        }
+        p.G = 16;
+        carve_smem(p);
+    }
     // Large grids / views (Empty-16x16 n=8 V=9: 19 KB per warp) leave few resident warps, and a modest
     // batch then fills only a fraction even of those: halve the group (twice the warps) as long as an
     // observation pass stays full (8 envs x n agents a multiple of 32). Measured 26.4 -> 24.4 us there.
@@ -1365,9 +1380,9 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
 __device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint2 ld_acquire_gpu_v2(const uint32_t *p) {
+    uint2 v;
+    asm volatile("ld.acquire.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -1648,44 +1663,53 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = blockIdx.x * p.wpb + warp;
     constexpr bool tickets = CHAIN;
-    if (group * p.G >= p.num_envs) {  // whole warp
-        pdl_launch_dependents();
-        return;
+    const bool live = group * p.G < p.num_envs;  // (whole warp)
+    // Chain tickets (p.chain[e] = {next ticket, tickets done}). Every chained launch takes, per env, the next
+    // ticket BEFORE it lets its dependents launch, so tickets follow launch order: the dependent grid's blocks
+    // only start once all blocks of this grid have passed launch_dependents. The trigger is per BLOCK (the first
+    // thread that executes it counts), so every warp of the block claims first, then a block barrier, then the
+    // trigger. An env may be touched once `done` equals the ticket, i.e. once the previous launch has finished
+    // THAT env (its stores complete, then a release store).
+    uint32_t ticket = 0, done0 = 0;
+    int env = -1;
+    if (tickets) {
+        if (p.chained == 2) pdl_wait();  // head of a chain: the whole previous grid first, like a plain launch
+        if (live) {
+            const int ne = p.num_envs - group * p.G < p.G ? p.num_envs - group * p.G : p.G;
+            const int i = lane & (p.G - 1);
+            env = i < ne ? i : -1;
+            if (env >= 0) {
+                uint32_t *slot = p.chain + 2 * (size_t)(group * p.G + env);
+                const uint2 nd = ld_acquire_gpu_v2(slot);
+                ticket = nd.x; done0 = nd.y;
+                slot[0] = ticket + 1u;  // (shadow lanes write the same value)
+            }
+        }
+        __threadfence();   // the claims are performed device-wide ...
+        __syncthreads();   // ... by every warp of the block, before the block's trigger
     }
+    pdl_launch_dependents();
+    if (!live) return;
     uint8_t *ws = smem + warp * p.warp_bytes;
     const Group g = group_view(p, ws, group);
     uint64_t *bar = (uint64_t *)(ws + p.off_mbar);
     // TMA needs 16-byte multiples: full groups only (G % 16 == 0 makes every span aligned)
     const bool bulk = p.use_bulk && g.ne == p.G;
-    const int env = lane_env(p, g, lane);
+    env = lane_env(p, g, lane);
     trace_mark(p, group, lane, 0);
     trace_mark(p, group, lane, 7);
-
-    // Chain tickets. Every step launch on this state takes, per env, the next ticket (chain_next) BEFORE it
-    // lets its dependents launch, so tickets follow launch order: the dependent grid's blocks only start once
-    // all blocks of this grid have passed launch_dependents. An env may be touched once chain_done equals the
-    // ticket, i.e. once the previous launch has finished THAT env (its stores complete, then a release store).
-    uint32_t ticket = 0;
-    if (tickets) {
-        if (env >= 0) {
-            ticket = ld_relaxed_gpu(p.chain_next + g.e0 + env);
-            p.chain_next[g.e0 + env] = ticket + 1u;  // (shadow lanes write the same value)
-        }
-        __threadfence();  // the claim is performed device-wide before the dependents may launch
-    }
-    pdl_launch_dependents();
     if (bulk && lane == 0) mbar_init(bar, 1);
-    // Plain launch or head of a chain: wait for the whole previous grid, nothing of it is read or overwritten
-    // before this point. Chained: only the per-env tickets order this launch after its predecessor on the state.
-    if (!tickets || p.chained == 2) pdl_wait();
     if (tickets) {
-        for (;;) {
-            const bool ready = env < 0 || ld_acquire_gpu(p.chain_done + g.e0 + env) == ticket;
-            if (__all_sync(0xffffffffu, ready)) break;
+        uint32_t *slot = p.chain + 2 * (size_t)(g.e0 + (env >= 0 ? env : 0));
+        bool ready = env < 0 || done0 == ticket;
+        while (!__all_sync(0xffffffffu, ready)) {
             __nanosleep(64);
+            ready = env < 0 || ld_acquire_gpu(slot + 1) == ticket;
         }
         fence_async_global();  // what the acquire made visible is also visible to the TMA loads below
         __syncwarp();
+    } else {
+        pdl_wait();  // plain launch: nothing of the previous launch is read or overwritten before this point
     }
     EnvRegs er;
     const int T = MULTI ? p.T : 1;
@@ -1783,7 +1807,7 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
         if (bulk && lane == 0) bulk_wait_all();
         __syncwarp();
         __threadfence();
-        if (env >= 0) st_release_gpu(p.chain_done + g.e0 + env, ticket + 1u);
+        if (env >= 0) st_release_gpu(p.chain + 2 * (size_t)(g.e0 + env) + 1, ticket + 1u);
         // completion order: a chained launch did not wait for its predecessor when it started; it must not
         // COMPLETE before it either, or the next unchained operation of the stream could overtake that grid
         if (p.chained == 1) pdl_wait();

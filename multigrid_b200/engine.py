@@ -106,8 +106,7 @@ class StepEngine:
         self.truncated = z((E,), torch.uint8)
         self.status = z((1,), torch.int32)
         # chain tickets (include/multigrid_b200.h, MG_FLAG_CHAINED): maintained by chained step launches
-        self.chain_next = z((E,), torch.int32)
-        self.chain_done = z((E,), torch.int32)
+        self.chain = z((E, 2), torch.int32)  # per env {next ticket, tickets done}
         self._chain_armed = None  # the stream whose last operation on this engine was a step launch
         self.pool_grid = None
         self.pool_agents = None
@@ -325,7 +324,7 @@ class StepEngine:
             p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
             st = _cabi.MgState(p(self.cells), p(self.agents), p(self.step_count), p(self.pcg_state),
                                p(self.pcg_inc), p(self.layout_idx), p(self.pool_grid),
-                               p(self.pool_agents), p(self.hook_state), p(self.chain_next), p(self.chain_done))
+                               p(self.pool_agents), p(self.hook_state), p(self.chain))
             out = _cabi.MgStepOut(p(self.obs_buf), p(self.reward), p(self.terminated),
                                   p(self.truncated), p(self.status))
             mk = lambda extra: _cabi.MgConfig(cfg.width, cfg.height, cfg.num_agents, cfg.view_size,  # noqa: E731

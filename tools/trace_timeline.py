@@ -23,10 +23,11 @@ from multigrid_b200.engine import EngineConfig, StepEngine  # noqa: E402
 
 ap = argparse.ArgumentParser(); ap.add_argument("--config", default="empty8"); ap.add_argument("--group", type=int, default=16)
 ap.add_argument("--rollout", type=int, default=0, help="trace one mg_rollout launch of this many steps instead")
+ap.add_argument("--chained", action="store_true", help="trace one launch in the middle of a run of chained launches")
 args = ap.parse_args()
 W, H, n, V, E, max_steps, _ = kbench.CONFIGS[args.config]
 dev = torch.device("cuda", 0); lib = _cabi.load()
-cfg = EngineConfig(width=W, height=H, num_agents=n, view_size=V, max_steps=max_steps, auto_reset=True)
+cfg = EngineConfig(width=W, height=H, num_agents=n, view_size=V, max_steps=max_steps, auto_reset=True, stream_state=True)
 pg, pa = kbench.layout(W, H, n)
 engines = []
 for r in range(8):
@@ -59,10 +60,19 @@ if args.rollout:
     life = (t[:, 4] - t[:, 0]) / 1e3
     print("warp life us min/p50/max:", life.min(), np.median(life), life.max())
     sys.exit(0)
-lib.mg_debug_set_trace(buf.data_ptr())
-engines[0].step(tape[0])
-torch.cuda.synchronize()
-lib.mg_debug_set_trace(None)
+if args.chained:
+    for k in range(12):  # launches 0..11 on rotating engines, all chained; launch 6 is traced
+        if k == 6:
+            lib.mg_debug_set_trace(buf.data_ptr())
+        engines[k % 8].step(tape[k % 32], chained=True)
+        if k == 6:
+            lib.mg_debug_set_trace(None)
+    torch.cuda.synchronize()
+else:
+    lib.mg_debug_set_trace(buf.data_ptr())
+    engines[0].step(tape[0])
+    torch.cuda.synchronize()
+    lib.mg_debug_set_trace(None)
 t = buf.cpu().numpy().astype(np.float64)
 t0 = t[:, 0].min()
 rel = (t[:, :5] - t0) / 1e3  # us
