@@ -52,7 +52,6 @@ int plan(mg::Params &p) {
     const bool k = any_mg_knob();
     p.use_bulk = env_int("MG_NO_BULK", 0, k) ? 0 : 1;
     p.generic_view = env_int("MG_GENERIC_VIEW", 0, k) ? 1 : 0;
-    p.xknob = env_int("MG_X", 0, k);
     p.pdl = env_int("MG_PDL", 1, k) ? 1 : 0;
     p.l2hint = env_int("MG_L2HINT", (p.flags & MG_FLAG_STREAM_STATE) ? 3 : 0, k);
     static thread_local int sms[64] = {0};

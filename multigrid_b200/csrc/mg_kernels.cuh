@@ -67,7 +67,6 @@ struct Params {
     // mg_rollout: T consecutive steps in ONE launch. Step t reads actions[t][E][n] and writes slice t of
     // every output array ([T][E]...); agents and the per-env scalars stay on chip between steps.
     int32_t T;
-    int32_t xknob;  // experiments (MG_X), timing only
     int32_t pdl;    // host side only: launch with programmatic stream serialization
     // Chained launches (MG_FLAG_CHAINED, MgState.chain_next / chain_done, see include/multigrid_b200.h):
     // per-env tickets order consecutive chained step launches on the same state env by env, so a launch need
@@ -1784,7 +1783,7 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
         if (t + 1 < T) {
             // this step's writes to the grid in HBM (dirty cells, reset layouts: generic proxy) must be
             // visible to the next step's TMA load of the cells (async proxy)
-            if (bulk && !(p.xknob & 1)) fence_async_global();
+            if (bulk) fence_async_global();
             __syncwarp();
             trace_mark(p, group, lane, 6);
         }

@@ -70,7 +70,7 @@ def time_config(name, steps, knobs, replicas=8):
     names = ("cells", "agents", "step_count", "pcg_state", "layout_idx", "hook_state")
     snap = [{k: getattr(e, k).clone() for k in names} for e in engines]
     for knob in knobs:
-        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_X", "CHAINED"):
+        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "CHAINED"):
             os.environ.pop(key, None)
         os.environ.update({k: str(v) for k, v in knob.items()})
         chained = bool(int(os.environ.get("CHAINED", "0")))  # (a kbench knob, not a library one)
@@ -123,7 +123,7 @@ def time_rollout(name, T, knobs):
     torch.cuda.synchronize()
     bpe = bench.rollout_bytes_per_env_step(n, V)
     for knob in knobs:
-        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_X"):
+        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT"):
             os.environ.pop(key, None)
         os.environ.update({k: str(v) for k, v in knob.items()})
         eng.rollout(tape, out)
