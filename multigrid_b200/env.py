@@ -444,14 +444,15 @@ class BatchedMultiGridEnv:
                 self._actions[:, i] = torch.as_tensor(np.asarray(a, dtype=np.int8), device=self.device)
         return self._actions
 
-    def step(self, actions):
+    def step(self, actions, chained: bool = False):
         """-> (obs, rewards, terminations, truncations, infos), dicts keyed by agent index whose
         values are batched device tensors (views of engine buffers, overwritten by the next call).
         Asynchronous: nothing here synchronises with the GPU. Out-of-range actions inside tensors
         are flagged on the device and raise ValueError at the next `reset()` / `check()`."""
         if self._needs_reset:
             raise RuntimeError("call reset() before step()")
-        image, reward, terminated, truncated = self.engine.step(self._action_tensor(actions))
+        # chained=True: StepEngine.step's MG_FLAG_CHAINED (open-loop action tapes only, see its docstring)
+        image, reward, terminated, truncated = self.engine.step(self._action_tensor(actions), chained=chained)
         if self._step_views is None or self._step_views[0] is not image:
             # every item is a view of a fixed engine buffer: build the per-agent views once (some 20 tensor
             # ops, twice the cost of the kernel launch) and hand out fresh dicts around them every step

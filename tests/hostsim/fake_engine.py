@@ -112,7 +112,7 @@ class HostSimStepEngine:
     def gen_obs(self):
         return torch.from_numpy(self._engine().gen_obs())
 
-    def step(self, actions):
+    def step(self, actions, chained=False):
         obs, rew, term, trunc = self._engine().step(actions.numpy())
         return (torch.from_numpy(obs), torch.from_numpy(rew), torch.from_numpy(term),
                 torch.from_numpy(trunc))
