@@ -183,6 +183,8 @@ int step_common(const MgConfig *cfg, int64_t num_envs, const MgState *state, con
     // a rollout re-reads its cells from L2 every step: never mark those loads evict_first
     if (MULTI) p.l2hint &= ~1;
     if (p.chained && !p.pdl) p.chained = 2;  // without programmatic launch every launch waits like a chain head
+    // the actions span of a group (G * n bytes) must be a multiple of 16 for the bulk copy: 8 envs x odd n is not
+    if ((p.G * p.n) & 15) p.use_bulk = 0;
     // TMA spans of step t start at t * E * n (actions) and t * E * n * stride (obs) bytes
     if (MULTI && (((size_t)num_envs * p.n) & 15u)) p.use_bulk = 0;
     // natural alignment of the per-env scalars (16-byte PCG words, 8-byte rewards, 4-byte counters and

@@ -154,7 +154,12 @@ inline int plan_launch(Params &p, int forced_G, int forced_wpb, int smem_per_blo
     p.G = (forced_G == 32 || forced_G == 8) ? forced_G : 16;
     if (carve_smem(p) > smem_per_block) {
         p.G = 16;
-        if (carve_smem(p) > smem_per_block) return MG_ERR_TOO_LARGE;
+        if (carve_smem(p) > smem_per_block) {
+            p.G = 8;  // very large grids (up to ~83 x 83): 8 envs per warp, one warp per block
+            if (carve_smem(p) > smem_per_block) return MG_ERR_TOO_LARGE;
+            p.wpb = 1;
+            return 0;
+        }
     }
     int best_wpb = 1;
     const int warps16 = best_warps_per_sm(p, smem_per_block, smem_per_sm, &best_wpb);

@@ -179,7 +179,7 @@ KNOBS = [dict(MG_NO_BULK="1"), dict(MG_GROUP="8"), dict(MG_GROUP="32"), dict(MG_
 
 
 @pytest.mark.parametrize("knobs", KNOBS, ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
-@pytest.mark.parametrize("seed,B,kw", [SOUP[0], SOUP[1], SOUP[4], SOUP[6]])
+@pytest.mark.parametrize("seed,B,kw", [SOUP[0], SOUP[1], SOUP[2], SOUP[4], SOUP[5], SOUP[6]])
 def test_launch_knobs_do_not_change_results(seed, B, kw, knobs, monkeypatch):
     """Group size, warps per block, TMA-vs-plain copies and the rolled-loop view are implementation choices only."""
     for k, v in knobs.items():
@@ -695,3 +695,29 @@ def test_random_configurations_vs_c_oracle(case):
         np.testing.assert_array_equal(t2, t1, err_msg=f"{msg} step {t}")
         np.testing.assert_array_equal(tr2, tr1, err_msg=f"{msg} step {t}")
     assert_same(g, ora, msg)
+
+
+def test_largest_grids():
+    """Grids beyond what 16 envs per warp can stage in shared memory fall back to 8 envs per warp (70 x 70
+    here); beyond that (127 x 127) the call is refused with MG_ERR_TOO_LARGE, not a launch failure."""
+    import ctypes as C
+    import torch
+    from multigrid_b200 import _cabi
+    cfg = O.OracleConfig(W=70, H=70, n=3, V=7, max_steps=30, auto_reset=True)
+    B, T = 50, 8
+    st = random_batch(cfg, B, 77, K=3)
+    ora, g = COracle(cfg, nthreads=NTHREADS, **st), GpuEngine(cfg, **st)
+    np.testing.assert_array_equal(g.gen_obs(), ora.gen_obs())
+    rng = np.random.default_rng(4)
+    for t in range(T):
+        a = rng.integers(-1, 7, size=(B, cfg.n)).astype(np.int8)
+        o1, r1, t1, tr1 = ora.step(a)
+        o2, r2, t2, tr2 = g.step(a)
+        np.testing.assert_array_equal(o2, o1)
+        assert (r1 == r2).all()
+    assert_same(g, ora, "70x70")
+    lib = _cabi.load()
+    c = _cabi.MgConfig(127, 127, 2, 7, 100, 0, 0, 148, 0, 1)
+    buf = torch.zeros(128 * 128 * 4 * 2 + 4096, dtype=torch.int8, device="cuda:0")
+    rc = lib.mg_gen_obs(C.byref(c), 2, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), None)
+    assert rc == -3 and b"too large" in lib.mg_error_string(rc)
