@@ -81,6 +81,9 @@ SOUP = [
     (7, 64, dict(W=6, H=9, n=2, V=13, allow_agent_overlap=False)),
     (8, 1, dict(W=19, H=19, n=3, V=7)),
     (9, 17, dict(W=25, H=25, n=2, V=15, auto_reset=True, max_steps=9)),
+    (10, 40, dict(W=12, H=12, n=32, V=15, auto_reset=True, max_steps=9)),            # MG_MAX_AGENTS, MG_MAX_VIEW
+    (11, 33, dict(W=3, H=3, n=1, V=3)),                                               # the smallest walled grid
+    (12, 130, dict(W=9, H=4, n=31, V=5, allow_agent_overlap=False, joint_reward=True, hook=1)),
 ]
 
 

@@ -61,6 +61,8 @@ def test_hostsim_obs_random_injected_states():
     (5, dict(W=7, H=7, n=3, V=5, see_through_walls=True, auto_reset=True, max_steps=12)),
     (6, dict(W=10, H=6, n=12, V=11, max_steps=30, auto_reset=True, layout_stride=3)),
     (7, dict(W=6, H=9, n=2, V=13, allow_agent_overlap=False)),
+    (10, dict(W=12, H=12, n=32, V=15, auto_reset=True, max_steps=9)),
+    (11, dict(W=3, H=3, n=1, V=3)),
 ])
 def test_hostsim_random_soup_vs_c_oracle(seed, kw):
     """Bigger ragged batches (tail block, many blocks) of dense random states."""
