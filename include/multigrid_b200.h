@@ -228,6 +228,20 @@ int mg_full_obs(int32_t width, int32_t height, int32_t num_agents, int64_t num_e
 int mg_one_hot(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
                uint8_t *out, void *stream);
 
+/*
+ * Network input of the reference's training script in one pass from the observations: out float32
+ * [A][V][V][23] = the 21 one-hot channels (0.0 / 1.0) + cos, sin of 2*pi*direction/4 broadcast over the view.
+ * Replaces: OneHotObsWrapper.one_hot (multigrid/wrappers.py:158-190) followed by preprocess_batch
+ * (scripts/train.py:56-63: concatenate the direction features, .float()).
+ *   direction     int8, one per agent, `direction_stride` bytes apart (the engine's agent records: stride 8)
+ *   dir_lut       float32 [4][2] = {cos, sin} of 2*pi*d/4, computed by the caller the way the reference does
+ *                 (torch float32), so the two feature channels are the reference's values bit for bit
+ *   out           16-byte aligned
+ */
+#define MG_FEATURE_CHANNELS 23
+int mg_obs_features(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
+                    const int8_t *direction, int32_t direction_stride, const float *dir_lut, float *out, void *stream);
+
 /* Diagnostics: when set to a device buffer of 8 uint64 per warp (= per group of envs), every
  * following launch records %globaltimer at its phase boundaries (slots 0..4) and the SM id (slot 7).
  * NULL (the default) disables it. Used by tools/trace_timeline.py; not part of the hot path. */

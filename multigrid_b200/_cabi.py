@@ -81,6 +81,8 @@ EXPORTS = {
     "mg_gen_layouts_locked_hallway": (C.c_int, [C.c_int32] * 5 + [C.c_int64] + [C.c_void_p] * 7),
     "mg_gen_layouts_playground": (C.c_int, [C.c_int32] * 4 + [C.c_int64] + [C.c_void_p] * 9),
     "mg_gen_layouts_bup": (C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 10),
+    "mg_obs_features": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "mg_unpack_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_gen_obs": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                              C.c_void_p]),

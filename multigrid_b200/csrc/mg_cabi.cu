@@ -337,6 +337,21 @@ int mg_gen_layouts_bup(int32_t room_size, int32_t num_agents, int64_t num_layout
     return (int)cudaGetLastError();
 }
 
+int mg_obs_features(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
+                    const int8_t *direction, int32_t direction_stride, const float *dir_lut, float *out, void *stream) {
+    if (view_size < 3 || view_size > MG_MAX_VIEW || num_agents_total < 0 || direction_stride < 1 ||
+        obs_agent_stride < 3 * view_size * view_size) return MG_ERR_BAD_ARG;
+    if (num_agents_total == 0) return 0;
+    if (!obs || !direction || !dir_lut || !out) return MG_ERR_BAD_ARG;
+    // 16 agents x V*V*23 floats is a multiple of 16 bytes, so every block's 16-byte stores are aligned
+    if (reinterpret_cast<uintptr_t>(out) & 15u) return MG_ERR_ALIGNMENT;
+    mg::obs_features_kernel<<<(unsigned)((num_agents_total + 15) / 16), 256, 0, (cudaStream_t)stream>>>(
+        view_size, num_agents_total, obs_agent_stride, mg::rcp32(view_size * view_size * 23), obs, direction,
+        direction_stride, dir_lut, (float4 *)out);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 int mg_unpack_grid(int32_t width, int32_t height, int64_t num_envs, const uint32_t *cells, int8_t *grid3,
                    void *stream) {
     if (width < 1 || height < 1 || width > 127 || height > 127 || num_envs < 0) return MG_ERR_BAD_ARG;

@@ -1618,6 +1618,53 @@ __global__ void one_hot_kernel(int V, int64_t agents, int ostride, const int8_t 
     }
 }
 
+// Network input of the reference's training script (scripts/train.py:56-63 preprocess_batch over the
+// OneHotObsWrapper image): float32 [A][V][V][23] = the 21 one-hot channels as 0.0 / 1.0 followed by
+// cos and sin of 2*pi*direction/4, broadcast over the view. One pass from the 3-byte observation instead of
+// uint8 one-hot (x7) -> concatenate -> .float() (x4.4 again). dir_lut[d] = {cos, sin} comes from the caller
+// (torch's float32 cos / sin, so the values are the reference's). One block = 16 agents, 4 floats per thread
+// and store; the (agent, cell, channel) position is divided out once per thread and then incremented.
+__global__ void __launch_bounds__(256) obs_features_kernel(int V, int64_t agents, int ostride, uint32_t rcp_per_agent,
+                                                           const int8_t *__restrict__ obs,
+                                                           const int8_t *__restrict__ direction, int dir_stride,
+                                                           const float *__restrict__ dir_lut, float4 *__restrict__ out) {
+    const uint32_t VV = (uint32_t)(V * V), per_agent = VV * 23u;
+    const int64_t a0 = (int64_t)blockIdx.x * 16;
+    const uint32_t na = (uint32_t)(agents - a0 < 16 ? agents - a0 : 16);
+    const uint32_t nfl = na * per_agent;  // floats of this block (<= 16 * 225 * 23 = 82 800)
+    const uint8_t *obs_b = (const uint8_t *)obs + a0 * ostride;
+    const int8_t *dir_b = direction + a0 * dir_stride;
+    float *out_b = (float *)out + a0 * per_agent;
+    for (uint32_t q0 = 4u * threadIdx.x; q0 < nfl; q0 += 4u * 256u) {
+        const uint32_t a = fastdiv(q0, rcp_per_agent), rem = q0 - a * per_agent;
+        const uint32_t cell = mulhi32(rem, 186737709u), ch = rem - cell * 23u;  // rem / 23, rem < 2^16
+        // the 4 floats lie in this cell and possibly the next: both cells as one 46-bit channel mask
+        // (bit k of a cell = channel k is hot; channels 21, 22 are the direction features)
+        const uint8_t *src = obs_b + a * (uint32_t)ostride + cell * 3u;
+        uint64_t bits = (1ull << src[0]) | (1ull << (11u + src[1])) | (1ull << (17u + src[2]));
+        const uint32_t d0 = (uint32_t)dir_b[a * dir_stride] & 3u;
+        if (ch > 19u && q0 + (23u - ch) < nfl) {  // (the next cell contributes its channels 0..2 at most)
+            uint32_t a1 = a, c1 = cell + 1u;
+            if (c1 == VV) { c1 = 0; a1++; }
+            const uint8_t *s1 = obs_b + a1 * (uint32_t)ostride + c1 * 3u;
+            bits |= ((1ull << s1[0]) | (1ull << (11u + s1[1])) | (1ull << (17u + s1[2]))) << 23;
+        }
+        const uint32_t w = (uint32_t)(bits >> ch);
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t pos = ch + (uint32_t)j;  // 0..25: 21, 22 = features of this cell; 23.. = next cell
+            v[j] = ((w >> j) & 1u) ? 1.0f : 0.0f;
+            if (pos == 21u || pos == 22u) v[j] = dir_lut[2u * d0 + (pos - 21u)];
+        }
+        if (q0 + 4u <= nfl) {
+            *(float4 *)(out_b + q0) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (uint32_t j = 0; q0 + j < nfl; j++) out_b[q0 + j] = v[j];
+        }
+    }
+}
+
 // MULTI = mg_rollout (p.T steps per launch); the single-step kernels compile with T == 1 and no loop.
 // Same result, 16 output bytes per thread (one 128-bit store): the 16 bytes [p0, p0+16) of the flat
 // [A][V][V][21] stream lie in at most two consecutive cells, i.e. hold at most six 1-bytes; each is

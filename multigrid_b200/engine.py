@@ -425,6 +425,21 @@ class StepEngine:
         out["obs"] = out["obs_buf"][..., :3 * V * V].unflatten(-1, (V, V, 3))
         return out
 
+    def obs_features(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        """mg_obs_features: the current observations as the reference's network input
+        (OneHotObsWrapper + scripts/train.py:56-63 preprocess_batch): float32 (E, n, V, V, 23)."""
+        E, n, V = self.num_envs, self.cfg.num_agents, self.cfg.view_size
+        if getattr(self, "_dir_lut", None) is None:
+            d = 2 * torch.pi * (torch.arange(4) / 4)  # exactly the reference's float32 expression, on the CPU
+            self._dir_lut = torch.stack([torch.cos(d), torch.sin(d)], dim=-1).contiguous().to(self.device)
+        if out is None:
+            out = torch.empty((E, n, V, V, 23), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.mg_obs_features(V, E * n, self.obs_stride, self.obs_buf.data_ptr(),
+                                                 self.agents.data_ptr(), 8, self._dir_lut.data_ptr(), out.data_ptr(),
+                                                 self._stream()), "mg_obs_features")
+        return out
+
     def host_buffers(self):
         """Pinned host mirrors used by `step_host` (allocated on first use)."""
         if self._host is None:

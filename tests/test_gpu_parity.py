@@ -724,3 +724,24 @@ def test_largest_grids():
     buf = torch.zeros(128 * 128 * 4 * 2 + 4096, dtype=torch.int8, device="cuda:0")
     rc = lib.mg_gen_obs(C.byref(c), 2, buf.data_ptr(), buf.data_ptr(), buf.data_ptr(), None)
     assert rc == -3 and b"too large" in lib.mg_error_string(rc)
+
+
+@pytest.mark.parametrize("V,n,E", [(7, 4, 300), (3, 1, 5), (9, 3, 37), (5, 2, 1)])
+def test_obs_features_kernel_vs_reference_expression(V, n, E):
+    """mg_obs_features == OneHotObsWrapper.one_hot (oracle restatement, pinned to the reference's numba output)
+    followed by scripts/train.py:56-63 preprocess_batch restated with torch on the CPU, bit for bit."""
+    import torch
+    from multigrid_b200.engine import EngineConfig, StepEngine
+    cfg = O.OracleConfig(W=9, H=8, n=n, V=V)
+    st = random_batch(cfg, E, V * 10 + n)
+    g = GpuEngine(cfg, **st)
+    img = g.gen_obs()                                   # (E, n, V, V, 3)
+    direction = torch.from_numpy(g.agents[..., O.A_DIR].astype(np.int64))
+    image = torch.from_numpy(O.one_hot(img))            # uint8 (E, n, V, V, 21)
+    d = 2 * torch.pi * (direction / 4)                  # the reference's expression (len(Direction) == 4)
+    d = torch.stack([torch.cos(d), torch.sin(d)], dim=-1)
+    d = d[..., None, None, :].expand(*image.shape[:-1], 2)
+    want = torch.cat([image, d], dim=-1).float()
+    got = g.eng.obs_features().cpu()
+    assert got.shape == want.shape == (E, n, V, V, 23) and got.dtype == torch.float32
+    assert torch.equal(got, want)

@@ -165,6 +165,22 @@ def time_one_hot(V=7, A=262144):
         print(json.dumps(dict(kernel=f"one_hot_{name}", agents=A, V=V, us=round(us, 2),
                               gbs=round(nbytes / us / 1e3, 1))), flush=True)
     os.environ.pop("MG_ONE_HOT_W32", None)
+    # mg_obs_features: the float32 23-channel network input straight from the observations
+    dirs = torch.randint(0, 4, (A, 8), device="cuda", dtype=torch.int32).to(torch.int8)
+    lut = torch.stack([torch.cos(2 * torch.pi * torch.arange(4) / 4), torch.sin(2 * torch.pi * torch.arange(4) / 4)], -1).cuda()
+    fouts = [torch.empty((A, V, V, 23), dtype=torch.float32, device="cuda") for _ in range(2)]
+    for o in fouts:
+        lib.mg_obs_features(V, A, stride, obs.data_ptr(), dirs.data_ptr(), 8, lut.data_ptr(), o.data_ptr(), None)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(20):
+        lib.mg_obs_features(V, A, stride, obs.data_ptr(), dirs.data_ptr(), 8, lut.data_ptr(), fouts[k % 2].data_ptr(), None)
+    ev1.record()
+    torch.cuda.synchronize()
+    us = 1e3 * ev0.elapsed_time(ev1) / 20
+    nbytes = A * V * V * 23 * 4 + A * stride
+    print(json.dumps(dict(kernel="obs_features", agents=A, V=V, us=round(us, 2), gbs=round(nbytes / us / 1e3, 1))), flush=True)
 
 
 def main():
