@@ -36,6 +36,7 @@
  *   pcg_inc     uint64[2]         {lo,hi} of its increment (constant)
  *   layout_idx  int32             cursor into the reset-layout pool (auto-reset only)
  *   hook_state  int32             post-hook state (LockedHallway: unlocked-door colour bits)
+ *   chain       uint32[2]         {next ticket, tickets done} of chained launches (MG_FLAG_CHAINED)
  * Outputs per env:
  *   obs         int8  [n][obs_agent_stride]  first 3*V*V bytes of each agent slot = image[V][V][3]
  *   reward      float64 [n]       bit-exact `1 - 0.9*(step_count/max_steps)` (base.py:598-602)
