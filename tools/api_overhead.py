@@ -15,6 +15,7 @@ env = make("MultiGrid-Empty-8x8-v0", agents=4, num_envs=args.envs, device="cuda:
 env.reset(seed=0)
 acts = torch.randint(0, 7, (64, args.envs, 4), device="cuda:0", dtype=torch.int32).to(torch.int8)
 for name, fn in (("engine.step", lambda a: env.engine.step(a)), ("env.step(tensor)", lambda a: env.step(a)),
+                 ("env.step(tensor, chained=True)", lambda a: env.step(a, chained=True)),
                  ("env.step(dict)", lambda a: env.step({i: a[:, i] for i in range(4)}))):
     for k in range(50):
         fn(acts[k % 64])
