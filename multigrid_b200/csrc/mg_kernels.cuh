@@ -1,4 +1,4 @@
-// multigrid_b200 -- device code of the batched MultiGrid step/observe engine (sm_100a), kernel v2.
+// multigrid_b200 -- device code of the batched MultiGrid step/observe engine (sm_100a).
 //
 // One WARP advances one group of G consecutive envs (G = 16 or 32) and never talks to another warp:
 // no block-wide barrier anywhere, warps of a block drift apart and hide each other's latencies.
@@ -24,6 +24,12 @@
 //
 // Reference semantics restated here (cited inline): multigrid/base.py:303-532,598-602,
 // multigrid/utils/obs.py:46-316, multigrid/core/world_object.py:197-233,452-474,599-605.
+//
+// Variants of the one kernel (template parameters of step_obs_kernel): MODE (observe only / step only / fused),
+// VT (unrolled view size or 0 = rolled loops), MULTI (mg_rollout: T steps per launch), CHAIN (MG_FLAG_CHAINED:
+// per-env chain tickets instead of the kernel-boundary barrier). Every launch uses programmatic dependent
+// launch. Further down: layout generation kernels (each env class's _gen_grid on in-kernel numpy generators),
+// one-hot / feature / full-observation kernels, grid pack / unpack, reset_where.
 //
 // The file also compiles as plain C++ (no __CUDACC__): tests/hostsim runs the very same phase
 // functions lane-by-lane on the CPU (a phase boundary == __syncwarp) to check the logic against the
