@@ -253,7 +253,8 @@ def run_engine(args):
         eng = StepEngine(cfg, E, dev, pg, pa)
         first = (rank * REPLICAS + r) * E  # seeds are a function of the global env id
         st, inc = pcg_words(first, E)
-        eng.load_state(np.repeat(pg, E, 0), np.repeat(pa, E, 0), None, st, inc, None)
+        eng.load_state(pcg_state=st, pcg_inc=inc)
+        eng.reset_from_pool()  # every env starts from the (single) pool layout, like env.reset()
         engines.append(eng)
 
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 5
+#define MG_ABI_VERSION 6
 
 /* MgConfig.flags */
 #define MG_FLAG_SEE_THROUGH_WALLS 0x01u /* agents[0].see_through_walls, base.py:364-365 */
@@ -116,6 +116,12 @@ typedef struct MgState {
     const int8_t *pool_agents; /* [K][n][8]    (may be NULL without MG_FLAG_AUTO_RESET) */
     int32_t *hook_state;       /* [E] per-env state of the post-hook; only MG_HOOK_LOCKED_HALLWAY uses it
                                   (bit per door colour already unlocked); may be NULL otherwise */
+    uint8_t *grid_dirty;       /* [E] single-layout dedup (both may be NULL = off): 1 = the env's grid may differ from
+                                  pool_grid[layout_idx]. The engine sets it on every cell write-through and clears it
+                                  on reset; the CALLER sets it (or passes NULL) whenever it writes `grid` itself. */
+    const uint32_t *pool_rep;  /* [32][W+1][H+1] 32 copies of pool layout 0, 16-byte aligned; used only when
+                                  num_layouts == 1: a group whose envs are all clean loads its cells from this
+                                  L2-resident buffer instead of reading 4*(W+1)*(H+1) bytes per env from HBM */
     uint32_t *chain;           /* [E][2] chain tickets {next, done} (may be NULL without MG_FLAG_CHAINED; zero-
                                   initialised, 8-byte aligned): a chained launch takes ticket next[e]++ and publishes
                                   done[e] = ticket + 1 when it is done with env e */

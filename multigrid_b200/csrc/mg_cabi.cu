@@ -53,6 +53,7 @@ int plan(mg::Params &p) {
     p.use_bulk = env_int("MG_NO_BULK", 0, k) ? 0 : 1;
     p.generic_view = env_int("MG_GENERIC_VIEW", 0, k) ? 1 : 0;
     p.pdl = env_int("MG_PDL", 1, k) ? 1 : 0;
+    if (env_int("MG_NO_DEDUP", 0, k)) p.pool_rep = nullptr;  // knob: always read every env's own grid
     p.l2hint = env_int("MG_L2HINT", (p.flags & MG_FLAG_STREAM_STATE) ? 3 : 0, k);
     static thread_local int sms[64] = {0};
     int dev = 0;
@@ -146,6 +147,9 @@ int fill_state(mg::Params &p, const MgState *s) {
     p.pool_grid = s->pool_grid; p.pool_agents = s->pool_agents;
     if (p.hook == MG_HOOK_LOCKED_HALLWAY && !s->hook_state) return MG_ERR_BAD_ARG;
     p.hook_state = s->hook_state;
+    if (reinterpret_cast<uintptr_t>(s->pool_rep) & 15u) return MG_ERR_ALIGNMENT;
+    p.grid_dirty = s->grid_dirty;
+    p.pool_rep = (s->pool_rep && s->grid_dirty && p.K == 1) ? s->pool_rep : nullptr;
     if (reinterpret_cast<uintptr_t>(s->chain) & 7u) return MG_ERR_ALIGNMENT;
     p.chain = s->chain;
     if ((p.flags & MG_FLAG_CHAINED) && !s->chain) return MG_ERR_BAD_ARG;

@@ -80,6 +80,12 @@ struct Params {
     // 2 = head of a chain (takes tickets AND waits for the whole previous grid of the stream).
     uint32_t *chain;  // [E][2] {next ticket, tickets done}
     int32_t chained;
+    // Single-layout dedup (MgState.grid_dirty / pool_rep): with ONE pool layout (all deterministic env ids) an
+    // env whose grid still equals it need not read its 324-byte copy from HBM: the group's cells come from a
+    // small L2-resident buffer of 32 copies of the layout, unless one of the group's envs is marked dirty.
+    uint8_t *grid_dirty;       // [E] 1 = the env's grid may differ from pool_grid[layout_idx] (NULL = not tracked)
+    const uint32_t *pool_rep;  // [32][cstride] copies of pool layout 0, only set when K == 1 (else NULL)
+
     int8_t *direction;  // [T][E][n] per-step 'direction' observation (rollout only; NULL otherwise)
     // state (device)
     uint32_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;
@@ -818,6 +824,7 @@ MG_HD void phase_reset_grid(const Params &p, const Group &g, uint32_t pending, i
         const uint32_t *src = p.pool_grid + (size_t)g.rk[i] * p.cstride;
         warp_copy(g.cells + i * p.cstride, src, p.cstride * 4, lane);
         warp_copy(p.grid + (size_t)(g.e0 + i) * p.cstride, src, p.cstride * 4, lane);
+        if (p.grid_dirty && lane == 0) p.grid_dirty[g.e0 + i] = 0;  // equal to its pool layout again
     }
 }
 
@@ -830,6 +837,7 @@ MG_HD uint32_t reset_mask_host(const Group &g) {  // hostsim only; the kernel us
 // ---- P4: transition --------------------------------------------------------------------------------
 MG_HD void store_cell(const Params &p, int e, int idx, uint32_t w) {  // dirty-cell write-through
     p.grid[(size_t)e * p.cstride + idx] = w;
+    if (p.grid_dirty) p.grid_dirty[e] = 1;  // the grid no longer equals its pool layout
 }
 
 MG_HD uint32_t all_agents(const Params &p) { return p.n >= 32 ? 0xffffffffu : (1u << p.n) - 1u; }
@@ -1417,14 +1425,32 @@ __device__ __forceinline__ void trace_mark(const Params &p, int group, int lane,
 }
 
 template <int MODE>
-__device__ __forceinline__ void load_bulk(const Params &p, const Group &g, uint64_t *bar, int t) {
+// dedup: 0 = everything now; 1 = everything but the cells (their source is decided once the group's dirty
+// flags have arrived); 2 = the cells from the 32-copy pool buffer; 3 = the cells from the group's own grids.
+// The transaction count of all parts is announced by the first call.
+__device__ __forceinline__ void load_bulk(const Params &p, const Group &g, uint64_t *bar, int t, int dedup = 0) {
     const size_t e0 = (size_t)g.e0;
     const uint32_t G = (uint32_t)p.G, n = (uint32_t)p.n;
     uint32_t total = G * p.cstride * 4;
     if (t == 0) total += G * n * 8;
     if (MODE != MODE_OBS) total += G * n;
-    mbar_expect_tx(bar, total);
     const int8_t *act = p.actions + ((size_t)t * p.num_envs + e0) * n;
+    if (dedup >= 2) {  // the cells: G copies of the one pool layout from the L2-resident buffer (no evict_first:
+                       // every warp re-reads it), or the group's own grids
+        if (dedup == 2) bulk_g2s(g.cells, p.pool_rep, G * p.cstride * 4, bar);
+        else if (p.l2hint & 1) bulk_g2s_hint(g.cells, p.grid + e0 * p.cstride, G * p.cstride * 4, bar, l2_policy_evict_first());
+        else bulk_g2s(g.cells, p.grid + e0 * p.cstride, G * p.cstride * 4, bar);
+        return;
+    }
+    mbar_expect_tx(bar, total);
+    if (dedup == 1) {
+        if (t == 0) bulk_g2s(g.ag, p.agents + e0 * n * 8, G * n * 8, bar);
+        if (MODE != MODE_OBS) {
+            if (p.l2hint & 1) bulk_g2s_hint(g.act, act, G * n, bar, l2_policy_evict_first());
+            else bulk_g2s(g.act, act, G * n, bar);
+        }
+        return;
+    }
     if (p.l2hint & 1) {
         const uint64_t pol = l2_policy_evict_first();
         bulk_g2s_hint(g.cells, p.grid + e0 * p.cstride, G * p.cstride * 4, bar, pol);
@@ -1576,6 +1602,7 @@ __global__ void reset_where_kernel(const __grid_constant__ Params p, const uint8
         p.layout_idx[e] = k;
         p.step_count[e] = 0;
         if (p.hook_state) p.hook_state[e] = 0;
+        if (p.grid_dirty) p.grid_dirty[e] = 0;
     }
 }
 
@@ -1774,13 +1801,19 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
     for (int t = 0; t < T; t++) {
         const size_t tE = (size_t)t * (size_t)p.num_envs;
         trace_mark(p, group, lane, 5);
+        const bool dedup = !MULTI && MODE != MODE_OBS && bulk && p.pool_rep != nullptr;
         if (bulk) {
             if (lane == 0) {
                 if (t > 0) bulk_wait_read();  // the last obs store has read its stage (which lies on the cells)
-                load_bulk<MODE>(p, g, bar, t);
+                load_bulk<MODE>(p, g, bar, t, dedup ? 1 : 0);
             }
         } else {
             phase_load_plain<MODE>(p, g, lane, t);
+        }
+        if (dedup) {  // one flag byte per env decides where the group's cells come from
+            const bool env_dirty = env >= 0 && p.grid_dirty[g.e0 + env] != 0;
+            const bool any_dirty = __any_sync(0xffffffffu, env_dirty);
+            if (lane == 0) load_bulk<MODE>(p, g, bar, t, any_dirty ? 3 : 2);
         }
         if (t == 0) env_load<MODE>(p, g, env, er);  // the env's scalars, straight into its lane's registers
         const OrderDraw draw = phase_draw<MODE>(p, g, env, er);

@@ -107,6 +107,9 @@ class StepEngine:
         self.status = z((1,), torch.int32)
         # chain tickets (include/multigrid_b200.h, MG_FLAG_CHAINED): maintained by chained step launches
         self.chain = z((E, 2), torch.int32)  # per env {next ticket, tickets done}
+        # single-layout dedup (MgState.grid_dirty / pool_rep): 1 = the env's grid may differ from its pool layout
+        self.grid_dirty = torch.ones((E,), dtype=torch.uint8, device=dev)
+        self.pool_rep = None
         self._chain_armed = None  # the stream whose last operation on this engine was a step launch
         self.pool_grid = None
         self.pool_agents = None
@@ -156,7 +159,7 @@ class StepEngine:
         self._pack(pg, self.pool_grid)
         self.pool_agents = pa.to(self.device)
         self._pool_rng = None
-        self._c = None
+        self._pool_changed()
 
     def gen_layout_pool_red_blue_doors(self, size, rng_state, rng_inc, rng_buf=None):
         """mg_gen_layouts_red_blue_doors (envs/redbluedoors.py:142-168); arguments and result as
@@ -238,7 +241,7 @@ class StepEngine:
             raise RecursionError("rejection sampling failed in place_obj")  # base.py:640-641
         self.pool_grid, self.pool_agents = cells, agents
         self._pool_rng = None
-        self._c = None
+        self._pool_changed()
         u64 = lambda t: t.cpu().numpy().view(np.uint64)  # noqa: E731
         return u64(ost), info.cpu().numpy(), u64(st), u64(buf)
 
@@ -263,6 +266,15 @@ class StepEngine:
             else:
                 _cabi.check(self.lib.mg_gen_layouts_empty_random(cfg.width, cfg.height, cfg.num_agents, *tail),
                             "mg_gen_layouts_empty_random")
+        self._pool_changed()
+
+    def _pool_changed(self) -> None:
+        """The layout pool was replaced: no env is known to equal its layout any more; with a single layout,
+        (re)build the 32-copy buffer clean groups load their cells from."""
+        self.grid_dirty.fill_(1)
+        self.pool_rep = (self.pool_grid[:1].repeat(32, 1, 1).contiguous()
+                         if self.pool_grid is not None and self.pool_grid.shape[0] == 1 else None)
+        self._c = None
 
     def load_state(self, grid=None, agents=None, step_count=None, pcg_state=None, pcg_inc=None,
                    layout_idx=None, hook_state=None) -> None:
@@ -278,6 +290,7 @@ class StepEngine:
                 dst.copy_(torch.as_tensor(arr).to(dst.dtype).reshape(dst.shape))
         if grid is not None:
             self._pack(grid, self.cells)
+            self.grid_dirty.fill_(1)
         put(self.agents, agents)
         put(self.step_count, step_count)
         put(self.pcg_state, pcg_state, bits64=True)
@@ -295,6 +308,7 @@ class StepEngine:
         self.agents.copy_(self.pool_agents[idx])
         self.step_count.zero_()
         self.hook_state.zero_()
+        self.grid_dirty.zero_()
 
     def reset_where(self, mask: torch.Tensor) -> None:
         """mg_reset_where: envs with a non-zero mask entry ((E,) bool / uint8 on the device) take the next
@@ -324,7 +338,8 @@ class StepEngine:
             p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
             st = _cabi.MgState(p(self.cells), p(self.agents), p(self.step_count), p(self.pcg_state),
                                p(self.pcg_inc), p(self.layout_idx), p(self.pool_grid),
-                               p(self.pool_agents), p(self.hook_state), p(self.chain))
+                               p(self.pool_agents), p(self.hook_state), p(self.grid_dirty), p(self.pool_rep),
+                               p(self.chain))
             out = _cabi.MgStepOut(p(self.obs_buf), p(self.reward), p(self.terminated),
                                   p(self.truncated), p(self.status))
             mk = lambda extra: _cabi.MgConfig(cfg.width, cfg.height, cfg.num_agents, cfg.view_size,  # noqa: E731

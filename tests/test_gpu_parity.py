@@ -745,3 +745,51 @@ def test_obs_features_kernel_vs_reference_expression(V, n, E):
     got = g.eng.obs_features().cpu()
     assert got.shape == want.shape == (E, n, V, V, 23) and got.dtype == torch.float32
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("chained", [False, True])
+@pytest.mark.parametrize("seed,B,kw", [
+    (0, 5000, dict(W=8, H=8, n=4, V=7, auto_reset=True, max_steps=6)),
+    (1, 3000, dict(W=11, H=6, n=2, V=7, hook=1, joint_reward=True, auto_reset=True, max_steps=9)),
+    (2, 700, dict(W=9, H=7, n=3, V=5, allow_agent_overlap=False, auto_reset=True, max_steps=5, failure_any=True)),
+    (3, 40000, dict(W=8, H=8, n=4, V=7, auto_reset=True, max_steps=7)),
+])
+def test_single_layout_dedup(seed, B, kw, chained):
+    """ONE pool layout (num_layouts == 1): groups whose envs all still equal it load their cells from the
+    32-copy buffer instead of their own grids. Random injected grids start dirty; auto-reset makes envs clean;
+    pickups / drops / toggles on the (object-rich) pool layout make them dirty again; reset_where and
+    load_state flip the flags from the host. Every step vs the C oracle."""
+    import torch
+    kw = dict(kw)
+    cfg = O.OracleConfig(**kw)
+    st = random_batch(cfg, B, 300 + seed, K=1)
+    ora, g = COracle(cfg, nthreads=NTHREADS, **st), GpuEngine(cfg, **st)
+    assert g.eng.pool_rep is not None and bool(g.eng.grid_dirty.all())
+    rng = np.random.default_rng(seed)
+    T = 30
+    for t in range(T):
+        a = rng.integers(-1, 7, size=(B, cfg.n)).astype(np.int8)
+        o1, r1, t1, tr1 = ora.step(a)
+        if chained:
+            g.eng.step(torch.from_numpy(a).cuda(), chained=True)
+            o2, r2 = g._obs(g.eng.obs_buf), g.eng.reward.cpu().numpy()
+        else:
+            o2, r2, _, _ = g.step(a)
+        np.testing.assert_array_equal(o2, o1, err_msg=f"step {t}")
+        assert (r1 == r2).all(), f"step {t}"
+        if t == 12:  # host-driven reset of a third of the envs: clean again
+            mask = rng.random(B) < 0.33
+            g.eng.reset_where(torch.from_numpy(mask).cuda())
+            K = 1
+            ora.layout_idx[mask] = (ora.layout_idx[mask] + cfg.layout_stride) % K
+            ora.grid[mask] = st["pool_grid"][0]
+            ora.agents[mask] = st["pool_agents"][0]
+            ora.step_count[mask] = 0
+            ora.hook_state[mask] = 0
+            ora.cell_flags[mask] = 0
+            assert not bool(g.eng.grid_dirty[torch.from_numpy(mask).cuda()].any())
+    assert_same(g, ora, "dedup")
+    dirty = g.eng.grid_dirty.cpu().numpy().astype(bool)
+    same = (g.grid == st["pool_grid"][0]).reshape(B, -1).all(1)
+    assert same[~dirty].all(), "an env marked clean differs from the pool layout"
+    assert (~dirty).sum() > 0, "no env ever became clean: the dedup path was not exercised"

@@ -55,7 +55,8 @@ def time_config(name, steps, knobs, replicas=8):
     for r in range(replicas):
         eng = StepEngine(cfg, E, dev, pg, pa)
         st, inc = bench.pcg_words(r * E, E)
-        eng.load_state(np.repeat(pg, E, 0), np.repeat(pa, E, 0), None, st, inc, None)
+        eng.load_state(pcg_state=st, pcg_inc=inc)
+        eng.reset_from_pool()
         engines.append(eng)
     gen = torch.Generator(device=dev).manual_seed(7)
     NT = 256  # long tape: a short action cycle keeps agents near their start cells and flatters the kernel
@@ -67,10 +68,10 @@ def time_config(name, steps, knobs, replicas=8):
     out = []
     # every knob set is timed from the SAME state (all envs of a fixed-start layout share their episode
     # phase: how far the agents have spread, and with it the cost of a launch, drifts with the step count)
-    names = ("cells", "agents", "step_count", "pcg_state", "layout_idx", "hook_state")
+    names = ("cells", "agents", "step_count", "pcg_state", "layout_idx", "hook_state", "grid_dirty")
     snap = [{k: getattr(e, k).clone() for k in names} for e in engines]
     for knob in knobs:
-        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "CHAINED"):
+        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_NO_DEDUP", "CHAINED"):
             os.environ.pop(key, None)
         os.environ.update({k: str(v) for k, v in knob.items()})
         chained = bool(int(os.environ.get("CHAINED", "0")))  # (a kbench knob, not a library one)

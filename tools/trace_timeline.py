@@ -33,13 +33,14 @@ engines = []
 for r in range(8):
     eng = StepEngine(cfg, E, dev, pg, pa)
     st, inc = bench.pcg_words(r * E, E)
-    eng.load_state(np.repeat(pg, E, 0), np.repeat(pa, E, 0), None, st, inc, None)
+    eng.load_state(pcg_state=st, pcg_inc=inc)
+    eng.reset_from_pool()
     engines.append(eng)
 tape = torch.randint(0, 7, (32, E, n), device=dev, dtype=torch.int32).to(torch.int8)
 for k in range(96):
     engines[k % 8].step(tape[k % 32])
 torch.cuda.synchronize()
-groups = (E + args.group - 1) // args.group
+groups = (E + 7) // 8  # (enough rows for any group size; unused rows stay zero and are dropped below)
 buf = torch.zeros((groups, 8), dtype=torch.int64, device=dev)
 if args.rollout:
     T = args.rollout
@@ -51,6 +52,7 @@ if args.rollout:
     torch.cuda.synchronize()
     lib.mg_debug_set_trace(None)
     t = buf.cpu().numpy().astype(np.float64)
+    t = t[t[:, 0] > 0]
     print(f"rollout T={T}: launch span {(t[:, 4].max() - t[:, 0].min()) / 1e3:.2f} us = {(t[:, 4].max() - t[:, 0].min()) / 1e3 / T:.2f} us/step")
     print("last iteration of every warp (slots: 5 iteration start, 1 loaded, 2 stepped, 3 observed; 6 = fence after the previous iteration):")
     for a, b, nm in [(5, 1, "load wait"), (1, 2, "reset+step"), (2, 3, "obs"), (6, 5, "loop edge"), (5, 3, "iteration"), (3, 4, "store+drain")]:
@@ -74,6 +76,8 @@ else:
     torch.cuda.synchronize()
     lib.mg_debug_set_trace(None)
 t = buf.cpu().numpy().astype(np.float64)
+t = t[t[:, 0] > 0]  # rows of warps that ran (the buffer is sized for the smallest group size)
+groups = len(t)
 t0 = t[:, 0].min()
 rel = (t[:, :5] - t0) / 1e3  # us
 names = ["start", "loaded", "stepped", "observed", "end"]
