@@ -219,6 +219,9 @@ def workload_config(n_gpus):
         "l2": f"{REPLICAS} state replicas rotated (each launch touches a batch last used "
               f"{REPLICAS} launches ago; {REPLICAS}x61 MB > 126 MB L2), no explicit flush; "
               "MG_FLAG_STREAM_STATE (L2 evict_first on state loads / obs stores, cache policy only)",
+        "dedup": "single-layout dedup (MgState.grid_dirty / pool_rep): Empty-8x8 has ONE reset layout, so groups whose envs "
+                 "still equal it take their cells from an L2-resident 32-copy buffer instead of reading their 324-byte grid "
+                 "copies from HBM (the algorithmic 929 B per env-step still count the 192-byte grid read)",
         "launches": "chained (MG_FLAG_CHAINED): each launch is ordered after the previous launch on the same replica env by "
                     "env through chain tickets, not by a kernel-boundary barrier, so it loads while its predecessor drains; "
                     "`unchained` in this line is the same graph with plain launches",
