@@ -36,7 +36,7 @@
  *   pcg_inc     uint64[2]         {lo,hi} of its increment (constant)
  *   layout_idx  int32             cursor into the reset-layout pool (auto-reset only)
  *   hook_state  int32             post-hook state (LockedHallway: unlocked-door colour bits)
- *   chain       uint32[2]         {next ticket, tickets done} of chained launches (MG_FLAG_CHAINED)
+ *   chain       uint32[4]         {next ticket, tickets done, grid dirty, -}: chained launches, single-layout dedup
  * Outputs per env:
  *   obs         int8  [n][obs_agent_stride]  first 3*V*V bytes of each agent slot = image[V][V][3]
  *   reward      float64 [n]       bit-exact `1 - 0.9*(step_count/max_steps)` (base.py:598-602)
@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 6
+#define MG_ABI_VERSION 7
 
 /* MgConfig.flags */
 #define MG_FLAG_SEE_THROUGH_WALLS 0x01u /* agents[0].see_through_walls, base.py:364-365 */
@@ -116,15 +116,16 @@ typedef struct MgState {
     const int8_t *pool_agents; /* [K][n][8]    (may be NULL without MG_FLAG_AUTO_RESET) */
     int32_t *hook_state;       /* [E] per-env state of the post-hook; only MG_HOOK_LOCKED_HALLWAY uses it
                                   (bit per door colour already unlocked); may be NULL otherwise */
-    uint8_t *grid_dirty;       /* [E] single-layout dedup (both may be NULL = off): 1 = the env's grid may differ from
-                                  pool_grid[layout_idx]. The engine sets it on every cell write-through and clears it
-                                  on reset; the CALLER sets it (or passes NULL) whenever it writes `grid` itself. */
-    const uint32_t *pool_rep;  /* [32][W+1][H+1] 32 copies of pool layout 0, 16-byte aligned; used only when
-                                  num_layouts == 1: a group whose envs are all clean loads its cells from this
-                                  L2-resident buffer instead of reading 4*(W+1)*(H+1) bytes per env from HBM */
-    uint32_t *chain;           /* [E][2] chain tickets {next, done} (may be NULL without MG_FLAG_CHAINED; zero-
-                                  initialised, 8-byte aligned): a chained launch takes ticket next[e]++ and publishes
-                                  done[e] = ticket + 1 when it is done with env e */
+    const uint32_t *pool_rep;  /* [32][W+1][H+1] 32 copies of pool layout 0, 16-byte aligned (may be NULL = no dedup);
+                                  used only when num_layouts == 1 and `chain` is given: a group whose envs are all
+                                  clean loads its cells from this L2-resident buffer instead of reading
+                                  4*(W+1)*(H+1) bytes per env from HBM */
+    uint32_t *chain;           /* [E][4] per-env record {next ticket, tickets done, grid dirty, reserved}, 16-byte
+                                  aligned, zero-initialised except dirty = 1 (may be NULL without MG_FLAG_CHAINED and
+                                  without dedup). A chained launch takes ticket next[e]++ and publishes done[e] =
+                                  ticket + 1 when it is done with env e. dirty = 1: the env's grid may differ from
+                                  pool_grid[layout_idx]; the engine sets it on every cell write-through and clears it
+                                  on reset; the CALLER sets it whenever it writes `grid` itself. */
 } MgState;
 
 typedef struct MgStepOut {

@@ -27,7 +27,7 @@ HOOK_BLOCKED_UNLOCK_PICKUP = 1
 HOOK_RED_BLUE_DOORS = 2
 HOOK_LOCKED_HALLWAY = 3
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_VIEW = 15
 MAX_AGENTS = 32
 
@@ -46,7 +46,7 @@ class MgState(C.Structure):
         ("grid", C.c_void_p), ("agents", C.c_void_p), ("step_count", C.c_void_p),
         ("pcg_state", C.c_void_p), ("pcg_inc", C.c_void_p), ("layout_idx", C.c_void_p),
         ("pool_grid", C.c_void_p), ("pool_agents", C.c_void_p), ("hook_state", C.c_void_p),
-        ("grid_dirty", C.c_void_p), ("pool_rep", C.c_void_p), ("chain", C.c_void_p),
+        ("pool_rep", C.c_void_p), ("chain", C.c_void_p),
     ]
 
 

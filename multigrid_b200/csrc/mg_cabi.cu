@@ -63,7 +63,7 @@ int plan(mg::Params &p) {
         if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (sms[dev] > 0) n_sm = sms[dev];
     }
-    return mg::plan_launch(p, env_int("MG_GROUP", 0, k), env_int("MG_WPB", 0, k), kSmemPerBlock, kSmemPerSM, n_sm);
+    return mg::plan_launch(p, env_int("MG_GROUP", 0, k), env_int("MG_WPB", 0, k), kSmemPerBlock - 16 /* the claim counter */, kSmemPerSM, n_sm);
 }
 
 template <int VT, int MODE, bool MULTI = false, bool CHAIN = false>
@@ -82,7 +82,7 @@ int launch(const mg::Params &p, cudaStream_t stream) {
     cudaLaunchConfig_t lc;
     std::memset(&lc, 0, sizeof(lc));
     lc.gridDim = dim3((unsigned)blocks); lc.blockDim = dim3((unsigned)(p.wpb * mg::LANES));
-    lc.dynamicSmemBytes = (size_t)(p.wpb * p.warp_bytes); lc.stream = stream;
+    lc.dynamicSmemBytes = (size_t)(p.wpb * p.warp_bytes) + 16; lc.stream = stream;  // + the block's claim counter
     // Programmatic dependent launch: the grid may be scheduled while the previous kernel of the
     // stream drains; the kernel executes griddepcontrol.wait before its first global access, so
     // stream-order semantics are unchanged (MG_PDL=0 turns the attribute off).
@@ -148,9 +148,8 @@ int fill_state(mg::Params &p, const MgState *s) {
     if (p.hook == MG_HOOK_LOCKED_HALLWAY && !s->hook_state) return MG_ERR_BAD_ARG;
     p.hook_state = s->hook_state;
     if (reinterpret_cast<uintptr_t>(s->pool_rep) & 15u) return MG_ERR_ALIGNMENT;
-    p.grid_dirty = s->grid_dirty;
-    p.pool_rep = (s->pool_rep && s->grid_dirty && p.K == 1) ? s->pool_rep : nullptr;
-    if (reinterpret_cast<uintptr_t>(s->chain) & 7u) return MG_ERR_ALIGNMENT;
+    p.pool_rep = (s->pool_rep && s->chain && p.K == 1) ? s->pool_rep : nullptr;
+    if (reinterpret_cast<uintptr_t>(s->chain) & 15u) return MG_ERR_ALIGNMENT;
     p.chain = s->chain;
     if ((p.flags & MG_FLAG_CHAINED) && !s->chain) return MG_ERR_BAD_ARG;
     p.chained = (p.flags & MG_FLAG_CHAINED) ? ((p.flags & MG_FLAG_CHAIN_HEAD) ? 2 : 1) : 0;

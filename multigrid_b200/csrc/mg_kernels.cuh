@@ -78,12 +78,12 @@ struct Params {
     // per-env tickets order consecutive chained step launches on the same state env by env, so a launch need
     // not wait for the whole previous grid. chained: 0 = plain launch (tickets untouched), 1 = chained,
     // 2 = head of a chain (takes tickets AND waits for the whole previous grid of the stream).
-    uint32_t *chain;  // [E][2] {next ticket, tickets done}
+    uint32_t *chain;  // [E][4] per-env record {next ticket, tickets done, grid dirty, reserved}: one 16-byte load
     int32_t chained;
     // Single-layout dedup (MgState.grid_dirty / pool_rep): with ONE pool layout (all deterministic env ids) an
     // env whose grid still equals it need not read its 324-byte copy from HBM: the group's cells come from a
     // small L2-resident buffer of 32 copies of the layout, unless one of the group's envs is marked dirty.
-    uint8_t *grid_dirty;       // [E] 1 = the env's grid may differ from pool_grid[layout_idx] (NULL = not tracked)
+    // (the flag is word 2 of the env's chain record: 1 = the grid may differ from pool_grid[layout_idx])
     const uint32_t *pool_rep;  // [32][cstride] copies of pool layout 0, only set when K == 1 (else NULL)
 
     int8_t *direction;  // [T][E][n] per-step 'direction' observation (rollout only; NULL otherwise)
@@ -151,7 +151,7 @@ inline int best_warps_per_sm(const Params &p, int smem_per_block, int smem_per_s
     for (int wpb = 4; wpb >= 1; wpb >>= 1) {
         const int bytes = wpb * p.warp_bytes;
         if (bytes > smem_per_block) continue;
-        int blocks = smem_per_sm / (bytes + 1024);  // 1 KB per block is reserved by the driver
+        int blocks = smem_per_sm / (bytes + 16 + 1024);  // 16 B claim counter; 1 KB per block is reserved by the driver
         if (blocks > 32) blocks = 32;
         int warps = blocks * wpb;
         if (warps > 64) warps = 64;
@@ -824,7 +824,7 @@ MG_HD void phase_reset_grid(const Params &p, const Group &g, uint32_t pending, i
         const uint32_t *src = p.pool_grid + (size_t)g.rk[i] * p.cstride;
         warp_copy(g.cells + i * p.cstride, src, p.cstride * 4, lane);
         warp_copy(p.grid + (size_t)(g.e0 + i) * p.cstride, src, p.cstride * 4, lane);
-        if (p.grid_dirty && lane == 0) p.grid_dirty[g.e0 + i] = 0;  // equal to its pool layout again
+        if (p.chain && lane == 0) p.chain[4 * (size_t)(g.e0 + i) + 2] = 0;  // equal to its pool layout again
     }
 }
 
@@ -837,7 +837,7 @@ MG_HD uint32_t reset_mask_host(const Group &g) {  // hostsim only; the kernel us
 // ---- P4: transition --------------------------------------------------------------------------------
 MG_HD void store_cell(const Params &p, int e, int idx, uint32_t w) {  // dirty-cell write-through
     p.grid[(size_t)e * p.cstride + idx] = w;
-    if (p.grid_dirty) p.grid_dirty[e] = 1;  // the grid no longer equals its pool layout
+    if (p.chain) p.chain[4 * (size_t)e + 2] = 1;  // the grid no longer equals its pool layout
 }
 
 MG_HD uint32_t all_agents(const Params &p) { return p.n >= 32 ? 0xffffffffu : (1u << p.n) - 1u; }
@@ -1398,9 +1398,10 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
 __device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint2 ld_acquire_gpu_v2(const uint32_t *p) {
-    uint2 v;
-    asm volatile("ld.acquire.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+__device__ __forceinline__ uint4 ld_acquire_gpu_v4(const uint32_t *p) {
+    uint4 v;
+    asm volatile("ld.acquire.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
@@ -1602,7 +1603,7 @@ __global__ void reset_where_kernel(const __grid_constant__ Params p, const uint8
         p.layout_idx[e] = k;
         p.step_count[e] = 0;
         if (p.hook_state) p.hook_state[e] = 0;
-        if (p.grid_dirty) p.grid_dirty[e] = 0;
+        if (p.chain) p.chain[4 * (size_t)e + 2] = 0;
     }
 }
 
@@ -1748,48 +1749,45 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
     const int group = blockIdx.x * p.wpb + warp;
     constexpr bool tickets = CHAIN;
     const bool live = group * p.G < p.num_envs;  // (whole warp)
-    // Chain tickets (p.chain[e] = {next ticket, tickets done}). Every chained launch takes, per env, the next
-    // ticket BEFORE it lets its dependents launch, so tickets follow launch order: the dependent grid's blocks
-    // only start once all blocks of this grid have passed launch_dependents. The trigger is per BLOCK (the first
-    // thread that executes it counts), so every warp of the block claims first, then a block barrier, then the
-    // trigger. An env may be touched once `done` equals the ticket, i.e. once the previous launch has finished
-    // THAT env (its stores complete, then a release store).
-    uint32_t ticket = 0, done0 = 0;
-    int env = -1;
+    // Chain tickets (p.chain[e] = {next ticket, tickets done, grid dirty, -}). Every chained launch takes, per env,
+    // the next ticket BEFORE it lets its dependents launch, so tickets follow launch order: the dependent grid's
+    // blocks only start once all blocks of this grid have passed launch_dependents. The trigger is per BLOCK (the
+    // first thread that executes it counts), so it is executed by the LAST warp of the block to have claimed
+    // (a shared counter). An env may be touched once `done` equals the ticket, i.e. once the previous launch has
+    // finished THAT env (its stores complete, then a release store). A warp whose envs are free (the common case)
+    // issues its loads first and claims while they are in flight.
+    unsigned &claimed = *(unsigned *)(smem + p.wpb * p.warp_bytes);  // (16 bytes behind the warps' regions)
     if (tickets) {
-        if (p.chained == 2) pdl_wait();  // head of a chain: the whole previous grid first, like a plain launch
-        if (live) {
-            const int ne = p.num_envs - group * p.G < p.G ? p.num_envs - group * p.G : p.G;
-            const int i = lane & (p.G - 1);
-            env = i < ne ? i : -1;
-            if (env >= 0) {
-                uint32_t *slot = p.chain + 2 * (size_t)(group * p.G + env);
-                const uint2 nd = ld_acquire_gpu_v2(slot);
-                ticket = nd.x; done0 = nd.y;
-                slot[0] = ticket + 1u;  // (shadow lanes write the same value)
-            }
-        }
-        __threadfence();   // the claims are performed device-wide ...
-        __syncthreads();   // ... by every warp of the block, before the block's trigger
+        if (threadIdx.x == 0) claimed = 0;
+        __syncthreads();  // (the only block barrier: every warp has just started)
+    } else {
+        pdl_launch_dependents();
     }
-    pdl_launch_dependents();
-    if (!live) return;
+    if (!live) {
+        if (tickets && lane == 0 && atomicAdd(&claimed, 1u) == blockDim.x / 32 - 1) pdl_launch_dependents();
+        return;
+    }
     uint8_t *ws = smem + warp * p.warp_bytes;
     const Group g = group_view(p, ws, group);
     uint64_t *bar = (uint64_t *)(ws + p.off_mbar);
     // TMA needs 16-byte multiples: full groups only (G % 16 == 0 makes every span aligned)
     const bool bulk = p.use_bulk && g.ne == p.G;
-    env = lane_env(p, g, lane);
+    const int env = lane_env(p, g, lane);
     trace_mark(p, group, lane, 0);
     trace_mark(p, group, lane, 7);
     if (bulk && lane == 0) mbar_init(bar, 1);
+    uint32_t ticket = 0;
+    bool rec_dirty = false;  // (tickets: the dirty flag arrives with the ticket)
     if (tickets) {
-        uint32_t *slot = p.chain + 2 * (size_t)(g.e0 + (env >= 0 ? env : 0));
-        bool ready = env < 0 || done0 == ticket;
-        while (!__all_sync(0xffffffffu, ready)) {
+        if (p.chained == 2) pdl_wait();  // head of a chain: the whole previous grid first, like a plain launch
+        uint32_t *slot = p.chain + 4 * (size_t)(g.e0 + (env >= 0 ? env : 0));
+        uint4 rec = ld_acquire_gpu_v4(slot);
+        ticket = rec.x;
+        while (!__all_sync(0xffffffffu, env < 0 || rec.y == ticket)) {
             __nanosleep(64);
-            ready = env < 0 || ld_acquire_gpu(slot + 1) == ticket;
+            rec = ld_acquire_gpu_v4(slot);  // (next is ours until we claim: only done / dirty can change)
         }
+        rec_dirty = env >= 0 && rec.z != 0;
         fence_async_global();  // what the acquire made visible is also visible to the TMA loads below
         __syncwarp();
     } else {
@@ -1810,10 +1808,18 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
         } else {
             phase_load_plain<MODE>(p, g, lane, t);
         }
-        if (dedup) {  // one flag byte per env decides where the group's cells come from
-            const bool env_dirty = env >= 0 && p.grid_dirty[g.e0 + env] != 0;
+        if (dedup) {  // one flag per env decides where the group's cells come from
+            const bool env_dirty = tickets ? rec_dirty : (env >= 0 && p.chain[4 * (size_t)(g.e0 + env) + 2] != 0);
             const bool any_dirty = __any_sync(0xffffffffu, env_dirty);
             if (lane == 0) load_bulk<MODE>(p, g, bar, t, any_dirty ? 3 : 2);
+        }
+        if (tickets && t == 0) {
+            // claim (performed device-wide) while the loads are in flight; the last warp of the block to get
+            // here lets the dependents launch
+            if (env >= 0) p.chain[4 * (size_t)(g.e0 + env)] = ticket + 1u;  // (shadow lanes write the same value)
+            __threadfence();
+            __syncwarp();
+            if (lane == 0 && atomicAdd(&claimed, 1u) == blockDim.x / 32 - 1) pdl_launch_dependents();
         }
         if (t == 0) env_load<MODE>(p, g, env, er);  // the env's scalars, straight into its lane's registers
         const OrderDraw draw = phase_draw<MODE>(p, g, env, er);
@@ -1897,7 +1903,7 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
         if (bulk && lane == 0) bulk_wait_all();
         __syncwarp();
         __threadfence();
-        if (env >= 0) st_release_gpu(p.chain + 2 * (size_t)(g.e0 + env) + 1, ticket + 1u);
+        if (env >= 0) st_release_gpu(p.chain + 4 * (size_t)(g.e0 + env) + 1, ticket + 1u);
         // completion order: a chained launch did not wait for its predecessor when it started; it must not
         // COMPLETE before it either, or the next unchained operation of the stream could overtake that grid
         if (p.chained == 1) pdl_wait();

@@ -106,9 +106,10 @@ class StepEngine:
         self.truncated = z((E,), torch.uint8)
         self.status = z((1,), torch.int32)
         # chain tickets (include/multigrid_b200.h, MG_FLAG_CHAINED): maintained by chained step launches
-        self.chain = z((E, 2), torch.int32)  # per env {next ticket, tickets done}
-        # single-layout dedup (MgState.grid_dirty / pool_rep): 1 = the env's grid may differ from its pool layout
-        self.grid_dirty = torch.ones((E,), dtype=torch.uint8, device=dev)
+        # per env {next ticket, tickets done, grid dirty, -}: chain tickets (MG_FLAG_CHAINED) and the flag of the
+        # single-layout dedup (1 = the env's grid may differ from its pool layout)
+        self.chain = z((E, 4), torch.int32)
+        self.chain[:, 2] = 1
         self.pool_rep = None
         self._chain_armed = None  # the stream whose last operation on this engine was a step launch
         self.pool_grid = None
@@ -268,6 +269,11 @@ class StepEngine:
                             "mg_gen_layouts_empty_random")
         self._pool_changed()
 
+    @property
+    def grid_dirty(self) -> torch.Tensor:
+        """(E,) int32 view: 1 = the env's grid may differ from its pool layout (word 2 of the chain records)."""
+        return self.chain[:, 2]
+
     def _pool_changed(self) -> None:
         """The layout pool was replaced: no env is known to equal its layout any more; with a single layout,
         (re)build the 32-copy buffer clean groups load their cells from."""
@@ -338,8 +344,7 @@ class StepEngine:
             p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
             st = _cabi.MgState(p(self.cells), p(self.agents), p(self.step_count), p(self.pcg_state),
                                p(self.pcg_inc), p(self.layout_idx), p(self.pool_grid),
-                               p(self.pool_agents), p(self.hook_state), p(self.grid_dirty), p(self.pool_rep),
-                               p(self.chain))
+                               p(self.pool_agents), p(self.hook_state), p(self.pool_rep), p(self.chain))
             out = _cabi.MgStepOut(p(self.obs_buf), p(self.reward), p(self.terminated),
                                   p(self.truncated), p(self.status))
             mk = lambda extra: _cabi.MgConfig(cfg.width, cfg.height, cfg.num_agents, cfg.view_size,  # noqa: E731

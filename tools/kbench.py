@@ -68,7 +68,7 @@ def time_config(name, steps, knobs, replicas=8):
     out = []
     # every knob set is timed from the SAME state (all envs of a fixed-start layout share their episode
     # phase: how far the agents have spread, and with it the cost of a launch, drifts with the step count)
-    names = ("cells", "agents", "step_count", "pcg_state", "layout_idx", "hook_state", "grid_dirty")
+    names = ("cells", "agents", "step_count", "pcg_state", "layout_idx", "hook_state", "chain")
     snap = [{k: getattr(e, k).clone() for k in names} for e in engines]
     for knob in knobs:
         for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_NO_DEDUP", "CHAINED"):
