@@ -392,7 +392,9 @@ class StepEngine:
         since that launch nothing else on the stream wrote `actions` or touched this engine's state or
         outputs (open-loop action tapes). The first chained launch after any other operation of the engine
         (plain step, load_state, gen_obs, reset_where, ...) is the head of a new chain and waits like a
-        plain launch; plain launches never touch the tickets.
+        plain launch; plain launches never touch the tickets. It pays when launches on DIFFERENT engines are
+        interleaved on the stream (several env batches in flight); on one engine stepped back to back every
+        env of launch k+1 waits for launch k anyway, and chained stepping is no faster or slower than plain.
         """
         if actions is None:
             actions = self.actions
