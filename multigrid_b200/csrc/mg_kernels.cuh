@@ -1800,6 +1800,7 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
         const size_t tE = (size_t)t * (size_t)p.num_envs;
         trace_mark(p, group, lane, 5);
         const bool dedup = !MULTI && MODE != MODE_OBS && bulk && p.pool_rep != nullptr;
+        uint32_t dirty_mask = 0xffffffffu;  // envs whose grid may differ from the (single) pool layout
         if (bulk) {
             if (lane == 0) {
                 if (t > 0) bulk_wait_read();  // the last obs store has read its stage (which lies on the cells)
@@ -1810,8 +1811,8 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
         }
         if (dedup) {  // one flag per env decides where the group's cells come from
             const bool env_dirty = tickets ? rec_dirty : (env >= 0 && p.chain[4 * (size_t)(g.e0 + env) + 2] != 0);
-            const bool any_dirty = __any_sync(0xffffffffu, env_dirty);
-            if (lane == 0) load_bulk<MODE>(p, g, bar, t, any_dirty ? 3 : 2);
+            dirty_mask = __ballot_sync(0xffffffffu, env_dirty);  // (bit i = env i; shadow lanes repeat the flags)
+            if (lane == 0) load_bulk<MODE>(p, g, bar, t, dirty_mask ? 3 : 2);
         }
         if (tickets && t == 0) {
             // claim (performed device-wide) while the loads are in flight; the last warp of the block to get
@@ -1829,9 +1830,11 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
         if (MODE != MODE_OBS && (p.flags & MG_FLAG_AUTO_RESET)) {
             phase_reset(p, g, env, er);
             const uint32_t pending = __ballot_sync(0xffffffffu, env >= 0 && g.rk[env] >= 0) & (p.G == 32 ? 0xffffffffu : (1u << p.G) - 1u);
-            if (pending) {
+            // single layout: a clean env that resets already holds the layout (in shared memory and in HBM)
+            const uint32_t to_copy = pending & dirty_mask;
+            if (to_copy) {
                 __syncwarp();
-                phase_reset_grid(p, g, pending, lane);
+                phase_reset_grid(p, g, to_copy, lane);
             }
             __syncwarp();
         }
