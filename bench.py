@@ -36,7 +36,7 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used if MEASU
 # `ncu --set full` capture summarised in profiles/r01_summary.md (r01c): 26.30 MB read (= the layout's
 # 401 B/env of inputs) + 3.04 MB written; the other ~41.6 MB of outputs are still dirty in the 126 MB L2
 # when the kernel ends (ncu flushes before each replay) and reach HBM during later launches.
-NCU_DRAM_BYTES_PER_LAUNCH = 7294976  # profiles/r01i_ncu_details.txt: dram read 6 123 008 + write 1 171 968 (single-layout dedup)
+NCU_DRAM_BYTES_PER_LAUNCH = 7608576  # profiles/r01j_ncu_details.txt: dram read 6 120 704 + write 1 487 872 (single-layout dedup)
 
 
 def algorithmic_bytes_per_env_step(W, H, n, V, mutable_grid=False):
@@ -379,7 +379,7 @@ def run_engine(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_note": "ncu dram read+write bytes of one launch (profiles/r01i_ncu_details.txt); "
+                         "traffic_note": "ncu dram read+write bytes of one launch (profiles/r01j_ncu_details.txt); "
                                          "outputs still dirty in L2 at kernel end are not in it; the grids come from the L2-resident layout buffer (dedup)",
                          "algorithmic_bytes_per_launch": bpe * E, "peak_source": peak_src,
                          "frac_of_8TBs_nominal": achieved / 8000.0,
