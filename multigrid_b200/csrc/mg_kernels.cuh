@@ -1593,9 +1593,14 @@ __global__ void reset_where_kernel(const __grid_constant__ Params p, const uint8
     int k = 0;
     if (lane == 0) k = (int)(((uint32_t)p.layout_idx[e] + (uint32_t)p.lstride) % (uint32_t)p.K);
     k = __shfl_sync(0xffffffffu, k, 0);
-    const uint32_t *src = p.pool_grid + (size_t)k * p.cstride;
-    uint32_t *dst = p.grid + (size_t)e * p.cstride;
-    for (int w = lane; w < p.cstride; w += LANES) dst[w] = src[w];
+    // (single layout: a clean env already holds it)
+    const bool clean = p.pool_rep != nullptr && p.chain[4 * (size_t)e + 2] == 0;
+    if (!clean) {
+        const uint32_t *src = p.pool_grid + (size_t)k * p.cstride;
+        uint32_t *dst = p.grid + (size_t)e * p.cstride;
+        for (int w = lane; w < p.cstride; w += LANES) dst[w] = src[w];
+    }
+    __syncwarp();  // (every lane has read the flag before lane 0 clears it below)
     const uint32_t *asrc = (const uint32_t *)(p.pool_agents + (size_t)k * p.n * 8);
     uint32_t *adst = (uint32_t *)(p.agents + (size_t)e * p.n * 8);
     for (int w = lane; w < p.n * 2; w += LANES) adst[w] = asrc[w];
