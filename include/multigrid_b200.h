@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 7
+#define MG_ABI_VERSION 8
 
 /* MgConfig.flags */
 #define MG_FLAG_SEE_THROUGH_WALLS 0x01u /* agents[0].see_through_walls, base.py:364-365 */
@@ -78,6 +78,19 @@ extern "C" {
                                            the state was not a chained step launch): takes tickets and also waits for
                                            the whole previous grid of the stream, like a plain launch. Launches
                                            without MG_FLAG_CHAINED never touch the tickets. */
+
+#define MG_FLAG_STATIC_GRID       0x200u /* the caller's PROMISE (results unchanged when it holds), needs MgState.static_obs:
+                                           no action can change any env's grid and every env's grid IS pool layout 0 --
+                                           num_layouts == 1, hook == MG_HOOK_NONE, the layout holds only empty / wall /
+                                           floor / goal / lava cells (no door, key, ball, box: every Empty-family env of
+                                           the reference, envs/empty.py), no agent carries anything and every agent stands
+                                           inside the grid on a cell that is not a wall. mg_step_obs then takes the static
+                                           path: observations come from the memoised per-(x, y, dir) views of
+                                           mg_build_static_obs plus the other agents drawn on top, the transition is
+                                           left / right / forward against the one layout, and `grid` is neither read nor
+                                           written. A violated promise that the kernel can see (an agent outside the grid
+                                           or carrying something) ORs 4 into MgStepOut.status. Ignored (general path) by
+                                           mg_step, mg_rollout and chained launches, and under MG_NO_STATIC=1. */
 
 /* MgConfig.hook: env-specific step() post-hooks */
 #define MG_HOOK_NONE 0
@@ -126,6 +139,8 @@ typedef struct MgState {
                                   ticket + 1 when it is done with env e. dirty = 1: the env's grid may differ from
                                   pool_grid[layout_idx]; the engine sets it on every cell write-through and clears it
                                   on reset; the CALLER sets it whenever it writes `grid` itself. */
+    const int8_t *static_obs;  /* mg_static_obs_bytes(W, H, obs_agent_stride) bytes filled by mg_build_static_obs,
+                                  16-byte aligned; only read under MG_FLAG_STATIC_GRID (may be NULL otherwise) */
 } MgState;
 
 typedef struct MgStepOut {
@@ -249,6 +264,22 @@ int mg_one_hot(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_st
 #define MG_FEATURE_CHANNELS 23
 int mg_obs_features(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
                     const int8_t *direction, int32_t direction_stride, const float *dir_lut, float *out, void *stream);
+
+/*
+ * Memoised observations and moves of a static layout (MG_FLAG_STATIC_GRID). `static_obs` holds, for EVERY cell
+ * (x, y) of the layout and direction dir, at entry ((x*H + y)*4 + dir):
+ *   - the packed view image[V][V][3] (obs_agent_stride bytes, zero padded to the entry stride) of a lone agent
+ *     there that carries nothing, computed by the engine's own observation code. Replaces: gen_obs_grid_encoding
+ *     (utils/obs.py:66-102) evaluated once per (position, direction) instead of once per agent and step;
+ *   - behind the W*H*4 views, one uint32 per entry: the agent's position word after `forward` (base.py:420-436:
+ *     the cell in front if it can be walked on, else unchanged) with flags for goal / lava.
+ * layout_cells: uint32 [W+1][H+1] cell words (e.g. pool_grid); uses cfg's width, height, view_size,
+ * obs_agent_stride and MG_FLAG_SEE_THROUGH_WALLS. The unrolled kernels (V = 7 with 4 or 2 agents, V = 9 with 8)
+ * need obs_agent_stride = 3*V*V rounded up to 16 (160 / 256); any other stride takes the rolled static kernel.
+ */
+int32_t mg_static_obs_stride(int32_t obs_agent_stride); /* bytes per entry: obs_agent_stride rounded up to 16 */
+int64_t mg_static_obs_bytes(int32_t width, int32_t height, int32_t obs_agent_stride); /* size of `static_obs` */
+int mg_build_static_obs(const MgConfig *cfg, const uint32_t *layout_cells, int8_t *static_obs, void *stream);
 
 /* Diagnostics: when set to a device buffer of 8 uint64 per warp (= per group of envs), every
  * following launch records %globaltimer at its phase boundaries (slots 0..4) and the SM id (slot 7).

@@ -21,13 +21,14 @@ FLAG_AUTO_RESET = 0x20
 FLAG_STREAM_STATE = 0x40
 FLAG_CHAINED = 0x80
 FLAG_CHAIN_HEAD = 0x100
+FLAG_STATIC_GRID = 0x200
 
 HOOK_NONE = 0
 HOOK_BLOCKED_UNLOCK_PICKUP = 1
 HOOK_RED_BLUE_DOORS = 2
 HOOK_LOCKED_HALLWAY = 3
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_VIEW = 15
 MAX_AGENTS = 32
 
@@ -46,7 +47,7 @@ class MgState(C.Structure):
         ("grid", C.c_void_p), ("agents", C.c_void_p), ("step_count", C.c_void_p),
         ("pcg_state", C.c_void_p), ("pcg_inc", C.c_void_p), ("layout_idx", C.c_void_p),
         ("pool_grid", C.c_void_p), ("pool_agents", C.c_void_p), ("hook_state", C.c_void_p),
-        ("pool_rep", C.c_void_p), ("chain", C.c_void_p),
+        ("pool_rep", C.c_void_p), ("chain", C.c_void_p), ("static_obs", C.c_void_p),
     ]
 
 
@@ -69,6 +70,9 @@ EXPORTS = {
     "mg_error_string": (C.c_char_p, [C.c_int]),
     "mg_obs_agent_stride": (C.c_int32, [C.c_int32]),
     "mg_launch_count": (C.c_int64, []),
+    "mg_static_obs_stride": (C.c_int32, [C.c_int32]),
+    "mg_static_obs_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "mg_build_static_obs": (C.c_int, [C.POINTER(MgConfig), C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_debug_set_trace": (None, [C.c_void_p]),
     "mg_cells_per_env": (C.c_int64, [C.c_int32, C.c_int32]),
     "mg_pack_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

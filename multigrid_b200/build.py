@@ -14,7 +14,7 @@ ROOT = os.path.dirname(PKG_DIR)
 SRC_DIR = os.path.join(PKG_DIR, "csrc")
 OUT = os.path.join(PKG_DIR, "_lib", "libmultigrid_b200.so")
 SOURCES = ["mg_cabi.cu"]
-DEPS = ["mg_cabi.cu", "mg_kernels.cuh", os.path.join(ROOT, "include", "multigrid_b200.h")]
+DEPS = ["mg_cabi.cu", "mg_kernels.cuh", "mg_static.cuh", os.path.join(ROOT, "include", "multigrid_b200.h")]
 
 
 def _nvcc() -> str:

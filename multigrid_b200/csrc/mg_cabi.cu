@@ -8,6 +8,7 @@
 #include <unistd.h>
 
 #include "mg_kernels.cuh"
+#include "mg_static.cuh"
 
 namespace {
 
@@ -127,6 +128,45 @@ int dispatch(const mg::Params &p, cudaStream_t stream) {
     }
 }
 
+// The static-grid path (mg_static.cuh): one warp per block; unrolled instantiations for the BASELINE shapes
+// (V = 7 with 4 or 2 agents, V = 9 with 8) at 8 / 16 / 32 envs per warp, rolled loops otherwise.
+template <typename K>
+int launch_static(K kernel, const mg::Params &p, cudaStream_t stream) {
+    const int groups = (p.num_envs + p.G - 1) / p.G;
+    cudaLaunchConfig_t lc;
+    std::memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)groups); lc.blockDim = dim3((unsigned)(p.wpb * mg::LANES));
+    lc.dynamicSmemBytes = (size_t)p.warp_bytes; lc.stream = stream;  // (carve_static: bytes of the whole block)
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = p.pdl ? 1 : 0;
+    if (p.warp_bytes > 48 * 1024) {
+        const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock);
+        if (err != cudaSuccess) return (int)err;
+    }
+    const cudaError_t err = cudaLaunchKernelEx(&lc, kernel, p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)err;
+}
+
+int dispatch_static(const mg::Params &p, cudaStream_t stream) {
+    if (mg::static_fast_shape(p)) {
+#define MG_STATIC_CASE(V_, N_, G_, W_) \
+        if (p.V == V_ && p.n == N_ && p.G == G_ && p.wpb == W_) \
+            return launch_static(mg::static_fast_kernel<V_, N_, G_, W_>, p, stream);
+        // (the instantiations listed in mg::STATIC_SHAPES)
+        MG_STATIC_CASE(7, 4, 16, 1) MG_STATIC_CASE(7, 4, 32, 2) MG_STATIC_CASE(7, 4, 32, 1)
+        MG_STATIC_CASE(7, 4, 16, 2) MG_STATIC_CASE(7, 4, 8, 1)
+        MG_STATIC_CASE(7, 2, 32, 1) MG_STATIC_CASE(7, 2, 32, 2) MG_STATIC_CASE(7, 2, 16, 1)
+        MG_STATIC_CASE(9, 8, 16, 4) MG_STATIC_CASE(9, 8, 32, 4) MG_STATIC_CASE(9, 8, 16, 2)
+        MG_STATIC_CASE(9, 8, 8, 2) MG_STATIC_CASE(9, 8, 8, 1)
+#undef MG_STATIC_CASE
+        return MG_ERR_BAD_ARG;  // (plan_static only produces the shapes above)
+    }
+    return launch_static(mg::static_rolled_kernel, p, stream);
+}
+
 void fill_config(mg::Params &p, const MgConfig *c, int64_t num_envs) {
     std::memset(&p, 0, sizeof(p));
     p.W = c->width; p.H = c->height; p.n = c->num_agents; p.V = c->view_size;
@@ -153,6 +193,10 @@ int fill_state(mg::Params &p, const MgState *s) {
     p.chain = s->chain;
     if ((p.flags & MG_FLAG_CHAINED) && !s->chain) return MG_ERR_BAD_ARG;
     p.chained = (p.flags & MG_FLAG_CHAINED) ? ((p.flags & MG_FLAG_CHAIN_HEAD) ? 2 : 1) : 0;
+    if (reinterpret_cast<uintptr_t>(s->static_obs) & 15u) return MG_ERR_ALIGNMENT;
+    p.static_obs = reinterpret_cast<const uint8_t *>(s->static_obs);
+    p.static_stride = mg::static_obs_stride(p.ostride);
+    p.static_move = reinterpret_cast<const uint32_t *>(p.static_obs + (size_t)p.W * p.H * 4 * p.static_stride);
     return 0;
 }
 
@@ -182,6 +226,35 @@ int step_common(const MgConfig *cfg, int64_t num_envs, const MgState *state, con
     p.direction = direction;
     if (MULTI || MODE != mg::MODE_STEP_OBS) p.chained = 0;  // only the fused single-step launch chains; a rollout
                                                             // or mg_step is a plain launch and leaves the tickets alone
+    // MG_FLAG_STATIC_GRID: the fused single-step launch on a grid no action can change (mg_static.cuh)
+    if (MODE == mg::MODE_STEP_OBS && !MULTI && (p.flags & MG_FLAG_STATIC_GRID) && !p.chained) {
+        if (!p.static_obs || p.hook != MG_HOOK_NONE || !state->pool_grid || !state->pool_agents) return MG_ERR_BAD_ARG;
+        if ((p.flags & MG_FLAG_AUTO_RESET) && p.K != 1) return MG_ERR_BAD_ARG;
+        const bool k = any_mg_knob();
+        if (!env_int("MG_NO_STATIC", 0, k)) {
+            p.use_bulk = env_int("MG_NO_BULK", 0, k) ? 0 : 1;
+            p.generic_view = env_int("MG_GENERIC_VIEW", 0, k) ? 1 : 0;
+            p.pdl = env_int("MG_PDL", 1, k) ? 1 : 0;
+            // (the observation stores always carry the L2 evict_first hint here: they are written once and, at
+            // 40+ MB per launch, would otherwise push the state out of L2; measured 12.1 -> 11.1 us per launch)
+            p.l2hint = env_int("MG_L2HINT", 3, k);
+            // the unrolled kernels read an env's actions as one 2 / 4 / 8-byte word
+            if (reinterpret_cast<uintptr_t>(p.actions) & 7u) p.generic_view = 1;
+            static thread_local int sms[64] = {0};
+            int dev = 0, n_sm = 148;
+            cudaGetDevice(&dev);
+            if (dev >= 0 && dev < 64) {
+                if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+                if (sms[dev] > 0) n_sm = sms[dev];
+            }
+            if ((rc = mg::plan_static(p, env_int("MG_GROUP", 0, k), env_int("MG_WPB", 0, k), kSmemPerBlock, n_sm))) return rc;
+            auto misaligned = [](const void *ptr, uintptr_t a) { return (reinterpret_cast<uintptr_t>(ptr) & (a - 1)) != 0; };
+            if (misaligned(p.pcg_state, 16) || misaligned(p.pcg_inc, 16) || misaligned(p.reward, 8) ||
+                misaligned(p.step_count, 4) || misaligned(p.terminated, 4) || misaligned(p.pool_grid, 4) ||
+                misaligned(p.pool_agents, 4)) return MG_ERR_ALIGNMENT;
+            return dispatch_static(p, (cudaStream_t)stream);
+        }
+    }
     if ((rc = plan(p))) return rc;
     // a rollout re-reads its cells from L2 every step: never mark those loads evict_first
     if (MULTI) p.l2hint &= ~1;
@@ -367,6 +440,28 @@ int mg_unpack_grid(int32_t width, int32_t height, int64_t num_envs, const uint32
 }
 
 int64_t mg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int32_t mg_static_obs_stride(int32_t obs_agent_stride) { return mg::static_obs_stride(obs_agent_stride); }
+
+int64_t mg_static_obs_bytes(int32_t width, int32_t height, int32_t obs_agent_stride) {
+    return mg::static_table_bytes(width, height, obs_agent_stride);
+}
+
+int mg_build_static_obs(const MgConfig *cfg, const uint32_t *layout_cells, int8_t *static_obs, void *stream) {
+    int rc = validate(cfg, 1);
+    if (rc) return rc;
+    if (!layout_cells || !static_obs) return MG_ERR_BAD_ARG;
+    if (!aligned16(static_obs)) return MG_ERR_ALIGNMENT;
+    mg::Params p;
+    fill_config(p, cfg, 1);
+    p.G = 16;
+    mg::carve_static(p, false, 1);  // derived geometry (Hp, cstride)
+    const int entries = p.W * p.H * 4;
+    mg::static_build_kernel<<<(unsigned)((entries + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        p, layout_cells, reinterpret_cast<uint8_t *>(static_obs));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
 
 void mg_debug_set_trace(void *device_buffer) { g_trace.store((unsigned long long *)device_buffer, std::memory_order_relaxed); }
 

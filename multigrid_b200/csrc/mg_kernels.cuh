@@ -86,6 +86,12 @@ struct Params {
     // (the flag is word 2 of the env's chain record: 1 = the grid may differ from pool_grid[layout_idx])
     const uint32_t *pool_rep;  // [32][cstride] copies of pool layout 0, only set when K == 1 (else NULL)
 
+    // Static-grid path (MG_FLAG_STATIC_GRID, mg_static.cuh): memoised per-(x, y, dir) views of the one layout
+    const uint8_t *static_obs;  // [W*H*4][static_stride]
+    const uint32_t *static_move;  // [W*H*4] memoised forward moves (behind the observation entries)
+    int32_t static_stride, nstage;  // nstage: observation stages of a block (one per warp)
+    int32_t lut_words;              // move words copied into the block's shared memory (0: read from global)
+
     int8_t *direction;  // [T][E][n] per-step 'direction' observation (rollout only; NULL otherwise)
     // state (device)
     uint32_t *grid; int8_t *agents; int32_t *step_count; uint64_t *pcg_state; const uint64_t *pcg_inc;

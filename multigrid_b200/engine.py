@@ -60,6 +60,27 @@ class EngineConfig:
                 | (_cabi.FLAG_STREAM_STATE if self.stream_state else 0))
 
 
+# Cell types a STATIC grid may hold (core/constants.py:34-48): empty, wall, floor, goal, lava. No action changes
+# such a grid: pickup needs a key / ball / box, toggle a door / box, drop a carried object (base.py:439-467).
+_STATIC_TYPES = (1, 2, 3, 8, 9)
+
+
+def static_layout_ok(pool_grid, pool_agents) -> bool:
+    """True when the promise of MG_FLAG_STATIC_GRID (include/multigrid_b200.h) holds for a batch whose envs all
+    start from this pool: ONE layout of empty / wall / floor / goal / lava cells only, whose agents carry nothing
+    and stand inside the grid on cells that are not walls. pool_grid (K,W,H,3), pool_agents (K,n,8) int8 arrays."""
+    g, a = np.asarray(pool_grid), np.asarray(pool_agents)
+    if g.shape[0] != 1 or not np.isin(g[..., 0], _STATIC_TYPES).all():
+        return False
+    W, H = g.shape[1:3]
+    x, y = a[0, :, 1].astype(np.int64), a[0, :, 2].astype(np.int64)
+    if ((x < 0) | (x >= W) | (y < 0) | (y >= H)).any() or (a[0, :, 4] != 1).any():
+        return False
+    if ((a[0, :, 0] < 0) | (a[0, :, 0] > 3)).any():
+        return False
+    return bool((g[0, x, y, 0] != 2).all())
+
+
 def _as_i64_bits(a) -> np.ndarray:
     """uint64 words -> int64 with the same bits (torch has no general uint64 support)."""
     return np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)
@@ -111,6 +132,11 @@ class StepEngine:
         self.chain = z((E, 4), torch.int32)
         self.chain[:, 2] = 1
         self.pool_rep = None
+        # static-grid path (MG_FLAG_STATIC_GRID): memoised per-(x, y, dir) views of the single pool layout, and
+        # whether the batch is known to satisfy the promise (True / False; None = injected state, check lazily)
+        self.static_obs = None
+        self._static_state = False
+        self.use_static = True  # set False to force the general kernel (comparisons, tests)
         self._chain_armed = None  # the stream whose last operation on this engine was a step launch
         self.pool_grid = None
         self.pool_agents = None
@@ -281,6 +307,51 @@ class StepEngine:
         self.pool_rep = (self.pool_grid[:1].repeat(32, 1, 1).contiguous()
                          if self.pool_grid is not None and self.pool_grid.shape[0] == 1 else None)
         self._c = None
+        self._build_static()
+
+    def _build_static(self) -> None:
+        """(Re)build the memoised observations of a single static layout (mg_build_static_obs); without one,
+        the engine only ever takes the general kernel."""
+        self.static_obs, self._static_state = None, False
+        cfg = self.cfg
+        if self.pool_grid is None or self.pool_grid.shape[0] != 1 or cfg.hook != _cabi.HOOK_NONE:
+            return
+        W, H = cfg.width, cfg.height
+        cells = self.pool_grid.cpu().numpy().view(np.uint32)
+        grid3 = np.stack([cells & 0xff, (cells >> 8) & 0xff, (cells >> 16) & 0xff], -1)[:, :W, :H]
+        if not static_layout_ok(grid3, self.pool_agents.cpu().numpy()):
+            return
+        # observation slots of the table's entry stride (3*V*V rounded up to 16 bytes: 160 for V = 7): the static
+        # kernel then moves whole 16-byte pieces; `obs` stays the (E, n, V, V, 3) view of the first 3*V*V bytes
+        stride = self.lib.mg_static_obs_stride(_cabi.obs_agent_stride(cfg.view_size))
+        if stride != self.obs_stride:
+            self.obs_stride = stride
+            self.obs_buf = torch.zeros((self.num_envs, cfg.num_agents, stride), dtype=torch.int8, device=self.device)
+            self._views, self._host = None, None
+        table = torch.zeros((self.lib.mg_static_obs_bytes(W, H, stride),), dtype=torch.int8, device=self.device)
+        c = _cabi.MgConfig(W, H, cfg.num_agents, cfg.view_size, cfg.max_steps, cfg.flags, cfg.hook,
+                           self.obs_stride, 1, cfg.layout_stride, cfg.hook_param)
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.mg_build_static_obs(C.byref(c), self.pool_grid.data_ptr(), table.data_ptr(),
+                                                     self._stream()), "mg_build_static_obs")
+        self.static_obs = table
+        self._static_state = None  # the layout qualifies; whether the STATE does is checked on first use
+
+    def _static_ok(self) -> bool:
+        """Does the batch satisfy MG_FLAG_STATIC_GRID right now? After a reset from the pool it does by
+        construction and no step can break it; after state injection (load_state) it is checked once on the
+        device: every grid equals the layout, every agent is inside the grid, off the walls, empty-handed."""
+        if self.static_obs is None or not self.use_static:
+            return False
+        if self._static_state is None:
+            W, H = self.cfg.width, self.cfg.height
+            a = self.agents.to(torch.int64)
+            x, y = a[..., 1], a[..., 2]
+            inside = (x >= 0) & (x < W) & (y >= 0) & (y < H) & (a[..., 4] == 1) & (a[..., 0] >= 0) & (a[..., 0] <= 3)
+            under = self.pool_grid[0].to(torch.int64)[x.clamp(0, W - 1), y.clamp(0, H - 1)] & 0xff
+            ok = inside.all() & (under != 2).all() & (self.cells == self.pool_grid[0]).all()
+            self._static_state = bool(ok.item())
+        return self._static_state
 
     def load_state(self, grid=None, agents=None, step_count=None, pcg_state=None, pcg_inc=None,
                    layout_idx=None, hook_state=None) -> None:
@@ -297,6 +368,8 @@ class StepEngine:
         if grid is not None:
             self._pack(grid, self.cells)
             self.grid_dirty.fill_(1)
+        if (grid is not None or agents is not None) and self.static_obs is not None:
+            self._static_state = None  # re-checked on the device before the next step
         put(self.agents, agents)
         put(self.step_count, step_count)
         put(self.pcg_state, pcg_state, bits64=True)
@@ -315,6 +388,8 @@ class StepEngine:
         self.step_count.zero_()
         self.hook_state.zero_()
         self.grid_dirty.zero_()
+        if self.static_obs is not None:
+            self._static_state = True  # every env holds the one layout and its agents
 
     def reset_where(self, mask: torch.Tensor) -> None:
         """mg_reset_where: envs with a non-zero mask entry ((E,) bool / uint8 on the device) take the next
@@ -344,16 +419,19 @@ class StepEngine:
             p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
             st = _cabi.MgState(p(self.cells), p(self.agents), p(self.step_count), p(self.pcg_state),
                                p(self.pcg_inc), p(self.layout_idx), p(self.pool_grid),
-                               p(self.pool_agents), p(self.hook_state), p(self.pool_rep), p(self.chain))
+                               p(self.pool_agents), p(self.hook_state), p(self.pool_rep), p(self.chain),
+                               p(self.static_obs))
             out = _cabi.MgStepOut(p(self.obs_buf), p(self.reward), p(self.terminated),
                                   p(self.truncated), p(self.status))
             mk = lambda extra: _cabi.MgConfig(cfg.width, cfg.height, cfg.num_agents, cfg.view_size,  # noqa: E731
                                               cfg.max_steps, cfg.flags | extra, cfg.hook, self.obs_stride, K,
                                               cfg.layout_stride, cfg.hook_param)
             cc, ch = mk(_cabi.FLAG_CHAINED), mk(_cabi.FLAG_CHAINED | _cabi.FLAG_CHAIN_HEAD)
+            cs = mk(_cabi.FLAG_STATIC_GRID)
             self._c = (c, st, out)
             self._refs = (C.byref(c), C.byref(st), C.byref(out))
             self._chained_cfg = (cc, C.byref(cc), ch, C.byref(ch))
+            self._static_cfg = (cs, C.byref(cs))
         return self._c
 
     def _stream(self) -> C.c_void_p:
@@ -405,7 +483,10 @@ class StepEngine:
         rc, rst, rout = self._refs
         fn = self.lib.mg_step_obs if fused else self.lib.mg_step
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        if chained and fused:  # head of a chain unless the engine's previous operation was a chained step on this stream
+        if fused and self._static_state is not False and self._static_ok():
+            rc = self._static_cfg[1]  # MG_FLAG_STATIC_GRID: a plain launch of the static-grid kernel (chained or not)
+            self._chain_armed = None
+        elif chained and fused:  # head of a chain unless the engine's previous operation was a chained step on this stream
             rc = self._chained_cfg[1] if self._chain_armed == stream else self._chained_cfg[3]
             self._chain_armed = stream
         else:
@@ -480,6 +561,8 @@ class StepEngine:
         self._chain_armed = None
         h = self.host_buffers()
         c, st, out = self._structs()
+        if self._static_state is not False and self._static_ok():
+            c = self._static_cfg[0]
         hout = _cabi.MgStepOut(h["obs"].data_ptr(), h["reward"].data_ptr(),
                                h["terminated"].data_ptr(), h["truncated"].data_ptr(), None)
         with torch.cuda.device(self.device):
@@ -493,8 +576,11 @@ class StepEngine:
 
     def check_status(self) -> None:
         """Raise ValueError if any kernel saw an action outside 0..6 (base.py:473-474). Syncs."""
-        if int(self.status.item()) & 1:
+        st = int(self.status.item())
+        if st & 5:
             self.status.zero_()
+            if st & 4:
+                raise RuntimeError("MG_FLAG_STATIC_GRID promise violated: an agent left the grid or carries an object")
             raise ValueError("Unknown action")
 
     def bytes_per_step(self) -> dict:

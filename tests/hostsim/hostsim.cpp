@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../multigrid_b200/csrc/mg_kernels.cuh"
+#include "../../multigrid_b200/csrc/mg_static.cuh"
 
 namespace {
 
@@ -68,6 +69,72 @@ void run_groups(const mg::Params &p) {
     }
 }
 
+// The static-grid kernels (mg_static.cuh), lane by lane: same phase order as static_rolled_kernel /
+// static_fast_kernel (whose cooperative table copy is a plain per-entry copy here).
+void run_groups_static_rolled(const mg::Params &p) {
+    std::vector<uint8_t> smem_store(p.warp_bytes + 128);
+    uint8_t *ws = smem_store.data();
+    ws += (128 - (reinterpret_cast<uintptr_t>(ws) & 127)) & 127;
+    const int groups = (p.num_envs + p.G - 1) / p.G;
+    const int L = mg::LANES;
+    for (int grp = 0; grp < groups; grp++) {
+        std::memset(ws, 0xCD, p.warp_bytes);
+        const mg::Group g = mg::group_view(p, ws, grp);
+        mg::EnvRegs er[mg::LANES];
+        mg::OrderDraw draw[mg::LANES];
+        int env[mg::LANES];
+        for (int l = 0; l < L; l++) env[l] = l < g.ne ? l : -1;
+        for (int l = 0; l < L; l++) mg::static_load(p, g, l);
+        for (int l = 0; l < L; l++) mg::static_env_load(p, g, env[l], er[l]);
+        for (int l = 0; l < L; l++) draw[l] = mg::phase_draw<mg::MODE_STEP_OBS>(p, g, env[l], er[l]);
+        for (int l = 0; l < L; l++) mg::static_env_step(p, g, env[l], er[l], draw[l]);
+        for (int l = 0; l < L; l++) mg::static_store_agents(p, g, l);
+        const int n = p.n, tasks = g.ne * n, passes = (tasks + L - 1) / L;
+        for (int pass = 0; pass < passes; pass++) {
+            for (int l = 0; l < L; l++) mg::static_obs_agent(p, g, pass, l, g.stage);
+            const int left = tasks - pass * L, cnt = left < L ? left : L;
+            for (int l = 0; l < L; l++)
+                mg::warp_copy(p.obs + ((size_t)g.e0 * n + (size_t)pass * L) * p.ostride, g.stage, cnt * p.ostride, l);
+        }
+    }
+}
+
+template <int VT, int NT>
+void run_groups_static_fast(const mg::Params &p) {
+    typedef mg::StaticCopy<VT> C;
+    std::vector<uint8_t> smem_store(p.warp_bytes + 128);
+    uint8_t *ws = smem_store.data();
+    ws += (128 - (reinterpret_cast<uintptr_t>(ws) & 127)) & 127;
+    const int groups = (p.num_envs + p.G - 1) / p.G;
+    const int L = mg::LANES;
+    uint32_t colors = 0;
+    for (int j = 0; j < NT; j++) colors |= (uint32_t)(uint8_t)p.pool_agents[j * 8 + 7] << (4 * j);
+    for (int grp = 0; grp < groups; grp++) {
+        std::memset(ws, 0xCD, p.warp_bytes);
+        const mg::Group g = mg::group_view(p, ws, grp);
+        uint32_t *a0T = g.ag;
+        for (int l = 0; l < L; l++) mg::static_fast_env<NT>(p, g, l, a0T, p.static_move);
+        const int tasks = g.ne * NT, passes = (tasks + L - 1) / L;
+        for (int pass = 0; pass < passes; pass++) {
+            uint8_t *stage = g.stage;
+            const int left = tasks - pass * L, cnt = left < L ? left : L;
+            uint32_t a0[mg::LANES], ent[mg::LANES];
+            for (int l = 0; l < L; l++) {
+                const int id = pass * L + l, el = mg::static_task_env<NT>(id), k = id & (NT - 1);
+                a0[l] = id < tasks ? a0T[k * L + el] : 0u;
+                ent[l] = mg::static_entry_offset(p, a0[l]);
+            }
+            for (int A = 0; A < cnt; A++) std::memcpy(stage + A * C::OS, p.static_obs + ent[A], C::OS);
+            for (int l = 0; l < cnt; l++) {
+                const int id = pass * L + l, el = mg::static_task_env<NT>(id), k = id & (NT - 1);
+                mg::static_overlay_fast<VT, NT>(a0[l], k, a0T + el, colors, stage + l * C::OS);
+            }
+            for (int l = 0; l < L; l++)
+                mg::warp_copy(p.obs + ((size_t)g.e0 * NT + (size_t)pass * L) * C::OS, stage, cnt * C::OS, l);
+        }
+    }
+}
+
 template <int MODE>
 void dispatch(const mg::Params &p, int generic) {
     if (MODE == mg::MODE_STEP) return run_groups<0, MODE>(p);
@@ -103,11 +170,40 @@ extern "C" int sim_run(int mode, const MgConfig *c, int64_t num_envs, const MgSt
     p.actions = actions;
     p.obs = o->obs; p.reward = o->reward; p.terminated = o->terminated; p.truncated = o->truncated;
     p.status = o->status;
+    if (mode == mg::MODE_STEP_OBS && num_steps == 1 && (p.flags & MG_FLAG_STATIC_GRID)) {
+        if (!s->static_obs || p.hook != MG_HOOK_NONE) return MG_ERR_BAD_ARG;
+        p.static_obs = reinterpret_cast<const uint8_t *>(s->static_obs);
+        p.static_stride = mg::static_obs_stride(p.ostride);
+        p.static_move = reinterpret_cast<const uint32_t *>(p.static_obs + (size_t)p.W * p.H * 4 * p.static_stride);
+        int rc = mg::plan_static(p, forced_group, 0, 227 * 1024);
+        if (rc) return rc;
+        if (!mg::static_fast_shape(p)) run_groups_static_rolled(p);
+        else if (p.V == 7 && p.n == 4) run_groups_static_fast<7, 4>(p);
+        else if (p.V == 9 && p.n == 8) run_groups_static_fast<9, 8>(p);
+        else run_groups_static_fast<7, 2>(p);
+        return 0;
+    }
     int rc = mg::plan_launch(p, forced_group, 0, 227 * 1024, 228 * 1024);
     if (rc) return rc;
     if (mode == mg::MODE_OBS) dispatch<mg::MODE_OBS>(p, generic);
     else if (mode == mg::MODE_STEP) dispatch<mg::MODE_STEP>(p, generic);
     else dispatch<mg::MODE_STEP_OBS>(p, generic);
+    return 0;
+}
+
+// mg_build_static_obs on the CPU: the same static_build_entry() the CUDA kernel calls.
+extern "C" int sim_build_static_obs(const MgConfig *c, const uint32_t *layout, uint8_t *table) {
+    mg::Params p;
+    std::memset(&p, 0, sizeof(p));
+    p.W = c->width; p.H = c->height; p.n = c->num_agents; p.V = c->view_size; p.flags = c->flags;
+    p.ostride = c->obs_agent_stride; p.G = 16;
+    mg::carve_static(p, false, 1);
+    for (int idx = 0; idx < p.W * p.H * 4; idx++) {
+        const int dir = idx & 3, xy = idx >> 2, x = xy / p.H, y = xy - x * p.H;
+        const int ts = mg::static_obs_stride(p.ostride);
+        mg::static_build_entry(p, layout, x, y, dir, table + (size_t)idx * ts);
+        ((uint32_t *)(table + (size_t)p.W * p.H * 4 * ts))[idx] = mg::static_move_word(p, layout, x, y, dir);
+    }
     return 0;
 }
 

@@ -137,7 +137,7 @@ class SimEngine:
     """Mirror of oracle.OracleBatch's interface on top of the host-simulated kernels."""
 
     def __init__(self, cfg, grid, agents, pcg_state, pcg_inc, pool_grid=None, pool_agents=None,
-                 layout_idx=None, step_count=None, forced_group=0, generic=0, split=False):
+                 layout_idx=None, step_count=None, forced_group=0, generic=0, split=False, static=False):
         self.cfg, self.forced_group, self.generic, self.split = cfg, forced_group, generic, split
         self.cells = aligned_copy(pack_cells(grid), np.uint32)
         self.agents = aligned_copy(agents, np.int8)
@@ -152,7 +152,8 @@ class SimEngine:
             self.layout_idx[...] = layout_idx
         self.pool_grid = aligned_copy(self.cells[:1] if pool_grid is None else pack_cells(pool_grid), np.uint32)
         self.pool_agents = aligned_copy(self.agents[:1] if pool_agents is None else pool_agents, np.int8)
-        self.stride = _cabi.obs_agent_stride(cfg.V)
+        # static path: observation slots of the table's entry stride (what StepEngine picks for a static layout)
+        self.stride = (_cabi.obs_agent_stride(cfg.V) + 15) & ~15 if static else _cabi.obs_agent_stride(cfg.V)
         flags = ((_cabi.FLAG_SEE_THROUGH_WALLS if cfg.see_through_walls else 0)
                  | (_cabi.FLAG_ALLOW_OVERLAP if cfg.allow_agent_overlap else 0)
                  | (_cabi.FLAG_JOINT_REWARD if cfg.joint_reward else 0)
@@ -177,13 +178,30 @@ class SimEngine:
         self.out = _cabi.MgStepOut(_p(self.obs).value, _p(self.reward).value,
                                    _p(self.terminated).value, _p(self.truncated).value,
                                    _p(self.status).value)
+        self.c_static = None
+        if static:  # MG_FLAG_STATIC_GRID: the caller's promise must hold (checked here like StepEngine does)
+            from multigrid_b200.engine import static_layout_ok
+            pg3 = unpack_cells(self.pool_grid, cfg.W, cfg.H)
+            assert cfg.hook == 0 and static_layout_ok(pg3, self.pool_agents), "not a static layout"
+            assert (self.cells == self.pool_grid[0]).all(), "grids differ from the layout"
+            assert static_layout_ok(pg3, self.agents.reshape(1, -1, 8)[:, :, :]), "agents break the promise"
+            ts = (self.stride + 15) & ~15
+            self.static_obs = aligned((cfg.W * cfg.H * 4 * (ts + 4),), np.uint8)
+            self.static_obs[...] = 0x77
+            rc = lib().sim_build_static_obs(C.byref(self.c), _p(self.pool_grid), _p(self.static_obs))
+            assert rc == 0, rc
+            self.state.static_obs = _p(self.static_obs).value
+            self.c_static = _cabi.MgConfig(cfg.W, cfg.H, cfg.n, cfg.V, cfg.max_steps, flags | _cabi.FLAG_STATIC_GRID,
+                                           cfg.hook, self.stride, self.pool_grid.shape[0], cfg.layout_stride,
+                                           getattr(cfg, "hook_param", 0))
 
     @property
     def grid(self):
         return unpack_cells(self.cells, self.cfg.W, self.cfg.H)
 
     def _run(self, mode, actions=None, out=None, T=1, direction=None):
-        rc = lib().sim_run(C.c_int(mode), C.byref(self.c), C.c_int64(self.B), C.byref(self.state),
+        c = self.c_static if (self.c_static is not None and mode == MODE_STEP_OBS and T == 1) else self.c
+        rc = lib().sim_run(C.c_int(mode), C.byref(c), C.c_int64(self.B), C.byref(self.state),
                            _p(actions), C.byref(self.out if out is None else out), C.c_int(self.forced_group),
                            C.c_int(self.generic), C.c_int(T), _p(direction))
         assert rc == 0, rc
@@ -224,4 +242,5 @@ class SimEngine:
             self._run(MODE_STEP_OBS, actions)
         if self.status[0] & 1:
             raise ValueError("Unknown action")
+        assert not (self.status[0] & 4), "static-grid promise violated"
         return self._obs_view(), self.reward, self.terminated, self.truncated

@@ -43,7 +43,7 @@ def test_abi_version_and_pure_helpers(lib):
 
 def test_struct_sizes_match_header():
     assert C.sizeof(_cabi.MgConfig) == 44
-    assert C.sizeof(_cabi.MgState) == 88  # 11 pointers (pool_rep, chain: ABI v7)
+    assert C.sizeof(_cabi.MgState) == 96  # 12 pointers (static_obs: ABI v8)
     assert C.sizeof(_cabi.MgRolloutOut) == 48
     assert C.sizeof(_cabi.MgStepOut) == 40
 

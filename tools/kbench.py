@@ -49,7 +49,8 @@ def layout(W, H, n):
 def time_config(name, steps, knobs, replicas=8):
     W, H, n, V, E, max_steps, mutable = CONFIGS[name]
     dev = torch.device("cuda", 0)
-    cfg = EngineConfig(width=W, height=H, num_agents=n, view_size=V, max_steps=max_steps, auto_reset=True)
+    cfg = EngineConfig(width=W, height=H, num_agents=n, view_size=V, max_steps=max_steps, auto_reset=True,
+                       stream_state=bool(int(os.environ.get("KB_STREAM", "1"))))
     pg, pa = layout(W, H, n)
     engines = []
     for r in range(replicas):
@@ -71,10 +72,14 @@ def time_config(name, steps, knobs, replicas=8):
     names = ("cells", "agents", "step_count", "pcg_state", "layout_idx", "hook_state", "chain")
     snap = [{k: getattr(e, k).clone() for k in names} for e in engines]
     for knob in knobs:
-        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_NO_DEDUP", "CHAINED"):
+        for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_NO_DEDUP", "CHAINED",
+                    "NOSTATIC", "REPLICAS"):
             os.environ.pop(key, None)
         os.environ.update({k: str(v) for k, v in knob.items()})
         chained = bool(int(os.environ.get("CHAINED", "0")))  # (a kbench knob, not a library one)
+        for e in engines:  # NOSTATIC=1 (a kbench knob): the general kernel on a static-grid batch
+            e.use_static = not int(os.environ.get("NOSTATIC", "0"))
+        nrep = int(os.environ.get("REPLICAS", str(replicas)))  # REPLICAS=1: one batch stepped closed-loop (L2-resident)
         for e, sn in zip(engines, snap):
             for k in names:
                 getattr(e, k).copy_(sn[k])
@@ -87,7 +92,7 @@ def time_config(name, steps, knobs, replicas=8):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
                 for k in range(steps):
-                    engines[k % replicas].step(tape[k % NT], chained=chained)
+                    engines[k % nrep].step(tape[k % NT], chained=chained)
         torch.cuda.synchronize()
         best = 1e9
         for rep in range(3):

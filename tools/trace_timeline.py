@@ -12,7 +12,7 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 TRACE_LIB = os.path.join(ROOT, "multigrid_b200", "_lib", "libmultigrid_b200_trace.so")
-_SRC = [os.path.join(ROOT, "multigrid_b200", "csrc", f) for f in ("mg_cabi.cu", "mg_kernels.cuh")] + \
+_SRC = [os.path.join(ROOT, "multigrid_b200", "csrc", f) for f in ("mg_cabi.cu", "mg_kernels.cuh", "mg_static.cuh")] + \
        [os.path.join(ROOT, "include", "multigrid_b200.h")]
 if not os.path.exists(TRACE_LIB) or any(os.path.getmtime(f) > os.path.getmtime(TRACE_LIB) for f in _SRC):
     subprocess.check_call([sys.executable, "-m", "multigrid_b200.build", "--trace"], cwd=ROOT)
