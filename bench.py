@@ -1,22 +1,28 @@
 #!/usr/bin/env python
-"""Benchmark of the MultiGrid step/observe hot path on B200 (contract: see DESIGN.md §Measurement).
+"""Benchmark of the MultiGrid step/observe hot path on B200 (contract: see DESIGN.md, Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA engine
-    python bench.py --impl reference [--steps K] [--warmup W]      # CPU oracle port, all host threads
-    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU, env axis sharded
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config empty8|bup|empty16]   # this repo's CUDA engine
+    python bench.py --impl reference [--steps K] [--warmup W] [--config ...]             # the reference on the host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...                                # one rank per GPU, env axis sharded
 
-Workload (BASELINE.json configs[1], per GPU): MultiGrid-Empty-8x8-v0, agents=4, view 7,
-num_envs=65536, uniform random actions over the 7 actions, "next-step" auto-reset; a step is one
-fused mg_step_obs launch over the whole batch. Metric: agent-steps/s (1 agent-step = one agent
-slot of one env advanced by one step; terminated/skipped agents count, on CPU and GPU alike).
+Workloads (BASELINE.json `configs`, per GPU; default = the configuration the metric is quoted on):
+    empty8   configs[1]  MultiGrid-Empty-8x8-v0, agents=4, view 7, num_envs=65536
+    bup      configs[2]  MultiGrid-BlockedUnlockPickup-v0, agents=2, view 7, num_envs=32768
+    empty16  configs[3]  MultiGrid-Empty-16x16-v0, agents=8, view 9, num_envs=16384
+uniform random actions over the 7 actions, "next-step" auto-reset; a step is one fused mg_step_obs launch over the
+whole batch. Metric: agent-steps/s (1 agent-step = one agent slot of one env advanced by one step; terminated /
+skipped agents count, on CPU and GPU alike).
 
-One JSON line is printed by rank 0.
+`value` is measured with PLAIN launches (each launch waits for the whole previous one: what a closed-loop caller
+gets), K of them captured in one CUDA graph over rotating state replicas so that every launch finds its inputs
+in HBM, not L2. One JSON line is printed by rank 0.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -27,37 +33,44 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "agent-steps/sec on Empty-8x8 agents=4 num_envs=65536; HBM GB/s vs 8 TB/s peak"
-SIZE, N_AGENTS, VIEW, ENVS_PER_GPU = 8, 4, 7, 65536
-MAX_STEPS = 4 * SIZE * SIZE  # envs/empty.py:145
+CONFIGS = {
+    # W, H, max_steps as the reference env classes set them (envs/empty.py:145, envs/blockedunlockpickup.py:132)
+    "empty8": dict(env_id="MultiGrid-Empty-8x8-v0", agents=4, view=7, envs=65536, W=8, H=8, max_steps=256,
+                   mutable_grid=False, baseline="BASELINE.json configs[1]; configs[4] at 8 GPUs"),
+    "bup": dict(env_id="MultiGrid-BlockedUnlockPickup-v0", agents=2, view=7, envs=32768, W=11, H=6, max_steps=576,
+                mutable_grid=True, baseline="BASELINE.json configs[2]"),
+    "empty16": dict(env_id="MultiGrid-Empty-16x16-v0", agents=8, view=9, envs=16384, W=16, H=16, max_steps=1024,
+                    mutable_grid=False, baseline="BASELINE.json configs[3]"),
+}
 REPLICAS = 8   # state replicas rotated through so each launch finds its inputs in HBM, not L2
 BURN_IN = 64   # untimed steps that de-synchronise the envs before anything is measured
+VERIFY_ENVS = 2048  # envs of a replica replayed on the C oracle after the timed region
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used if MEASURED_PEAKS.json is absent
-# dram__bytes_read.sum + dram__bytes_write.sum of one steady-state launch of the fused kernel, from the
-# `ncu --set full` capture summarised in profiles/r01_summary.md (r01c): 26.30 MB read (= the layout's
-# 401 B/env of inputs) + 3.04 MB written; the other ~41.6 MB of outputs are still dirty in the 126 MB L2
-# when the kernel ends (ncu flushes before each replay) and reach HBM during later launches.
-NCU_DRAM_BYTES_PER_LAUNCH = 7608576  # profiles/r01j_ncu_details.txt: dram read 6 120 704 + write 1 487 872 (single-layout dedup)
+REF_CHUNK = 4096  # --impl reference: one bench "step" = this many env steps on each worker process
 
 
 def algorithmic_bytes_per_env_step(W, H, n, V, mutable_grid=False):
-    """SURVEY.md §8(d): packed state round trip + outputs, per env-step."""
+    """SURVEY.md section 8(d): packed state round trip + outputs, per env-step."""
     reads = 3 * W * H + 7 * n + 2 + 16 + 16 + n
     writes = (3 * W * H if mutable_grid else 0) + 7 * n + 2 + 16 + 3 * n * V * V + 8 * n + n + 1
     return reads + writes
 
 
 def rollout_bytes_per_env_step(n, V):
-    """SURVEY.md §8(d), in-kernel multi-step rollout: state stays on chip, so the per-env-step floor
+    """SURVEY.md section 8(d), in-kernel multi-step rollout: state stays on chip, so the per-env-step floor
     is actions in + outputs out (obs, f64 reward, terminated, truncated, direction)."""
     return n + 3 * n * V * V + 8 * n + n + 1 + n
 
 
-def layout_bytes_per_env_step(W, H, n, V, auto_reset=True):
-    """Bytes the engine's HBM layout actually moves per env-step: padded 4-byte
-    cell words, 8-byte agent records, int32 counters, 148-byte obs slots."""
-    ostride = (3 * V * V + 3) & ~3
-    reads = 4 * (W + 1) * (H + 1) + 8 * n + 4 + 16 + 16 + n + (4 if auto_reset else 0)
-    writes = 8 * n + 4 + 16 + n * ostride + 8 * n + n + 1 + (4 if auto_reset else 0)
+def moved_bytes_per_env_step(W, H, n, ostride, static):
+    """Bytes the launch really moves through HBM per env-step with the engine's layout:
+    8-byte agent records, int32 counters, obs slots of `ostride` bytes; the general kernel also reads the env's
+    padded 4-byte cell words and its layout cursor, the static-grid kernel reads no grid at all."""
+    reads = 8 * n + 4 + 16 + 16 + n
+    writes = 8 * n + 4 + 16 + n * ostride + 8 * n + n + 1
+    if not static:
+        reads += 4 * (W + 1) * (H + 1) + 4 + 16  # cells, layout cursor, dirty flag record
+        writes += 4
     return reads + writes
 
 
@@ -155,25 +168,52 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(config):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu
+    capture of this bench command (profiles/r02_traffic.json; written by tools/ncu_traffic.py). None when no
+    capture of this configuration is committed: the bench itself cannot read DRAM counters."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            rec = json.load(f).get(config)
+        return rec
+    except Exception:
+        return None
+
+
 # -------------------------------------------------------------------------------------------------
-# CPU side: the oracle port (oracle/mg_oracle.c) -- bench.py's cpu_baseline / --impl reference leg
+# CPU side. The reference's own path (oracle/_ref + oracle/ref_runner.py, kind "reference") when it is staged and
+# numba imports; the C port of the oracle (oracle/mg_oracle.c, kind "port") otherwise and as a second figure.
 # -------------------------------------------------------------------------------------------------
-def make_cpu_oracle(num_envs, nthreads):
+def time_reference_processes(cfg, procs, steps=None, seconds=None, warm=200):
+    """The unmodified reference on `procs` worker processes, in a clean subprocess."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_runner.py"), "--env", cfg["env_id"],
+           "--agents", str(cfg["agents"]), "--view", str(cfg["view"]), "--procs", str(procs), "--warm", str(warm)]
+    cmd += ["--steps", str(steps)] if steps else ["--seconds", str(seconds)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as exc:  # noqa: BLE001
+        return {"unavailable": f"oracle/ref_runner.py failed: {exc}"}
+
+
+def make_cpu_oracle(cfg, num_envs, nthreads):
+    """C oracle port on Empty layouts (the port leg is only quoted for the Empty configurations)."""
     from oracle.c_oracle import COracle, build
     from oracle.mg_oracle import OracleConfig
     build()
-    cfg = OracleConfig(W=SIZE, H=SIZE, n=N_AGENTS, V=VIEW, max_steps=MAX_STEPS, auto_reset=True)
-    pg, pa = empty_layout(SIZE, N_AGENTS)
+    n, size = cfg["agents"], cfg["W"]
+    ocfg = OracleConfig(W=size, H=size, n=n, V=cfg["view"], max_steps=cfg["max_steps"], auto_reset=True)
+    pg, pa = empty_layout(size, n)
     st, inc = pcg_words(0, num_envs)
-    return COracle(cfg, np.repeat(pg, num_envs, 0), np.repeat(pa, num_envs, 0), st, inc,
+    return COracle(ocfg, np.repeat(pg, num_envs, 0), np.repeat(pa, num_envs, 0), st, inc,
                    pool_grid=pg, pool_agents=pa, nthreads=nthreads)
 
 
-def time_cpu_oracle(num_envs, steps, warmup, nthreads, budget_s=None):
+def time_cpu_port(cfg, num_envs, steps, warmup, nthreads, budget_s=None):
     """Returns (agent_steps_per_s, steps_done, seconds)."""
-    ora = make_cpu_oracle(num_envs, nthreads)
+    ora = make_cpu_oracle(cfg, num_envs, nthreads)
     rng = np.random.default_rng(0)
-    tape = rng.integers(0, 7, size=(64, num_envs, N_AGENTS)).astype(np.int8)
+    tape = rng.integers(0, 7, size=(64, num_envs, cfg["agents"])).astype(np.int8)
     for t in range(warmup):
         ora.step(tape[t % 64])
     t0 = time.perf_counter()
@@ -184,58 +224,169 @@ def time_cpu_oracle(num_envs, steps, warmup, nthreads, budget_s=None):
         if budget_s is not None and time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return num_envs * N_AGENTS * done / dt, done, dt
+    return num_envs * cfg["agents"] * done / dt, done, dt
+
+
+def cpu_baseline(cfg, seconds):
+    """cpu_baseline object of the bench line: the reference itself when it can run here, else the port."""
+    cores = len(os.sched_getaffinity(0))
+    ref = time_reference_processes(cfg, cores, seconds=seconds)
+    port = None
+    if not cfg["mutable_grid"]:
+        v, done, dt = time_cpu_port(cfg, cfg["envs"], 10**9, 2, cores, budget_s=min(seconds, 6.0))
+        port = {"value": v, "unit": "agent-steps/s", "cores": cores,
+                "sample": f"{done} steps x {cfg['envs']} envs ({dt:.1f} s), oracle/mg_oracle.c with OpenMP"}
+    if "unavailable" not in ref:
+        out = {"value": ref["agent_steps_per_s"], "unit": "agent-steps/s", "cores": ref["processes"], "kind": "reference",
+               "sample": f"the unmodified reference (multigrid/base.py:303-346, Python + numba) in {ref['processes']} "
+                         f"processes, one env each, {ref['env_steps_per_process']} env steps per process "
+                         f"({ref['seconds']:.1f} s) after 200 warm-up steps; {ref['cpu_model']}",
+               "per_process_median": float(np.median(ref["per_process"]))}
+        if port:
+            out["port"] = port
+        return out
+    if port is None:
+        return {"value": None, "unit": "agent-steps/s", "cores": cores, "kind": "reference", "unavailable": ref["unavailable"]}
+    return {**port, "kind": "port", "reference_unavailable": ref["unavailable"]}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # the CPU arm runs once per box, on rank 0
+    cfg = CONFIGS[args.config]
     cores = len(os.sched_getaffinity(0))
-    value, done, dt = time_cpu_oracle(ENVS_PER_GPU, args.steps, args.warmup, cores)
-    sample = f"{done} steps x {ENVS_PER_GPU} envs ({dt:.2f} s)"
+    K, W = args.steps, args.warmup
+    ref = time_reference_processes(cfg, cores, steps=K * REF_CHUNK, warm=200 + W * REF_CHUNK)
+    if "unavailable" not in ref:
+        value, kind = ref["agent_steps_per_s"], "reference"
+        dt = ref["seconds"]
+        sample = (f"the unmodified reference (Python + numba) in {cores} processes, one env each; one bench step = "
+                  f"{REF_CHUNK} env steps per process; {K} steps = {ref['env_steps_per_process']} env steps per process in "
+                  f"{dt:.1f} s, after 200 + {W} x {REF_CHUNK} warm-up steps; {ref['cpu_model']}")
+        note = "the reference's own CPU path, staged under oracle/_ref by oracle/make_ref.py, run by oracle/ref_runner.py"
+    else:
+        value, done, dt = time_cpu_port(cfg, cfg["envs"], K, W, cores)
+        kind, sample = "port", f"{done} steps x {cfg['envs']} envs ({dt:.2f} s), oracle/mg_oracle.c with OpenMP"
+        note = f"C port of the oracle: the reference itself cannot run here ({ref['unavailable']})"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "agent-steps/s",
-        "n_gpus": args.gpus, "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic",
-        "config": workload_config(args.gpus) | {"note": "CPU oracle port (oracle/mg_oracle.c, OpenMP); the reference itself is Python+numba and cannot travel to the GPU box"},
-        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                         "sample": sample},
-        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0},
+        "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * dt / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args.config, args.gpus),
+        "note": note,
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
+def workload_config(name, n_gpus):
+    c = CONFIGS[name]
     return {
-        "workload": "MultiGrid-Empty-8x8-v0 agents=4 view=7 num_envs=65536 per GPU, uniform random "
-                    "actions, next-step auto-reset (BASELINE.json configs[1]; configs[4] at 8 GPUs)",
-        "num_envs_per_gpu": ENVS_PER_GPU, "num_envs_total": ENVS_PER_GPU * n_gpus,
-        "agents": N_AGENTS, "view_size": VIEW, "grid": f"{SIZE}x{SIZE}", "max_steps": MAX_STEPS,
+        "workload": f"{c['env_id']} agents={c['agents']} view={c['view']} num_envs={c['envs']} per GPU, uniform random "
+                    f"actions, next-step auto-reset ({c['baseline']})",
+        "name": name, "num_envs_per_gpu": c["envs"], "num_envs_total": c["envs"] * n_gpus,
+        "agents": c["agents"], "view_size": c["view"], "grid": f"{c['W']}x{c['H']}", "max_steps": c["max_steps"],
         "sharding": f"env axis split over {n_gpus} GPU(s), no collective on the step path",
-        "l2": f"{REPLICAS} state replicas rotated (each launch touches a batch last used "
-              f"{REPLICAS} launches ago; {REPLICAS}x61 MB > 126 MB L2), no explicit flush; "
-              "MG_FLAG_STREAM_STATE (L2 evict_first on state loads / obs stores, cache policy only)",
-        "dedup": "single-layout dedup (MgState.grid_dirty / pool_rep): Empty-8x8 has ONE reset layout, so groups whose envs "
-                 "still equal it take their cells from an L2-resident 32-copy buffer instead of reading their 324-byte grid "
-                 "copies from HBM (the algorithmic 929 B per env-step still count the 192-byte grid read)",
-        "launches": "chained (MG_FLAG_CHAINED): each launch is ordered after the previous launch on the same replica env by "
-                    "env through chain tickets, not by a kernel-boundary barrier, so it loads while its predecessor drains; "
-                    "`unchained` in this line is the same graph with plain launches",
+        "l2": f"{REPLICAS} state replicas rotated (each launch touches a batch last used {REPLICAS} launches ago; "
+              f"{REPLICAS} x state+outputs > 126 MB L2), no explicit flush",
+        "launches": "plain (every launch waits for the whole previous launch), K of them in one CUDA graph",
     }
 
 
 # -------------------------------------------------------------------------------------------------
 # GPU side
 # -------------------------------------------------------------------------------------------------
+def bind_to_local_cpus(gpu_index):
+    """Best effort: run this rank's host-buffer leg on the CPUs next to its GPU (NVML's ideal CPU affinity), so that
+    pinned buffers allocated afterwards land on the GPU's NUMA node. A no-op when NVML or the cpuset says no."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def graph_of(stream, torch, fn, K):
+    with torch.cuda.stream(stream):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for k in range(K):
+                fn(k)
+        g.replay()  # untimed: the first replay of an instantiated graph also uploads it to the device
+    torch.cuda.synchronize()
+    return g
+
+
+def time_graph(stream, torch, g):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        g.replay()
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1)
+
+
+def verify_against_oracle(torch, eng, replay, launches_of_replica, tape, n_tape, M):
+    """Replays what the timed graph does to one state replica on the C oracle (first M envs) and compares the state
+    and the outputs of its last launch: the exact pattern that was timed (rotating replicas, graph, static / dedup /
+    streaming cache policy) against the checker. Outside every timed region. Returns a short report."""
+    from oracle import mg_oracle as O
+    from oracle.c_oracle import COracle
+    c = eng.cfg
+    ocfg = O.OracleConfig(W=c.width, H=c.height, n=c.num_agents, V=c.view_size, max_steps=c.max_steps,
+                          see_through_walls=c.see_through_walls, allow_agent_overlap=c.allow_agent_overlap,
+                          joint_reward=c.joint_reward, success_any=c.success_termination_mode == "any",
+                          failure_any=c.failure_termination_mode == "any", hook=c.hook, hook_param=c.hook_param,
+                          auto_reset=c.auto_reset, layout_stride=c.layout_stride)
+    torch.cuda.synchronize()
+    W, H = c.width, c.height
+    pool_cells = eng.pool_grid.cpu().numpy().view(np.uint32)
+    pool_grid = np.stack([pool_cells & 0xff, (pool_cells >> 8) & 0xff, (pool_cells >> 16) & 0xff], -1)[:, :W, :H].astype(np.int8)
+    ora = COracle(ocfg, eng.grid[:M].cpu().numpy(), eng.agents[:M].cpu().numpy(),
+                  eng.pcg_state[:M].cpu().numpy().view(np.uint64), eng.pcg_inc[:M].cpu().numpy().view(np.uint64),
+                  pool_grid=pool_grid, pool_agents=eng.pool_agents.cpu().numpy(),
+                  layout_idx=eng.layout_idx[:M].cpu().numpy(), step_count=eng.step_count[:M].cpu().numpy(),
+                  nthreads=len(os.sched_getaffinity(0)))
+    ora.hook_state[:] = eng.hook_state[:M].cpu().numpy()
+    replay()
+    torch.cuda.synchronize()
+    out = None
+    for k in launches_of_replica:
+        out = ora.step(tape[k % n_tape][:M].cpu().numpy())
+    V = c.view_size
+    checks = {
+        "grid": np.array_equal(eng.grid[:M].cpu().numpy(), ora.grid),
+        "agents": np.array_equal(eng.agents[:M].cpu().numpy(), ora.agents),
+        "step_count": np.array_equal(eng.step_count[:M].cpu().numpy(), ora.step_count),
+        "pcg_state": np.array_equal(eng.pcg_state[:M].cpu().numpy().view(np.uint64), ora.pcg_state),
+        "obs": np.array_equal(eng.obs[:M].cpu().numpy(), out[0]),
+        "reward": bool((eng.reward[:M].cpu().numpy() == out[1]).all()),
+        "terminated": np.array_equal(eng.terminated[:M].cpu().numpy(), out[2]),
+        "truncated": np.array_equal(eng.truncated[:M].cpu().numpy(), out[3]),
+    }
+    eng.check_status()
+    bad = [k for k, ok in checks.items() if not ok]
+    if bad:
+        raise AssertionError(f"bench verification failed: {bad} differ from the C oracle")
+    return {"envs": M, "steps": len(launches_of_replica), "compared": sorted(checks)}
+
+
 def run_engine(args):
     import torch
     import torch.distributed as dist
     from multigrid_b200 import _cabi
-    from multigrid_b200.engine import EngineConfig, StepEngine
+    from multigrid_b200.envs import make
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -245,29 +396,27 @@ def run_engine(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _cabi.load()
+    cfg = CONFIGS[args.config]
     K, Wm = args.steps, max(args.warmup, 3)
-    E, n = ENVS_PER_GPU, N_AGENTS
+    E, n = cfg["envs"], cfg["agents"]
 
-    cfg = EngineConfig(width=SIZE, height=SIZE, num_agents=n, view_size=VIEW, max_steps=MAX_STEPS,
-                       auto_reset=True, stream_state=True)
-    pg, pa = empty_layout(SIZE, n)
-    engines = []
+    # REPLICAS independent batches through the public API; seeds are a function of the global env id
+    envs = []
     for r in range(REPLICAS):
-        eng = StepEngine(cfg, E, dev, pg, pa)
-        first = (rank * REPLICAS + r) * E  # seeds are a function of the global env id
-        st, inc = pcg_words(first, E)
-        eng.load_state(pcg_state=st, pcg_inc=inc)
-        eng.reset_from_pool()  # every env starts from the (single) pool layout, like env.reset()
-        engines.append(eng)
+        env = make(cfg["env_id"], agents=n, agent_view_size=cfg["view"], num_envs=E, device=dev, auto_reset=True,
+                   first_env=(rank * REPLICAS + r) * E, layout_seed=7, stream_state=True)
+        env.reset(seed=2024)
+        envs.append(env)
+    engines = [env.engine for env in envs]
+    eng = engines[0]
+    static = bool(eng._static_ok())
 
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    n_tape = max(64, K)  # no action set is replayed inside the timed region (a short cycle keeps agents
-                         # near their start cells, which flatters the kernel by ~15 %)
+    n_tape = max(64, K)  # no action set is replayed inside the timed region (a short cycle keeps agents near
+                         # their start cells, which flatters the kernel)
     tape = torch.randint(0, 7, (n_tape, E, n), generator=gen, device=dev, dtype=torch.int32).to(torch.int8)
 
-    def launch(k, chained=True):
-        # MG_FLAG_CHAINED: consecutive launches are ordered per env by the engine's chain tickets instead of a
-        # kernel-boundary barrier (the action tape is staged before the timed region, nothing else runs on the stream)
+    def launch(k, chained=False):
         engines[k % REPLICAS].step(tape[k % n_tape], chained=chained)
 
     for k in range(BURN_IN):
@@ -277,72 +426,70 @@ def run_engine(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
 
-    # ---- `value`: K fused launches, inputs resident in HBM, captured in one CUDA graph --------
+    # ---- `value`: K plain fused launches, inputs resident in HBM, captured in one CUDA graph ----------
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):
         for k in range(Wm):
             launch(k)
         stream.synchronize()
-        before = lib.mg_launch_count()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            for k in range(K):
-                launch(Wm + k)
-        launches = lib.mg_launch_count() - before
-        graph.replay()  # untimed: the first replay of an instantiated graph also uploads it to the device
-    torch.cuda.synchronize()
+    before = lib.mg_launch_count()
+    graph = graph_of(stream, torch, lambda k: launch(Wm + k), K)
+    launches = (lib.mg_launch_count() - before)  # (capture issues each launch once)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev0.record(stream)
-        graph.replay()
-        ev1.record(stream)
-    torch.cuda.synchronize()
+    ms = time_graph(stream, torch, graph)
     if world > 1:
         dist.barrier()
-    ms = ev0.elapsed_time(ev1)
 
-    # ---- informational: the same K launches as PLAIN launches (every launch waits for the whole previous grid)
-    with torch.cuda.stream(stream):
-        graph2 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph2, stream=stream):
-            for k in range(K):
-                launch(Wm + k, chained=False)
-        graph2.replay()
-    torch.cuda.synchronize()
-    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(stream):
-        ev2.record(stream)
-        graph2.replay()
-        ev3.record(stream)
-    torch.cuda.synchronize()
-    ms2 = ev2.elapsed_time(ev3)
+    # ---- informational: closed loop on ONE batch (state + outputs stay in L2), and chained launches where the
+    # general kernel runs (MG_FLAG_CHAINED; the static-grid kernel has no chained form)
+    graph_cl = graph_of(stream, torch, lambda k: engines[0].step(tape[(Wm + k) % n_tape]), K)
+    ms_closed = time_graph(stream, torch, graph_cl)
+    ms_chained = None
+    if not static:
+        graph_ch = graph_of(stream, torch, lambda k: launch(Wm + k, chained=True), K)
+        ms_chained = time_graph(stream, torch, graph_ch)
 
-    # ---- `e2e`: the host-buffer call (mg_step_obs_host): H2D actions, kernel, D2H results -------
-    eng = engines[0]
-    h = eng.host_buffers()
+    # ---- verification of what was timed: two replicas of the timed graph against the C oracle -------
+    verified = None
+    if not args.no_verify and rank == 0:
+        verified = []
+        for r in (0, REPLICAS - 1):
+            ks = [Wm + k for k in range(K) if (Wm + k) % REPLICAS == r]
+            verified.append(dict(replica=r, **verify_against_oracle(
+                torch, engines[r], graph.replay, ks, tape, n_tape, min(VERIFY_ENVS, E))))
+
+    # ---- `e2e`: the host-buffer call: H2D actions from pinned memory, kernel, D2H results into pinned memory.
+    # Headline = mg_step_obs_host_packed (observations cross PCIe in the 9-bit-per-cell wire format, decoded on the
+    # host by engine.unpack_obs); the unpacked call (mg_step_obs_host, raw 3-byte cells) is timed beside it.
+    bind_to_local_cpus(local_rank)
     host_tape = tape[:8].cpu()
     K2 = max(3, min(K, 50))
-    for k in range(3):
-        h["actions"].copy_(host_tape[k % 8])
-        eng.step_host()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for k in range(K2):
-        h["actions"].copy_(host_tape[k % 8])  # the caller's actions land in the pinned buffer
-        eng.step_host(synchronize=True)       # results are in pinned host memory on return
-    e2e_s = time.perf_counter() - t0
-    checksum = int(h["obs"].view(torch.uint8).sum()) + float(h["reward"].sum())
 
-    # ---- informational: the public Python env API, eager (no graph), device-resident actions: one
-    # BatchedMultiGridEnv stepped back to back (its 61 MB of state + outputs stay L2-resident)
-    from multigrid_b200.envs import make
-    api_env = make("MultiGrid-Empty-8x8-v0", agents=n, num_envs=E, device=dev, auto_reset=True, first_env=rank * E)
-    api_env.reset(seed=1234)
+    def time_host(packed):
+        h = eng.host_buffers(packed)
+        for k in range(3):
+            h["actions"].copy_(host_tape[k % 8])
+            eng.step_host(packed=packed)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(K2):
+            h["actions"].copy_(host_tape[k % 8])          # the caller's actions land in the pinned buffer
+            eng.step_host(synchronize=True, packed=packed)  # results are in pinned host memory on return
+        return time.perf_counter() - t0, h
+
+    e2e_raw_s, h = time_host(False)
+    e2e_s, h = time_host(True)
+    from multigrid_b200.engine import unpack_obs
+    M = min(VERIFY_ENVS, E)  # the packed result decodes to exactly the device-side observations
+    assert np.array_equal(unpack_obs(h["obs_packed"][:M], cfg["view"]), eng.obs[:M].cpu().numpy()), "packed e2e obs mismatch"
+    checksum = int(h["obs_packed"].sum(dtype=torch.int64)) + float(h["reward"].sum())
+
+    # ---- informational: the public Python env API, eager (no graph), device-resident actions
+    api_env = envs[1]
     K3 = 2000
     for k in range(64):
         api_env.step(tape[k % n_tape])
@@ -354,61 +501,90 @@ def run_engine(args):
     api_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
-    t = torch.tensor([ms, e2e_s, ms2], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s, ms_closed, ms_chained or 0.0, clocks.get("sm_mhz") or 0.0, e2e_raw_s],
+                     dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        allr = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allr, t)
+        per_rank = torch.stack(allr).cpu().numpy()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_s, ms2 = float(t[0]), float(t[1]), float(t[2])
+    ms, e2e_s, ms_closed, ms_chained_max, e2e_raw_s = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[5])
 
     if rank == 0:
+        W, H, V = cfg["W"], cfg["H"], cfg["view"]
         total_envs = E * world
         value = total_envs * n * K / (ms * 1e-3)
-        bpe = algorithmic_bytes_per_env_step(SIZE, SIZE, n, VIEW)
+        bpe = algorithmic_bytes_per_env_step(W, H, n, V, cfg["mutable_grid"])
+        moved = moved_bytes_per_env_step(W, H, n, eng.obs_stride, static)
         peak, peak_src = hbm_peak()
-        achieved = bpe * E / (ms * 1e-3 / K) / 1e9  # per GPU: one launch = E envs
-        bytes_io = eng.bytes_per_step()
+        us = 1e3 * ms / K
+        achieved = bpe * E / us / 1e3  # GB/s per GPU: one launch = E env-steps
+        grid_read = 3 * W * H
+        traffic = ncu_traffic(args.config)
+        bytes_io, bytes_raw = eng.bytes_per_step(packed=True), eng.bytes_per_step(packed=False)
+        kernel = ("mg::static_fast_kernel / static_rolled_kernel (MG_FLAG_STATIC_GRID: memoised views + agent overlay)"
+                  if static else "mg::step_obs_kernel<V, MODE_STEP_OBS> (general kernel: per-env cells in shared memory)")
         line = {
             "metric": METRIC, "value": value, "unit": "agent-steps/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(args.config, world),
             "clocks": clocks,
             "e2e": {"value": total_envs * n * K2 / e2e_s, "unit": "agent-steps/s",
                     "h2d_bytes_per_step": bytes_io["h2d"], "d2h_bytes_per_step": bytes_io["d2h"],
-                    "steps": K2, "timing": "wall clock around mg_step_obs_host + stream sync per step",
+                    "steps": K2, "timing": "wall clock around mg_step_obs_host_packed + stream sync per step",
+                    "call": "mg_step_obs_host_packed: observations in the 9-bit-per-cell wire format (lossless; "
+                            "engine.unpack_obs decodes), rewards f64, terminated / truncated bytes",
+                    "pcie_gbs": (bytes_io["h2d"] + bytes_io["d2h"]) * K2 / e2e_s / 1e9 / world,
+                    "pcie_frac_of_64GBs": (bytes_io["h2d"] + bytes_io["d2h"]) * K2 / e2e_s / 1e9 / world / 64.0,
+                    "unpacked": {"value": total_envs * n * K2 / e2e_raw_s, "d2h_bytes_per_step": bytes_raw["d2h"],
+                                 "pcie_gbs": (bytes_raw["h2d"] + bytes_raw["d2h"]) * K2 / e2e_raw_s / 1e9 / world,
+                                 "call": "mg_step_obs_host (raw 3-byte cells)"},
+                    "cpu_affinity": sorted(os.sched_getaffinity(0))[:4] + ["..."] if len(os.sched_getaffinity(0)) > 4
+                                    else sorted(os.sched_getaffinity(0)),
                     "checksum": checksum},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                         "traffic_note": "ncu dram read+write bytes of one launch (profiles/r01j_ncu_details.txt); "
-                                         "outputs still dirty in L2 at kernel end are not in it; the grids come from the L2-resident layout buffer (dedup)",
-                         "algorithmic_bytes_per_launch": bpe * E, "peak_source": peak_src,
-                         "frac_of_8TBs_nominal": achieved / 8000.0,
-                         "algorithmic_bytes_per_env_step": bpe,
-                         "actual_bytes_per_env_step": layout_bytes_per_env_step(SIZE, SIZE, n, VIEW),
-                         "kernel": "mg::step_obs_kernel<7, MODE_STEP_OBS, MULTI=false, CHAIN=true> (one launch = 65536 env-steps)",
-                         "launch_time_note": "avg_launch_us = timed region / launches; chained launches overlap (a launch "
-                                             "loads while its predecessor drains), so this is the throughput time per "
-                                             "launch, not the latency of one launch (see `unchained`)",
-                         "avg_launch_us": 1e3 * ms / K},
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None if traffic is None else traffic.get("dram_bytes_per_launch"),
+                "traffic_source": None if traffic is None else traffic.get("source"),
+                "peak_source": peak_src, "frac_of_8TBs_nominal": achieved / 8000.0,
+                "plain_us": us, "plain_frac": achieved / peak,
+                "launches": "plain: `value`, `achieved` and `frac` are all measured with plain launches",
+                "algorithmic_bytes_per_env_step": bpe, "algorithmic_bytes_per_launch": bpe * E,
+                # the static-grid kernel (and the single-layout dedup before it) does not read the env's grid from
+                # HBM at all: the same launch time against the algorithmic bytes WITHOUT that read
+                "frac_excluding_dedup": ((bpe - grid_read) if static else bpe) * E / us / 1e3 / peak,
+                "moved_bytes_per_env_step": moved, "moved_gbs": moved * E / us / 1e3,
+                "frac_moved": moved * E / us / 1e3 / peak,
+                "kernel": kernel, "static_grid_path": static, "obs_agent_stride": eng.obs_stride,
+            },
+            "closed_loop": {
+                "note": "informational: the same K plain launches on ONE batch stepped back to back (its state and "
+                        "outputs stay in L2; what a closed-loop caller with a device-side policy sees)",
+                "us_per_launch": 1e3 * ms_closed / K, "value": total_envs * n * K / (ms_closed * 1e-3)},
+            "api_device_resident": {
+                "note": "informational: env.step(actions_on_device) of the public Python API, eager launches, per-agent "
+                        "dict results left on the device, one batch stepped back to back, this rank",
+                "us_per_step": 1e6 * api_s / K3, "value": E * n * K3 / api_s, "steps": K3},
+            "verified": verified,
         }
-        line["unchained"] = {
-            "note": "informational: the same K launches as plain launches (kernel-boundary barrier between them)",
-            "us_per_launch": 1e3 * ms2 / K, "value": total_envs * n * K / (ms2 * 1e-3),
-            "achieved_gbs": bpe * E / (ms2 * 1e-3 / K) / 1e9}
-        line["api_device_resident"] = {
-            "note": "informational: env.step(actions_on_device) of the public Python API, eager launches, per-agent "
-                    "dict results left on the device, one batch stepped back to back (state stays in L2), this rank",
-            "us_per_step": 1e6 * api_s / K3, "value": E * n * K3 / api_s, "steps": K3}
+        if ms_chained is not None:
+            line["chained"] = {
+                "note": "informational: the same K launches with MG_FLAG_CHAINED (per-env tickets instead of the "
+                        "kernel-boundary barrier; pays only across DIFFERENT batches, as here)",
+                "us_per_launch": 1e3 * ms_chained_max / K, "value": total_envs * n * K / (ms_chained_max * 1e-3),
+                "achieved_gbs": bpe * E / (1e3 * ms_chained_max / K) / 1e3}
+        if per_rank is not None:
+            line["per_rank"] = {"graph_ms": [float(v) for v in per_rank[:, 0]], "e2e_s": [float(v) for v in per_rank[:, 1]],
+                                "sm_mhz": [float(v) for v in per_rank[:, 4]],
+                                "note": "value uses the slowest rank's graph time (max over ranks)"}
         if world == 1 and not args.no_cpu_baseline:
-            cores = len(os.sched_getaffinity(0))
-            v, done, dt = time_cpu_oracle(E, 10**9, 2, cores, budget_s=args.cpu_seconds)
-            v1, done1, dt1 = time_cpu_oracle(4096, 10**9, 2, 1, budget_s=3.0)
-            line["cpu_baseline"] = {
-                "value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                "sample": f"{done} steps x {E} envs of the same workload ({dt:.1f} s), C oracle "
-                          f"port with OpenMP; 1 thread: {v1:.3g} agent-steps/s"}
+            line["cpu_baseline"] = cpu_baseline(cfg, args.cpu_seconds)
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -418,8 +594,10 @@ def main():
     ap.add_argument("--steps", type=int, default=512)
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--config", default="empty8", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

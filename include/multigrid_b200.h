@@ -353,6 +353,27 @@ int mg_step_obs_host(const MgConfig *cfg, int64_t num_envs, const MgState *state
                      const int8_t *h_actions, int8_t *d_actions, const MgStepOut *d_out,
                      const MgStepOut *h_out, void *stream);
 
+/*
+ * Compact wire format for host consumers. The host-buffer path is bound by PCIe, and 99 % of its bytes are
+ * observations (148 of 157 bytes per agent and step for V = 7). Every cell -- type < 16, colour < 8, state < 4
+ * (core/constants.py:34-97; an agent cell is (10, colour, dir)) -- becomes the 9-bit code
+ * type | colour << 4 | state << 7; the V*V codes of an agent are packed little-endian, cell (a, b) of image[a][b]
+ * at bits [9*(a*V + b), +9) of its mg_packed_obs_stride(V)-byte record (56 bytes for V = 7, 96 for V = 9; the
+ * record is a whole number of 8-byte words, unused bits are zero). Lossless.
+ *   mg_pack_obs              obs int8 [A][obs_agent_stride] (device, 16-byte aligned) -> packed uint8 [A][stride]
+ *   mg_step_obs_host_packed  mg_step_obs_host whose h_out->obs receives the PACKED observations (d_packed: device
+ *                            scratch of num_envs * n * mg_packed_obs_stride(V) bytes); reward / terminated / truncated
+ *                            as in mg_step_obs_host.
+ * Replaces nothing in the reference (its observations never leave the host); it is the transport encoding of
+ * MultiGridEnv.step's `image` observations (base.py:370) for a CPU-side consumer of a GPU-resident batch.
+ */
+int32_t mg_packed_obs_stride(int32_t view_size);
+int mg_pack_obs(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
+                uint8_t *packed, void *stream);
+int mg_step_obs_host_packed(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *h_actions,
+                            int8_t *d_actions, const MgStepOut *d_out, uint8_t *d_packed, const MgStepOut *h_out,
+                            void *stream);
+
 #ifdef __cplusplus
 }
 #endif

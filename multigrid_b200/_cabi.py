@@ -97,6 +97,10 @@ EXPORTS = {
     "mg_rollout": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.c_int32, C.POINTER(MgState), C.c_void_p,
                              C.POINTER(MgRolloutOut), C.c_void_p]),
     "mg_reset_where": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p, C.c_void_p]),
+    "mg_packed_obs_stride": (C.c_int32, [C.c_int32]),
+    "mg_pack_obs": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mg_step_obs_host_packed": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p, C.c_void_p,
+                                          C.POINTER(MgStepOut), C.c_void_p, C.POINTER(MgStepOut), C.c_void_p]),
     "mg_step_obs_host": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p,
                                    C.c_void_p, C.POINTER(MgStepOut), C.POINTER(MgStepOut),
                                    C.c_void_p]),

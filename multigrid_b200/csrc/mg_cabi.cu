@@ -538,4 +538,45 @@ int mg_step_obs_host(const MgConfig *cfg, int64_t num_envs, const MgState *state
     return 0;
 }
 
+int32_t mg_packed_obs_stride(int32_t view_size) { return mg::packed_obs_stride(view_size); }
+
+int mg_pack_obs(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
+                uint8_t *packed, void *stream) {
+    if (view_size < 3 || view_size > MG_MAX_VIEW || num_agents_total < 0 || (obs_agent_stride & 3) ||
+        obs_agent_stride < 3 * view_size * view_size) return MG_ERR_BAD_ARG;
+    if (num_agents_total == 0) return 0;
+    if (!obs || !packed) return MG_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(packed) & 7u) || (reinterpret_cast<uintptr_t>(obs) & 15u)) return MG_ERR_ALIGNMENT;
+    const unsigned blocks = (unsigned)((num_agents_total + 127) / 128);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (view_size == 7) mg::pack_obs_kernel<7><<<blocks, 128, 0, s>>>(7, num_agents_total, obs_agent_stride, obs, packed);
+    else if (view_size == 9) mg::pack_obs_kernel<9><<<blocks, 128, 0, s>>>(9, num_agents_total, obs_agent_stride, obs, packed);
+    else mg::pack_obs_kernel<0><<<blocks, 128, 0, s>>>(view_size, num_agents_total, obs_agent_stride, obs, packed);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int mg_step_obs_host_packed(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *h_actions,
+                            int8_t *d_actions, const MgStepOut *d_out, uint8_t *d_packed, const MgStepOut *h_out,
+                            void *stream) {
+    int rc = validate(cfg, num_envs);
+    if (rc) return rc;
+    if (!h_actions || !d_actions || !d_out || !d_packed || !h_out || !h_out->obs || !h_out->reward ||
+        !h_out->terminated || !h_out->truncated) return MG_ERR_BAD_ARG;
+    if (num_envs == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t E = (size_t)num_envs, n = (size_t)cfg->num_agents;
+    cudaError_t err = cudaMemcpyAsync(d_actions, h_actions, E * n, cudaMemcpyHostToDevice, s);
+    if (err != cudaSuccess) return (int)err;
+    rc = step_common<mg::MODE_STEP_OBS>(cfg, num_envs, state, d_actions, d_out, stream);
+    if (rc) return rc;
+    if ((rc = mg_pack_obs(cfg->view_size, (int64_t)(E * n), cfg->obs_agent_stride, d_out->obs, d_packed, stream))) return rc;
+    const size_t pbytes = E * n * (size_t)mg::packed_obs_stride(cfg->view_size);
+    if ((err = cudaMemcpyAsync(h_out->obs, d_packed, pbytes, cudaMemcpyDeviceToHost, s))) return (int)err;
+    if ((err = cudaMemcpyAsync(h_out->reward, d_out->reward, E * n * sizeof(double), cudaMemcpyDeviceToHost, s))) return (int)err;
+    if ((err = cudaMemcpyAsync(h_out->terminated, d_out->terminated, E * n, cudaMemcpyDeviceToHost, s))) return (int)err;
+    if ((err = cudaMemcpyAsync(h_out->truncated, d_out->truncated, E, cudaMemcpyDeviceToHost, s))) return (int)err;
+    return 0;
+}
+
 }  // extern "C"

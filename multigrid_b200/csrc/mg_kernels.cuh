@@ -1710,6 +1710,72 @@ __global__ void __launch_bounds__(256) obs_features_kernel(int V, int64_t agents
     }
 }
 
+#endif
+// Compact wire format of an observation batch for HOST consumers (PCIe is what bounds the host-buffer path:
+// 148 bytes per agent and step for V = 7). Every cell (type < 16, colour < 8, state < 4: core/constants.py:34-97)
+// becomes the 9-bit code type | colour << 4 | state << 7; the V*V codes of an agent are packed little-endian,
+// cell a*V+b at bits [9*(a*V+b), +9), into mg_packed_obs_stride(V) bytes (56 for V = 7, 96 for V = 9).
+// Lossless: multigrid_b200.engine.unpack_obs restores image[V][V][3]. One thread per agent.
+MG_HD int packed_obs_stride(int V) { return ((9 * V * V + 63) / 64) * 8; }
+
+#ifdef __CUDACC__
+template <int VT>
+__global__ void __launch_bounds__(128) pack_obs_kernel(int Vr, int64_t agents, int ostride, const int8_t *__restrict__ obs,
+                                                       uint8_t *__restrict__ packed) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= agents) return;
+    const int V = VT ? VT : Vr, NC = V * V, pstride = packed_obs_stride(V);
+    const uint8_t *src = (const uint8_t *)obs + a * ostride;
+    uint64_t *dst = (uint64_t *)(packed + a * pstride);
+    uint64_t acc = 0;
+    int bits = 0, w = 0;
+    if constexpr (VT != 0) {
+        constexpr int NW = (3 * VT * VT + 3) / 4;
+        uint32_t r[NW];
+        if ((ostride & 15) == 0) {  // 16-byte slots: vector loads
+#pragma unroll
+            for (int q = 0; q < (NW + 3) / 4; q++) {
+                const uint4 v = *(const uint4 *)(src + 16 * q);
+                if (4 * q + 0 < NW) r[4 * q + 0] = v.x;
+                if (4 * q + 1 < NW) r[4 * q + 1] = v.y;
+                if (4 * q + 2 < NW) r[4 * q + 2] = v.z;
+                if (4 * q + 3 < NW) r[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NW; q++) r[q] = *(const uint32_t *)(src + 4 * q);
+        }
+#pragma unroll
+        for (int c = 0; c < VT * VT; c++) {
+            const int b0 = 3 * c, b1 = 3 * c + 1, b2 = 3 * c + 2;
+            const uint32_t t = (r[b0 >> 2] >> (8 * (b0 & 3))) & 0xff, col = (r[b1 >> 2] >> (8 * (b1 & 3))) & 0xff,
+                           st = (r[b2 >> 2] >> (8 * (b2 & 3))) & 0xff;
+            acc |= (uint64_t)((t & 15u) | ((col & 7u) << 4) | ((st & 3u) << 7)) << bits;
+            bits += 9;
+            if (bits >= 64) {
+                dst[w++] = acc;
+                bits -= 64;
+                acc = (uint64_t)((t & 15u) | ((col & 7u) << 4) | ((st & 3u) << 7)) >> (9 - bits);
+            }
+        }
+    } else {
+        for (int c = 0; c < NC; c++) {
+            const uint32_t code = (src[3 * c] & 15u) | ((src[3 * c + 1] & 7u) << 4) | ((src[3 * c + 2] & 3u) << 7);
+            acc |= (uint64_t)code << bits;
+            bits += 9;
+            if (bits >= 64) {
+                dst[w++] = acc;
+                bits -= 64;
+                acc = (uint64_t)code >> (9 - bits);
+            }
+        }
+    }
+    if (bits > 0) dst[w++] = acc;
+    for (; w * 8 < pstride; w++) dst[w] = 0;
+}
+#endif
+
+#ifdef __CUDACC__
 // MULTI = mg_rollout (p.T steps per launch); the single-step kernels compile with T == 1 and no loop.
 // Same result, 16 output bytes per thread (one 128-bit store): the 16 bytes [p0, p0+16) of the flat
 // [A][V][V][21] stream lie in at most two consecutive cells, i.e. hold at most six 1-bytes; each is

@@ -81,6 +81,34 @@ def static_layout_ok(pool_grid, pool_agents) -> bool:
     return bool((g[0, x, y, 0] != 2).all())
 
 
+def packed_obs_stride(view_size: int) -> int:
+    """Bytes per agent of the packed wire format (mg_packed_obs_stride): 9 bits per cell, whole 8-byte words."""
+    return ((9 * view_size * view_size + 63) // 64) * 8
+
+
+def unpack_obs(packed, view_size: int) -> np.ndarray:
+    """Decoder of the packed observation wire format (include/multigrid_b200.h, mg_pack_obs): uint8 [..., stride]
+    -> int8 image [..., V, V, 3]. Cell (a, b) is the 9-bit code type | colour << 4 | state << 7 at bits
+    [9*(a*V + b), +9) of the agent's little-endian record. Host-side numpy; torch tensors are accepted."""
+    if isinstance(packed, torch.Tensor):
+        packed = packed.cpu().numpy()
+    V = int(view_size)
+    p = np.ascontiguousarray(packed, dtype=np.uint8)
+    assert p.shape[-1] == packed_obs_stride(V), (p.shape, V)
+    words = p.view("<u8")                                   # [..., stride / 8]
+    off = 9 * np.arange(V * V, dtype=np.int64)
+    lo, sh = off // 64, (off % 64).astype(np.uint64)
+    code = words[..., lo] >> sh
+    spill = sh > np.uint64(55)                               # the code continues in the next word
+    hi = np.minimum(lo + 1, words.shape[-1] - 1)
+    code = np.where(spill, code | (words[..., hi] << ((np.uint64(64) - sh) & np.uint64(63))), code) & np.uint64(0x1ff)
+    out = np.empty(code.shape + (3,), np.int8)
+    out[..., 0] = code & np.uint64(15)
+    out[..., 1] = (code >> np.uint64(4)) & np.uint64(7)
+    out[..., 2] = code >> np.uint64(7)
+    return out.reshape(code.shape[:-1] + (V, V, 3))
+
+
 def _as_i64_bits(a) -> np.ndarray:
     """uint64 words -> int64 with the same bits (torch has no general uint64 support)."""
     return np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)
@@ -543,33 +571,47 @@ class StepEngine:
                                                  self._stream()), "mg_obs_features")
         return out
 
-    def host_buffers(self):
-        """Pinned host mirrors used by `step_host` (allocated on first use)."""
+    def host_buffers(self, packed: bool = False):
+        """Pinned host mirrors used by `step_host` (allocated on first use). packed=True adds `obs_packed`
+        (E, n, packed_obs_stride(V)) uint8, the compact wire format of the observations (see unpack_obs)."""
+        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
         if self._host is None:
-            pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
-            self._host = dict(actions=pin(self.actions), obs=pin(self.obs_buf),
-                              reward=pin(self.reward), terminated=pin(self.terminated),
+            self._host = dict(actions=pin(self.actions), reward=pin(self.reward), terminated=pin(self.terminated),
                               truncated=pin(self.truncated))
+        if packed and "obs_packed" not in self._host:
+            ps = packed_obs_stride(self.cfg.view_size)
+            self._packed = torch.zeros((self.num_envs, self.cfg.num_agents, ps), dtype=torch.uint8, device=self.device)
+            self._host["obs_packed"] = pin(self._packed)
+        if not packed and "obs" not in self._host:
+            self._host["obs"] = pin(self.obs_buf)
         return self._host
 
-    def step_host(self, synchronize: bool = True):
+    def step_host(self, synchronize: bool = True, packed: bool = False):
         """mg_step_obs_host: actions come from, and results go to, pinned HOST buffers.
 
         Fill `host_buffers()['actions']` first. This is the end-to-end path a CPU-side caller of
         `env.step()` sees: H2D actions + kernel + D2H (obs, reward, terminated, truncated).
+        packed=True (mg_step_obs_host_packed): the observations cross PCIe in the 9-bit-per-cell wire format
+        (`obs_packed`, 56 instead of 148+ bytes per agent for V = 7; `unpack_obs` decodes it), everything else
+        is unchanged.
         """
         self._chain_armed = None
-        h = self.host_buffers()
+        h = self.host_buffers(packed)
         c, st, out = self._structs()
         if self._static_state is not False and self._static_ok():
             c = self._static_cfg[0]
-        hout = _cabi.MgStepOut(h["obs"].data_ptr(), h["reward"].data_ptr(),
+        hout = _cabi.MgStepOut(h["obs_packed" if packed else "obs"].data_ptr(), h["reward"].data_ptr(),
                                h["terminated"].data_ptr(), h["truncated"].data_ptr(), None)
         with torch.cuda.device(self.device):
-            _cabi.check(self.lib.mg_step_obs_host(
-                C.byref(c), self.num_envs, C.byref(st), h["actions"].data_ptr(),
-                self.actions.data_ptr(), C.byref(out), C.byref(hout), self._stream()),
-                "mg_step_obs_host")
+            if packed:
+                _cabi.check(self.lib.mg_step_obs_host_packed(
+                    C.byref(c), self.num_envs, C.byref(st), h["actions"].data_ptr(), self.actions.data_ptr(),
+                    C.byref(out), self._packed.data_ptr(), C.byref(hout), self._stream()), "mg_step_obs_host_packed")
+            else:
+                _cabi.check(self.lib.mg_step_obs_host(
+                    C.byref(c), self.num_envs, C.byref(st), h["actions"].data_ptr(),
+                    self.actions.data_ptr(), C.byref(out), C.byref(hout), self._stream()),
+                    "mg_step_obs_host")
             if synchronize:
                 torch.cuda.current_stream(self.device).synchronize()
         return h
@@ -583,7 +625,8 @@ class StepEngine:
                 raise RuntimeError("MG_FLAG_STATIC_GRID promise violated: an agent left the grid or carries an object")
             raise ValueError("Unknown action")
 
-    def bytes_per_step(self) -> dict:
+    def bytes_per_step(self, packed: bool = False) -> dict:
         """h2d / d2h bytes of one `step_host` call."""
         E, n = self.num_envs, self.cfg.num_agents
-        return dict(h2d=E * n, d2h=E * n * self.obs_stride + E * n * 8 + E * n + E)
+        obs = packed_obs_stride(self.cfg.view_size) if packed else self.obs_stride
+        return dict(h2d=E * n, d2h=E * n * obs + E * n * 8 + E * n + E)

@@ -239,7 +239,8 @@ class BatchedMultiGridEnv:
                  joint_reward: bool = False, success_termination_mode: str = "any",
                  failure_termination_mode: str = "all", auto_reset: bool = False,
                  pool_size: int | None = None, layout_seed: int | None = None,
-                 first_env: int = 0, render_mode: str | None = None, device_layouts: bool = True):
+                 first_env: int = 0, render_mode: str | None = None, device_layouts: bool = True,
+                 stream_state: bool = False):
         if render_mode is not None:
             raise NotImplementedError("rendering is out of scope of the batched engine")
         self.layout = layout
@@ -266,7 +267,8 @@ class BatchedMultiGridEnv:
             see_through_walls=see_through_walls, allow_agent_overlap=allow_agent_overlap,
             joint_reward=joint_reward, success_termination_mode=success_termination_mode,
             failure_termination_mode=failure_termination_mode, hook=layout.hook,
-            hook_param=getattr(layout, "hook_param", 0), auto_reset=auto_reset)
+            hook_param=getattr(layout, "hook_param", 0), auto_reset=auto_reset,
+            stream_state=stream_state)  # (cache policy only, see EngineConfig.stream_state)
         self.engine = StepEngine(cfg, self.num_envs, device)
         self.device = self.engine.device
         self.grid = BatchedGrid(self.engine)
