@@ -67,9 +67,9 @@ int plan(mg::Params &p) {
     return mg::plan_launch(p, env_int("MG_GROUP", 0, k), env_int("MG_WPB", 0, k), kSmemPerBlock - 16 /* the claim counter */, kSmemPerSM, n_sm);
 }
 
-template <int VT, int MODE, bool MULTI = false, bool CHAIN = false>
+template <int VT, int MODE, bool MULTI = false, bool CHAIN = false, int NT = 0, int HK = -1>
 int launch(const mg::Params &p, cudaStream_t stream) {
-    auto kernel = mg::step_obs_kernel<VT, MODE, MULTI, CHAIN>;
+    auto kernel = mg::step_obs_kernel<VT, MODE, MULTI, CHAIN, NT, HK>;
     static thread_local bool configured_dev[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -114,6 +114,11 @@ int dispatch(const mg::Params &p, cudaStream_t stream) {
                 }
                 return launch<0, MODE, false, true>(p, stream);
             }
+        }
+        if constexpr (MODE == mg::MODE_STEP_OBS && !MULTI) {
+            // BASELINE configs[2] (BlockedUnlockPickup, 2 agents, view 7): agent count and hook compiled in
+            if (!p.generic_view && p.V == 7 && p.n == 2 && p.hook == MG_HOOK_BLOCKED_UNLOCK_PICKUP)
+                return launch<7, MODE, false, false, 2, MG_HOOK_BLOCKED_UNLOCK_PICKUP>(p, stream);
         }
         if (!p.generic_view) {
             switch (p.V) {

@@ -1819,8 +1819,14 @@ __global__ void __launch_bounds__(256) one_hot_kernel_v16(int V, int64_t agents,
 }
 
 // CHAIN = the launch takes part in the chain tickets (MG_FLAG_CHAINED); plain launches compile without them.
-template <int VT, int MODE, bool MULTI = false, bool CHAIN = false>
-__global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __grid_constant__ Params p) {
+// NT / HK: the agent count and the post-hook as compile-time constants (0 / -1 = read them from Params). The phase
+// functions take `p.n` and `p.hook` from a kernel-local copy of Params whose two fields are overwritten with the
+// constants, so after inlining the agent loops unroll and the other env classes' hooks disappear from the hot path.
+template <int VT, int MODE, bool MULTI = false, bool CHAIN = false, int NT = 0, int HK = -1>
+__global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __grid_constant__ Params p_in) {
+    Params p = p_in;
+    if (NT > 0) { p.n = NT; p.rcp_n = NT <= 1 ? 0u : (uint32_t)((1ull << 32) / (uint32_t)NT + 1ull); }
+    if (HK >= 0) p.hook = HK;
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int group = blockIdx.x * p.wpb + warp;

@@ -11,6 +11,7 @@ constructing a StepEngine raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -343,6 +344,8 @@ class StepEngine:
         self.static_obs, self._static_state = None, False
         cfg = self.cfg
         if self.pool_grid is None or self.pool_grid.shape[0] != 1 or cfg.hook != _cabi.HOOK_NONE:
+            return
+        if os.environ.get("MG_NO_STATIC") == "1":  # knob (comparisons): never build the table, general kernel only
             return
         W, H = cfg.width, cfg.height
         cells = self.pool_grid.cpu().numpy().view(np.uint32)

@@ -72,8 +72,8 @@ def main():
     ks = [k for k in sass_rows(args.rep) if args.kernel in k["name"]]
     k = ks[args.index]
     print("kernel:", k["name"], " SASS rows:", len(k["rows"]))
-    m = re.findall(r"\(int\)(\d+)", k["name"])
-    pat = args.mangled or (f"{args.kernel}I" + "".join(f"Li{v}E" for v in m) + "E" if m else args.kernel)
+    m = re.findall(r"\((int|bool)\)(\d+)", k["name"])
+    pat = args.mangled or (f"{args.kernel}I" + "".join(f"L{'i' if t == 'int' else 'b'}{v}E" for t, v in m) + "E" if m else args.kernel)
     lm = line_map(args.so, pat)
     assert len(lm) == 1, list(lm)
     lm = next(iter(lm.values()))
