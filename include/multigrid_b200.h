@@ -250,6 +250,10 @@ int mg_full_obs(int32_t width, int32_t height, int32_t num_agents, int64_t num_e
 #define MG_ONE_HOT_CHANNELS 21
 int mg_one_hot(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
                uint8_t *out, void *stream);
+/* The same encoding for images of any cell count (e.g. FullyObsWrapper's W*H-cell grids under OneHotObsWrapper):
+ * images int8 [num_images][image_stride] with 3 bytes per cell -> out uint8 [num_images][cells_per_image][21]. */
+int mg_one_hot_cells(int64_t cells_per_image, int64_t num_images, int32_t image_stride, const int8_t *images,
+                     uint8_t *out, void *stream);
 
 /*
  * Network input of the reference's training script in one pass from the observations: out float32

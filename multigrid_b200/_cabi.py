@@ -79,6 +79,7 @@ EXPORTS = {
     "mg_full_obs": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]),
     "mg_one_hot": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mg_one_hot_cells": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_gen_layouts_empty_random": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_gen_layouts_red_blue_doors": (C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 7),

@@ -326,24 +326,34 @@ int mg_full_obs(int32_t width, int32_t height, int32_t num_agents, int64_t num_e
     return (int)cudaGetLastError();
 }
 
-int mg_one_hot(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
-               uint8_t *out, void *stream) {
-    if (view_size < 3 || view_size > MG_MAX_VIEW || num_agents_total < 0 ||
-        obs_agent_stride < 3 * view_size * view_size) return MG_ERR_BAD_ARG;
-    if (num_agents_total == 0) return 0;
+// One-hot of `images` images of `cells` cells each (3 bytes per cell, `stride` bytes apart).
+static int one_hot_cells(int64_t cells, int64_t images, int32_t stride, const int8_t *obs, uint8_t *out, void *stream) {
+    if (cells < 1 || cells > 127 * 127 || images < 0 || stride < 3 * cells) return MG_ERR_BAD_ARG;
+    if (images == 0) return 0;
     if (!obs || !out) return MG_ERR_BAD_ARG;
     if (reinterpret_cast<uintptr_t>(out) & 3u) return MG_ERR_ALIGNMENT;
-    if ((reinterpret_cast<uintptr_t>(out) & 15u) == 0 && !env_int("MG_ONE_HOT_W32", 0)) {
-        mg::one_hot_kernel_v16<<<(unsigned)((num_agents_total + 15) / 16), 256, 0, (cudaStream_t)stream>>>(
-            view_size, num_agents_total, obs_agent_stride, mg::rcp32(view_size * view_size), obs, (uint4 *)out);
+    // the 16-byte kernel needs 16-byte aligned blocks of 16 images: cells * 21 * 16 bytes each, always a multiple of 16
+    if ((reinterpret_cast<uintptr_t>(out) & 15u) == 0 && cells <= 1024 && !env_int("MG_ONE_HOT_W32", 0)) {
+        mg::one_hot_kernel_v16<<<(unsigned)((images + 15) / 16), 256, 0, (cudaStream_t)stream>>>(
+            (int)cells, images, stride, mg::rcp32((int)cells), obs, (uint4 *)out);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return (int)cudaGetLastError();
     }
-    const int64_t words = (num_agents_total * view_size * view_size * 21 + 3) / 4;
-    mg::one_hot_kernel<<<(unsigned)((words + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        view_size, num_agents_total, obs_agent_stride, obs, out);
+    const int64_t words = (images * cells * 21 + 3) / 4;
+    mg::one_hot_kernel<<<(unsigned)((words + 255) / 256), 256, 0, (cudaStream_t)stream>>>((int)cells, images, stride, obs, out);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
+}
+
+int mg_one_hot(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
+               uint8_t *out, void *stream) {
+    if (view_size < 3 || view_size > MG_MAX_VIEW) return MG_ERR_BAD_ARG;
+    return one_hot_cells((int64_t)view_size * view_size, num_agents_total, obs_agent_stride, obs, out, stream);
+}
+
+int mg_one_hot_cells(int64_t cells_per_image, int64_t num_images, int32_t image_stride, const int8_t *images,
+                     uint8_t *out, void *stream) {
+    return one_hot_cells(cells_per_image, num_images, image_stride, images, out, stream);
 }
 
 int mg_gen_layouts_empty_random(int32_t width, int32_t height, int32_t num_agents, int64_t num_layouts,

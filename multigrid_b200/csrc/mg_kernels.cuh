@@ -718,17 +718,16 @@ MG_HD Group group_view(const Params &p, uint8_t *ws, int group) {
     return g;
 }
 
-// The per-env phases (reset decision, transition) run one lane per env. With G = 16 the upper half
-// warp SHADOWS the lower half on the GPU: lane l and lane l+16 do identical work on identical data
-// (duplicate stores of identical values), so the warp never splits into two half-warps that would
-// then run the observation phase twice at half width. The host simulator runs lanes one after the
-// other, so there only lanes < G act.
+// The per-env phases (reset decision, transition) run one lane per env: lanes >= G (G = 16 or 8) sit them out
+// and rejoin at the __syncwarp that ends the phase. (Round 1 let them SHADOW the lower lanes -- same work on the
+// same shared-memory words -- which compute-sanitizer racecheck rightly reports as intra-warp hazards. Without
+// the shadows the hardware keeps the two halves of a G = 16 warp apart for the rest of the kernel, i.e. the
+// observation passes issue twice at half width: 16.5 -> 23.4 us on a 65 536-env 4-agent batch that takes this
+// kernel, no change for 2-agent batches such as BlockedUnlockPickup. Neither an explicit bar.warp.sync nor hiding
+// the branch condition from the compiler brings them back together; grids no action can change -- the Empty
+// family -- take the static-grid kernel of mg_static.cuh, which has a single divergent region and reconverges.)
 MG_HD int lane_env(const Params &p, const Group &g, int lane) {
-#ifdef __CUDA_ARCH__
-    const int i = lane & (p.G - 1);
-#else
     const int i = lane < p.G ? lane : p.G;
-#endif
     return i < g.ne ? i : -1;
 }
 
@@ -1359,15 +1358,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    // (a C++ loop around try_wait, not a branch inside the asm: with asm-level branches the compiler no longer
+    // knows the control flow and stops marking the regions that follow as reconvergent)
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
 }
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -1640,9 +1641,9 @@ __global__ void full_obs_kernel(int W, int H, int n, int64_t total, const uint32
 // OneHotObsWrapper.one_hot (multigrid/wrappers.py:158-190) over a whole observation batch:
 // image (type,color,state) -> 21 channels = 11 type + 6 colour + 4 state/direction, uint8.
 // The output [agents][V][V][21] is written as one flat stream of 32-bit words (4 channels each).
-__global__ void one_hot_kernel(int V, int64_t agents, int ostride, const int8_t *__restrict__ obs,
+__global__ void one_hot_kernel(int cells, int64_t agents, int ostride, const int8_t *__restrict__ obs,
                                uint8_t *__restrict__ out) {
-    const int64_t per_agent = (int64_t)V * V * 21, total = agents * per_agent;
+    const int64_t per_agent = (int64_t)cells * 21, total = agents * per_agent;
     const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, p0 = 4 * w;
     if (p0 >= total) return;
     uint32_t word = 0;
@@ -1782,9 +1783,9 @@ __global__ void __launch_bounds__(128) pack_obs_kernel(int Vr, int64_t agents, i
 // placed with one shift into a 16-bit mask that a multiply spreads into bytes. The output is 7x the
 // observation (270 MB for the 65 536 x 4 x 7 x 7 bench batch): HBM writes are the floor.
 // One block = 16 consecutive agents = VV*21 16-byte vectors: every index below is a small 32-bit number.
-__global__ void __launch_bounds__(256) one_hot_kernel_v16(int V, int64_t agents, int ostride, uint32_t rcp_vv,
+__global__ void __launch_bounds__(256) one_hot_kernel_v16(int cells, int64_t agents, int ostride, uint32_t rcp_vv,
                                                           const int8_t *__restrict__ obs, uint4 *__restrict__ out) {
-    const uint32_t VV = (uint32_t)(V * V), nvec = VV * 21u;          // vectors per full block
+    const uint32_t VV = (uint32_t)cells, nvec = VV * 21u;            // vectors per full block
     const int64_t a0 = (int64_t)blockIdx.x * 16;
     const uint32_t na = (uint32_t)(agents - a0 < 16 ? agents - a0 : 16);
     const uint32_t nbytes = na * VV * 21u;                            // bytes of this block (tail block: fewer)
@@ -1894,13 +1895,13 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
         }
         if (dedup) {  // one flag per env decides where the group's cells come from
             const bool env_dirty = tickets ? rec_dirty : (env >= 0 && p.chain[4 * (size_t)(g.e0 + env) + 2] != 0);
-            dirty_mask = __ballot_sync(0xffffffffu, env_dirty);  // (bit i = env i; shadow lanes repeat the flags)
+            dirty_mask = __ballot_sync(0xffffffffu, env_dirty);  // (bit i = env i)
             if (lane == 0) load_bulk<MODE>(p, g, bar, t, dirty_mask ? 3 : 2);
         }
         if (tickets && t == 0) {
             // claim (performed device-wide) while the loads are in flight; the last warp of the block to get
             // here lets the dependents launch
-            if (env >= 0) p.chain[4 * (size_t)(g.e0 + env)] = ticket + 1u;  // (shadow lanes write the same value)
+            if (env >= 0) p.chain[4 * (size_t)(g.e0 + env)] = ticket + 1u;
             __threadfence();
             __syncwarp();
             if (lane == 0 && atomicAdd(&claimed, 1u) == blockDim.x / 32 - 1) pdl_launch_dependents();

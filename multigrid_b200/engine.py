@@ -507,7 +507,8 @@ class StepEngine:
         """
         if actions is None:
             actions = self.actions
-        if actions.dtype != torch.int8 or not actions.is_contiguous() or actions.device != self.device:
+        if (actions.dtype != torch.int8 or not actions.is_contiguous() or actions.device != self.device
+                or tuple(actions.shape) != (self.num_envs, self.cfg.num_agents)):
             raise TypeError("actions must be a contiguous int8 CUDA tensor of shape (num_envs, n)")
         if self._c is None:
             self._structs()

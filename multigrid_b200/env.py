@@ -418,10 +418,19 @@ class BatchedMultiGridEnv:
                 raise ValueError(f"actions tensor must have shape ({E}, {n})")
             if actions.dtype == torch.int8 and actions.device == self.device and actions.is_contiguous():
                 return actions
+            self.engine._chain_armed = None  # staged below: the launch must not rely on a chained predecessor
+            if actions.dtype != torch.int8 and not actions.is_floating_point():
+                # values that do not fit int8 must not wrap into valid actions: anything outside -1..6 becomes the
+                # invalid code 7, which the kernel flags (the reference raises ValueError, base.py:473-474)
+                actions = torch.where((actions < -1) | (actions > 6), 7, actions)
             self._actions.copy_(actions)
             return self._actions
+        self.engine._chain_armed = None
         if isinstance(actions, np.ndarray):
-            self._actions.copy_(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.int8)).reshape(E, n))
+            a = np.asarray(actions)
+            if a.dtype != np.int8:
+                a = np.where((a < -1) | (a > 6), 7, a)
+            self._actions.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.int8)).reshape(E, n))
             return self._actions
         # dict {agent_id: action}; ids missing from the dict do not act (base.py:403-404)
         if len(actions) == n and all(isinstance(actions.get(i), torch.Tensor) and actions[i].device == self.device

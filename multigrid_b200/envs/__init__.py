@@ -56,7 +56,20 @@ def make(env_id: str, agents: int = 1, **kwargs) -> BatchedMultiGridEnv:
     if env_id not in CONFIGURATIONS:
         raise KeyError(f"unknown environment id {env_id!r}")
     if not isinstance(agents, int):
-        raise TypeError("the batched engine takes the NUMBER of agents (agents=<int>)")
+        # gym.make(id, agents=Iterable[Agent]) (base.py:85-103, 156-180): the batched engine keeps no per-agent
+        # objects, so an iterable only says how many agents there are; their settings must be the env's
+        # (one view size and see_through_walls for all: gen_obs uses agents[0]'s anyway, base.py:364-365)
+        try:
+            agent_list = list(agents)
+        except TypeError as exc:
+            raise TypeError("agents must be an int or an iterable of agents") from exc
+        for a in agent_list:
+            vs = getattr(a, "view_size", None)
+            if vs is not None and vs != kwargs.get("agent_view_size", 7):
+                raise ValueError("per-agent view sizes are not supported: pass agent_view_size=<int> for all agents")
+        agents = len(agent_list)
+        if agents < 1:
+            raise ValueError("at least one agent is needed")
     layout_cls, layout_kw, env_defaults = CONFIGURATIONS[env_id]
     layout_kw = dict(layout_kw)
     for key in _LAYOUT_KEYS[layout_cls]:

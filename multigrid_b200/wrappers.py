@@ -38,8 +38,8 @@ class _Wrapper:
         obs, infos = self.env.reset(*args, **kwargs)
         return self.observation(obs), infos
 
-    def step(self, actions):
-        obs, rewards, terminations, truncations, infos = self.env.step(actions)
+    def step(self, actions, **kwargs):
+        obs, rewards, terminations, truncations, infos = self.env.step(actions, **kwargs)
         return self.observation(obs), rewards, terminations, truncations, infos
 
 
@@ -58,13 +58,32 @@ class OneHotObsWrapper(_Wrapper):
     def observation(self, obs):
         base = self.env.unwrapped
         eng = base.engine
-        with torch.cuda.device(base.device):
-            _cabi.check(eng.lib.mg_one_hot(base.agent_view_size, base.num_envs * base.num_agents,
-                                           eng.obs_stride, eng.obs_buf.data_ptr(), self._out.data_ptr(),
-                                           C.c_void_p(torch.cuda.current_stream(base.device).cuda_stream)),
-                        "mg_one_hot")
+        stream = C.c_void_p(torch.cuda.current_stream(base.device).cuda_stream)
+        img0 = obs[0]["image"]
+        if img0.data_ptr() == eng.obs_buf.data_ptr() and img0.shape[1:] == self._out.shape[2:4] + (3,):
+            # the wrapped env's own partial views: the whole observation buffer in one launch
+            with torch.cuda.device(base.device):
+                _cabi.check(eng.lib.mg_one_hot(base.agent_view_size, base.num_envs * base.num_agents,
+                                               eng.obs_stride, eng.obs_buf.data_ptr(), self._out.data_ptr(), stream),
+                            "mg_one_hot")
+            for i in obs:
+                obs[i]["image"] = self._out[:, i]
+            return obs
+        # images of another wrapper (e.g. FullyObsWrapper's whole-grid image): encode what `obs` holds
+        # (wrappers.py:176-177 encodes obs[agent]['image'] whatever produced it)
+        cache = {}
         for i in obs:
-            obs[i]["image"] = self._out[:, i]
+            img = obs[i]["image"]
+            key = (img.data_ptr(), tuple(img.shape))
+            if key not in cache:
+                src = img.contiguous()
+                cells = int(np.prod(src.shape[1:-1]))
+                out = torch.empty(tuple(src.shape[:-1]) + (ONE_HOT_CHANNELS,), dtype=torch.uint8, device=src.device)
+                with torch.cuda.device(base.device):
+                    _cabi.check(eng.lib.mg_one_hot_cells(cells, src.shape[0], 3 * cells, src.data_ptr(), out.data_ptr(),
+                                                         stream), "mg_one_hot_cells")
+                cache[key] = out
+            obs[i]["image"] = cache[key]
         return obs
 
 

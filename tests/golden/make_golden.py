@@ -127,8 +127,9 @@ def bup_teleport(env):
 
 
 def run_case(name, env_id, kwargs, B, T, seed, p_absent=0.0, action_p=None, auto_reset=False,
-             tweak=None):
-    """Roll B reference envs for T steps, recording everything. See module docstring."""
+             tweak=None, save=True):
+    """Roll B reference envs for T steps, recording everything. See module docstring.
+    save=False returns the record instead of writing tests/golden/<name>.npz (tests/test_live_reference.py)."""
     rng = np.random.default_rng(seed)
     envs, rec = [], {}
     init_grid, init_agents, pcg_state, pcg_inc, obs0, dir0 = [], [], [], [], [], []
@@ -232,6 +233,8 @@ def run_case(name, env_id, kwargs, B, T, seed, p_absent=0.0, action_p=None, auto
         pool_grid=pg, pool_agents=pa,
         **{f"meta_{k}": np.array(v) for k, v in meta.items()},
     )
+    if not save:
+        return rec, meta
     path = os.path.join(HERE, f"{name}.npz")
     np.savez_compressed(path, **rec)
     print(f"{name}: B={B} T={T} n={n} V={V} {W}x{H} events={n_events} "

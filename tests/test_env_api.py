@@ -286,3 +286,56 @@ def test_bup_reset_device_layout_path_equals_host_path(monkeypatch):
         ra, rb = a.step(acts), b.step(acts)
         np.testing.assert_array_equal(ra[0][0]["image"].numpy(), rb[0][0]["image"].numpy())
         np.testing.assert_array_equal(a.agent_states.numpy(), b.agent_states.numpy())
+
+
+def test_make_accepts_an_iterable_of_agents(monkeypatch):
+    """gym.make(id, agents=Iterable[Agent]) (base.py:85-103): the iterable's length is the agent count."""
+    from tests.hostsim.fake_engine import HostSimStepEngine
+    monkeypatch.setattr(env_mod, "StepEngine", HostSimStepEngine)
+
+    class FakeAgent:
+        def __init__(self, view_size=7):
+            self.view_size = view_size
+
+    env = make("MultiGrid-Empty-5x5-v0", agents=[FakeAgent(), FakeAgent(), FakeAgent()], num_envs=2, device="cpu")
+    assert env.num_agents == 3 and len(env.agents) == 3
+    with pytest.raises(ValueError):
+        make("MultiGrid-Empty-5x5-v0", agents=[FakeAgent(5)], num_envs=2, device="cpu")
+    with pytest.raises(TypeError):
+        make("MultiGrid-Empty-5x5-v0", agents=2.5, num_envs=2, device="cpu")
+
+
+@pytest.mark.gpu
+def test_wide_action_tensors_do_not_wrap_into_valid_actions():
+    """int64 actions outside -1..6 (256 would narrow to 0 = left) are flagged like the reference's ValueError."""
+    env = make("MultiGrid-Empty-5x5-v0", agents=2, num_envs=8, device="cuda:0")
+    env.reset(seed=3)
+    before = env.agent_states.clone()
+    env.step(torch.full((8, 2), 256, dtype=torch.int64, device="cuda:0"))
+    with pytest.raises(ValueError):
+        env.check()
+    assert torch.equal(env.agent_states, before)  # nobody turned left
+    env.step(np.full((8, 2), -3, dtype=np.int64))
+    with pytest.raises(ValueError):
+        env.check()
+    with pytest.raises(TypeError):
+        env.engine.step(torch.zeros((4, 2), dtype=torch.int8, device="cuda:0"))  # wrong batch size
+
+
+@pytest.mark.gpu
+def test_one_hot_over_fully_obs_encodes_the_wrapped_image():
+    """OneHotObsWrapper(FullyObsWrapper(env)): the one-hot of the whole-grid image, not of the partial views
+    (wrappers.py:176-177 encodes whatever image the wrapped env produced)."""
+    from multigrid_b200.wrappers import FullyObsWrapper, OneHotObsWrapper
+    env = OneHotObsWrapper(FullyObsWrapper(make("MultiGrid-BlockedUnlockPickup-v0", agents=2, num_envs=33,
+                                                device="cuda:0")))
+    obs, _ = env.reset(seed=4)
+    base = env.unwrapped
+    for t in range(5):
+        obs, *_ = env.step({0: 2, 1: t % 3}, chained=False)
+        full = np.stack([O.full_obs(g, a) for g, a in zip(base.grid.state.cpu().numpy(),
+                                                          base.agent_states.cpu().numpy())])
+        for i in (0, 1):
+            got = obs[i]["image"].cpu().numpy()
+            assert got.shape == (33, base.width, base.height, 21)
+            np.testing.assert_array_equal(got, np.stack([O.one_hot(f) for f in full]), err_msg=f"step {t}")
