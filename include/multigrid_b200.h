@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 8
+#define MG_ABI_VERSION 9
 
 /* MgConfig.flags */
 #define MG_FLAG_SEE_THROUGH_WALLS 0x01u /* agents[0].see_through_walls, base.py:364-365 */
@@ -217,21 +217,24 @@ int mg_gen_layouts_locked_hallway(int32_t num_rooms, int32_t room_size, int32_t 
  */
 int mg_gen_layouts_playground(int32_t room_size, int32_t num_rows, int32_t num_cols, int32_t num_agents,
                               int64_t num_layouts, uint64_t *rng_state, const uint64_t *rng_inc, uint64_t *rng_buf,
-                              uint64_t *order_state, const uint64_t *order_inc, uint32_t *cells, int8_t *agents,
-                              int32_t *status, void *stream);
+                              uint64_t *order_state, const uint64_t *order_inc, uint64_t *order_buf, uint32_t *cells,
+                              int8_t *agents, int32_t *status, void *stream);
 
 /*
  * On-device layouts of BlockedUnlockPickupEnv (envs/blockedunlockpickup.py:142-164 over
  * core/roomgrid.py:203-404: add_object, add_door, place_in_room on a 1 x 2 RoomGrid of `room_size`), same
  * generator conventions as mg_gen_layouts_empty_random plus the ORDER generator of each layout
  * (env.np_random: the door height is drawn from it, roomgrid.py:324): order_state [K][2] is advanced in
- * place, order_inc [K][2]. info [K] (may be NULL) receives the box colour index (the mission names it).
+ * place, order_inc [K][2]; order_buf [K] (may be NULL = empty, dropped) is the stream's buffered 32-bit half in
+ * the rng_buf format, in and out: integers() leaves the unused half of a 64-bit draw there and the env's NEXT
+ * reset consumes it first. info [K] (may be NULL) receives the box colour index (the mission names it).
  * Grid is (2*(room_size-1)+1) x room_size. status |= 2 when a placement exceeded the reference's
  * max_tries = 1000 (the reference raises RecursionError).
  */
 int mg_gen_layouts_bup(int32_t room_size, int32_t num_agents, int64_t num_layouts, uint64_t *rng_state,
                        const uint64_t *rng_inc, uint64_t *rng_buf, uint64_t *order_state, const uint64_t *order_inc,
-                       uint32_t *cells, int8_t *agents, int32_t *info, int32_t *status, void *stream);
+                       uint64_t *order_buf, uint32_t *cells, int8_t *agents, int32_t *info, int32_t *status,
+                       void *stream);
 
 /*
  * Fully observable image: out int8 [E][W][H][3] = Grid.state with every agent (terminated or not)
@@ -348,6 +351,41 @@ int mg_rollout(const MgConfig *cfg, int64_t num_envs, int32_t num_steps, const M
 int mg_reset_where(const MgConfig *cfg, int64_t num_envs, const MgState *state, const uint8_t *mask, void *stream);
 
 /*
+ * Fresh layouts on auto-reset. The reference draws a NEW layout at every reset() from the env's own generator
+ * (base.py:250-301 -> the env class's _gen_grid). With ONE POOL SLOT PER ENV -- num_layouts == num_envs,
+ * layout_idx[e] == e, layout_stride == 0 -- this call gives the same behaviour to MG_FLAG_AUTO_RESET: enqueue it
+ * after every step launch; every env that is done (all agents terminated, step limit reached, or -- LockedHallway --
+ * all doors unlocked) and will therefore be reset by the NEXT step launch gets its slot (pool_grid[e], pool_agents[e])
+ * regenerated from generator e, which advances. Door positions (RoomGrid families) are drawn from a copy of the env's
+ * order stream (pcg_state / pcg_inc; roomgrid.py:324 draws them from env.np_random); that stream itself is not
+ * advanced by a reset in this engine. One thread per env; envs that are not done cost one predicate evaluation.
+ *   gen->family        MG_LAYOUT_*; gen->params: EMPTY_RANDOM {}, BUP {room_size}, RED_BLUE_DOORS {size},
+ *                      LOCKED_HALLWAY {num_rooms, room_size, max_hallway_keys, max_keys_per_room},
+ *                      PLAYGROUND {room_size, num_rows, num_cols}
+ *   gen->rng_state/inc/buf   uint64 [E][2] / [E][2] / [E]: the envs' layout generators (as mg_gen_layouts_*)
+ *   gen->order_buf     uint64 [E] (may be NULL = empty): buffered 32-bit half of the order streams, as left by
+ *                      mg_gen_layouts_bup / _playground; read, not advanced (like the stream itself)
+ *   gen->info          int32 [E] (may be NULL): BlockedUnlockPickup box colour of the regenerated slots
+ *   status             device word OR-ed with 2 when a placement gave up (may be NULL)
+ */
+#define MG_LAYOUT_EMPTY_RANDOM 1
+#define MG_LAYOUT_BUP 2
+#define MG_LAYOUT_RED_BLUE_DOORS 3
+#define MG_LAYOUT_LOCKED_HALLWAY 4
+#define MG_LAYOUT_PLAYGROUND 5
+typedef struct MgLayoutGen {
+    int32_t family;
+    int32_t params[4];
+    uint64_t *rng_state;
+    const uint64_t *rng_inc;
+    uint64_t *rng_buf;
+    const uint64_t *order_buf;
+    int32_t *info;
+} MgLayoutGen;
+int mg_refresh_done_layouts(const MgConfig *cfg, int64_t num_envs, const MgState *state, const MgLayoutGen *gen,
+                            int32_t *status, void *stream);
+
+/*
  * Host-buffer variant of mg_step_obs (what a CPU-side caller of env.step() sees):
  * copies h_actions -> d_actions, runs the fused kernel, copies the outputs in `d_out` to the
  * matching pointers in `h_out` (obs, reward, terminated, truncated; status is not copied).
@@ -356,6 +394,20 @@ int mg_reset_where(const MgConfig *cfg, int64_t num_envs, const MgState *state, 
 int mg_step_obs_host(const MgConfig *cfg, int64_t num_envs, const MgState *state,
                      const int8_t *h_actions, int8_t *d_actions, const MgStepOut *d_out,
                      const MgStepOut *h_out, void *stream);
+
+/*
+ * Prepared steps: mg_step_obs split into "validate + plan once" and "launch". A plan fixes the configuration
+ * (flags included: build one per MG_FLAG_* variant you use), the batch size, every pointer of `state` and `out`, and
+ * the launch geometry -- the MG_* tuning knobs are read when the plan is created; only the actions pointer
+ * (16-byte aligned, as the one given at creation) and the stream change per call. mg_step_plan_run launches exactly
+ * the kernel mg_step_obs would have launched (one driver call, ~3 us of host time instead of ~8). Not thread-safe
+ * per plan; destroy it before freeing the buffers it points to, and re-create it when they move.
+ */
+typedef struct MgStepPlan MgStepPlan;
+int mg_step_plan_create(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *actions,
+                        const MgStepOut *out, MgStepPlan **plan_out);
+int mg_step_plan_run(MgStepPlan *plan, const int8_t *actions, void *stream);
+void mg_step_plan_destroy(MgStepPlan *plan);
 
 /*
  * Compact wire format for host consumers. The host-buffer path is bound by PCIe, and 99 % of its bytes are

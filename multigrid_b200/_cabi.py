@@ -28,7 +28,7 @@ HOOK_BLOCKED_UNLOCK_PICKUP = 1
 HOOK_RED_BLUE_DOORS = 2
 HOOK_LOCKED_HALLWAY = 3
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 MAX_VIEW = 15
 MAX_AGENTS = 32
 
@@ -58,6 +58,16 @@ class MgStepOut(C.Structure):
     ]
 
 
+class MgLayoutGen(C.Structure):
+    _fields_ = [
+        ("family", C.c_int32), ("params", C.c_int32 * 4), ("rng_state", C.c_void_p), ("rng_inc", C.c_void_p),
+        ("rng_buf", C.c_void_p), ("order_buf", C.c_void_p), ("info", C.c_void_p),
+    ]
+
+
+LAYOUT_EMPTY_RANDOM, LAYOUT_BUP, LAYOUT_RED_BLUE_DOORS, LAYOUT_LOCKED_HALLWAY, LAYOUT_PLAYGROUND = 1, 2, 3, 4, 5
+
+
 class MgRolloutOut(C.Structure):
     _fields_ = [
         ("obs", C.c_void_p), ("direction", C.c_void_p), ("reward", C.c_void_p),
@@ -84,8 +94,8 @@ EXPORTS = {
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_gen_layouts_red_blue_doors": (C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
     "mg_gen_layouts_locked_hallway": (C.c_int, [C.c_int32] * 5 + [C.c_int64] + [C.c_void_p] * 7),
-    "mg_gen_layouts_playground": (C.c_int, [C.c_int32] * 4 + [C.c_int64] + [C.c_void_p] * 9),
-    "mg_gen_layouts_bup": (C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 10),
+    "mg_gen_layouts_playground": (C.c_int, [C.c_int32] * 4 + [C.c_int64] + [C.c_void_p] * 10),
+    "mg_gen_layouts_bup": (C.c_int, [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 11),
     "mg_obs_features": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
     "mg_unpack_grid": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -98,6 +108,12 @@ EXPORTS = {
     "mg_rollout": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.c_int32, C.POINTER(MgState), C.c_void_p,
                              C.POINTER(MgRolloutOut), C.c_void_p]),
     "mg_reset_where": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p, C.c_void_p]),
+    "mg_refresh_done_layouts": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.POINTER(MgLayoutGen),
+                                          C.c_void_p, C.c_void_p]),
+    "mg_step_plan_create": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p,
+                                      C.POINTER(MgStepOut), C.POINTER(C.c_void_p)]),
+    "mg_step_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mg_step_plan_destroy": (None, [C.c_void_p]),
     "mg_packed_obs_stride": (C.c_int32, [C.c_int32]),
     "mg_pack_obs": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_step_obs_host_packed": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p, C.c_void_p,

@@ -15,6 +15,41 @@ namespace {
 std::atomic<int64_t> g_launches{0};
 std::atomic<unsigned long long *> g_trace{nullptr};  // diagnostics only (mg_debug_set_trace)
 
+// A prepared launch (mg_step_plan_*): what a step call would hand to cudaLaunchKernelEx, kept so that later steps
+// skip validation, planning and the knob lookups.
+struct LaunchRecord {
+    mg::Params p;
+    const void *func;
+    dim3 grid, block;
+    size_t smem;
+    int pdl;
+};
+thread_local LaunchRecord *g_capture = nullptr;  // non-null while mg_step_plan_create runs the planning code
+
+int launch_record(const LaunchRecord &r, cudaStream_t stream) {
+    cudaLaunchConfig_t lc;
+    std::memset(&lc, 0, sizeof(lc));
+    lc.gridDim = r.grid; lc.blockDim = r.block; lc.dynamicSmemBytes = r.smem; lc.stream = stream;
+    // Programmatic dependent launch: the grid may be scheduled while the previous kernel of the stream drains; the
+    // kernels execute griddepcontrol.wait before their first global access, so stream-order semantics are unchanged
+    // (MG_PDL=0 turns the attribute off).
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr; lc.numAttrs = r.pdl ? 1 : 0;
+    void *args[1] = {const_cast<mg::Params *>(&r.p)};
+    const cudaError_t err = cudaLaunchKernelExC(&lc, r.func, args);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)err;
+}
+
+int launch_or_record(const mg::Params &p, const void *func, dim3 grid, dim3 block, size_t smem, cudaStream_t stream) {
+    LaunchRecord local;
+    LaunchRecord &r = g_capture ? *g_capture : local;
+    r.p = p; r.func = func; r.grid = grid; r.block = block; r.smem = smem; r.pdl = p.pdl;
+    return g_capture ? 0 : launch_record(r, stream);
+}
+
 constexpr int kSmemPerBlock = 227 * 1024;  // B200 opt-in maximum per block
 constexpr int kSmemPerSM = 228 * 1024;
 
@@ -80,20 +115,8 @@ int launch(const mg::Params &p, cudaStream_t stream) {
     }
     const int groups = (p.num_envs + p.G - 1) / p.G;
     const int blocks = (groups + p.wpb - 1) / p.wpb;
-    cudaLaunchConfig_t lc;
-    std::memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3((unsigned)blocks); lc.blockDim = dim3((unsigned)(p.wpb * mg::LANES));
-    lc.dynamicSmemBytes = (size_t)(p.wpb * p.warp_bytes) + 16; lc.stream = stream;  // + the block's claim counter
-    // Programmatic dependent launch: the grid may be scheduled while the previous kernel of the
-    // stream drains; the kernel executes griddepcontrol.wait before its first global access, so
-    // stream-order semantics are unchanged (MG_PDL=0 turns the attribute off).
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = attr; lc.numAttrs = p.pdl ? 1 : 0;
-    const cudaError_t err = cudaLaunchKernelEx(&lc, kernel, p);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return (int)err;
+    return launch_or_record(p, (const void *)kernel, dim3((unsigned)blocks), dim3((unsigned)(p.wpb * mg::LANES)),
+                            (size_t)(p.wpb * p.warp_bytes) + 16 /* the block's claim counter */, stream);
 }
 
 template <int MODE, bool MULTI = false>
@@ -138,21 +161,13 @@ int dispatch(const mg::Params &p, cudaStream_t stream) {
 template <typename K>
 int launch_static(K kernel, const mg::Params &p, cudaStream_t stream) {
     const int groups = (p.num_envs + p.G - 1) / p.G;
-    cudaLaunchConfig_t lc;
-    std::memset(&lc, 0, sizeof(lc));
-    lc.gridDim = dim3((unsigned)groups); lc.blockDim = dim3((unsigned)(p.wpb * mg::LANES));
-    lc.dynamicSmemBytes = (size_t)p.warp_bytes; lc.stream = stream;  // (carve_static: bytes of the whole block)
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    lc.attrs = attr; lc.numAttrs = p.pdl ? 1 : 0;
     if (p.warp_bytes > 48 * 1024) {
         const cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemPerBlock);
         if (err != cudaSuccess) return (int)err;
     }
-    const cudaError_t err = cudaLaunchKernelEx(&lc, kernel, p);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return (int)err;
+    // (carve_static: warp_bytes = the bytes of the whole block)
+    return launch_or_record(p, (const void *)kernel, dim3((unsigned)groups), dim3((unsigned)(p.wpb * mg::LANES)),
+                            (size_t)p.warp_bytes, stream);
 }
 
 int dispatch_static(const mg::Params &p, cudaStream_t stream) {
@@ -400,8 +415,8 @@ int mg_gen_layouts_locked_hallway(int32_t num_rooms, int32_t room_size, int32_t 
 
 int mg_gen_layouts_playground(int32_t room_size, int32_t num_rows, int32_t num_cols, int32_t num_agents,
                               int64_t num_layouts, uint64_t *rng_state, const uint64_t *rng_inc, uint64_t *rng_buf,
-                              uint64_t *order_state, const uint64_t *order_inc, uint32_t *cells, int8_t *agents,
-                              int32_t *status, void *stream) {
+                              uint64_t *order_state, const uint64_t *order_inc, uint64_t *order_buf, uint32_t *cells,
+                              int8_t *agents, int32_t *status, void *stream) {
     if (room_size < 4 || num_rows < 1 || num_cols < 1 || num_rows * num_cols > 16 || num_layouts < 0 ||
         num_cols * (room_size - 1) + 1 > 127 || num_rows * (room_size - 1) + 1 > 127 || num_agents < 1 ||
         num_agents > MG_MAX_AGENTS) return MG_ERR_BAD_ARG;
@@ -409,21 +424,22 @@ int mg_gen_layouts_playground(int32_t room_size, int32_t num_rows, int32_t num_c
     if (!rng_state || !rng_inc || !order_state || !order_inc || !cells || !agents) return MG_ERR_BAD_ARG;
     mg::gen_layouts_playground_kernel<<<(unsigned)((num_layouts + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         room_size, num_rows, num_cols, num_agents, num_layouts, rng_state, rng_inc, rng_buf, order_state, order_inc,
-        cells, agents, status);
+        order_buf, cells, agents, status);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
 
 int mg_gen_layouts_bup(int32_t room_size, int32_t num_agents, int64_t num_layouts, uint64_t *rng_state,
                        const uint64_t *rng_inc, uint64_t *rng_buf, uint64_t *order_state, const uint64_t *order_inc,
-                       uint32_t *cells, int8_t *agents, int32_t *info, int32_t *status, void *stream) {
+                       uint64_t *order_buf, uint32_t *cells, int8_t *agents, int32_t *info, int32_t *status,
+                       void *stream) {
     if (room_size < 4 || room_size > 60 || num_layouts < 0 || num_agents < 1 || num_agents > MG_MAX_AGENTS)
         return MG_ERR_BAD_ARG;
     if (num_layouts == 0) return 0;
     if (!rng_state || !rng_inc || !order_state || !order_inc || !cells || !agents) return MG_ERR_BAD_ARG;
     mg::gen_layouts_bup_kernel<<<(unsigned)((num_layouts + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        room_size, num_agents, num_layouts, rng_state, rng_inc, rng_buf, order_state, order_inc, cells, agents,
-        info, status);
+        room_size, num_agents, num_layouts, rng_state, rng_inc, rng_buf, order_state, order_inc, order_buf, cells,
+        agents, info, status);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }
@@ -532,6 +548,31 @@ int mg_reset_where(const MgConfig *cfg, int64_t num_envs, const MgState *state, 
     return (int)cudaGetLastError();
 }
 
+int mg_refresh_done_layouts(const MgConfig *cfg, int64_t num_envs, const MgState *state, const MgLayoutGen *gen,
+                            int32_t *status, void *stream) {
+    int rc = validate(cfg, num_envs);
+    if (rc) return rc;
+    if (num_envs == 0) return 0;
+    if (!state || !gen || !gen->rng_state || !gen->rng_inc || !state->pool_grid || !state->pool_agents ||
+        !state->agents || !state->step_count) return MG_ERR_BAD_ARG;
+    if (gen->family < mg::LAYOUT_EMPTY_RANDOM || gen->family > mg::LAYOUT_PLAYGROUND) return MG_ERR_BAD_ARG;
+    if (cfg->num_layouts != num_envs) return MG_ERR_BAD_ARG;  // one pool slot per env
+    if ((gen->family == mg::LAYOUT_BUP || gen->family == mg::LAYOUT_PLAYGROUND) && (!state->pcg_state || !state->pcg_inc))
+        return MG_ERR_BAD_ARG;
+    mg::Params p;
+    fill_config(p, cfg, num_envs);
+    if ((rc = fill_state(p, state))) return rc;
+    p.status = status;
+    p.G = 16;
+    mg::carve_smem(p);  // derived geometry (cstride)
+    mg::LayoutGen lg;
+    lg.family = gen->family; lg.a = gen->params[0]; lg.b = gen->params[1]; lg.c = gen->params[2]; lg.d = gen->params[3];
+    lg.rng_state = gen->rng_state; lg.rng_inc = gen->rng_inc; lg.rng_buf = gen->rng_buf; lg.order_buf = gen->order_buf; lg.info = gen->info;
+    mg::refresh_done_kernel<<<(unsigned)((num_envs + 63) / 64), 64, 0, (cudaStream_t)stream>>>(p, lg);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
 int mg_step_obs_host(const MgConfig *cfg, int64_t num_envs, const MgState *state,
                      const int8_t *h_actions, int8_t *d_actions, const MgStepOut *d_out,
                      const MgStepOut *h_out, void *stream) {
@@ -593,5 +634,35 @@ int mg_step_obs_host_packed(const MgConfig *cfg, int64_t num_envs, const MgState
     if ((err = cudaMemcpyAsync(h_out->truncated, d_out->truncated, E, cudaMemcpyDeviceToHost, s))) return (int)err;
     return 0;
 }
+
+struct MgStepPlan { LaunchRecord rec; };
+
+int mg_step_plan_create(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *actions,
+                        const MgStepOut *out, MgStepPlan **plan_out) {
+    if (!plan_out) return MG_ERR_BAD_ARG;
+    *plan_out = nullptr;
+    if (num_envs <= 0) return MG_ERR_BAD_ARG;
+    MgStepPlan *plan = new MgStepPlan();
+    plan->rec.func = nullptr;
+    g_capture = &plan->rec;
+    const int rc = step_common<mg::MODE_STEP_OBS>(cfg, num_envs, state, actions, out, nullptr);
+    g_capture = nullptr;
+    if (rc || !plan->rec.func) {
+        delete plan;
+        return rc ? rc : MG_ERR_BAD_ARG;
+    }
+    *plan_out = plan;
+    return 0;
+}
+
+int mg_step_plan_run(MgStepPlan *plan, const int8_t *actions, void *stream) {
+    if (!plan || !actions) return MG_ERR_BAD_ARG;
+    if (reinterpret_cast<uintptr_t>(actions) & 15u) return MG_ERR_ALIGNMENT;  // (the plan assumed 16-byte alignment)
+    plan->rec.p.actions = actions;
+    plan->rec.p.trace = g_trace.load(std::memory_order_relaxed);
+    return launch_record(plan->rec, (cudaStream_t)stream);
+}
+
+void mg_step_plan_destroy(MgStepPlan *plan) { delete plan; }
 
 }  // extern "C"

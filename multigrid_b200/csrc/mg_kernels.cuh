@@ -633,6 +633,61 @@ MG_HD bool gen_layout_playground(int S, int rows, int cols, int n, LayoutRng &g,
     return true;
 }
 
+// ---- fresh layouts on auto-reset -------------------------------------------------------------------------
+// The reference draws a NEW layout at every reset() from the env's own RandomMixin generator (base.py:250-301 ->
+// _gen_grid). With one pool slot per env (K = E, layout_idx[e] = e, layout_stride = 0) the same happens here:
+// after a step, every env that will auto-reset at its next step (the predicate of phase_reset) gets its slot
+// regenerated from ITS generator, which advances; door positions come from a COPY of the env's order stream
+// (roomgrid.py:324 draws them from env.np_random; a reset does not advance that stream in this engine, and the
+// fixtures recorded from the reference restore it the same way, tests/golden/make_golden.py).
+enum : int { LAYOUT_EMPTY_RANDOM = 1, LAYOUT_BUP = 2, LAYOUT_RED_BLUE_DOORS = 3, LAYOUT_LOCKED_HALLWAY = 4, LAYOUT_PLAYGROUND = 5 };
+
+struct LayoutGen {
+    int32_t family, a, b, c, d;  // family parameters: size | room_size | (num_rooms, room_size, max_hallway_keys,
+                                 // max_keys_per_room) | (room_size, num_rows, num_cols)
+    uint64_t *rng_state; const uint64_t *rng_inc; uint64_t *rng_buf;  // [E] the envs' layout generators
+    const uint64_t *order_buf;   // [E] buffered 32-bit half of the envs' order streams (may be NULL = empty)
+    int32_t *info;               // [E] BlockedUnlockPickup: box colour of the slot's layout (may be NULL)
+};
+
+// Will env e be reset by the next step launch? (phase_reset's predicate; is_done, base.py:534-539)
+MG_HD bool env_is_done(const Params &p, size_t e) {
+    const uint32_t *ag = (const uint32_t *)(p.agents + e * p.n * 8);
+    uint32_t all_term = 1;
+    for (int j = 0; j < p.n; j++) all_term &= ((ag[j * 2] >> 24) & 0xff) != 0;
+    if (p.hook == MG_HOOK_LOCKED_HALLWAY && __builtin_popcount((unsigned)p.hook_state[e]) == p.hook_param) all_term = 1;
+    return all_term || p.step_count[e] >= p.max_steps;
+}
+
+// Regenerates pool slot e from generator e. Returns false when a placement gave up.
+MG_HD bool refresh_slot(const Params &p, const LayoutGen &lg, size_t e) {
+    LayoutRng g, o;
+    g.lo = lg.rng_state[2 * e]; g.hi = lg.rng_state[2 * e + 1]; g.ilo = lg.rng_inc[2 * e]; g.ihi = lg.rng_inc[2 * e + 1];
+    const uint64_t b = lg.rng_buf ? lg.rng_buf[e] : 0ull;
+    g.has32 = (uint32_t)(b >> 32) & 1u; g.buf32 = (uint32_t)b;
+    o.lo = o.hi = o.ilo = o.ihi = 0; o.has32 = 0; o.buf32 = 0;
+    if (p.pcg_state) {  // (a copy: the env's own stream is not advanced, neither is its buffered half)
+        o.lo = p.pcg_state[2 * e]; o.hi = p.pcg_state[2 * e + 1]; o.ilo = p.pcg_inc[2 * e]; o.ihi = p.pcg_inc[2 * e + 1];
+        const uint64_t ob = lg.order_buf ? lg.order_buf[e] : 0ull;
+        o.has32 = (uint32_t)(ob >> 32) & 1u; o.buf32 = (uint32_t)ob;
+    }
+    uint32_t *cells = const_cast<uint32_t *>(p.pool_grid) + e * (size_t)p.cstride;
+    int8_t *agents = const_cast<int8_t *>(p.pool_agents) + e * (size_t)p.n * 8;
+    bool ok = true;
+    if (lg.family == LAYOUT_EMPTY_RANDOM) ok = gen_layout_empty_random(p.W, p.H, p.n, g, cells, agents);
+    else if (lg.family == LAYOUT_RED_BLUE_DOORS) ok = gen_layout_red_blue_doors(lg.a, p.n, g, cells, agents);
+    else if (lg.family == LAYOUT_LOCKED_HALLWAY) ok = gen_layout_locked_hallway(lg.a, lg.b, lg.c, lg.d, p.n, g, cells, agents);
+    else if (lg.family == LAYOUT_PLAYGROUND) ok = gen_layout_playground(lg.a, lg.b, lg.c, p.n, g, o, cells, agents);
+    else if (lg.family == LAYOUT_BUP) {
+        const int color = gen_layout_bup(lg.a, p.n, g, o, cells, agents);
+        ok = color >= 0;
+        if (lg.info) lg.info[e] = color;
+    }
+    lg.rng_state[2 * e] = g.lo; lg.rng_state[2 * e + 1] = g.hi;
+    if (lg.rng_buf) lg.rng_buf[e] = ((uint64_t)g.has32 << 32) | g.buf32;
+    return ok;
+}
+
 // base.py:598-602: `1 - 0.9 * (step_count / max_steps)` in float64, round-to-nearest at every
 // operation, never contracted into an FMA.
 MG_HD double reward_value(int32_t step_count, int32_t max_steps) {
@@ -1550,8 +1605,8 @@ __global__ void gen_layouts_locked_hallway_kernel(int num_rooms, int S, int mhk,
 // Playground layouts (two generators, like BUP below).
 __global__ void gen_layouts_playground_kernel(int S, int rows, int cols, int n, int64_t K, uint64_t *rng_state,
                                               const uint64_t *rng_inc, uint64_t *rng_buf, uint64_t *order_state,
-                                              const uint64_t *order_inc, uint32_t *cells, int8_t *agents,
-                                              int32_t *status) {
+                                              const uint64_t *order_inc, uint64_t *order_buf, uint32_t *cells,
+                                              int8_t *agents, int32_t *status) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     LayoutRng g, o;
@@ -1559,20 +1614,23 @@ __global__ void gen_layouts_playground_kernel(int S, int rows, int cols, int n, 
     const uint64_t b = rng_buf ? rng_buf[k] : 0ull;
     g.has32 = (uint32_t)(b >> 32) & 1u; g.buf32 = (uint32_t)b;
     o.lo = order_state[2 * k]; o.hi = order_state[2 * k + 1]; o.ilo = order_inc[2 * k]; o.ihi = order_inc[2 * k + 1];
-    o.has32 = 0; o.buf32 = 0;
+    const uint64_t ob = order_buf ? order_buf[k] : 0ull;
+    o.has32 = (uint32_t)(ob >> 32) & 1u; o.buf32 = (uint32_t)ob;
     const int64_t cs = (int64_t)(cols * (S - 1) + 2) * (rows * (S - 1) + 2);
     if (!gen_layout_playground(S, rows, cols, n, g, o, cells + k * cs, agents + k * n * 8)) status_or(status, 2);
     rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
     if (rng_buf) rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
     order_state[2 * k] = o.lo; order_state[2 * k + 1] = o.hi;
+    if (order_buf) order_buf[k] = ((uint64_t)o.has32 << 32) | o.buf32;
 }
 
 // BlockedUnlockPickup layouts, one thread per layout. order_state/order_inc: the env's own generator
-// (env.np_random), advanced by the door-height draw; its buffered 32-bit half starts empty and is dropped,
-// like the host path. info[k] = box colour.
+// (env.np_random), advanced by the door-height draw; order_buf = its buffered 32-bit half (integers() leaves the
+// unused half of a 64-bit draw there and the NEXT reset's door draw consumes it). info[k] = box colour.
 __global__ void gen_layouts_bup_kernel(int S, int n, int64_t K, uint64_t *rng_state, const uint64_t *rng_inc,
                                        uint64_t *rng_buf, uint64_t *order_state, const uint64_t *order_inc,
-                                       uint32_t *cells, int8_t *agents, int32_t *info, int32_t *status) {
+                                       uint64_t *order_buf, uint32_t *cells, int8_t *agents, int32_t *info,
+                                       int32_t *status) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     LayoutRng g, o;
@@ -1580,7 +1638,8 @@ __global__ void gen_layouts_bup_kernel(int S, int n, int64_t K, uint64_t *rng_st
     const uint64_t b = rng_buf ? rng_buf[k] : 0ull;
     g.has32 = (uint32_t)(b >> 32) & 1u; g.buf32 = (uint32_t)b;
     o.lo = order_state[2 * k]; o.hi = order_state[2 * k + 1]; o.ilo = order_inc[2 * k]; o.ihi = order_inc[2 * k + 1];
-    o.has32 = 0; o.buf32 = 0;
+    const uint64_t ob = order_buf ? order_buf[k] : 0ull;
+    o.has32 = (uint32_t)(ob >> 32) & 1u; o.buf32 = (uint32_t)ob;
     const int W = 2 * (S - 1) + 1;
     const int color = gen_layout_bup(S, n, g, o, cells + k * (int64_t)(W + 1) * (S + 1), agents + k * n * 8);
     if (color < 0) status_or(status, 2);
@@ -1588,6 +1647,14 @@ __global__ void gen_layouts_bup_kernel(int S, int n, int64_t K, uint64_t *rng_st
     rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
     if (rng_buf) rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
     order_state[2 * k] = o.lo; order_state[2 * k + 1] = o.hi;
+    if (order_buf) order_buf[k] = ((uint64_t)o.has32 << 32) | o.buf32;
+}
+
+// One thread per env: regenerate the slot of every env that is done (see refresh_slot).
+__global__ void refresh_done_kernel(const __grid_constant__ Params p, const LayoutGen lg) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.num_envs || !env_is_done(p, (size_t)e)) return;
+    if (!refresh_slot(p, lg, (size_t)e)) status_or(p.status, 2);
 }
 
 // Host-driven reset of selected envs from the layout pool, one warp per env: exactly what the step

@@ -115,6 +115,30 @@ def _as_i64_bits(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)
 
 
+try:  # the raw current stream / device without building torch.cuda.Stream objects (~1.5 us per step saved)
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+    _current_device = torch._C._cuda_getDevice
+except AttributeError:  # pragma: no cover  (other torch builds)
+    def _raw_stream(index):
+        return torch.cuda.current_stream(index).cuda_stream
+    _current_device = torch.cuda.current_device
+
+
+class _Plan:
+    """Owner of one MgStepPlan handle (destroyed with the object)."""
+
+    def __init__(self, lib, handle):
+        self.lib, self.handle = lib, handle
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.mg_step_plan_destroy(self.handle)
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+        self.handle = None
+
+
 class StepEngine:
     """HBM-resident state of `num_envs` envs + fused step/observe launches.
 
@@ -161,6 +185,7 @@ class StepEngine:
         self.chain = z((E, 4), torch.int32)
         self.chain[:, 2] = 1
         self.pool_rep = None
+        self._fresh = None  # MgLayoutGen of enable_fresh_layouts()
         # static-grid path (MG_FLAG_STATIC_GRID): memoised per-(x, y, dir) views of the single pool layout, and
         # whether the batch is known to satisfy the promise (True / False; None = injected state, check lazily)
         self.static_obs = None
@@ -174,6 +199,9 @@ class StepEngine:
             self.set_layout_pool(pool_grid, pool_agents)
         self._host = None
         self._c = None
+        self._plans = {}    # prepared launches per variant (mg_step_plan_*), dropped whenever the structs are rebuilt
+        self._plan_run = self.lib.mg_step_plan_run
+        self._act_shape = torch.Size((self.num_envs, self.cfg.num_agents))
         self._views = None  # (obs, reward, terminated, truncated): views of fixed buffers, built once
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -248,6 +276,7 @@ class StepEngine:
         agents = torch.empty((K, cfg.num_agents, 8), dtype=torch.int8, device=dev)
         self.pool_grid, self.pool_agents = cells, agents
         self._pool_rng = (st, inc, buf)  # stays on the device: refresh_layout_pool() continues these streams
+        self._pool_gen = (st, inc, buf, None, None)
         self._pool_family = _family
         self._c = None
         self.refresh_layout_pool()
@@ -276,6 +305,7 @@ class StepEngine:
         st, inc = t64(rng_state).reshape(K, 2), t64(rng_inc).reshape(K, 2)
         buf = t64(np.zeros(K, np.uint64) if rng_buf is None else rng_buf)
         ost, oinc = t64(order_state).reshape(K, 2), t64(order_inc).reshape(K, 2)
+        obuf = torch.zeros((K,), dtype=torch.int64, device=dev)  # buffered 32-bit half of the order streams
         rows, cols = _grid or (1, 2)
         assert (cfg.width, cfg.height) == (cols * (room_size - 1) + 1, rows * (room_size - 1) + 1)
         cells = torch.empty((K, cfg.width + 1, cfg.height + 1), dtype=torch.int32, device=dev)
@@ -285,18 +315,20 @@ class StepEngine:
             if _grid is not None:
                 _cabi.check(self.lib.mg_gen_layouts_playground(
                     room_size, rows, cols, cfg.num_agents, K, st.data_ptr(), inc.data_ptr(), buf.data_ptr(),
-                    ost.data_ptr(), oinc.data_ptr(), cells.data_ptr(), agents.data_ptr(), self.status.data_ptr(),
-                    self._stream()), "mg_gen_layouts_playground")
+                    ost.data_ptr(), oinc.data_ptr(), obuf.data_ptr(), cells.data_ptr(), agents.data_ptr(),
+                    self.status.data_ptr(), self._stream()), "mg_gen_layouts_playground")
             else:
                 _cabi.check(self.lib.mg_gen_layouts_bup(
                     room_size, cfg.num_agents, K, st.data_ptr(), inc.data_ptr(), buf.data_ptr(), ost.data_ptr(),
-                    oinc.data_ptr(), cells.data_ptr(), agents.data_ptr(), info.data_ptr(), self.status.data_ptr(),
-                    self._stream()), "mg_gen_layouts_bup")
+                    oinc.data_ptr(), obuf.data_ptr(), cells.data_ptr(), agents.data_ptr(), info.data_ptr(),
+                    self.status.data_ptr(), self._stream()), "mg_gen_layouts_bup")
         if int(self.status.item()) & 2:
             self.status.zero_()
             raise RecursionError("rejection sampling failed in place_obj")  # base.py:640-641
         self.pool_grid, self.pool_agents = cells, agents
-        self._pool_rng = None
+        self._pool_rng = None  # (refresh_layout_pool is for the single-generator families)
+        self._pool_gen = (st, inc, buf, info, obuf)  # the generators stay on the device for fresh layouts on auto-reset
+        self._pool_family = ("pg", room_size, rows, cols) if _grid is not None else ("bup", room_size)
         self._pool_changed()
         u64 = lambda t: t.cpu().numpy().view(np.uint64)  # noqa: E731
         return u64(ost), info.cpu().numpy(), u64(st), u64(buf)
@@ -323,6 +355,36 @@ class StepEngine:
                 _cabi.check(self.lib.mg_gen_layouts_empty_random(cfg.width, cfg.height, cfg.num_agents, *tail),
                             "mg_gen_layouts_empty_random")
         self._pool_changed()
+
+    def enable_fresh_layouts(self) -> None:
+        """A NEW layout for every episode under auto_reset, like the reference's reset() (base.py:250-301): needs a
+        device-generated pool with one slot per env (K == num_envs, generator e = env e's RandomMixin generator).
+        From now on every step launch is followed by mg_refresh_done_layouts, which regenerates the slot of each env
+        that is done (and will be reset by the next launch) from that env's generator."""
+        gen = getattr(self, "_pool_gen", None)
+        if gen is None or self.pool_grid is None or self.pool_grid.shape[0] != self.num_envs:
+            raise RuntimeError("fresh layouts need a device-generated layout pool with one slot per env")
+        if not self.cfg.auto_reset:
+            raise RuntimeError("fresh layouts are a mode of auto_reset")
+        fam = self._pool_family
+        code = {"empty": _cabi.LAYOUT_EMPTY_RANDOM, "bup": _cabi.LAYOUT_BUP, "rbd": _cabi.LAYOUT_RED_BLUE_DOORS,
+                "lh": _cabi.LAYOUT_LOCKED_HALLWAY, "pg": _cabi.LAYOUT_PLAYGROUND}[fam[0]]
+        params = [int(v) for v in fam[1:]] if fam[0] != "empty" else []
+        params += [0] * (4 - len(params))
+        st, inc, buf, info, obuf = gen
+        self._fresh = _cabi.MgLayoutGen(code, (C.c_int32 * 4)(*params), st.data_ptr(), inc.data_ptr(), buf.data_ptr(),
+                                        None if obuf is None else obuf.data_ptr(),
+                                        None if info is None else info.data_ptr())
+        self.cfg.layout_stride = 0  # an env always resets from ITS slot
+        self.layout_idx.copy_(torch.arange(self.num_envs, dtype=torch.int32, device=self.device))
+        self._c = None
+
+    def _refresh_done(self, stream) -> None:
+        c, st, _ = self._c
+        rc = self.lib.mg_refresh_done_layouts(C.byref(c), self.num_envs, C.byref(st), C.byref(self._fresh),
+                                              self.status.data_ptr(), stream)
+        if rc:
+            _cabi.check(rc, "mg_refresh_done_layouts")
 
     @property
     def grid_dirty(self) -> torch.Tensor:
@@ -440,6 +502,7 @@ class StepEngine:
     # -- C structs ---------------------------------------------------------------------------
     def _structs(self):
         if self._c is None:
+            self._plans = {}  # (they point into the structs built below)
             cfg = self.cfg
             if cfg.auto_reset and self.pool_grid is None:
                 raise RuntimeError("auto_reset needs a layout pool (set_layout_pool)")
@@ -507,32 +570,59 @@ class StepEngine:
         """
         if actions is None:
             actions = self.actions
-        if (actions.dtype != torch.int8 or not actions.is_contiguous() or actions.device != self.device
-                or tuple(actions.shape) != (self.num_envs, self.cfg.num_agents)):
+        if (actions.dtype != torch.int8 or actions.shape != self._act_shape or actions.device != self.device
+                or not actions.is_contiguous()):
             raise TypeError("actions must be a contiguous int8 CUDA tensor of shape (num_envs, n)")
         if self._c is None:
             self._structs()
-        rc, rst, rout = self._refs
-        fn = self.lib.mg_step_obs if fused else self.lib.mg_step
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        if fused and self._static_state is not False and self._static_ok():
-            rc = self._static_cfg[1]  # MG_FLAG_STATIC_GRID: a plain launch of the static-grid kernel (chained or not)
+        stream = _raw_stream(self.device.index)
+        if not fused:
             self._chain_armed = None
-        elif chained and fused:  # head of a chain unless the engine's previous operation was a chained step on this stream
-            rc = self._chained_cfg[1] if self._chain_armed == stream else self._chained_cfg[3]
-            self._chain_armed = stream
-        else:
-            self._chain_armed = None
-        if torch.cuda.current_device() == self.device.index:  # (a device guard costs more than the launch)
-            rc_ = fn(rc, self.num_envs, rst, actions.data_ptr(), rout, stream)
-        else:
+            rc, rst, rout = self._refs
             with torch.cuda.device(self.device):
-                rc_ = fn(rc, self.num_envs, rst, actions.data_ptr(), rout, stream)
-        if rc_:
-            _cabi.check(rc_, "mg_step_obs" if fused else "mg_step")
+                _cabi.check(self.lib.mg_step(rc, self.num_envs, rst, actions.data_ptr(), rout, stream), "mg_step")
+        else:
+            # one prepared launch per variant (mg_step_plan_*): validation, planning and knob lookups happen once
+            if self._static_state is not False and self._static_ok():
+                key = 1  # MG_FLAG_STATIC_GRID: a plain launch of the static-grid kernel (chained or not)
+                self._chain_armed = None
+            elif chained:  # head of a chain unless the engine's previous operation was a chained step on this stream
+                key = 2 if self._chain_armed == stream else 3
+                self._chain_armed = stream
+            else:
+                key = 0
+                self._chain_armed = None
+            plan = self._plans.get(key)
+            ptr = actions.data_ptr()
+            if plan is None or (ptr & 15):
+                plan = self._make_plan(key, ptr)
+            if _current_device() == self.device.index:  # (a device guard costs more than the launch)
+                rc_ = self._plan_run(plan.handle, ptr, stream)
+            else:
+                with torch.cuda.device(self.device):
+                    rc_ = self._plan_run(plan.handle, ptr, stream)
+            if rc_:
+                _cabi.check(rc_, "mg_step_obs")
+            if self._fresh is not None:  # a new layout for every env that this step finished (see enable_fresh_layouts)
+                self._chain_armed = None
+                with torch.cuda.device(self.device):
+                    self._refresh_done(stream)
         if self._views is None:
             self._views = (self.obs, self.reward, self.terminated, self.truncated)
         return self._views
+
+    def _make_plan(self, key: int, actions_ptr: int):
+        """mg_step_plan_create for variant `key` (0 plain, 1 static-grid, 2 chained, 3 chain head). A misaligned
+        actions pointer gets a throw-away plan of its own (the planning depends on the alignment)."""
+        cfg_ref = (self._refs[0], self._static_cfg[1], self._chained_cfg[1], self._chained_cfg[3])[key]
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(self.lib.mg_step_plan_create(cfg_ref, self.num_envs, self._refs[1], actions_ptr, self._refs[2],
+                                                     C.byref(handle)), "mg_step_plan_create")
+        plan = _Plan(self.lib, handle)
+        if not actions_ptr & 15:
+            self._plans[key] = plan
+        return plan
 
     def rollout(self, actions: torch.Tensor, out: dict | None = None) -> dict:
         """mg_rollout: T = actions.shape[0] consecutive fused steps in ONE launch on an open-loop
@@ -623,6 +713,9 @@ class StepEngine:
     def check_status(self) -> None:
         """Raise ValueError if any kernel saw an action outside 0..6 (base.py:473-474). Syncs."""
         st = int(self.status.item())
+        if st & 2:
+            self.status.zero_()
+            raise RecursionError("rejection sampling failed in place_obj")  # base.py:640-641
         if st & 5:
             self.status.zero_()
             if st & 4:

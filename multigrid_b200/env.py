@@ -240,7 +240,7 @@ class BatchedMultiGridEnv:
                  failure_termination_mode: str = "all", auto_reset: bool = False,
                  pool_size: int | None = None, layout_seed: int | None = None,
                  first_env: int = 0, render_mode: str | None = None, device_layouts: bool = True,
-                 stream_state: bool = False):
+                 stream_state: bool = False, fresh_layouts: bool = False):
         if render_mode is not None:
             raise NotImplementedError("rendering is out of scope of the batched engine")
         self.layout = layout
@@ -260,7 +260,14 @@ class BatchedMultiGridEnv:
         self.device_layouts = bool(device_layouts) and (
             (isinstance(layout, EmptyLayout) and not layout.deterministic)
             or isinstance(layout, (BlockedUnlockPickupLayout, RedBlueDoorsLayout, LockedHallwayLayout, PlaygroundLayout)))
-        self.pool_size = 1 if layout.deterministic else min(self.num_envs, pool_size or 4096)
+        # fresh_layouts=True: every episode of every env gets a new _gen_grid draw from the env's own generator, like the
+        # reference's reset() (one pool slot per env, regenerated on the device when the env is done); the default
+        # cycles a fixed pool of `pool_size` layouts drawn at reset() (SURVEY.md section 8d's measurement protocol)
+        self.fresh_layouts = bool(fresh_layouts) and auto_reset and self.device_layouts
+        if fresh_layouts and not self.fresh_layouts and not layout.deterministic:
+            raise ValueError("fresh_layouts needs auto_reset=True and device-side layout generation")
+        self.pool_size = 1 if layout.deterministic else (
+            self.num_envs if self.fresh_layouts else min(self.num_envs, pool_size or 4096))
         cfg = EngineConfig(
             width=self.width, height=self.height, num_agents=self.num_agents,
             view_size=agent_view_size, max_steps=self.max_steps,
@@ -375,6 +382,11 @@ class BatchedMultiGridEnv:
             self.engine.load_state(layout_idx=idx, pcg_state=st, pcg_inc=inc)
             self.engine.reset_from_pool()
             self.missions = Missions(table, None if len(set(table)) == 1 else self.engine.layout_idx)
+            if self.fresh_layouts:
+                self.engine.enable_fresh_layouts()
+                if isinstance(self.layout, BlockedUnlockPickupLayout):  # the mission names the slot's box colour
+                    names = [c.value for c in Color]
+                    self.missions = Missions([f"pick up the {nm} box" for nm in names], self.engine._pool_gen[3])
             self._needs_reset = False
             return self._obs(self.engine.gen_obs()), defaultdict(dict)
 

@@ -455,6 +455,11 @@ if __name__ == "__main__":
              B=6, T=150, seed=31, action_p=FWD_HEAVY, auto_reset=True)
     run_case("bup_n2_autoreset", "MultiGrid-BlockedUnlockPickup-v0", dict(agents=2, max_steps=30),
              B=4, T=120, seed=32, action_p=FWD_HEAVY, auto_reset=True)
+    # several episodes per env of the random-layout ids: every reset draws a NEW layout from the env's generator
+    run_case("empty6r_n3_autoreset", "MultiGrid-Empty-Random-6x6-v0", dict(agents=3, max_steps=18),
+             B=5, T=100, seed=35, auto_reset=True)
+    run_case("playground_n2_autoreset", "MultiGrid-Playground-v0", dict(agents=2, max_steps=20),
+             B=3, T=90, seed=36, action_p=FWD_HEAVY, auto_reset=True)
     # RedBlueDoors post-hook (success / failure / blue door closed again), SURVEY.md section 8f N3
     run_case("rbd_n2", "MultiGrid-RedBlueDoors-8x8-v0", dict(agents=2), B=8, T=150, seed=40,
              action_p=TOGGLE_HEAVY, tweak=rbd_open_doors)

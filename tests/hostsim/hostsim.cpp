@@ -191,6 +191,25 @@ extern "C" int sim_run(int mode, const MgConfig *c, int64_t num_envs, const MgSt
     return 0;
 }
 
+// mg_refresh_done_layouts on the CPU: the same env_is_done() / refresh_slot() the CUDA kernel calls.
+extern "C" int sim_refresh_done_layouts(const MgConfig *c, int64_t num_envs, const MgState *s, const MgLayoutGen *gen) {
+    mg::Params p;
+    std::memset(&p, 0, sizeof(p));
+    p.W = c->width; p.H = c->height; p.n = c->num_agents; p.V = c->view_size; p.max_steps = c->max_steps;
+    p.flags = c->flags; p.hook = c->hook; p.hook_param = c->hook_param; p.ostride = c->obs_agent_stride;
+    p.num_envs = (int32_t)num_envs; p.G = 16;
+    mg::carve_smem(p);
+    p.agents = s->agents; p.step_count = s->step_count; p.pcg_state = s->pcg_state; p.pcg_inc = s->pcg_inc;
+    p.pool_grid = s->pool_grid; p.pool_agents = s->pool_agents; p.hook_state = s->hook_state;
+    mg::LayoutGen lg;
+    lg.family = gen->family; lg.a = gen->params[0]; lg.b = gen->params[1]; lg.c = gen->params[2]; lg.d = gen->params[3];
+    lg.rng_state = gen->rng_state; lg.rng_inc = gen->rng_inc; lg.rng_buf = gen->rng_buf; lg.order_buf = gen->order_buf; lg.info = gen->info;
+    int bad = 0;
+    for (int64_t e = 0; e < num_envs; e++)
+        if (mg::env_is_done(p, (size_t)e) && !mg::refresh_slot(p, lg, (size_t)e)) bad = 1;
+    return bad;
+}
+
 // mg_build_static_obs on the CPU: the same static_build_entry() the CUDA kernel calls.
 extern "C" int sim_build_static_obs(const MgConfig *c, const uint32_t *layout, uint8_t *table) {
     mg::Params p;
@@ -225,7 +244,7 @@ extern "C" int sim_gen_layouts_empty_random(int W, int H, int n, int64_t K, uint
 
 extern "C" int sim_gen_layouts_bup(int S, int n, int64_t K, uint64_t *rng_state, const uint64_t *rng_inc,
                                    uint64_t *rng_buf, uint64_t *order_state, const uint64_t *order_inc,
-                                   uint32_t *cells, int8_t *agents, int32_t *info) {
+                                   uint64_t *order_buf, uint32_t *cells, int8_t *agents, int32_t *info) {
     int bad = 0;
     const int W = 2 * (S - 1) + 1;
     for (int64_t k = 0; k < K; k++) {
@@ -233,12 +252,13 @@ extern "C" int sim_gen_layouts_bup(int S, int n, int64_t K, uint64_t *rng_state,
         g.lo = rng_state[2 * k]; g.hi = rng_state[2 * k + 1]; g.ilo = rng_inc[2 * k]; g.ihi = rng_inc[2 * k + 1];
         g.has32 = (uint32_t)(rng_buf[k] >> 32) & 1u; g.buf32 = (uint32_t)rng_buf[k];
         o.lo = order_state[2 * k]; o.hi = order_state[2 * k + 1]; o.ilo = order_inc[2 * k]; o.ihi = order_inc[2 * k + 1];
-        o.has32 = 0; o.buf32 = 0;
+        o.has32 = (uint32_t)(order_buf[k] >> 32) & 1u; o.buf32 = (uint32_t)order_buf[k];
         info[k] = mg::gen_layout_bup(S, n, g, o, cells + k * (int64_t)(W + 1) * (S + 1), agents + k * n * 8);
         if (info[k] < 0) bad = 1;
         rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
         rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
         order_state[2 * k] = o.lo; order_state[2 * k + 1] = o.hi;
+        order_buf[k] = ((uint64_t)o.has32 << 32) | o.buf32;
     }
     return bad;
 }
@@ -275,7 +295,8 @@ extern "C" int sim_gen_layouts_locked_hallway(int num_rooms, int S, int mhk, int
 
 extern "C" int sim_gen_layouts_playground(int S, int rows, int cols, int n, int64_t K, uint64_t *rng_state,
                                           const uint64_t *rng_inc, uint64_t *rng_buf, uint64_t *order_state,
-                                          const uint64_t *order_inc, uint32_t *cells, int8_t *agents) {
+                                          const uint64_t *order_inc, uint64_t *order_buf, uint32_t *cells,
+                                          int8_t *agents) {
     int bad = 0;
     const int64_t cs = (int64_t)(cols * (S - 1) + 2) * (rows * (S - 1) + 2);
     for (int64_t k = 0; k < K; k++) {
@@ -283,11 +304,12 @@ extern "C" int sim_gen_layouts_playground(int S, int rows, int cols, int n, int6
         g.lo = rng_state[2 * k]; g.hi = rng_state[2 * k + 1]; g.ilo = rng_inc[2 * k]; g.ihi = rng_inc[2 * k + 1];
         g.has32 = (uint32_t)(rng_buf[k] >> 32) & 1u; g.buf32 = (uint32_t)rng_buf[k];
         o.lo = order_state[2 * k]; o.hi = order_state[2 * k + 1]; o.ilo = order_inc[2 * k]; o.ihi = order_inc[2 * k + 1];
-        o.has32 = 0; o.buf32 = 0;
+        o.has32 = (uint32_t)(order_buf[k] >> 32) & 1u; o.buf32 = (uint32_t)order_buf[k];
         if (!mg::gen_layout_playground(S, rows, cols, n, g, o, cells + k * cs, agents + k * n * 8)) bad = 1;
         rng_state[2 * k] = g.lo; rng_state[2 * k + 1] = g.hi;
         rng_buf[k] = ((uint64_t)g.has32 << 32) | g.buf32;
         order_state[2 * k] = o.lo; order_state[2 * k + 1] = o.hi;
+        order_buf[k] = ((uint64_t)o.has32 << 32) | o.buf32;
     }
     return bad;
 }

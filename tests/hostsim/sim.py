@@ -115,9 +115,11 @@ def gen_layouts_playground(S, rows, cols, n, rng_state, rng_inc, rng_buf, order_
     st, inc, buf = aligned_copy(rng_state, np.uint64), aligned_copy(rng_inc, np.uint64), aligned_copy(rng_buf, np.uint64)
     ost, oinc = aligned_copy(order_state, np.uint64), aligned_copy(order_inc, np.uint64)
     cells, agents = aligned((K, W + 1, H + 1), np.uint32), aligned((K, n, 8), np.int8)
+    obuf = aligned((K,), np.uint64)
     rc = lib().sim_gen_layouts_playground(C.c_int(S), C.c_int(rows), C.c_int(cols), C.c_int(n), C.c_int64(K), _p(st),
-                                          _p(inc), _p(buf), _p(ost), _p(oinc), _p(cells), _p(agents))
+                                          _p(inc), _p(buf), _p(ost), _p(oinc), _p(obuf), _p(cells), _p(agents))
     assert rc == 0, rc
+    gen_layouts_playground.order_buf = obuf  # (buffered half of the order streams, for sim_refresh_done_layouts)
     return unpack_cells(cells, W, H), agents, st, buf, ost
 
 
@@ -127,9 +129,11 @@ def gen_layouts_bup(S, n, rng_state, rng_inc, rng_buf, order_state, order_inc):
     st, inc, buf = aligned_copy(rng_state, np.uint64), aligned_copy(rng_inc, np.uint64), aligned_copy(rng_buf, np.uint64)
     ost, oinc = aligned_copy(order_state, np.uint64), aligned_copy(order_inc, np.uint64)
     cells, agents, info = aligned((K, W + 1, H + 1), np.uint32), aligned((K, n, 8), np.int8), aligned((K,), np.int32)
+    obuf = aligned((K,), np.uint64)
     rc = lib().sim_gen_layouts_bup(C.c_int(S), C.c_int(n), C.c_int64(K), _p(st), _p(inc), _p(buf), _p(ost), _p(oinc),
-                                   _p(cells), _p(agents), _p(info))
+                                   _p(obuf), _p(cells), _p(agents), _p(info))
     assert rc == 0, rc
+    gen_layouts_bup.order_buf = obuf  # (buffered half of the order streams, for sim_refresh_done_layouts)
     return unpack_cells(cells, W, H), agents, st, buf, ost, info
 
 
