@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 9
+#define MG_ABI_VERSION 10
 
 /* MgConfig.flags */
 #define MG_FLAG_SEE_THROUGH_WALLS 0x01u /* agents[0].see_through_walls, base.py:364-365 */
@@ -151,6 +151,12 @@ typedef struct MgStepOut {
     int32_t *status;           /* [1] device word, OR-ed with 1 when an action outside 0..6
                                   (and != -1) was seen: the reference raises ValueError there
                                   (base.py:473-474). May be NULL. */
+    uint8_t *one_hot;          /* [E][n][V][V][21], 16-byte aligned, or NULL. mg_step_obs only: the fused kernel ALSO
+                                  writes OneHotObsWrapper.one_hot(image) of every observation (wrappers.py:158-190:
+                                  11 type + 6 colour + 4 state channels, uint8) straight from its shared-memory
+                                  stage -- what RLlib consumers of the reference read (rllib/__init__.py:110-111) --
+                                  instead of a second pass (mg_one_hot) over `obs`. Plain launches only
+                                  (MG_ERR_BAD_ARG together with MG_FLAG_CHAINED). */
 } MgStepOut;
 
 int mg_abi_version(void);

@@ -28,7 +28,7 @@ HOOK_BLOCKED_UNLOCK_PICKUP = 1
 HOOK_RED_BLUE_DOORS = 2
 HOOK_LOCKED_HALLWAY = 3
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 MAX_VIEW = 15
 MAX_AGENTS = 32
 
@@ -54,7 +54,7 @@ class MgState(C.Structure):
 class MgStepOut(C.Structure):
     _fields_ = [
         ("obs", C.c_void_p), ("reward", C.c_void_p), ("terminated", C.c_void_p),
-        ("truncated", C.c_void_p), ("status", C.c_void_p),
+        ("truncated", C.c_void_p), ("status", C.c_void_p), ("one_hot", C.c_void_p),
     ]
 
 

@@ -102,9 +102,9 @@ int plan(mg::Params &p) {
     return mg::plan_launch(p, env_int("MG_GROUP", 0, k), env_int("MG_WPB", 0, k), kSmemPerBlock - 16 /* the claim counter */, kSmemPerSM, n_sm);
 }
 
-template <int VT, int MODE, bool MULTI = false, bool CHAIN = false, int NT = 0, int HK = -1>
+template <int VT, int MODE, bool MULTI = false, bool CHAIN = false, int NT = 0, int HK = -1, bool OH = false>
 int launch(const mg::Params &p, cudaStream_t stream) {
-    auto kernel = mg::step_obs_kernel<VT, MODE, MULTI, CHAIN, NT, HK>;
+    auto kernel = mg::step_obs_kernel<VT, MODE, MULTI, CHAIN, NT, HK, OH>;
     static thread_local bool configured_dev[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -125,6 +125,18 @@ int dispatch(const mg::Params &p, cudaStream_t stream) {
         return launch<0, MODE>(p, stream);  // no observation phase: view size is irrelevant
     } else {
         if constexpr (MODE == mg::MODE_STEP_OBS && !MULTI) {
+            if (p.one_hot) {  // the launch also writes the one-hot images (plain launches only: step_common)
+                if (!p.generic_view) {
+                    switch (p.V) {
+                        case 3: return launch<3, MODE, false, false, 0, -1, true>(p, stream);
+                        case 5: return launch<5, MODE, false, false, 0, -1, true>(p, stream);
+                        case 7: return launch<7, MODE, false, false, 0, -1, true>(p, stream);
+                        case 9: return launch<9, MODE, false, false, 0, -1, true>(p, stream);
+                        default: break;
+                    }
+                }
+                return launch<0, MODE, false, false, 0, -1, true>(p, stream);
+            }
             if (p.chained) {
                 if (!p.generic_view) {
                     switch (p.V) {
@@ -194,6 +206,7 @@ void fill_config(mg::Params &p, const MgConfig *c, int64_t num_envs) {
     p.ostride = c->obs_agent_stride; p.K = c->num_layouts; p.lstride = c->layout_stride;
     p.num_envs = (int32_t)num_envs;
     p.T = 1;
+    p.rcp_vv = mg::rcp32(p.V * p.V);
     p.trace = g_trace.load(std::memory_order_relaxed);
 }
 
@@ -226,6 +239,8 @@ int fill_out(mg::Params &p, const MgStepOut *o, bool need_obs) {
     if (need_obs && !aligned16(o->obs)) return MG_ERR_ALIGNMENT;
     p.obs = o->obs; p.reward = o->reward; p.terminated = o->terminated; p.truncated = o->truncated;
     p.status = o->status;
+    if (need_obs && o->one_hot && !aligned16(o->one_hot)) return MG_ERR_ALIGNMENT;
+    p.one_hot = need_obs ? o->one_hot : nullptr;  // (mg_step produces no observations: ignored there)
     return 0;
 }
 
@@ -244,6 +259,8 @@ int step_common(const MgConfig *cfg, int64_t num_envs, const MgState *state, con
     p.actions = actions;
     p.T = num_steps;
     p.direction = direction;
+    if (MULTI || MODE != mg::MODE_STEP_OBS) p.one_hot = nullptr;  // (fill_out rejects it for mg_step; a rollout has none)
+    if (p.one_hot && (p.flags & MG_FLAG_CHAINED)) return MG_ERR_BAD_ARG;  // the one-hot variants are plain launches
     if (MULTI || MODE != mg::MODE_STEP_OBS) p.chained = 0;  // only the fused single-step launch chains; a rollout
                                                             // or mg_step is a plain launch and leaves the tickets alone
     // MG_FLAG_STATIC_GRID: the fused single-step launch on a grid no action can change (mg_static.cuh)
@@ -526,7 +543,7 @@ int mg_step_obs(const MgConfig *cfg, int64_t num_envs, const MgState *state, con
 int mg_rollout(const MgConfig *cfg, int64_t num_envs, int32_t num_steps, const MgState *state,
                const int8_t *actions, const MgRolloutOut *out, void *stream) {
     if (!out) return MG_ERR_BAD_ARG;
-    const MgStepOut so = {out->obs, out->reward, out->terminated, out->truncated, out->status};
+    const MgStepOut so = {out->obs, out->reward, out->terminated, out->truncated, out->status, nullptr};
     return step_common<mg::MODE_STEP_OBS, true>(cfg, num_envs, state, actions, &so, stream, num_steps,
                                                 out->direction);
 }

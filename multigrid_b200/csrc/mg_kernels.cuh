@@ -99,6 +99,8 @@ struct Params {
     const int8_t *actions;
     // outputs (device)
     int8_t *obs; double *reward; uint8_t *terminated; uint8_t *truncated; int32_t *status;
+    uint8_t *one_hot;  // [E][n][V][V][21] fused OneHotObsWrapper image (MgStepOut.one_hot; NULL = not wanted)
+    uint32_t rcp_vv;   // ceil(2^32 / (V*V)) (see fastdiv)
     unsigned long long *trace;  // diagnostics: 8 timestamps per warp (mg_debug_set_trace), normally NULL
     // derived geometry. The cell array of an env is (W+1) x (H+1) words, row stride Hp = H+1:
     // row x = W and column y = H hold WALL sentinels, every out-of-range coordinate maps there.
@@ -1401,6 +1403,87 @@ MG_HD void phase_store_plain(const Params &p, const Group &g, int lane) {
     warp_copy(p.agents + (size_t)g.e0 * p.n * 8, g.ag, g.ne * p.n * 8, lane);
 }
 
+// ---- fused one-hot observations (MgStepOut.one_hot) ------------------------------------------------------
+// OneHotObsWrapper.one_hot (multigrid/wrappers.py:158-190) of the observations a pass has just packed into its
+// stage: image (type, colour, state) -> 21 channels = 11 type + 6 colour + 4 state/direction, uint8, written as
+// the contiguous tensor [E][n][V][V][21] the wrapper returns -- straight from shared memory, so the 7x larger
+// tensor costs its HBM writes and nothing else (no second launch, no re-read of the observations).
+// Bytes [first * VV * 21, (first + cnt) * VV * 21) of `out` belong to the pass (first = index of its first
+// agent); they are cut at ABSOLUTE 16-byte boundaries of the tensor (base 16-byte aligned): a lane produces
+// whole 16-byte vectors, the ragged head / tail bytes of a span that does not start or end on a boundary
+// (n * G not a multiple of 16, tail groups) go out bytewise. A vector covers parts of at most two cells; the
+// <= 6 one-bytes of its window are placed with one shift each into a 16-bit mask that a multiply spreads.
+MG_HD uint32_t shl1(uint32_t q) {  // 1 << q, 0 for q >= 32 (PTX shift semantics; "negative" q wrapped)
+#ifdef __CUDA_ARCH__
+    uint32_t r; asm("shl.b32 %0, 1, %1;" : "=r"(r) : "r"(q)); return r;
+#else
+    return q < 32u ? 1u << q : 0u;
+#endif
+}
+
+MG_HD uint32_t one_hot_mask(const uint8_t *stage, int sstride, uint32_t VV, uint32_t rcp_vv, uint32_t rel,
+                            uint32_t nbytes) {
+    // bit q of the result <=> byte rel + q of the span is 1 (q < 16; higher bits are garbage to be masked off).
+    // Branch-free: the lanes of a warp sit at different offsets inside their cells, and a branch on "does my window
+    // reach the next cell" splits the warp for the rest of the (unrolled) loop body.
+    const uint32_t c = mulhi32(rel, 204522253u), off = rel - c * 21u;  // rel / 21 (rel < 2^21)
+    const uint32_t a = fastdiv(c, rcp_vv), cia = c - a * VV;
+    const uint8_t *src = stage + a * (uint32_t)sstride + cia * 3u;
+    // the next cell (the first of the next agent's slot after the last cell of this one); its bits start at 21 - off:
+    // at 16 or beyond -- nothing of it is in the window -- when off <= 5. Past the end of the span: same cell, no bits.
+    const bool more = rel + (21u - off) < nbytes, wrap = cia + 1u == VV;
+    const uint8_t *nxt = !more ? src : (wrap ? src + (sstride - (int)(cia * 3u)) : src + 3);
+    const uint32_t base = 0u - off, base2 = more ? 21u - off : 64u;
+    return shl1(base + src[0]) | shl1(base + 11u + src[1]) | shl1(base + 17u + src[2]) |
+           shl1(base2 + nxt[0]) | shl1(base2 + 11u + nxt[1]) | shl1(base2 + 17u + nxt[2]);
+}
+
+// (explicit scalars instead of `const Params &`: the out-of-line copies below must not force the kernel's
+// parameter block into local memory)
+MG_HD void one_hot_emit(uint8_t *one_hot, uint32_t VV, uint32_t rcp_vv, const uint8_t *stage, int sstride, size_t first,
+                        int cnt, int lane) {
+    const uint32_t nbytes = (uint32_t)cnt * VV * 21u;
+    const size_t b0 = first * VV * 21u;
+    uint8_t *out = one_hot + b0;
+    const uint32_t head = (uint32_t)((16u - (uint32_t)(b0 & 15u)) & 15u);  // bytes before the first boundary
+    if (head >= nbytes) {  // (tiny span inside one vector)
+        for (uint32_t b = lane; b < nbytes; b += LANES) out[b] = (uint8_t)(one_hot_mask(stage, sstride, VV, rcp_vv, b, nbytes) & 1u);
+        return;
+    }
+    const uint32_t nvec = (nbytes - head) >> 4, tail0 = head + (nvec << 4);
+#pragma unroll 4
+    for (uint32_t v = lane; v < nvec; v += LANES) {
+        const uint32_t rel = head + (v << 4);
+        const uint32_t mask = one_hot_mask(stage, sstride, VV, rcp_vv, rel, nbytes);
+        // 4 mask bits -> 4 bytes of 0/1: the multiply puts bit i at bit 8*i (no two products collide)
+        U128 w;
+        w.lo = (uint64_t)(((mask & 15u) * 0x00204081u) & 0x01010101u) |
+               ((uint64_t)((((mask >> 4) & 15u) * 0x00204081u) & 0x01010101u) << 32);
+        w.hi = (uint64_t)((((mask >> 8) & 15u) * 0x00204081u) & 0x01010101u) |
+               ((uint64_t)((((mask >> 12) & 15u) * 0x00204081u) & 0x01010101u) << 32);
+        *(U128 *)(out + rel) = w;
+    }
+    // ragged head and tail (fewer than 16 bytes each)
+    const uint32_t ragged = head + (nbytes - tail0);
+    for (uint32_t q = lane; q < ragged; q += LANES) {
+        const uint32_t b = q < head ? q : tail0 + (q - head);
+        out[b] = (uint8_t)(one_hot_mask(stage, sstride, VV, rcp_vv, b, nbytes) & 1u);
+    }
+}
+
+// Out of line (one copy per module; the plain launch's registers and instruction footprint stay what they are).
+MG_HD_COLD void one_hot_emit_cold(uint8_t *one_hot, uint32_t VV, uint32_t rcp_vv, const uint8_t *stage, int sstride,
+                                  size_t first, int cnt, int lane) {
+    one_hot_emit(one_hot, VV, rcp_vv, stage, sstride, first, cnt, lane);
+}
+
+// The fused one-hot image of a pass of the general kernel, from the pass's complete stage.
+MG_HD void phase_one_hot(const Params &p, const Group &g, int pass, int lane) {
+    const int left = g.ne * p.n - pass * LANES;
+    one_hot_emit(p.one_hot, (uint32_t)(p.V * p.V), p.rcp_vv, stage_of(p, g, pass), p.ostride,
+                 (size_t)g.e0 * p.n + (size_t)pass * LANES, left < LANES ? left : LANES, lane);
+}
+
 #ifdef __CUDACC__
 // ---- TMA bulk copies + mbarrier (sm_90+/sm_100a PTX) -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
@@ -1890,7 +1973,9 @@ __global__ void __launch_bounds__(256) one_hot_kernel_v16(int cells, int64_t age
 // NT / HK: the agent count and the post-hook as compile-time constants (0 / -1 = read them from Params). The phase
 // functions take `p.n` and `p.hook` from a kernel-local copy of Params whose two fields are overwritten with the
 // constants, so after inlining the agent loops unroll and the other env classes' hooks disappear from the hot path.
-template <int VT, int MODE, bool MULTI = false, bool CHAIN = false, int NT = 0, int HK = -1>
+// OH: the launch also writes the one-hot images (MgStepOut.one_hot) -- separate instantiations, so that the plain
+// launch's code, registers and spills are exactly what they are without the feature.
+template <int VT, int MODE, bool MULTI = false, bool CHAIN = false, int NT = 0, int HK = -1, bool OH = false>
 __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __grid_constant__ Params p_in) {
     Params p = p_in;
     if (NT > 0) { p.n = NT; p.rcp_n = NT <= 1 ? 0u : (uint32_t)((1ull << 32) / (uint32_t)NT + 1ull); }
@@ -2023,9 +2108,11 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
                         else bulk_s2g(dst, stage, cnt * p.ostride);
                         bulk_commit();
                     }
+                    if constexpr (OH) phase_one_hot(p, g, pass, lane);  // (under the TMA store: both only read the stage)
                 } else {
                     __syncwarp();
                     phase_obs_store_plain(p, g, pass, lane, tE);
+                    if constexpr (OH) phase_one_hot(p, g, pass, lane);
                     __syncwarp();
                 }
             }

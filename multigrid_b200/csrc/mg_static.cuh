@@ -715,6 +715,10 @@ static_fast_kernel(const __grid_constant__ Params p) {
             warp_copy(dst, stage, cnt * C::OS, lane);
             __syncwarp();
         }
+        // fused one-hot image (MgStepOut.one_hot): expanded from the stage, under the TMA store
+        if (p.one_hot)
+            one_hot_emit_cold(p.one_hot, (uint32_t)(VT * VT), p.rcp_vv, stage, C::OS, (size_t)g.e0 * NT + (size_t)pass * LANES,
+                              cnt, lane);
     }
     trace_mark(p, group * NWARP + warp, lane, 3);
     if (bulk && lane == 0) bulk_wait_read();  // smem must stay valid until the TMA store has read it
@@ -761,6 +765,9 @@ __global__ void __launch_bounds__(32, 24) static_rolled_kernel(const __grid_cons
             __syncwarp();
             warp_copy(dst, stage, cnt * p.ostride, lane);
         }
+        if (p.one_hot)
+            one_hot_emit_cold(p.one_hot, (uint32_t)(p.V * p.V), p.rcp_vv, stage, p.ostride,
+                              (size_t)g.e0 * n + (size_t)pass * LANES, (int)cnt, lane);
     }
     if (bulk && lane == 0) bulk_wait_read();
 }

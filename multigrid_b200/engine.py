@@ -186,6 +186,7 @@ class StepEngine:
         self.chain[:, 2] = 1
         self.pool_rep = None
         self._fresh = None  # MgLayoutGen of enable_fresh_layouts()
+        self.one_hot = None  # (E, n, V, V, 21) uint8 once enable_one_hot() asked the step kernel for it
         # static-grid path (MG_FLAG_STATIC_GRID): memoised per-(x, y, dir) views of the single pool layout, and
         # whether the batch is known to satisfy the promise (True / False; None = injected state, check lazily)
         self.static_obs = None
@@ -516,7 +517,7 @@ class StepEngine:
                                p(self.pool_agents), p(self.hook_state), p(self.pool_rep), p(self.chain),
                                p(self.static_obs))
             out = _cabi.MgStepOut(p(self.obs_buf), p(self.reward), p(self.terminated),
-                                  p(self.truncated), p(self.status))
+                                  p(self.truncated), p(self.status), p(self.one_hot))
             mk = lambda extra: _cabi.MgConfig(cfg.width, cfg.height, cfg.num_agents, cfg.view_size,  # noqa: E731
                                               cfg.max_steps, cfg.flags | extra, cfg.hook, self.obs_stride, K,
                                               cfg.layout_stride, cfg.hook_param)
@@ -530,6 +531,17 @@ class StepEngine:
 
     def _stream(self) -> C.c_void_p:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def enable_one_hot(self) -> torch.Tensor:
+        """From now on every fused step launch ALSO writes OneHotObsWrapper.one_hot of its observations
+        (wrappers.py:158-190) into `self.one_hot` (E, n, V, V, 21) uint8, straight from the kernel's shared-memory
+        stage (MgStepOut.one_hot): no second pass over `obs`. gen_obs() fills it with the standalone kernel."""
+        if self.one_hot is None:
+            V = self.cfg.view_size
+            self.one_hot = torch.zeros((self.num_envs, self.cfg.num_agents, V, V, 21), dtype=torch.uint8,
+                                       device=self.device)
+            self._c = None
+        return self.one_hot
 
     @property
     def obs(self) -> torch.Tensor:
@@ -551,6 +563,10 @@ class StepEngine:
             _cabi.check(self.lib.mg_gen_obs(C.byref(c), self.num_envs, self.cells.data_ptr(),
                                             self.agents.data_ptr(), self.obs_buf.data_ptr(),
                                             self._stream()), "mg_gen_obs")
+            if self.one_hot is not None:  # (reset-time observations: the standalone pass)
+                _cabi.check(self.lib.mg_one_hot(self.cfg.view_size, self.num_envs * self.cfg.num_agents,
+                                                self.obs_stride, self.obs_buf.data_ptr(), self.one_hot.data_ptr(),
+                                                self._stream()), "mg_one_hot")
         return self.obs
 
     def step(self, actions: torch.Tensor | None = None, fused: bool = True, chained: bool = False):
@@ -586,7 +602,8 @@ class StepEngine:
             if self._static_state is not False and self._static_ok():
                 key = 1  # MG_FLAG_STATIC_GRID: a plain launch of the static-grid kernel (chained or not)
                 self._chain_armed = None
-            elif chained:  # head of a chain unless the engine's previous operation was a chained step on this stream
+            elif chained and self.one_hot is None:  # (the one-hot variants are plain launches)
+                # head of a chain unless the engine's previous operation was a chained step on this stream
                 key = 2 if self._chain_armed == stream else 3
                 self._chain_armed = stream
             else:

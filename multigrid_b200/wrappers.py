@@ -1,8 +1,9 @@
 """Batched counterparts of the reference's observation / agent wrappers (multigrid/wrappers.py).
 
 They wrap a `BatchedMultiGridEnv` and keep its batched, on-device conventions:
-  * `OneHotObsWrapper`  (wrappers.py:101-190): image -> uint8 (E, V, V, 21) one-hot, by the CUDA
-    kernel `mg_one_hot` (no torch fallback);
+  * `OneHotObsWrapper`  (wrappers.py:101-190): image -> uint8 (E, V, V, 21) one-hot, written by the fused step
+    kernel itself (MgStepOut.one_hot) when it wraps the base env directly, else by the CUDA kernel `mg_one_hot`
+    (no torch fallback);
   * `ImgObsWrapper`     (wrappers.py:61-98):  observations are the bare image tensors;
   * `SingleAgentWrapper`(wrappers.py:193-233): agent 0's items instead of per-agent dicts.
   * `FullyObsWrapper`   (wrappers.py:17-58):  the whole grid with all agents drawn in, the same
@@ -50,7 +51,14 @@ class OneHotObsWrapper(_Wrapper):
         super().__init__(env)
         base = env.unwrapped
         E, n, V = base.num_envs, base.num_agents, base.agent_view_size
-        self._out = torch.zeros((E, n, V, V, ONE_HOT_CHANNELS), dtype=torch.uint8, device=base.device)
+        # wrapping the base env itself: its fused step kernel emits the one-hot images from now on (`fused=False`
+        # or a wrapped env in between: a separate pass over whatever image the observation holds)
+        # (measured, DESIGN.md section 7: the fused image wins on the static-grid kernels, -31 %, and on the general
+        # kernel with 2 agents; with more agents the general kernel runs its observation phase as two half-warps and
+        # the separate pass is faster)
+        self._fused = env is base and (base.engine.static_obs is not None or base.num_agents <= 2)
+        self._out = base.engine.enable_one_hot() if self._fused else torch.zeros(
+            (E, n, V, V, ONE_HOT_CHANNELS), dtype=torch.uint8, device=base.device)
         for agent in base.agents:
             agent.observation_space["image"] = spaces.Box(low=0, high=1, shape=(V, V, ONE_HOT_CHANNELS),
                                                           dtype=np.uint8)
@@ -61,6 +69,10 @@ class OneHotObsWrapper(_Wrapper):
         stream = C.c_void_p(torch.cuda.current_stream(base.device).cuda_stream)
         img0 = obs[0]["image"]
         if img0.data_ptr() == eng.obs_buf.data_ptr() and img0.shape[1:] == self._out.shape[2:4] + (3,):
+            if self._fused and eng.one_hot is self._out:  # already written by the launch that produced `obs`
+                for i in obs:
+                    obs[i]["image"] = self._out[:, i]
+                return obs
             # the wrapped env's own partial views: the whole observation buffer in one launch
             with torch.cuda.device(base.device):
                 _cabi.check(eng.lib.mg_one_hot(base.agent_view_size, base.num_envs * base.num_agents,

@@ -2,6 +2,8 @@
 interface as oracle.OracleBatch, so the parity tests read the same for every implementation."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -22,8 +24,12 @@ def engine_config(cfg) -> EngineConfig:
 
 class GpuEngine:
     def __init__(self, cfg, grid, agents, pcg_state, pcg_inc, pool_grid=None, pool_agents=None,
-                 layout_idx=None, step_count=None, host_path=False, fused=True):
+                 layout_idx=None, step_count=None, host_path=False, fused=True, one_hot=None):
         self.cfg, self.host_path, self.fused = cfg, host_path, fused
+        # MG_TEST_ONE_HOT=1 (tests/test_fused_one_hot.py): every fused device step ALSO asks the kernel for the
+        # one-hot image (MgStepOut.one_hot) and checks it against the oracle's OneHotObsWrapper.one_hot
+        self.one_hot = (os.environ.get("MG_TEST_ONE_HOT", "0") == "1") if one_hot is None else one_hot
+        self.one_hot = self.one_hot and fused and not host_path
         grid = np.asarray(grid)
         self.B = grid.shape[0]
         if pool_grid is None:
@@ -31,6 +37,8 @@ class GpuEngine:
         self.eng = StepEngine(engine_config(cfg), self.B, "cuda:0", pool_grid, pool_agents)
         self.eng.load_state(grid, agents, step_count, pcg_state, pcg_inc, layout_idx)
         self.eng.obs_buf.fill_(0x55)
+        if self.one_hot:
+            self.eng.enable_one_hot()
 
     def _obs(self, buf):
         V = self.cfg.V
@@ -53,7 +61,13 @@ class GpuEngine:
                     h["terminated"].numpy().copy(), h["truncated"].numpy().copy())
         a = torch.from_numpy(actions).to("cuda:0")
         if self.fused:
+            if self.one_hot:
+                self.eng.one_hot.fill_(0x99)  # every byte must be written
             self.eng.step(a)
+            if self.one_hot:
+                from oracle.mg_oracle import one_hot
+                np.testing.assert_array_equal(self.eng.one_hot.cpu().numpy(), one_hot(self._obs(self.eng.obs_buf)),
+                                              err_msg="fused one-hot")
         else:  # mg_step + mg_gen_obs (only equivalent without post-hook / auto-reset)
             self.eng.step(a, fused=False)
             self.eng.gen_obs()

@@ -61,6 +61,8 @@ void run_groups(const mg::Params &p) {
                 for (int pass = 0; pass < passes; pass++) {
                     obs_pass<VT>(p, g, pass);
                     for (int l = 0; l < L; l++) mg::phase_obs_store_plain(p, g, pass, l, tE);
+                    if (p.one_hot && p.T == 1)
+                        for (int l = 0; l < L; l++) mg::phase_one_hot(p, g, pass, l);
                 }
             }
         }
@@ -95,6 +97,10 @@ void run_groups_static_rolled(const mg::Params &p) {
             const int left = tasks - pass * L, cnt = left < L ? left : L;
             for (int l = 0; l < L; l++)
                 mg::warp_copy(p.obs + ((size_t)g.e0 * n + (size_t)pass * L) * p.ostride, g.stage, cnt * p.ostride, l);
+            if (p.one_hot)
+                for (int l = 0; l < L; l++)
+                    mg::one_hot_emit_cold(p.one_hot, (uint32_t)(p.V * p.V), p.rcp_vv, g.stage, p.ostride,
+                                          (size_t)g.e0 * n + (size_t)pass * L, cnt, l);
         }
     }
 }
@@ -131,6 +137,10 @@ void run_groups_static_fast(const mg::Params &p) {
             }
             for (int l = 0; l < L; l++)
                 mg::warp_copy(p.obs + ((size_t)g.e0 * NT + (size_t)pass * L) * C::OS, stage, cnt * C::OS, l);
+            if (p.one_hot)
+                for (int l = 0; l < L; l++)
+                    mg::one_hot_emit_cold(p.one_hot, (uint32_t)(VT * VT), p.rcp_vv, stage, C::OS,
+                                          (size_t)g.e0 * NT + (size_t)pass * L, cnt, l);
         }
     }
 }
@@ -170,6 +180,8 @@ extern "C" int sim_run(int mode, const MgConfig *c, int64_t num_envs, const MgSt
     p.actions = actions;
     p.obs = o->obs; p.reward = o->reward; p.terminated = o->terminated; p.truncated = o->truncated;
     p.status = o->status;
+    p.one_hot = mode == mg::MODE_STEP_OBS && num_steps == 1 ? o->one_hot : nullptr;
+    p.rcp_vv = mg::rcp32(p.V * p.V);
     if (mode == mg::MODE_STEP_OBS && num_steps == 1 && (p.flags & MG_FLAG_STATIC_GRID)) {
         if (!s->static_obs || p.hook != MG_HOOK_NONE) return MG_ERR_BAD_ARG;
         p.static_obs = reinterpret_cast<const uint8_t *>(s->static_obs);

@@ -179,9 +179,12 @@ class SimEngine:
                                    _p(self.pcg_inc).value, _p(self.layout_idx).value,
                                    _p(self.pool_grid).value, _p(self.pool_agents).value,
                                    _p(self.hook_state).value)
+        # the fused one-hot image (MgStepOut.one_hot), poisoned so that every byte must be written
+        self.one_hot = aligned((self.B, cfg.n, cfg.V, cfg.V, 21), np.uint8)
+        self.one_hot[...] = 0x99
         self.out = _cabi.MgStepOut(_p(self.obs).value, _p(self.reward).value,
                                    _p(self.terminated).value, _p(self.truncated).value,
-                                   _p(self.status).value)
+                                   _p(self.status).value, _p(self.one_hot).value)
         self.c_static = None
         if static:  # MG_FLAG_STATIC_GRID: the caller's promise must hold (checked here like StepEngine does)
             from multigrid_b200.engine import static_layout_ok
@@ -219,7 +222,7 @@ class SimEngine:
         rew, term = aligned((T, self.B, cfg.n), np.float64), aligned((T, self.B, cfg.n), np.uint8)
         trunc, dirs = aligned((T, self.B), np.uint8), aligned((T, self.B, cfg.n), np.int8)
         out = _cabi.MgStepOut(_p(obs).value, _p(rew).value, _p(term).value, _p(trunc).value,
-                              _p(self.status).value)
+                              _p(self.status).value, None)
         self._run(MODE_STEP_OBS, actions, out=out, T=T, direction=dirs)
         if self.status[0] & 1:
             raise ValueError("Unknown action")
@@ -243,7 +246,12 @@ class SimEngine:
             self._run(MODE_STEP, actions)
             self._run(MODE_OBS)
         else:
+            self.one_hot[...] = 0x99
             self._run(MODE_STEP_OBS, actions)
+            # every fused step of every hostsim test also checks the fused one-hot image (MgStepOut.one_hot)
+            # against the oracle's restatement of OneHotObsWrapper.one_hot applied to the observations
+            from oracle.mg_oracle import one_hot
+            np.testing.assert_array_equal(self.one_hot, one_hot(self._obs_view()), err_msg="fused one-hot")
         if self.status[0] & 1:
             raise ValueError("Unknown action")
         assert not (self.status[0] & 4), "static-grid promise violated"

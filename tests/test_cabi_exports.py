@@ -45,7 +45,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_cabi.MgConfig) == 44
     assert C.sizeof(_cabi.MgState) == 96  # 12 pointers (static_obs: ABI v8)
     assert C.sizeof(_cabi.MgRolloutOut) == 48
-    assert C.sizeof(_cabi.MgStepOut) == 40
+    assert C.sizeof(_cabi.MgStepOut) == 48  # 6 pointers (one_hot: ABI v10)
 
 
 def test_argument_validation_needs_no_gpu(lib):

@@ -73,13 +73,23 @@ def time_config(name, steps, knobs, replicas=8):
     snap = [{k: getattr(e, k).clone() for k in names} for e in engines]
     for knob in knobs:
         for key in ("MG_GROUP", "MG_WPB", "MG_NO_BULK", "MG_GENERIC_VIEW", "MG_PDL", "MG_L2HINT", "MG_NO_DEDUP", "CHAINED",
-                    "NOSTATIC", "REPLICAS"):
+                    "NOSTATIC", "REPLICAS", "ONEHOT"):
             os.environ.pop(key, None)
         os.environ.update({k: str(v) for k, v in knob.items()})
         chained = bool(int(os.environ.get("CHAINED", "0")))  # (a kbench knob, not a library one)
         for e in engines:  # NOSTATIC=1 (a kbench knob): the general kernel on a static-grid batch
             e.use_static = not int(os.environ.get("NOSTATIC", "0"))
         nrep = int(os.environ.get("REPLICAS", str(replicas)))  # REPLICAS=1: one batch stepped closed-loop (L2-resident)
+        # ONEHOT (a kbench knob): 1 = the step kernel also writes the one-hot images (MgStepOut.one_hot),
+        # 2 = a separate mg_one_hot pass after every step (what the fused image replaces)
+        onehot = int(os.environ.get("ONEHOT", "0"))
+        for e in engines:
+            if onehot:
+                e.enable_one_hot()
+            e._oh_keep = e.one_hot if e.one_hot is not None else getattr(e, "_oh_keep", None)
+            e.one_hot = e._oh_keep if onehot == 1 else None
+            e._c = None      # rebuild the structs (one_hot pointer) and
+            e._plans = {}    # the prepared launches (they captured the previous knobs)
         for e, sn in zip(engines, snap):
             for k in names:
                 getattr(e, k).copy_(sn[k])
@@ -92,7 +102,11 @@ def time_config(name, steps, knobs, replicas=8):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
                 for k in range(steps):
-                    engines[k % nrep].step(tape[k % NT], chained=chained)
+                    e = engines[k % nrep]
+                    e.step(tape[k % NT], chained=chained)
+                    if onehot == 2:
+                        e.lib.mg_one_hot(V, E * n, e.obs_stride, e.obs_buf.data_ptr(), e._oh_keep.data_ptr(),
+                                         stream.cuda_stream)
         torch.cuda.synchronize()
         best = 1e9
         for rep in range(3):

@@ -72,8 +72,8 @@ def main():
     ks = [k for k in sass_rows(args.rep) if args.kernel in k["name"]]
     k = ks[args.index]
     print("kernel:", k["name"], " SASS rows:", len(k["rows"]))
-    m = re.findall(r"\((int|bool)\)(\d+)", k["name"])
-    pat = args.mangled or (f"{args.kernel}I" + "".join(f"L{'i' if t == 'int' else 'b'}{v}E" for t, v in m) + "E" if m else args.kernel)
+    m = re.findall(r"\((int|bool)\)(-?\d+)", k["name"])
+    pat = args.mangled or (f"{args.kernel}I" + "".join(f"L{'i' if t == 'int' else 'b'}{v.replace('-', 'n')}E" for t, v in m) + "E" if m else args.kernel)
     lm = line_map(args.so, pat)
     assert len(lm) == 1, list(lm)
     lm = next(iter(lm.values()))
@@ -101,7 +101,7 @@ def main():
     def show(label, c):
         st = sorted(((v, s[6:]) for s, v in c.items() if s.startswith("stall_") and v), reverse=True)[:3]
         print(f"{label:28s} samples {c['samples']:7d} ({100*c['samples']/max(1,tot['samples']):5.1f}%)  inst {c['inst']:9d} "
-              f"({100*c['inst']/max(1,tot['inst']):5.1f}%)  smem_wf {c['smem_wf']:8d}/{c['smem_wf_ideal']:8d}  "
+              f"({100*c['inst']/max(1,tot['inst']):5.1f}%, {c['thread_inst']/max(1,c['inst']):4.1f} thr)  smem_wf {c['smem_wf']:8d}/{c['smem_wf_ideal']:8d}  "
               f"gsect {c['gsect']:8d}/{c['gsect_ideal']:8d}  " + " ".join(f"{s}:{v}" for v, s in st))
 
     if args.ranges:
