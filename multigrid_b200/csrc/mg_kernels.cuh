@@ -2012,6 +2012,7 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
     trace_mark(p, group, lane, 0);
     trace_mark(p, group, lane, 7);
     if (bulk && lane == 0) mbar_init(bar, 1);
+    if (lane == 0) *(uint32_t *)(ws + p.off_mbar + 8) = 0u;  // the join counter of the transition phase (below)
     uint32_t ticket = 0;
     bool rec_dirty = false;  // (tickets: the dirty flag arrives with the ticket)
     if (tickets) {
@@ -2074,7 +2075,25 @@ __global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __
             }
             __syncwarp();
         }
-        phase_step<MODE>(p, g, env, er, draw, tE);
+        if (MODE != MODE_OBS && p.G < LANES && p.n > 2) {
+            // Fewer envs than lanes: the env lanes run the (long, serial) transition while the others have nothing
+            // to do. If the idle lanes simply branched around it they would sit at the region's convergence barrier
+            // for microseconds, and the hardware then lets the two halves continue as separate groups for the rest
+            // of the kernel -- the whole observation phase at half width, twice the instructions (ncu: 16.0 active
+            // threads per instruction, profiles/r02_summary.md). So the idle lanes poll a shared counter instead and
+            // reach the barrier together with the last env lane. (With 2 agents the region is short enough for the
+            // halves to merge on their own, and the polling only costs: measured +0.3 us on BlockedUnlockPickup.)
+            uint32_t *join = (uint32_t *)(ws + p.off_mbar + 8);
+            if (env >= 0) {
+                phase_step<MODE>(p, g, env, er, draw, tE);
+                atomicAdd(join, 1u);
+            } else {
+                const uint32_t want = (uint32_t)g.ne * (uint32_t)(t + 1);
+                while (atomicAdd(join, 0u) < want) __nanosleep(64);
+            }
+        } else {
+            phase_step<MODE>(p, g, env, er, draw, tE);
+        }
         __syncwarp();
         trace_mark(p, group, lane, 2);
         if (MODE != MODE_STEP) {

@@ -53,10 +53,8 @@ class OneHotObsWrapper(_Wrapper):
         E, n, V = base.num_envs, base.num_agents, base.agent_view_size
         # wrapping the base env itself: its fused step kernel emits the one-hot images from now on (`fused=False`
         # or a wrapped env in between: a separate pass over whatever image the observation holds)
-        # (measured, DESIGN.md section 7: the fused image wins on the static-grid kernels, -31 %, and on the general
-        # kernel with 2 agents; with more agents the general kernel runs its observation phase as two half-warps and
-        # the separate pass is faster)
-        self._fused = env is base and (base.engine.static_obs is not None or base.num_agents <= 2)
+        # (measured, profiles/r02_summary.md: step + one-hot 82 -> 55 us on Empty-8x8 x 65536)
+        self._fused = env is base
         self._out = base.engine.enable_one_hot() if self._fused else torch.zeros(
             (E, n, V, V, ONE_HOT_CHANNELS), dtype=torch.uint8, device=base.device)
         for agent in base.agents:
