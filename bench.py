@@ -482,11 +482,24 @@ def run_engine(args):
         return time.perf_counter() - t0, h
 
     e2e_raw_s, h = time_host(False)
-    e2e_s, h = time_host(True)
+    e2e_p9_s, h = time_host(True)
     from multigrid_b200.engine import unpack_obs
     M = min(VERIFY_ENVS, E)  # the packed result decodes to exactly the device-side observations
     assert np.array_equal(unpack_obs(h["obs_packed"][:M], cfg["view"]), eng.obs[:M].cpu().numpy()), "packed e2e obs mismatch"
-    checksum = int(h["obs_packed"].sum(dtype=torch.int64)) + float(h["reward"].sum())
+    # headline: the host wire = ONE device-to-host copy of the observations in the palette format (the batch's
+    # distinct cell values indexed with ceil(log2) bits per cell) + a 16-byte record per env (reward value and
+    # counts, terminated mask, truncated); both checked for losslessness on the device, decoded by unpack_wire
+    pal_bits, pal_codes = eng.wire_palette()
+    e2e_pal_s, h = time_host("palette")
+    e2e_s, h = time_host("wire")
+    eng.check_status()  # (raises if a cell fell outside the palette or a reward did not fit its record)
+    from multigrid_b200.engine import unpack_wire
+    w_img, w_rew, w_term, w_trunc = unpack_wire(h["wire"], E, n, cfg["view"], pal_bits, pal_codes)
+    assert np.array_equal(w_img[:M], eng.obs[:M].cpu().numpy()), "wire e2e obs mismatch"
+    assert (w_rew == eng.reward.cpu().numpy()).all(), "wire e2e reward mismatch"
+    assert np.array_equal(w_term, eng.terminated.cpu().numpy().astype(bool)), "wire e2e terminated mismatch"
+    assert np.array_equal(w_trunc, eng.truncated.cpu().numpy().astype(bool)), "wire e2e truncated mismatch"
+    checksum = int(h["wire"].sum(dtype=torch.int64)) + float(w_rew.sum())
 
     # ---- informational: the public Python env API, eager (no graph), device-resident actions
     api_env = envs[1]
@@ -501,7 +514,7 @@ def run_engine(args):
     api_s = time.perf_counter() - t0
     clocks = sampler.stop()
 
-    t = torch.tensor([ms, e2e_s, ms_closed, ms_chained or 0.0, clocks.get("sm_mhz") or 0.0, e2e_raw_s],
+    t = torch.tensor([ms, e2e_s, ms_closed, ms_chained or 0.0, clocks.get("sm_mhz") or 0.0, e2e_raw_s, e2e_p9_s, e2e_pal_s],
                      dtype=torch.float64, device=dev)
     per_rank = None
     if world > 1:
@@ -510,6 +523,7 @@ def run_engine(args):
         per_rank = torch.stack(allr).cpu().numpy()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_s, ms_closed, ms_chained_max, e2e_raw_s = float(t[0]), float(t[1]), float(t[2]), float(t[3]), float(t[5])
+    e2e_p9_s, e2e_pal_s = float(t[6]), float(t[7])
 
     if rank == 0:
         W, H, V = cfg["W"], cfg["H"], cfg["view"]
@@ -522,7 +536,8 @@ def run_engine(args):
         achieved = bpe * E / us / 1e3  # GB/s per GPU: one launch = E env-steps
         grid_read = 3 * W * H
         traffic = ncu_traffic(args.config)
-        bytes_io, bytes_raw = eng.bytes_per_step(packed=True), eng.bytes_per_step(packed=False)
+        bytes_io, bytes_raw = eng.bytes_per_step(packed="wire"), eng.bytes_per_step(packed=False)
+        bytes_p9, bytes_pal = eng.bytes_per_step(packed=True), eng.bytes_per_step(packed="palette")
         kernel = ("mg::static_fast_kernel / static_rolled_kernel (MG_FLAG_STATIC_GRID: memoised views + agent overlay)"
                   if static else "mg::step_obs_kernel<V, MODE_STEP_OBS> (general kernel: per-env cells in shared memory)")
         line = {
@@ -533,11 +548,22 @@ def run_engine(args):
             "clocks": clocks,
             "e2e": {"value": total_envs * n * K2 / e2e_s, "unit": "agent-steps/s",
                     "h2d_bytes_per_step": bytes_io["h2d"], "d2h_bytes_per_step": bytes_io["d2h"],
-                    "steps": K2, "timing": "wall clock around mg_step_obs_host_packed + stream sync per step",
-                    "call": "mg_step_obs_host_packed: observations in the 9-bit-per-cell wire format (lossless; "
-                            "engine.unpack_obs decodes), rewards f64, terminated / truncated bytes",
+                    "steps": K2, "timing": "wall clock around mg_step_obs_host_wire + stream sync per step",
+                    "call": f"mg_step_obs_host_wire: ONE device-to-host copy = observations in the palette format "
+                            f"({pal_bits} bits per cell = index into the {len(pal_codes)} cell values this batch can show) + "
+                            f"{eng.lib.mg_wire_record_bytes(n)} bytes per env (reward value and per-agent counts, terminated "
+                            "mask, truncated); lossless, checked on the device, decoded by engine.unpack_wire and "
+                            "compared with the device tensors here",
+                    "palette_bits": pal_bits, "palette_size": int(len(pal_codes)),
+                    "palette": {"value": total_envs * n * K2 / e2e_pal_s, "d2h_bytes_per_step": bytes_pal["d2h"],
+                                "pcie_gbs": (bytes_pal["h2d"] + bytes_pal["d2h"]) * K2 / e2e_pal_s / 1e9 / world,
+                                "call": "mg_step_obs_host_palette (palette observations; rewards f64 x n, terminated, "
+                                        "truncated as four copies)"},
                     "pcie_gbs": (bytes_io["h2d"] + bytes_io["d2h"]) * K2 / e2e_s / 1e9 / world,
                     "pcie_frac_of_64GBs": (bytes_io["h2d"] + bytes_io["d2h"]) * K2 / e2e_s / 1e9 / world / 64.0,
+                    "packed9": {"value": total_envs * n * K2 / e2e_p9_s, "d2h_bytes_per_step": bytes_p9["d2h"],
+                                "pcie_gbs": (bytes_p9["h2d"] + bytes_p9["d2h"]) * K2 / e2e_p9_s / 1e9 / world,
+                                "call": "mg_step_obs_host_packed (9 bits per cell, no palette)"},
                     "unpacked": {"value": total_envs * n * K2 / e2e_raw_s, "d2h_bytes_per_step": bytes_raw["d2h"],
                                  "pcie_gbs": (bytes_raw["h2d"] + bytes_raw["d2h"]) * K2 / e2e_raw_s / 1e9 / world,
                                  "call": "mg_step_obs_host (raw 3-byte cells)"},

@@ -52,7 +52,7 @@
 extern "C" {
 #endif
 
-#define MG_ABI_VERSION 10
+#define MG_ABI_VERSION 11
 
 /* MgConfig.flags */
 #define MG_FLAG_SEE_THROUGH_WALLS 0x01u /* agents[0].see_through_walls, base.py:364-365 */
@@ -400,6 +400,41 @@ int mg_refresh_done_layouts(const MgConfig *cfg, int64_t num_envs, const MgState
 int mg_step_obs_host(const MgConfig *cfg, int64_t num_envs, const MgState *state,
                      const int8_t *h_actions, int8_t *d_actions, const MgStepOut *d_out,
                      const MgStepOut *h_out, void *stream);
+
+/*
+ * Palette wire format (ABI v11): `bits` (1..8) per cell instead of 9 -- the index of the cell's 9-bit code
+ * (type | colour << 4 | state << 7) in a palette chosen by the caller. The cell values a batch can show are few
+ * (Empty-8x8 with 4 agents: unseen, empty, wall, goal and 16 agent encodings = 20 -> 5 bits: 32 instead of 56 bytes
+ * per 7x7 view); lut is a DEVICE array uint8 [512], lut[code] = index (< 255) or 0xff when the code is not in the palette:
+ * such a cell is written as index 0 and bit 3 (value 8) of `status` is set, so a palette that turns out too small
+ * is noticed, never silently wrong. Record layout as mg_pack_obs with `bits` in place of 9;
+ * mg_packed_obs_stride_bits(V, bits) = bytes per agent. mg_step_obs_host_palette = mg_step_obs_host_packed in this
+ * format. Host decoder: multigrid_b200.engine.unpack_obs(packed, V, bits, palette).
+ */
+int32_t mg_packed_obs_stride_bits(int32_t view_size, int32_t bits);
+int mg_pack_obs_palette(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
+                        int32_t bits, const uint8_t *lut, uint8_t *packed, int32_t *status, void *stream);
+int mg_step_obs_host_palette(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *h_actions,
+                             int8_t *d_actions, const MgStepOut *d_out, uint8_t *d_packed, int32_t bits,
+                             const uint8_t *lut, const MgStepOut *h_out, void *stream);
+
+/*
+ * The host wire (ABI v11): everything a CPU-side caller of env.step() needs from one step in ONE device-to-host
+ * copy. Layout of the buffer (mg_wire_bytes bytes; 16-byte aligned on the device):
+ *   [0, mg_wire_obs_bytes)   observations in the palette format (mg_pack_obs_palette), [E][n][stride_bits]
+ *   then E records of mg_wire_record_bytes(n) bytes:
+ *       float64 value; uint32 terminated mask (bit j = agent j) | truncated << 31; uint32 counts[ceil(n / 8)]
+ *   with reward[e][j] = `value` added counts[j] times (4 bits per agent; 0 -> 0.0): a step's rewards are 0 or ONE
+ *   value per env (base.py:598-602), added once per unlocked door by the LockedHallway hook. The kernel checks that
+ *   the record reproduces every float64 reward bit for bit and sets bit 4 (value 16) of the status word otherwise
+ *   (bit 3: a cell outside the palette). n <= 31. Host decoder: multigrid_b200.engine.unpack_wire.
+ */
+int32_t mg_wire_record_bytes(int32_t num_agents);
+int64_t mg_wire_obs_bytes(int32_t view_size, int32_t bits, int32_t num_agents, int64_t num_envs);
+int64_t mg_wire_bytes(int32_t view_size, int32_t bits, int32_t num_agents, int64_t num_envs);
+int mg_step_obs_host_wire(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *h_actions,
+                          int8_t *d_actions, const MgStepOut *d_out, uint8_t *d_wire, int32_t bits, const uint8_t *lut,
+                          uint8_t *h_wire, void *stream);
 
 /*
  * Prepared steps: mg_step_obs split into "validate + plan once" and "launch". A plan fixes the configuration

@@ -28,7 +28,7 @@ HOOK_BLOCKED_UNLOCK_PICKUP = 1
 HOOK_RED_BLUE_DOORS = 2
 HOOK_LOCKED_HALLWAY = 3
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 MAX_VIEW = 15
 MAX_AGENTS = 32
 
@@ -115,6 +115,17 @@ EXPORTS = {
     "mg_step_plan_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_step_plan_destroy": (None, [C.c_void_p]),
     "mg_packed_obs_stride": (C.c_int32, [C.c_int32]),
+    "mg_packed_obs_stride_bits": (C.c_int32, [C.c_int32, C.c_int32]),
+    "mg_wire_record_bytes": (C.c_int32, [C.c_int32]),
+    "mg_wire_obs_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
+    "mg_wire_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int64]),
+    "mg_step_obs_host_wire": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p, C.c_void_p,
+                                        C.POINTER(MgStepOut), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mg_pack_obs_palette": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "mg_step_obs_host_palette": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p, C.c_void_p,
+                                           C.POINTER(MgStepOut), C.c_void_p, C.c_int32, C.c_void_p,
+                                           C.POINTER(MgStepOut), C.c_void_p]),
     "mg_pack_obs": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mg_step_obs_host_packed": (C.c_int, [C.POINTER(MgConfig), C.c_int64, C.POINTER(MgState), C.c_void_p, C.c_void_p,
                                           C.POINTER(MgStepOut), C.c_void_p, C.POINTER(MgStepOut), C.c_void_p]),

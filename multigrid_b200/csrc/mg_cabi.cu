@@ -652,6 +652,88 @@ int mg_step_obs_host_packed(const MgConfig *cfg, int64_t num_envs, const MgState
     return 0;
 }
 
+int32_t mg_packed_obs_stride_bits(int32_t view_size, int32_t bits) { return mg::packed_obs_stride_bits(view_size, bits); }
+
+int mg_pack_obs_palette(int32_t view_size, int64_t num_agents_total, int32_t obs_agent_stride, const int8_t *obs,
+                        int32_t bits, const uint8_t *lut, uint8_t *packed, int32_t *status, void *stream) {
+    if (view_size < 3 || view_size > MG_MAX_VIEW || num_agents_total < 0 || (obs_agent_stride & 3) ||
+        obs_agent_stride < 3 * view_size * view_size || bits < 1 || bits > 8) return MG_ERR_BAD_ARG;
+    if (num_agents_total == 0) return 0;
+    if (!obs || !packed || !lut) return MG_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(packed) & 7u) || (reinterpret_cast<uintptr_t>(obs) & 15u) ||
+        (reinterpret_cast<uintptr_t>(lut) & 3u)) return MG_ERR_ALIGNMENT;
+    const unsigned blocks = (unsigned)((num_agents_total + 127) / 128);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (view_size == 7) mg::pack_obs_palette_kernel<7><<<blocks, 128, 0, s>>>(7, num_agents_total, obs_agent_stride, obs, bits, lut, packed, status);
+    else if (view_size == 9) mg::pack_obs_palette_kernel<9><<<blocks, 128, 0, s>>>(9, num_agents_total, obs_agent_stride, obs, bits, lut, packed, status);
+    else mg::pack_obs_palette_kernel<0><<<blocks, 128, 0, s>>>(view_size, num_agents_total, obs_agent_stride, obs, bits, lut, packed, status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int mg_step_obs_host_palette(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *h_actions,
+                             int8_t *d_actions, const MgStepOut *d_out, uint8_t *d_packed, int32_t bits,
+                             const uint8_t *lut, const MgStepOut *h_out, void *stream) {
+    int rc = validate(cfg, num_envs);
+    if (rc) return rc;
+    if (!h_actions || !d_actions || !d_out || !d_packed || !lut || !h_out || !h_out->obs || !h_out->reward ||
+        !h_out->terminated || !h_out->truncated) return MG_ERR_BAD_ARG;
+    if (num_envs == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t E = (size_t)num_envs, n = (size_t)cfg->num_agents;
+    cudaError_t err = cudaMemcpyAsync(d_actions, h_actions, E * n, cudaMemcpyHostToDevice, s);
+    if (err != cudaSuccess) return (int)err;
+    rc = step_common<mg::MODE_STEP_OBS>(cfg, num_envs, state, d_actions, d_out, stream);
+    if (rc) return rc;
+    if ((rc = mg_pack_obs_palette(cfg->view_size, (int64_t)(E * n), cfg->obs_agent_stride, d_out->obs, bits, lut,
+                                  d_packed, d_out->status, stream))) return rc;
+    // the small arrays first: they are ready as soon as the step kernel is, the observations follow
+    if ((err = cudaMemcpyAsync(h_out->reward, d_out->reward, E * n * sizeof(double), cudaMemcpyDeviceToHost, s))) return (int)err;
+    if ((err = cudaMemcpyAsync(h_out->terminated, d_out->terminated, E * n, cudaMemcpyDeviceToHost, s))) return (int)err;
+    if ((err = cudaMemcpyAsync(h_out->truncated, d_out->truncated, E, cudaMemcpyDeviceToHost, s))) return (int)err;
+    const size_t pbytes = E * n * (size_t)mg::packed_obs_stride_bits(cfg->view_size, bits);
+    if ((err = cudaMemcpyAsync(h_out->obs, d_packed, pbytes, cudaMemcpyDeviceToHost, s))) return (int)err;
+    return 0;
+}
+
+int32_t mg_wire_record_bytes(int32_t num_agents) { return mg::wire_record_bytes(num_agents); }
+
+int64_t mg_wire_obs_bytes(int32_t view_size, int32_t bits, int32_t num_agents, int64_t num_envs) {
+    const int64_t b = num_envs * num_agents * (int64_t)mg::packed_obs_stride_bits(view_size, bits);
+    return (b + 15) & ~(int64_t)15;
+}
+
+int64_t mg_wire_bytes(int32_t view_size, int32_t bits, int32_t num_agents, int64_t num_envs) {
+    return mg_wire_obs_bytes(view_size, bits, num_agents, num_envs) + num_envs * (int64_t)mg::wire_record_bytes(num_agents);
+}
+
+int mg_step_obs_host_wire(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *h_actions,
+                          int8_t *d_actions, const MgStepOut *d_out, uint8_t *d_wire, int32_t bits, const uint8_t *lut,
+                          uint8_t *h_wire, void *stream) {
+    int rc = validate(cfg, num_envs);
+    if (rc) return rc;
+    if (!h_actions || !d_actions || !d_out || !d_wire || !lut || !h_wire || !d_out->status) return MG_ERR_BAD_ARG;
+    if (cfg->num_agents > 31) return MG_ERR_BAD_ARG;  // (terminated mask + the truncated bit share one word)
+    if (reinterpret_cast<uintptr_t>(d_wire) & 15u) return MG_ERR_ALIGNMENT;
+    if (num_envs == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t E = (size_t)num_envs, n = (size_t)cfg->num_agents;
+    cudaError_t err = cudaMemcpyAsync(d_actions, h_actions, E * n, cudaMemcpyHostToDevice, s);
+    if (err != cudaSuccess) return (int)err;
+    rc = step_common<mg::MODE_STEP_OBS>(cfg, num_envs, state, d_actions, d_out, stream);
+    if (rc) return rc;
+    if ((rc = mg_pack_obs_palette(cfg->view_size, (int64_t)(E * n), cfg->obs_agent_stride, d_out->obs, bits, lut,
+                                  d_wire, d_out->status, stream))) return rc;
+    uint8_t *records = d_wire + mg_wire_obs_bytes(cfg->view_size, bits, cfg->num_agents, num_envs);
+    mg::wire_env_records_kernel<<<(unsigned)((E + 127) / 128), 128, 0, s>>>(
+        (int)n, (int64_t)E, d_out->reward, d_out->terminated, d_out->truncated, records, d_out->status);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if ((err = cudaGetLastError()) != cudaSuccess) return (int)err;
+    const size_t bytes = (size_t)mg_wire_bytes(cfg->view_size, bits, cfg->num_agents, num_envs);
+    if ((err = cudaMemcpyAsync(h_wire, d_wire, bytes, cudaMemcpyDeviceToHost, s))) return (int)err;  // ONE copy
+    return 0;
+}
+
 struct MgStepPlan { LaunchRecord rec; };
 
 int mg_step_plan_create(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *actions,

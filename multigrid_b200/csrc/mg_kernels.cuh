@@ -1926,6 +1926,111 @@ __global__ void __launch_bounds__(128) pack_obs_kernel(int Vr, int64_t agents, i
 }
 #endif
 
+// Palette wire format: `bits` (1..8) per cell = the index of the cell's 9-bit code in a caller-provided palette
+// (lut[code] = index, 0xff = not in the palette -> status |= 8 and index 0). The cell values a batch can show are
+// few (Empty-8x8 with 4 agents: unseen, empty, wall, goal and 16 agent encodings = 20 -> 5 bits, 32 instead of 56
+// bytes per 7x7 view), and the host path is PCIe-bound.
+MG_HD int packed_obs_stride_bits(int V, int bits) { return ((bits * V * V + 63) / 64) * 8; }
+
+#ifdef __CUDACC__
+template <int VT>
+__global__ void __launch_bounds__(128) pack_obs_palette_kernel(int Vr, int64_t agents, int ostride, const int8_t *__restrict__ obs,
+                                                               int pb, const uint8_t *__restrict__ lut,
+                                                               uint8_t *__restrict__ packed, int32_t *status) {
+    __shared__ uint8_t slut[512];
+    for (int q = threadIdx.x; q < 128; q += blockDim.x) ((uint32_t *)slut)[q] = __ldg((const uint32_t *)lut + q);
+    __syncthreads();
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= agents) return;
+    const int V = VT ? VT : Vr, NC = V * V, pstride = packed_obs_stride_bits(V, pb);
+    const uint8_t *src = (const uint8_t *)obs + a * ostride;
+    uint64_t *dst = (uint64_t *)(packed + a * pstride);
+    uint64_t acc = 0;
+    int bits = 0, w = 0;
+    uint32_t bad = 0;
+    auto put = [&](uint32_t t, uint32_t col, uint32_t st) {
+        uint32_t idx = slut[(t & 15u) | ((col & 7u) << 4) | ((st & 3u) << 7)];
+        bad |= (uint32_t)(idx == 0xffu);  // the code is not in the palette (at most 255 entries)
+        idx = idx == 0xffu ? 0u : idx;
+        acc |= (uint64_t)idx << bits;
+        bits += pb;
+        if (bits >= 64) {
+            dst[w++] = acc;
+            bits -= 64;
+            acc = bits ? (uint64_t)idx >> (pb - bits) : 0ull;
+        }
+    };
+    if constexpr (VT != 0) {
+        constexpr int NW = (3 * VT * VT + 3) / 4;
+        uint32_t r[NW];
+        if ((ostride & 15) == 0) {  // 16-byte slots: vector loads
+#pragma unroll
+            for (int q = 0; q < (NW + 3) / 4; q++) {
+                const uint4 v = *(const uint4 *)(src + 16 * q);
+                if (4 * q + 0 < NW) r[4 * q + 0] = v.x;
+                if (4 * q + 1 < NW) r[4 * q + 1] = v.y;
+                if (4 * q + 2 < NW) r[4 * q + 2] = v.z;
+                if (4 * q + 3 < NW) r[4 * q + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NW; q++) r[q] = *(const uint32_t *)(src + 4 * q);
+        }
+#pragma unroll
+        for (int c = 0; c < VT * VT; c++) {
+            const int b0 = 3 * c, b1 = 3 * c + 1, b2 = 3 * c + 2;
+            put((r[b0 >> 2] >> (8 * (b0 & 3))) & 0xff, (r[b1 >> 2] >> (8 * (b1 & 3))) & 0xff, (r[b2 >> 2] >> (8 * (b2 & 3))) & 0xff);
+        }
+    } else {
+        for (int c = 0; c < NC; c++) put(src[3 * c], src[3 * c + 1], src[3 * c + 2]);
+    }
+    if (bits > 0) dst[w++] = acc;
+    for (; w * 8 < pstride; w++) dst[w] = 0;
+    if (bad) status_or(status, 8);
+}
+#endif
+
+// Compact per-env record of the host wire (mg_step_obs_host_wire): a step's rewards are 0 or sums of ONE value per
+// env -- `1 - 0.9 * step_count / max_steps` (base.py:598-602), the same for every agent rewarded in that step; the
+// LockedHallway hook adds it once per door unlocked (envs/locked_hallway.py:203-227) -- so n float64 travel as
+//   { float64 value; uint32 terminated mask | truncated << 31; uint32 counts[ceil(n / 8)] (4 bits per agent) }
+// with reward[j] = value added counts[j] times (0 -> 0.0). The kernel CHECKS that this reproduces every reward bit
+// for bit and sets bit 4 (value 16) of the status word otherwise.
+MG_HD int wire_record_bytes(int n) { return (8 + 4 + 4 * ((n + 7) / 8) + 7) & ~7; }
+
+MG_HD bool wire_env_record(int n, const double *reward, const uint8_t *terminated, uint8_t truncated, uint8_t *rec) {
+    double v = 0.0;
+    for (int j = 0; j < n; j++)
+        if (reward[j] != 0.0 && (v == 0.0 || (reward[j] < v) == (v > 0.0))) v = reward[j];  // the smallest magnitude
+    uint32_t tmask = (uint32_t)(truncated != 0) << 31;
+    bool ok = true;
+    uint32_t *counts = (uint32_t *)(rec + 12);
+    for (int w = 0; w < (n + 7) / 8; w++) counts[w] = 0;
+    for (int j = 0; j < n; j++) {
+        tmask |= (uint32_t)(terminated[j] != 0) << j;
+        double acc = 0.0;
+        uint32_t c = 0;
+        while (acc != reward[j] && c < 15u) { acc += v; c++; }
+        ok &= acc == reward[j];
+        counts[j >> 3] |= c << (4 * (j & 7));
+    }
+    *(double *)rec = v;
+    *(uint32_t *)(rec + 8) = tmask;
+    return ok;
+}
+
+#ifdef __CUDACC__
+__global__ void __launch_bounds__(128) wire_env_records_kernel(int n, int64_t E, const double *__restrict__ reward,
+                                                               const uint8_t *__restrict__ terminated,
+                                                               const uint8_t *__restrict__ truncated,
+                                                               uint8_t *__restrict__ records, int32_t *status) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    if (!wire_env_record(n, reward + e * n, terminated + e * n, truncated[e], records + e * wire_record_bytes(n)))
+        status_or(status, 16);
+}
+#endif
+
 #ifdef __CUDACC__
 // MULTI = mg_rollout (p.T steps per launch); the single-step kernels compile with T == 1 and no loop.
 // Same result, 16 output bytes per thread (one 128-bit store): the 16 bytes [p0, p0+16) of the flat

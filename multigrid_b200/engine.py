@@ -82,32 +82,65 @@ def static_layout_ok(pool_grid, pool_agents) -> bool:
     return bool((g[0, x, y, 0] != 2).all())
 
 
-def packed_obs_stride(view_size: int) -> int:
-    """Bytes per agent of the packed wire format (mg_packed_obs_stride): 9 bits per cell, whole 8-byte words."""
-    return ((9 * view_size * view_size + 63) // 64) * 8
+def packed_obs_stride(view_size: int, bits: int = 9) -> int:
+    """Bytes per agent of the packed wire formats (mg_packed_obs_stride / _bits): `bits` per cell, whole 8-byte words."""
+    return ((bits * view_size * view_size + 63) // 64) * 8
 
 
-def unpack_obs(packed, view_size: int) -> np.ndarray:
-    """Decoder of the packed observation wire format (include/multigrid_b200.h, mg_pack_obs): uint8 [..., stride]
-    -> int8 image [..., V, V, 3]. Cell (a, b) is the 9-bit code type | colour << 4 | state << 7 at bits
-    [9*(a*V + b), +9) of the agent's little-endian record. Host-side numpy; torch tensors are accepted."""
+def unpack_obs(packed, view_size: int, bits: int = 9, palette=None) -> np.ndarray:
+    """Decoder of the packed observation wire formats (include/multigrid_b200.h, mg_pack_obs / mg_pack_obs_palette):
+    uint8 [..., stride] -> int8 image [..., V, V, 3]. Cell (a, b) occupies bits [bits*(a*V + b), +bits) of the agent's
+    little-endian record: with bits = 9 it IS the code type | colour << 4 | state << 7, with a palette (uint16 codes,
+    `StepEngine.wire_palette()`) it is the index of that code. Host-side numpy; torch tensors are accepted."""
     if isinstance(packed, torch.Tensor):
         packed = packed.cpu().numpy()
-    V = int(view_size)
+    V, B = int(view_size), int(bits)
     p = np.ascontiguousarray(packed, dtype=np.uint8)
-    assert p.shape[-1] == packed_obs_stride(V), (p.shape, V)
+    assert p.shape[-1] == packed_obs_stride(V, B), (p.shape, V, B)
     words = p.view("<u8")                                   # [..., stride / 8]
-    off = 9 * np.arange(V * V, dtype=np.int64)
+    off = B * np.arange(V * V, dtype=np.int64)
     lo, sh = off // 64, (off % 64).astype(np.uint64)
     code = words[..., lo] >> sh
-    spill = sh > np.uint64(55)                               # the code continues in the next word
+    spill = sh > np.uint64(64 - B)                           # the field continues in the next word
     hi = np.minimum(lo + 1, words.shape[-1] - 1)
-    code = np.where(spill, code | (words[..., hi] << ((np.uint64(64) - sh) & np.uint64(63))), code) & np.uint64(0x1ff)
+    code = np.where(spill, code | (words[..., hi] << ((np.uint64(64) - sh) & np.uint64(63))), code) & np.uint64((1 << B) - 1)
+    if palette is not None:
+        code = np.asarray(palette, dtype=np.uint64)[code.astype(np.int64)]
     out = np.empty(code.shape + (3,), np.int8)
     out[..., 0] = code & np.uint64(15)
     out[..., 1] = (code >> np.uint64(4)) & np.uint64(7)
     out[..., 2] = code >> np.uint64(7)
     return out.reshape(code.shape[:-1] + (V, V, 3))
+
+
+def wire_record_bytes(num_agents: int) -> int:
+    """Bytes of one env record of the host wire (mg_wire_record_bytes)."""
+    return (8 + 4 + 4 * ((num_agents + 7) // 8) + 7) & ~7
+
+
+def unpack_wire(wire, num_envs: int, num_agents: int, view_size: int, bits: int, palette):
+    """Decoder of the host wire (include/multigrid_b200.h, mg_step_obs_host_wire): one uint8 buffer ->
+    (image int8 [E, n, V, V, 3], reward float64 [E, n], terminated bool [E, n], truncated bool [E]).
+    reward[e, j] = the env's value added counts[e, j] times -- the additions are done here in float64, like the
+    kernel that checked the record, so the rewards are the engine's bit for bit."""
+    if isinstance(wire, torch.Tensor):
+        wire = wire.cpu().numpy()
+    E, n, V = int(num_envs), int(num_agents), int(view_size)
+    w = np.ascontiguousarray(wire, dtype=np.uint8).reshape(-1)
+    ps, rb = packed_obs_stride(V, bits), wire_record_bytes(n)
+    obs_bytes = (E * n * ps + 15) & ~15
+    image = unpack_obs(w[:E * n * ps].reshape(E, n, ps), V, bits, palette)
+    rec = w[obs_bytes:obs_bytes + E * rb].reshape(E, rb)
+    value = rec[:, :8].copy().view("<f8").reshape(E)
+    tmask = rec[:, 8:12].copy().view("<u4").reshape(E)
+    cw = rec[:, 12:12 + 4 * ((n + 7) // 8)].copy().view("<u4").reshape(E, -1)
+    j = np.arange(n)
+    counts = (cw[:, j >> 3] >> (4 * (j & 7)).astype(np.uint32)) & np.uint32(15)
+    reward = np.zeros((E, n), np.float64)
+    for k in range(1, int(counts.max(initial=0)) + 1):  # (1 almost always: repeated addition, not a multiply)
+        reward = np.where(counts >= k, reward + value[:, None], reward)
+    terminated = ((tmask[:, None] >> j.astype(np.uint32)) & np.uint32(1)).astype(bool)
+    return image, reward, terminated, (tmask >> np.uint32(31)).astype(bool)
 
 
 def _as_i64_bits(a) -> np.ndarray:
@@ -187,6 +220,7 @@ class StepEngine:
         self.pool_rep = None
         self._fresh = None  # MgLayoutGen of enable_fresh_layouts()
         self.one_hot = None  # (E, n, V, V, 21) uint8 once enable_one_hot() asked the step kernel for it
+        self._palette = None  # (bits, codes, device lut) of the palette wire format, see wire_palette()
         # static-grid path (MG_FLAG_STATIC_GRID): memoised per-(x, y, dir) views of the single pool layout, and
         # whether the batch is known to satisfy the promise (True / False; None = injected state, check lazily)
         self.static_obs = None
@@ -396,6 +430,7 @@ class StepEngine:
         """The layout pool was replaced: no env is known to equal its layout any more; with a single layout,
         (re)build the 32-copy buffer clean groups load their cells from."""
         self.grid_dirty.fill_(1)
+        self._palette = None
         self.pool_rep = (self.pool_grid[:1].repeat(32, 1, 1).contiguous()
                          if self.pool_grid is not None and self.pool_grid.shape[0] == 1 else None)
         self._c = None
@@ -462,6 +497,8 @@ class StepEngine:
         if grid is not None:
             self._pack(grid, self.cells)
             self.grid_dirty.fill_(1)
+        if grid is not None or agents is not None:
+            self._palette = None
         if (grid is not None or agents is not None) and self.static_obs is not None:
             self._static_state = None  # re-checked on the device before the next step
         put(self.agents, agents)
@@ -682,14 +719,59 @@ class StepEngine:
                                                  self._stream()), "mg_obs_features")
         return out
 
-    def host_buffers(self, packed: bool = False):
+    def wire_palette(self):
+        """(bits, codes) of the palette wire format (mg_pack_obs_palette): `codes` (uint16, sorted) = every 9-bit cell
+        code type | colour << 4 | state << 7 an observation of this batch can show -- unseen, empty, the out-of-bounds
+        wall, every cell of the layout pool and of the current grids (a door in all three states: toggling changes
+        only the state), everything an agent carries, and the agents themselves (colour x 4 directions) -- and `bits`
+        = ceil(log2(len(codes))). Derived once per pool / injected state on the device. A code outside it (objects
+        injected later without telling the engine) sets bit 3 of the status word: check_status() raises."""
+        if self._palette is None:
+            dev = self.device
+            code = lambda w: ((w & 15) | (((w >> 8) & 7) << 4) | (((w >> 16) & 3) << 7))  # noqa: E731
+            found = [torch.tensor([0, 1, 2 | (5 << 4)], dtype=torch.int64, device=dev)]  # unseen, empty, wall
+            for cells in (self.pool_grid, self.cells):
+                if cells is not None:
+                    found.append(torch.unique(code(cells.to(torch.int64).flatten())))
+            for ag in (self.pool_agents, self.agents):
+                if ag is not None:
+                    a = ag.to(torch.int64).reshape(-1, 8)
+                    found.append(torch.unique((a[:, 4] & 15) | ((a[:, 5] & 7) << 4) | ((a[:, 6] & 3) << 7)))  # carried
+                    colours = torch.unique(a[:, 7] & 7)
+                    found.append((10 | (colours[:, None] << 4) | (torch.arange(4, device=dev)[None, :] << 7)).flatten())
+            codes = torch.unique(torch.cat(found))
+            doors = codes[(codes & 15) == 4] & 0x7f  # (type 4: every state of every door colour present)
+            if doors.numel():
+                codes = torch.unique(torch.cat([codes, (doors[:, None] | (torch.arange(3, device=dev)[None, :] << 7)).flatten()]))
+            codes = codes.cpu().numpy().astype(np.uint16)
+            bits = max(1, int(np.ceil(np.log2(len(codes)))))
+            if len(codes) > 255:  # (index 0xff means "not in the palette")
+                raise RuntimeError("more than 255 distinct cell values: use the 9-bit wire format")
+            lut = np.full(512, 0xff, np.uint8)
+            lut[codes] = np.arange(len(codes), dtype=np.uint8)
+            self._palette = (bits, codes, torch.from_numpy(lut).to(dev))
+        return self._palette[0], self._palette[1]
+
+    def host_buffers(self, packed=False):
         """Pinned host mirrors used by `step_host` (allocated on first use). packed=True adds `obs_packed`
-        (E, n, packed_obs_stride(V)) uint8, the compact wire format of the observations (see unpack_obs)."""
+        (E, n, packed_obs_stride(V)) uint8, the compact wire format of the observations (see unpack_obs);
+        packed="palette" adds `obs_palette` (E, n, packed_obs_stride(V, bits)) for the palette format."""
         pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # noqa: E731
         if self._host is None:
             self._host = dict(actions=pin(self.actions), reward=pin(self.reward), terminated=pin(self.terminated),
                               truncated=pin(self.truncated))
-        if packed and "obs_packed" not in self._host:
+        if packed == "wire":
+            nbytes = self.lib.mg_wire_bytes(self.cfg.view_size, self.wire_palette()[0], self.cfg.num_agents, self.num_envs)
+            if "wire" not in self._host or self._host["wire"].numel() != nbytes:
+                self._wire = torch.zeros((nbytes,), dtype=torch.uint8, device=self.device)
+                self._host["wire"] = pin(self._wire)
+            return self._host
+        if packed == "palette":
+            ps = packed_obs_stride(self.cfg.view_size, self.wire_palette()[0])
+            if "obs_palette" not in self._host or self._host["obs_palette"].shape[-1] != ps:
+                self._packed_pal = torch.zeros((self.num_envs, self.cfg.num_agents, ps), dtype=torch.uint8, device=self.device)
+                self._host["obs_palette"] = pin(self._packed_pal)
+        elif packed and "obs_packed" not in self._host:
             ps = packed_obs_stride(self.cfg.view_size)
             self._packed = torch.zeros((self.num_envs, self.cfg.num_agents, ps), dtype=torch.uint8, device=self.device)
             self._host["obs_packed"] = pin(self._packed)
@@ -697,24 +779,43 @@ class StepEngine:
             self._host["obs"] = pin(self.obs_buf)
         return self._host
 
-    def step_host(self, synchronize: bool = True, packed: bool = False):
+    def step_host(self, synchronize: bool = True, packed=False):
         """mg_step_obs_host: actions come from, and results go to, pinned HOST buffers.
 
         Fill `host_buffers()['actions']` first. This is the end-to-end path a CPU-side caller of
         `env.step()` sees: H2D actions + kernel + D2H (obs, reward, terminated, truncated).
         packed=True (mg_step_obs_host_packed): the observations cross PCIe in the 9-bit-per-cell wire format
         (`obs_packed`, 56 instead of 148+ bytes per agent for V = 7; `unpack_obs` decodes it), everything else
-        is unchanged.
+        is unchanged. packed="palette" (mg_step_obs_host_palette): `wire_palette()[0]` bits per cell (`obs_palette`:
+        32 bytes per agent on Empty-8x8 with 4 agents; `unpack_obs(h["obs_palette"], V, *eng.wire_palette())`).
+        packed="wire" (mg_step_obs_host_wire): ONE device-to-host copy of `h["wire"]` = palette observations followed by
+        a 16-byte record per env (reward value + counts, terminated mask, truncated) instead of n float64 + n + 1 bytes;
+        `unpack_wire(h["wire"], E, n, V, *eng.wire_palette())` decodes all four results.
         """
         self._chain_armed = None
         h = self.host_buffers(packed)
         c, st, out = self._structs()
         if self._static_state is not False and self._static_ok():
             c = self._static_cfg[0]
-        hout = _cabi.MgStepOut(h["obs_packed" if packed else "obs"].data_ptr(), h["reward"].data_ptr(),
-                               h["terminated"].data_ptr(), h["truncated"].data_ptr(), None)
+        if packed == "wire":  # ONE device-to-host copy: palette observations + compact per-env records (unpack_wire)
+            with torch.cuda.device(self.device):
+                _cabi.check(self.lib.mg_step_obs_host_wire(
+                    C.byref(c), self.num_envs, C.byref(st), h["actions"].data_ptr(), self.actions.data_ptr(),
+                    C.byref(out), self._wire.data_ptr(), self._palette[0], self._palette[2].data_ptr(),
+                    h["wire"].data_ptr(), self._stream()), "mg_step_obs_host_wire")
+                if synchronize:
+                    torch.cuda.current_stream(self.device).synchronize()
+            return h
+        key = "obs_palette" if packed == "palette" else ("obs_packed" if packed else "obs")
+        hout = _cabi.MgStepOut(h[key].data_ptr(), h["reward"].data_ptr(),
+                               h["terminated"].data_ptr(), h["truncated"].data_ptr(), None, None)
         with torch.cuda.device(self.device):
-            if packed:
+            if packed == "palette":
+                _cabi.check(self.lib.mg_step_obs_host_palette(
+                    C.byref(c), self.num_envs, C.byref(st), h["actions"].data_ptr(), self.actions.data_ptr(),
+                    C.byref(out), self._packed_pal.data_ptr(), self._palette[0], self._palette[2].data_ptr(),
+                    C.byref(hout), self._stream()), "mg_step_obs_host_palette")
+            elif packed:
                 _cabi.check(self.lib.mg_step_obs_host_packed(
                     C.byref(c), self.num_envs, C.byref(st), h["actions"].data_ptr(), self.actions.data_ptr(),
                     C.byref(out), self._packed.data_ptr(), C.byref(hout), self._stream()), "mg_step_obs_host_packed")
@@ -733,14 +834,25 @@ class StepEngine:
         if st & 2:
             self.status.zero_()
             raise RecursionError("rejection sampling failed in place_obj")  # base.py:640-641
+        if st & 16:
+            self.status.zero_()
+            raise RuntimeError("host wire: a step's rewards are not sums of one value per env; use packed='palette'")
+        if st & 8:
+            self.status.zero_()
+            raise RuntimeError("palette wire format: an observation holds a cell value outside wire_palette() "
+                               "(state injected without load_state?); use packed=True")
         if st & 5:
             self.status.zero_()
             if st & 4:
                 raise RuntimeError("MG_FLAG_STATIC_GRID promise violated: an agent left the grid or carries an object")
             raise ValueError("Unknown action")
 
-    def bytes_per_step(self, packed: bool = False) -> dict:
+    def bytes_per_step(self, packed=False) -> dict:
         """h2d / d2h bytes of one `step_host` call."""
         E, n = self.num_envs, self.cfg.num_agents
-        obs = packed_obs_stride(self.cfg.view_size) if packed else self.obs_stride
+        V = self.cfg.view_size
+        if packed == "wire":
+            return dict(h2d=E * n, d2h=int(self.lib.mg_wire_bytes(V, self.wire_palette()[0], n, E)))
+        obs = (packed_obs_stride(V, self.wire_palette()[0]) if packed == "palette"
+               else packed_obs_stride(V) if packed else self.obs_stride)
         return dict(h2d=E * n, d2h=E * n * obs + E * n * 8 + E * n + E)

@@ -325,3 +325,13 @@ extern "C" int sim_gen_layouts_playground(int S, int rows, int cols, int n, int6
     }
     return bad;
 }
+
+// mg_step_obs_host_wire's per-env record on the CPU: the same wire_env_record() the CUDA kernel calls.
+extern "C" int sim_wire_env_records(int n, int64_t E, const double *reward, const uint8_t *terminated,
+                                    const uint8_t *truncated, uint8_t *records) {
+    int bad = 0;
+    for (int64_t e = 0; e < E; e++)
+        if (!mg::wire_env_record(n, reward + e * n, terminated + e * n, truncated[e], records + e * mg::wire_record_bytes(n)))
+            bad = 1;
+    return bad;
+}
