@@ -99,12 +99,13 @@ int plan(mg::Params &p) {
         if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         if (sms[dev] > 0) n_sm = sms[dev];
     }
+    p.num_sms = env_int("MG_NO_ROOMY", 0, k) ? 0 : n_sm;  // (knob: 0 disables the uncapped instantiations)
     return mg::plan_launch(p, env_int("MG_GROUP", 0, k), env_int("MG_WPB", 0, k), kSmemPerBlock - 16 /* the claim counter */, kSmemPerSM, n_sm);
 }
 
-template <int VT, int MODE, bool MULTI = false, bool CHAIN = false, int NT = 0, int HK = -1, bool OH = false>
+template <int VT, int MODE, bool MULTI = false, bool CHAIN = false, int NT = 0, int HK = -1, bool OH = false, bool ROOMY = false>
 int launch(const mg::Params &p, cudaStream_t stream) {
-    auto kernel = mg::step_obs_kernel<VT, MODE, MULTI, CHAIN, NT, HK, OH>;
+    auto kernel = mg::step_obs_kernel<VT, MODE, MULTI, CHAIN, NT, HK, OH, ROOMY>;
     static thread_local bool configured_dev[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -151,9 +152,14 @@ int dispatch(const mg::Params &p, cudaStream_t stream) {
             }
         }
         if constexpr (MODE == mg::MODE_STEP_OBS && !MULTI) {
+            // a launch whose blocks are all resident at 4 per SM takes the instantiation without the register cap
+            const int groups = (p.num_envs + p.G - 1) / p.G, blocks = (groups + p.wpb - 1) / p.wpb;
+            const bool roomy = p.wpb == 4 && blocks <= 4 * p.num_sms;
             // BASELINE configs[2] (BlockedUnlockPickup, 2 agents, view 7): agent count and hook compiled in
             if (!p.generic_view && p.V == 7 && p.n == 2 && p.hook == MG_HOOK_BLOCKED_UNLOCK_PICKUP)
-                return launch<7, MODE, false, false, 2, MG_HOOK_BLOCKED_UNLOCK_PICKUP>(p, stream);
+                return roomy ? launch<7, MODE, false, false, 2, MG_HOOK_BLOCKED_UNLOCK_PICKUP, false, true>(p, stream)
+                             : launch<7, MODE, false, false, 2, MG_HOOK_BLOCKED_UNLOCK_PICKUP>(p, stream);
+            if (!p.generic_view && p.V == 7 && roomy) return launch<7, MODE, false, false, 0, -1, false, true>(p, stream);
         }
         if (!p.generic_view) {
             switch (p.V) {

@@ -74,6 +74,7 @@ struct Params {
     // every output array ([T][E]...); agents and the per-env scalars stay on chip between steps.
     int32_t T;
     int32_t pdl;    // host side only: launch with programmatic stream serialization
+    int32_t num_sms;  // host side only: SMs of the launching device (picks the ROOMY instantiations)
     // Chained launches (MG_FLAG_CHAINED, MgState.chain_next / chain_done, see include/multigrid_b200.h):
     // per-env tickets order consecutive chained step launches on the same state env by env, so a launch need
     // not wait for the whole previous grid. chained: 0 = plain launch (tickets untouched), 1 = chained,
@@ -2080,8 +2081,11 @@ __global__ void __launch_bounds__(256) one_hot_kernel_v16(int cells, int64_t age
 // constants, so after inlining the agent loops unroll and the other env classes' hooks disappear from the hot path.
 // OH: the launch also writes the one-hot images (MgStepOut.one_hot) -- separate instantiations, so that the plain
 // launch's code, registers and spills are exactly what they are without the feature.
-template <int VT, int MODE, bool MULTI = false, bool CHAIN = false, int NT = 0, int HK = -1, bool OH = false>
-__global__ void __launch_bounds__(128, VT >= 9 ? 4 : 7) step_obs_kernel(const __grid_constant__ Params p_in) {
+// ROOMY: compiled for 4 blocks per SM (up to 128 registers: no spills) instead of 7 (72 registers). For launches whose
+// blocks are all resident at 4 per SM anyway -- BASELINE configs[2], BlockedUnlockPickup x 32 768, is half a wave --
+// the register cap only costs: 9.7 -> 8.5 us per launch.
+template <int VT, int MODE, bool MULTI = false, bool CHAIN = false, int NT = 0, int HK = -1, bool OH = false, bool ROOMY = false>
+__global__ void __launch_bounds__(128, (VT >= 9 || ROOMY) ? 4 : 7) step_obs_kernel(const __grid_constant__ Params p_in) {
     Params p = p_in;
     if (NT > 0) { p.n = NT; p.rcp_n = NT <= 1 ? 0u : (uint32_t)((1ull << 32) / (uint32_t)NT + 1ull); }
     if (HK >= 0) p.hook = HK;
