@@ -761,7 +761,10 @@ class StepEngine:
             self._host = dict(actions=pin(self.actions), reward=pin(self.reward), terminated=pin(self.terminated),
                               truncated=pin(self.truncated))
         if packed == "wire":
+            if "wire" in self._host and self._palette is not None and self._host.get("_wire_for") is self._palette:
+                return self._host  # (fast path: buffers match the current palette)
             nbytes = self.lib.mg_wire_bytes(self.cfg.view_size, self.wire_palette()[0], self.cfg.num_agents, self.num_envs)
+            self._host["_wire_for"] = self._palette
             if "wire" not in self._host or self._host["wire"].numel() != nbytes:
                 self._wire = torch.zeros((nbytes,), dtype=torch.uint8, device=self.device)
                 self._host["wire"] = pin(self._wire)
@@ -779,7 +782,7 @@ class StepEngine:
             self._host["obs"] = pin(self.obs_buf)
         return self._host
 
-    def step_host(self, synchronize: bool = True, packed=False):
+    def step_host(self, synchronize: bool = True, packed=False, actions: torch.Tensor | None = None):
         """mg_step_obs_host: actions come from, and results go to, pinned HOST buffers.
 
         Fill `host_buffers()['actions']` first. This is the end-to-end path a CPU-side caller of
@@ -797,10 +800,17 @@ class StepEngine:
         c, st, out = self._structs()
         if self._static_state is not False and self._static_ok():
             c = self._static_cfg[0]
+        if actions is None:
+            h_act = h["actions"].data_ptr()
+        else:  # the caller's own pinned int8 (E, n) tensor instead of host_buffers()['actions'] (no staging copy)
+            if (actions.dtype != torch.int8 or actions.shape != self._act_shape or not actions.is_contiguous()
+                    or actions.is_cuda or not actions.is_pinned()):
+                raise TypeError("actions must be a contiguous pinned int8 host tensor of shape (num_envs, n)")
+            h_act = actions.data_ptr()
         if packed == "wire":  # ONE device-to-host copy: palette observations + compact per-env records (unpack_wire)
             with torch.cuda.device(self.device):
                 _cabi.check(self.lib.mg_step_obs_host_wire(
-                    C.byref(c), self.num_envs, C.byref(st), h["actions"].data_ptr(), self.actions.data_ptr(),
+                    C.byref(c), self.num_envs, C.byref(st), h_act, self.actions.data_ptr(),
                     C.byref(out), self._wire.data_ptr(), self._palette[0], self._palette[2].data_ptr(),
                     h["wire"].data_ptr(), self._stream()), "mg_step_obs_host_wire")
                 if synchronize:
@@ -812,16 +822,16 @@ class StepEngine:
         with torch.cuda.device(self.device):
             if packed == "palette":
                 _cabi.check(self.lib.mg_step_obs_host_palette(
-                    C.byref(c), self.num_envs, C.byref(st), h["actions"].data_ptr(), self.actions.data_ptr(),
+                    C.byref(c), self.num_envs, C.byref(st), h_act, self.actions.data_ptr(),
                     C.byref(out), self._packed_pal.data_ptr(), self._palette[0], self._palette[2].data_ptr(),
                     C.byref(hout), self._stream()), "mg_step_obs_host_palette")
             elif packed:
                 _cabi.check(self.lib.mg_step_obs_host_packed(
-                    C.byref(c), self.num_envs, C.byref(st), h["actions"].data_ptr(), self.actions.data_ptr(),
+                    C.byref(c), self.num_envs, C.byref(st), h_act, self.actions.data_ptr(),
                     C.byref(out), self._packed.data_ptr(), C.byref(hout), self._stream()), "mg_step_obs_host_packed")
             else:
                 _cabi.check(self.lib.mg_step_obs_host(
-                    C.byref(c), self.num_envs, C.byref(st), h["actions"].data_ptr(),
+                    C.byref(c), self.num_envs, C.byref(st), h_act,
                     self.actions.data_ptr(), C.byref(out), C.byref(hout), self._stream()),
                     "mg_step_obs_host")
             if synchronize:
