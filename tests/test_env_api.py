@@ -339,3 +339,43 @@ def test_one_hot_over_fully_obs_encodes_the_wrapped_image():
             got = obs[i]["image"].cpu().numpy()
             assert got.shape == (33, base.width, base.height, 21)
             np.testing.assert_array_equal(got, np.stack([O.one_hot(f) for f in full]), err_msg=f"step {t}")
+
+
+def test_world_object_view_matches_the_reference_encodings():
+    """core/world_object.py: the reference's class names, encodings and rule predicates (world_object.py:28-605)."""
+    from multigrid_b200.core.world_object import Ball, Box, Door, Floor, Goal, Key, Lava, Wall, WorldObj
+    assert Wall().encode() == (2, 5, 0) and Goal().encode() == (8, 1, 0) and Lava().encode() == (9, 0, 0)
+    assert Floor("purple").encode() == (3, 3, 0) and Key("yellow").encode() == (5, 4, 0)
+    assert Ball("green").encode() == (6, 1, 0) and Box("red").encode() == (7, 0, 0)
+    assert Door("red").encode() == (4, 0, 1) and Door("blue", is_open=True).encode() == (4, 2, 0)
+    assert Door("grey", is_locked=True).encode() == (4, 5, 2)
+    # can_overlap: empty, floor, goal, lava, OPEN door; can_pickup: key, ball, box (SURVEY.md section 8a A2)
+    assert [o.can_overlap() for o in (WorldObj.empty(), Floor(), Goal(), Lava(), Door(is_open=True), Door(), Wall(), Key())] == \
+        [True, True, True, True, True, False, False, False]
+    assert [o.can_pickup() for o in (Key(), Ball(), Box(), Door(), Wall(), Goal())] == [True, True, True, False, False, False]
+    assert WorldObj.from_array((1, 0, 0)) is None
+    d = WorldObj.from_array((4, 3, 2))
+    assert isinstance(d, Door) and d.is_locked and not d.is_open and d.color.value == "purple"
+    d.is_locked = False
+    d.is_open = True
+    assert d.encode() == (4, 3, 0)
+    with pytest.raises(ValueError):
+        WorldObj.from_array((11, 0, 0))
+    assert Key() != Key()  # identity, like the reference
+
+
+def test_grid_get_set_over_the_tensor_state(monkeypatch):
+    """env.grid.get / set (core/grid.py:102-131) read and write single cells of the batched tensor state."""
+    from multigrid_b200.core.world_object import Ball, Door, Goal, Wall
+    from tests.hostsim.fake_engine import HostSimStepEngine
+    monkeypatch.setattr(env_mod, "StepEngine", HostSimStepEngine)
+    env = make("MultiGrid-Empty-8x8-v0", agents=2, num_envs=3, device="cpu")
+    env.reset(seed=0)
+    assert isinstance(env.grid.get(0, 0, 0), Wall) and isinstance(env.grid.get(2, 6, 6), Goal)
+    assert env.grid.get(1, 3, 3) is None and env.grid.get(1, -1, 3) is None
+    env.grid.set(1, 3, 3, Ball("purple"))
+    env.grid.set(2, 2, 5, Door("red", is_locked=True))
+    env.grid.set(0, 6, 6, None)
+    assert env.grid.get(1, 3, 3).encode() == (6, 3, 0) and env.grid.get(0, 3, 3) is None
+    assert env.grid.get(2, 2, 5).is_locked and env.grid.get(0, 6, 6) is None
+    assert tuple(int(v) for v in env.grid.state[1, 3, 3]) == (6, 3, 0)

@@ -30,4 +30,11 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:stat
     python bench.py --steps 640 --warmup 4 --no-cpu-baseline --no-verify > $OUT/${TAG}_ncu_static.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_obs_kernel -s 600 -c 1 -f -o $OUT/${TAG}_bup_prof \
     python bench.py --config bup --steps 640 --warmup 4 --no-cpu-baseline --no-verify > $OUT/${TAG}_ncu_bup.log 2>&1
+# step + one-hot (fused vs separate pass), general kernels, reset / fresh-layout timings, host cost of a step
+timeout 300 python tools/kbench.py --configs empty8,bup,empty16 --extra ONEHOT=1,ONEHOT=2 > $OUT/${TAG}_kbench.jsonl 2> $OUT/${TAG}_kbench.err
+MG_NO_STATIC=1 timeout 300 python tools/kbench.py --configs empty8,bup,empty16 --extra ONEHOT=1,ONEHOT=2,CHAINED=1 > $OUT/${TAG}_kbench_general.jsonl 2>> $OUT/${TAG}_kbench.err
+timeout 300 python tools/reset_bench.py > $OUT/${TAG}_reset.jsonl 2> $OUT/${TAG}_reset.err
+timeout 200 python tools/api_overhead.py > $OUT/${TAG}_api.jsonl 2>&1
+# memcheck over the kernels added in round 2 (palette / wire packers, fused one-hot, layout refresh)
+timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_packed_obs.py tests/test_fresh_layouts.py tests/test_fused_one_hot.py -m gpu -x -q -k "palette or wire or fresh or ragged or static_grid_random or wrapper" > $OUT/${TAG}_memcheck_new.log 2>&1; tail -3 $OUT/${TAG}_memcheck_new.log
 ls -la $OUT/${TAG}_*
