@@ -433,6 +433,35 @@ struct alignas(16) SV16 { uint32_t x, y, z, w; };
 struct alignas(8) SV8 { uint32_t x, y; };
 #endif
 
+// PCG64 jump-ahead: the state after K steps of s' = s * A + inc (mod 2^128) is s * A^K + inc * (1 + A + ... + A^(K-1)).
+// The two constants are compile-time 128-bit values (numpy's PCG64 multiplier, numpy/random/src/pcg64/pcg64.h).
+constexpr unsigned __int128 PCG64_MULT = ((unsigned __int128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+#ifdef __CUDACC__
+#define MG_CONSTEXPR_HD __host__ __device__ constexpr
+#else
+#define MG_CONSTEXPR_HD constexpr
+#endif
+MG_CONSTEXPR_HD unsigned __int128 pcg64_pow(int k) {
+    unsigned __int128 r = 1;
+    for (int i = 0; i < k; i++) r *= PCG64_MULT;
+    return r;
+}
+MG_CONSTEXPR_HD unsigned __int128 pcg64_geo(int k) {
+    unsigned __int128 r = 0, q = 1;
+    for (int i = 0; i < k; i++) { r += q; q *= PCG64_MULT; }
+    return r;
+}
+template <int K>
+MG_HD void pcg64_jump(uint64_t &lo, uint64_t &hi, uint64_t inc_lo, uint64_t inc_hi) {
+    constexpr unsigned __int128 A = pcg64_pow(K), G = pcg64_geo(K);
+    constexpr uint64_t A_LO = (uint64_t)A, A_HI = (uint64_t)(A >> 64), G_LO = (uint64_t)G, G_HI = (uint64_t)(G >> 64);
+    const uint64_t rlo = lo * A_LO, rhi = mulhi64(lo, A_LO) + lo * A_HI + hi * A_LO;
+    const uint64_t glo = inc_lo * G_LO, ghi = mulhi64(inc_lo, G_LO) + inc_lo * G_HI + inc_hi * G_LO;
+    const uint64_t slo = rlo + glo;
+    hi = rhi + ghi + (slo < rlo ? 1ull : 0ull);
+    lo = slo;
+}
+
 // handle_actions on a static grid, unrolled and branch-free except for the rare goal / lava outcome: every
 // agent of the drawn order selects between its rotated word and the memoised `forward` word of its
 // (x, y, dir) (static_move_word: one 4-byte load from a 1 KB table instead of the front-cell arithmetic).
@@ -509,7 +538,6 @@ MG_HD void static_fast_env(const Params &p, const Group &g, int lane, uint32_t *
         r.lo = s.lo; r.hi = s.hi; r.ilo = c.lo; r.ihi = c.hi;
     }
     const uint64_t lo0 = r.lo, hi0 = r.hi;
-    const uint32_t ord = static_draw_order<NT>(r);
     // ---- auto-reset decision (is_done, base.py:534-539)
     bool was_reset = false;
     if (p.flags & MG_FLAG_AUTO_RESET) {
@@ -528,7 +556,42 @@ MG_HD void static_fast_env(const Params &p, const Group &g, int lane, uint32_t *
     bool truncated = false;
     if (!was_reset) {
         r.sc += 1;  // base.py:333
-        static_transition_fast<NT>(p, moves, col, ord, acts0, acts1, rewarded);
+        // Order-independent fast path. The drawn order (base.py:396-399) only matters when agents interact: through
+        // the no-overlap test (base.py:425-429) or through a goal / lava outcome (termination of the others, rewards).
+        // With overlap allowed (the reference's default) and no agent stepping onto goal or lava in this step -- some
+        // 98 % of the env-steps of Empty-8x8 -- every agent's move is independent of the others': the n moves are
+        // computed side by side in registers, the permutation is never materialised (no draws' outputs, no sort, no
+        // serial loop through shared memory), and the env's PCG64 stream is advanced by its n draws with ONE
+        // jump-ahead. Anything else takes the exact serial path below from the same state.
+        const uint32_t TERM = 1u << 24;
+        bool slow = !(p.flags & MG_FLAG_ALLOW_OVERLAP), bad = false;
+        uint32_t na[NT];
+        if (!slow) {
+            const uint32_t last = (uint32_t)(p.W * p.H * 4 - 1);
+#pragma unroll
+            for (int j = 0; j < NT; j++) {
+                const int act = (int)(int8_t)((NT > 4 && j >= 4 ? acts1 : acts0) >> (8 * (j & 3)));
+                const uint32_t a0 = col[j * LANES], dir = a0 & 3u;
+                const bool live = act >= 0 && a0 < TERM;  // id in the action dict and not terminated (base.py:403-409)
+                uint32_t idx = ((((a0 >> 8) & 0xff) * (uint32_t)p.H + ((a0 >> 16) & 0xff)) << 2) | dir;
+                idx = idx < last ? idx : last;
+                const uint32_t mv = moves[idx];
+                const uint32_t turn = act == ACT_LEFT ? 3u : (act == ACT_RIGHT ? 1u : 0u);  // base.py:412-417
+                const bool move = live && act == ACT_FORWARD && (mv & MOVE_OK);             // base.py:420-423
+                na[j] = !live ? a0 : (move ? (mv & 0x00ffffffu) : ((a0 & ~0xffu) | ((dir + turn) & 3u)));
+                slow |= move && (mv & (MOVE_GOAL | MOVE_LAVA)) != 0;
+                bad |= live && act > ACT_DONE;  // reference: ValueError (base.py:473-474)
+            }
+        }
+        if (!slow) {
+#pragma unroll
+            for (int j = 0; j < NT; j++) col[j * LANES] = na[j];
+            if (bad) status_or(p.status, 1);
+            pcg64_jump<NT>(r.lo, r.hi, r.ilo, r.ihi);  // the n draws of np_random.random(size=n), base.py:399
+        } else {
+            const uint32_t ord = static_draw_order<NT>(r);
+            static_transition_fast<NT>(p, moves, col, ord, acts0, acts1, rewarded);
+        }
         truncated = r.sc >= p.max_steps;  // base.py:339
     } else {
         r.lo = lo0; r.hi = hi0;  // no step, no draw
