@@ -328,8 +328,12 @@ def graph_of(stream, torch, fn, K):
 
 
 def time_graph(stream, torch, g):
+    """Device time of one replay. A ~100 us spin kernel is enqueued first, so that the start event and the graph launch
+    are both queued behind it when it ends: the timed window is the K launches on the device, not the host's latency
+    between `ev0.record()` and the arrival of the graph launch (under torchrun, N Python processes share the host)."""
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
+        torch.cuda._sleep(200_000)
         ev0.record(stream)
         g.replay()
         ev1.record(stream)
