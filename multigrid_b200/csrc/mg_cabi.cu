@@ -290,6 +290,7 @@ int step_common(const MgConfig *cfg, int64_t num_envs, const MgState *state, con
                 if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
                 if (sms[dev] > 0) n_sm = sms[dev];
             }
+            p.no_lut = env_int("MG_NO_LUT", 0, k);
             if ((rc = mg::plan_static(p, env_int("MG_GROUP", 0, k), env_int("MG_WPB", 0, k), kSmemPerBlock, n_sm))) return rc;
             auto misaligned = [](const void *ptr, uintptr_t a) { return (reinterpret_cast<uintptr_t>(ptr) & (a - 1)) != 0; };
             if (misaligned(p.pcg_state, 16) || misaligned(p.pcg_inc, 16) || misaligned(p.reward, 8) ||

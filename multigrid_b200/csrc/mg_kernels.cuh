@@ -92,6 +92,7 @@ struct Params {
     const uint32_t *static_move;  // [W*H*4] memoised forward moves (behind the observation entries)
     int32_t static_stride, nstage;  // nstage: observation stages of a block (one per warp)
     int32_t lut_words;              // move words copied into the block's shared memory (0: read from global)
+    int32_t no_lut;                 // host side only (knob MG_NO_LUT): never copy them
 
     int8_t *direction;  // [T][E][n] per-step 'direction' observation (rollout only; NULL otherwise)
     // state (device)

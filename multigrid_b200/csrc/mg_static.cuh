@@ -55,7 +55,7 @@ inline int carve_static(Params &p, bool fast, int nstage) {
         p.off_keys = off;
         p.off_ag = off; off += n * LANES * 4;  // a0T
         p.off_act = off;                       // the block's copy of the move words (small layouts)
-        p.lut_words = p.W * p.H * 4 <= 1024 ? align16(p.W * p.H * 16) / 4 : 0;
+        p.lut_words = (p.W * p.H * 4 <= 1024 && !p.no_lut) ? align16(p.W * p.H * 16) / 4 : 0;
         off += p.lut_words * 4;
     } else {
         p.off_keys = off;  off += n > 4 ? align16(G * n * 8) + align16(G * n) : 0;

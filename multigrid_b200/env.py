@@ -189,14 +189,14 @@ class BatchedGrid:
         outside the grid. Reads one cell from the device (synchronises)."""
         if not (0 <= x < self.width and 0 <= y < self.height):
             return None
-        from .core.world_object import WorldObj
+        from .core.objects import WorldObj
         return WorldObj.from_array(self._engine.grid[e, x, y].cpu().numpy())
 
     def set(self, e, x: int, y: int, obj) -> None:
         """Grid.set (core/grid.py:119-131): put `obj` (a WorldObj, an (type, colour, state) triple, or None = empty)
         at (x, y) of env `e` (an int, a slice, or an index tensor). Goes through the engine, which keeps the cell
         words' opaque bit, the dedup / static-grid bookkeeping and the wire palette consistent."""
-        from .core.world_object import WorldObj
+        from .core.objects import WorldObj
         enc = (1, 0, 0) if obj is None else tuple(int(v) for v in (obj.encode() if isinstance(obj, WorldObj) else obj))
         grid = self._engine.grid.clone()
         grid[e, x, y] = torch.tensor(enc, dtype=grid.dtype, device=grid.device)

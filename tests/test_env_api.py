@@ -343,7 +343,7 @@ def test_one_hot_over_fully_obs_encodes_the_wrapped_image():
 
 def test_world_object_view_matches_the_reference_encodings():
     """core/world_object.py: the reference's class names, encodings and rule predicates (world_object.py:28-605)."""
-    from multigrid_b200.core.world_object import Ball, Box, Door, Floor, Goal, Key, Lava, Wall, WorldObj
+    from multigrid_b200.core.objects import Ball, Box, Door, Floor, Goal, Key, Lava, Wall, WorldObj
     assert Wall().encode() == (2, 5, 0) and Goal().encode() == (8, 1, 0) and Lava().encode() == (9, 0, 0)
     assert Floor("purple").encode() == (3, 3, 0) and Key("yellow").encode() == (5, 4, 0)
     assert Ball("green").encode() == (6, 1, 0) and Box("red").encode() == (7, 0, 0)
@@ -366,7 +366,7 @@ def test_world_object_view_matches_the_reference_encodings():
 
 def test_grid_get_set_over_the_tensor_state(monkeypatch):
     """env.grid.get / set (core/grid.py:102-131) read and write single cells of the batched tensor state."""
-    from multigrid_b200.core.world_object import Ball, Door, Goal, Wall
+    from multigrid_b200.core.objects import Ball, Door, Goal, Wall
     from tests.hostsim.fake_engine import HostSimStepEngine
     monkeypatch.setattr(env_mod, "StepEngine", HostSimStepEngine)
     env = make("MultiGrid-Empty-8x8-v0", agents=2, num_envs=3, device="cpu")
