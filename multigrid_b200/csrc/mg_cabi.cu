@@ -373,8 +373,12 @@ static int one_hot_cells(int64_t cells, int64_t images, int32_t stride, const in
     if (reinterpret_cast<uintptr_t>(out) & 3u) return MG_ERR_ALIGNMENT;
     // the 16-byte kernel needs 16-byte aligned blocks of 16 images: cells * 21 * 16 bytes each, always a multiple of 16
     if ((reinterpret_cast<uintptr_t>(out) & 15u) == 0 && cells <= 1024 && !env_int("MG_ONE_HOT_W32", 0)) {
-        mg::one_hot_kernel_v16<<<(unsigned)((images + 15) / 16), 256, 0, (cudaStream_t)stream>>>(
-            (int)cells, images, stride, mg::rcp32((int)cells), obs, (uint4 *)out);
+        if (!env_int("MG_ONE_HOT_V16", 0))  // (knob: the previous 16-bytes-per-thread kernel)
+            mg::one_hot_tile_kernel<<<(unsigned)((images + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+                (int)cells, images, stride, mg::rcp32((int)cells), obs, out);
+        else
+            mg::one_hot_kernel_v16<<<(unsigned)((images + 15) / 16), 256, 0, (cudaStream_t)stream>>>(
+                (int)cells, images, stride, mg::rcp32((int)cells), obs, (uint4 *)out);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return (int)cudaGetLastError();
     }
@@ -476,9 +480,15 @@ int mg_obs_features(int32_t view_size, int64_t num_agents_total, int32_t obs_age
     if (!obs || !direction || !dir_lut || !out) return MG_ERR_BAD_ARG;
     // 16 agents x V*V*23 floats is a multiple of 16 bytes, so every block's 16-byte stores are aligned
     if (reinterpret_cast<uintptr_t>(out) & 15u) return MG_ERR_ALIGNMENT;
-    mg::obs_features_kernel<<<(unsigned)((num_agents_total + 15) / 16), 256, 0, (cudaStream_t)stream>>>(
-        view_size, num_agents_total, obs_agent_stride, mg::rcp32(view_size * view_size * 23), obs, direction,
-        direction_stride, dir_lut, (float4 *)out);
+    if (env_int("MG_FEATURES_DIRECT", 0, any_mg_knob())) {  // knob: the first version (one 16-byte store per thread)
+        mg::obs_features_kernel<<<(unsigned)((num_agents_total + 15) / 16), 256, 0, (cudaStream_t)stream>>>(
+            view_size, num_agents_total, obs_agent_stride, mg::rcp32(view_size * view_size * 23), obs, direction,
+            direction_stride, dir_lut, (float4 *)out);
+    } else {  // 32 agents per block: 32 * V*V * 23 floats is a multiple of 16 bytes as well
+        mg::obs_features_tile_kernel<<<(unsigned)((num_agents_total + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+            view_size, num_agents_total, obs_agent_stride, mg::rcp32(view_size * view_size), obs, direction,
+            direction_stride, dir_lut, out);
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return (int)cudaGetLastError();
 }

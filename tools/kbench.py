@@ -169,8 +169,9 @@ def time_one_hot(V=7, A=262144):
     stride = _cabi.obs_agent_stride(V)
     obs = torch.randint(0, 4, (A, stride), device="cuda", dtype=torch.int32).to(torch.int8)
     outs = [torch.empty((A, V, V, 21), dtype=torch.uint8, device="cuda") for _ in range(3)]  # 3 x 270 MB > L2
-    for name, env in (("v16", "0"), ("w32", "1")):
-        os.environ["MG_ONE_HOT_W32"] = env
+    for name, env in (("tile", "0"), ("v16", "v16"), ("w32", "1")):
+        os.environ["MG_ONE_HOT_W32"] = "1" if env == "1" else "0"
+        os.environ["MG_ONE_HOT_V16"] = "1" if env == "v16" else "0"
         for o in outs:
             lib.mg_one_hot(V, A, stride, obs.data_ptr(), o.data_ptr(), None)
         torch.cuda.synchronize()
@@ -185,6 +186,7 @@ def time_one_hot(V=7, A=262144):
         print(json.dumps(dict(kernel=f"one_hot_{name}", agents=A, V=V, us=round(us, 2),
                               gbs=round(nbytes / us / 1e3, 1))), flush=True)
     os.environ.pop("MG_ONE_HOT_W32", None)
+    os.environ.pop("MG_ONE_HOT_V16", None)
     # mg_obs_features: the float32 23-channel network input straight from the observations
     dirs = torch.randint(0, 4, (A, 8), device="cuda", dtype=torch.int32).to(torch.int8)
     lut = torch.stack([torch.cos(2 * torch.pi * torch.arange(4) / 4), torch.sin(2 * torch.pi * torch.arange(4) / 4)], -1).cuda()
