@@ -419,8 +419,11 @@ int mg_step_obs_host_palette(const MgConfig *cfg, int64_t num_envs, const MgStat
                              const uint8_t *lut, const MgStepOut *h_out, void *stream);
 
 /*
- * The host wire (ABI v11): everything a CPU-side caller of env.step() needs from one step in ONE device-to-host
- * copy. Layout of the buffer (mg_wire_bytes bytes; 16-byte aligned on the device):
+ * The host wire (ABI v11): everything a CPU-side caller of env.step() needs from one step in ONE compact buffer
+ * (one device-to-host copy; for batches of 32 768 envs or more the envs are stepped and packed in 4 slices on the
+ * caller's stream while a side stream copies the finished slices, so the kernels hide behind the PCIe transfer; the
+ * caller's stream waits for the side stream before the call's work is complete; MG_WIRE_CHUNKS=1..8 overrides).
+ * Layout of the buffer (mg_wire_bytes bytes; 16-byte aligned on the device):
  *   [0, mg_wire_obs_bytes)   observations in the palette format (mg_pack_obs_palette), [E][n][stride_bits]
  *   then E records of mg_wire_record_bytes(n) bytes:
  *       float64 value; uint32 terminated mask (bit j = agent j) | truncated << 31; uint32 counts[ceil(n / 8)]

@@ -724,12 +724,39 @@ int64_t mg_wire_bytes(int32_t view_size, int32_t bits, int32_t num_agents, int64
     return mg_wire_obs_bytes(view_size, bits, num_agents, num_envs) + num_envs * (int64_t)mg::wire_record_bytes(num_agents);
 }
 
+}  // extern "C"
+
+namespace {
+// Side stream + events of the chunked host wire (one set per device, created on first use).
+struct WirePipe { cudaStream_t side = nullptr; cudaEvent_t ready[8] = {}, done = nullptr; };
+WirePipe *wire_pipe() {
+    static WirePipe pipes[64];
+    static std::atomic<int> made[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    WirePipe &w = pipes[dev];
+    int expect = 0;
+    if (made[dev].load(std::memory_order_acquire) == 2) return &w;
+    if (made[dev].compare_exchange_strong(expect, 1)) {
+        bool ok = cudaStreamCreateWithFlags(&w.side, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 8 && ok; i++) ok = cudaEventCreateWithFlags(&w.ready[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming) == cudaSuccess;
+        made[dev].store(ok ? 2 : 3, std::memory_order_release);
+        return ok ? &w : nullptr;
+    }
+    while (made[dev].load(std::memory_order_acquire) == 1) {}
+    return made[dev].load(std::memory_order_acquire) == 2 ? &w : nullptr;
+}
+}  // namespace
+
+extern "C" {
+
 int mg_step_obs_host_wire(const MgConfig *cfg, int64_t num_envs, const MgState *state, const int8_t *h_actions,
                           int8_t *d_actions, const MgStepOut *d_out, uint8_t *d_wire, int32_t bits, const uint8_t *lut,
                           uint8_t *h_wire, void *stream) {
     int rc = validate(cfg, num_envs);
     if (rc) return rc;
-    if (!h_actions || !d_actions || !d_out || !d_wire || !lut || !h_wire || !d_out->status) return MG_ERR_BAD_ARG;
+    if (!h_actions || !d_actions || !d_out || !d_wire || !lut || !h_wire || !d_out->status || !state) return MG_ERR_BAD_ARG;
     if (cfg->num_agents > 31) return MG_ERR_BAD_ARG;  // (terminated mask + the truncated bit share one word)
     if (reinterpret_cast<uintptr_t>(d_wire) & 15u) return MG_ERR_ALIGNMENT;
     if (num_envs == 0) return 0;
@@ -737,17 +764,56 @@ int mg_step_obs_host_wire(const MgConfig *cfg, int64_t num_envs, const MgState *
     const size_t E = (size_t)num_envs, n = (size_t)cfg->num_agents;
     cudaError_t err = cudaMemcpyAsync(d_actions, h_actions, E * n, cudaMemcpyHostToDevice, s);
     if (err != cudaSuccess) return (int)err;
-    rc = step_common<mg::MODE_STEP_OBS>(cfg, num_envs, state, d_actions, d_out, stream);
-    if (rc) return rc;
-    if ((rc = mg_pack_obs_palette(cfg->view_size, (int64_t)(E * n), cfg->obs_agent_stride, d_out->obs, bits, lut,
-                                  d_wire, d_out->status, stream))) return rc;
-    uint8_t *records = d_wire + mg_wire_obs_bytes(cfg->view_size, bits, cfg->num_agents, num_envs);
-    mg::wire_env_records_kernel<<<(unsigned)((E + 127) / 128), 128, 0, s>>>(
-        (int)n, (int64_t)E, d_out->reward, d_out->terminated, d_out->truncated, records, d_out->status);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    if ((err = cudaGetLastError()) != cudaSuccess) return (int)err;
-    const size_t bytes = (size_t)mg_wire_bytes(cfg->view_size, bits, cfg->num_agents, num_envs);
-    if ((err = cudaMemcpyAsync(h_wire, d_wire, bytes, cudaMemcpyDeviceToHost, s))) return (int)err;  // ONE copy
+    const size_t ps = (size_t)mg::packed_obs_stride_bits(cfg->view_size, bits), rb = (size_t)mg::wire_record_bytes((int)n);
+    const size_t obs_bytes = (size_t)mg_wire_obs_bytes(cfg->view_size, bits, cfg->num_agents, num_envs);
+    // Chunked pipeline: the envs are stepped and packed in C slices on the caller's stream while a side stream copies
+    // the finished slices to the host, so only the first slice's kernels are not hidden behind the PCIe transfer.
+    // (Slices of a multiple of 256 envs keep every per-env array 16-byte aligned. Big batches only; MG_WIRE_CHUNKS=1
+    // turns it off.)
+    const bool k = any_mg_knob();
+    int C = env_int("MG_WIRE_CHUNKS", num_envs >= 32768 ? 4 : 1, k);
+    C = C < 1 ? 1 : (C > 8 ? 8 : C);
+    WirePipe *pipe = C > 1 ? wire_pipe() : nullptr;
+    if (!pipe) C = 1;
+    const size_t chunk = C == 1 ? E : (((E + C - 1) / C + 255) & ~(size_t)255);
+    const size_t cs = (size_t)mg::cells_per_env(cfg->width, cfg->height);
+    int used = 0;
+    for (size_t e0 = 0; e0 < E; e0 += chunk, used++) {
+        const size_t ne = E - e0 < chunk ? E - e0 : chunk;
+        MgState st = *state;
+        MgStepOut out = *d_out;
+        st.grid = state->grid + e0 * cs; st.agents = state->agents + e0 * n * 8; st.step_count = state->step_count + e0;
+        if (state->pcg_state) st.pcg_state = state->pcg_state + 2 * e0;
+        if (state->pcg_inc) st.pcg_inc = state->pcg_inc + 2 * e0;
+        if (state->layout_idx) st.layout_idx = state->layout_idx + e0;
+        if (state->hook_state) st.hook_state = state->hook_state + e0;
+        if (state->chain) st.chain = state->chain + 4 * e0;
+        out.obs = d_out->obs + e0 * n * (size_t)cfg->obs_agent_stride;
+        out.reward = d_out->reward + e0 * n; out.terminated = d_out->terminated + e0 * n; out.truncated = d_out->truncated + e0;
+        if (d_out->one_hot) out.one_hot = d_out->one_hot + e0 * n * (size_t)cfg->view_size * cfg->view_size * 21;
+        if ((rc = step_common<mg::MODE_STEP_OBS>(cfg, (int64_t)ne, &st, d_actions + e0 * n, &out, stream))) return rc;
+        if ((rc = mg_pack_obs_palette(cfg->view_size, (int64_t)(ne * n), cfg->obs_agent_stride, out.obs, bits, lut,
+                                      d_wire + e0 * n * ps, d_out->status, stream))) return rc;
+        mg::wire_env_records_kernel<<<(unsigned)((ne + 127) / 128), 128, 0, s>>>(
+            (int)n, (int64_t)ne, out.reward, out.terminated, out.truncated, d_wire + obs_bytes + e0 * rb, d_out->status);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if ((err = cudaGetLastError()) != cudaSuccess) return (int)err;
+        if (C == 1) break;
+        // this slice's observations go out while the next slice is computed
+        if ((err = cudaEventRecord(pipe->ready[used], s))) return (int)err;
+        if ((err = cudaStreamWaitEvent(pipe->side, pipe->ready[used], 0))) return (int)err;
+        if ((err = cudaMemcpyAsync(h_wire + e0 * n * ps, d_wire + e0 * n * ps, ne * n * ps, cudaMemcpyDeviceToHost, pipe->side)))
+            return (int)err;
+    }
+    if (C == 1) {  // ONE copy
+        const size_t bytes = (size_t)mg_wire_bytes(cfg->view_size, bits, cfg->num_agents, num_envs);
+        if ((err = cudaMemcpyAsync(h_wire, d_wire, bytes, cudaMemcpyDeviceToHost, s))) return (int)err;
+        return 0;
+    }
+    // the env records of all slices in one copy behind the last slice, then the caller's stream waits for the side stream
+    if ((err = cudaMemcpyAsync(h_wire + obs_bytes, d_wire + obs_bytes, E * rb, cudaMemcpyDeviceToHost, pipe->side))) return (int)err;
+    if ((err = cudaEventRecord(pipe->done, pipe->side))) return (int)err;
+    if ((err = cudaStreamWaitEvent(s, pipe->done, 0))) return (int)err;
     return 0;
 }
 

@@ -277,3 +277,45 @@ def test_gpu_host_wire_matches_reference_fixtures(name):
         np.testing.assert_array_equal(term, d["terminated"][t].astype(bool), err_msg=msg)
         np.testing.assert_array_equal(trunc, d["truncated"][t].astype(bool), err_msg=msg)
     g.eng.check_status()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", ["2", "4", "8"])
+@pytest.mark.parametrize("seed,B,kw", [
+    (0, 1000, dict(W=8, H=8, n=4, V=7)),
+    (1, 777, dict(W=11, H=6, n=2, V=7, hook=1, joint_reward=True, auto_reset=True, max_steps=9)),
+    (2, 600, dict(W=9, H=7, n=3, V=5, see_through_walls=True)),
+])
+def test_gpu_host_wire_chunked_pipeline(seed, B, kw, chunks, monkeypatch):
+    """MG_WIRE_CHUNKS: the envs are stepped and packed in slices (multiples of 256 envs, ragged last slice) on the
+    caller's stream while a side stream copies finished slices; results and state equal the C oracle's."""
+    import torch
+    from multigrid_b200.engine import unpack_wire
+    from tests.gpu_adapter import GpuEngine
+    monkeypatch.setenv("MG_WIRE_CHUNKS", chunks)
+    kw = dict(kw)
+    cfg = O.OracleConfig(max_steps=kw.pop("max_steps", 40), **kw)
+    st = random_batch(cfg, B, seed)
+    ora, g = COracle(cfg, **st), GpuEngine(cfg, **st)
+    bits, codes = g.eng.wire_palette()
+    rng = np.random.default_rng(seed)
+    for t in range(12):
+        actions = rng.integers(-1, 7, size=(B, cfg.n)).astype(np.int8)
+        o1, r1, t1, tr1 = ora.step(actions)
+        h = g.eng.host_buffers(packed="wire")
+        h["actions"].copy_(torch.from_numpy(actions))
+        h = g.eng.step_host(packed="wire")
+        img, rew, term, trunc = unpack_wire(h["wire"], B, cfg.n, cfg.V, bits, codes)
+        np.testing.assert_array_equal(img, o1, err_msg=f"step {t}")
+        assert (rew == r1).all()
+        np.testing.assert_array_equal(term, t1.astype(bool))
+        np.testing.assert_array_equal(trunc, tr1.astype(bool))
+    g.eng.check_status()
+    P_assert_same(g, ora)
+
+
+def P_assert_same(a, b):
+    np.testing.assert_array_equal(a.grid, b.grid)
+    np.testing.assert_array_equal(a.agents, b.agents)
+    np.testing.assert_array_equal(a.step_count, b.step_count)
+    np.testing.assert_array_equal(a.pcg_state, b.pcg_state)
